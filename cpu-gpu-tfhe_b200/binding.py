@@ -1,0 +1,275 @@
+"""ctypes binding of include/tfhe_b200.h and a thin tensor-level wrapper.
+
+Function names and argument meaning mirror the reference's operator interface
+for the path (gpuParallel/tfhe_gate_bootstrapping_functions.h:14-198):
+``Engine.gate("NAND", ca, cb)`` is the batched ``bootsNAND`` and so on; errors
+raise ``EngineError`` (the reference aborts the process instead,
+tfhe_gate_bootstrapping.cu:11-15).
+"""
+import ctypes
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+GATES = ["NAND", "OR", "AND", "XOR", "XNOR", "NOR", "ANDNY", "ANDYN", "ORNY", "ORYN"]
+GATE_ID = {g: i for i, g in enumerate(GATES)}
+MU = 0x20000000  # modSwitchToTorus32(1, 8)
+
+_vp = ctypes.c_void_p
+_i = ctypes.c_int
+
+
+class EngineError(RuntimeError):
+    pass
+
+
+class Params(ctypes.Structure):
+    _fields_ = [(k, ctypes.c_int32) for k in ("n", "N", "k", "l", "Bgbit", "ks_t", "ks_basebit")]
+
+
+def lib_path():
+    return os.path.join(_HERE, "libtfhe_b200.so")
+
+
+_lib = None
+
+
+def lib():
+    """Loads libtfhe_b200.so (raises if it has not been built)."""
+    global _lib
+    if _lib is None:
+        p = lib_path()
+        if not os.path.exists(p):
+            raise EngineError("%s not built: run `python cpu-gpu-tfhe_b200/build.py`" % p)
+        L = ctypes.CDLL(p)
+        L.tfhe_b200_last_error.restype = ctypes.c_char_p
+        L.tfhe_b200_key_bytes.restype = ctypes.c_size_t
+        L.tfhe_b200_launch_count.restype = ctypes.c_ulonglong
+        L.tfhe_b200_key_bytes.argtypes = [_vp]
+        L.tfhe_b200_launch_count.argtypes = [_vp]
+        L.tfhe_b200_sm_count.argtypes = [_vp]
+        L.tfhe_b200_ctx_create.argtypes = [ctypes.POINTER(_vp), ctypes.POINTER(Params), _i]
+        L.tfhe_b200_ctx_destroy.argtypes = [_vp]
+        L.tfhe_b200_load_keys.argtypes = [_vp, _vp, _vp]
+        L.tfhe_b200_load_keys_device.argtypes = [_vp, _vp, _vp, _vp]
+        L.tfhe_b200_load_bk_fourier.argtypes = [_vp, _vp]
+        L.tfhe_b200_load_ks.argtypes = [_vp, _vp]
+        L.tfhe_b200_gate.argtypes = [_vp, _i, _vp, _vp, _vp, _i, _vp]
+        L.tfhe_b200_gate2.argtypes = [_vp, _i, _i, _vp, _vp, _vp, _i, _vp]
+        L.tfhe_b200_gate_pair.argtypes = [_vp, _i, _vp, _vp, _i, _vp, _vp, _vp, _i, _vp]
+        L.tfhe_b200_mux.argtypes = [_vp, _vp, _vp, _vp, _vp, _i, _vp]
+        L.tfhe_b200_not.argtypes = [_vp, _vp, _vp, _i, _vp]
+        L.tfhe_b200_copy.argtypes = [_vp, _vp, _vp, _i, _vp]
+        L.tfhe_b200_constant.argtypes = [_vp, _vp, _i, _i, _vp]
+        L.tfhe_b200_bootstrap_woks.argtypes = [_vp, _vp, _vp, ctypes.c_int32, _i, _vp]
+        L.tfhe_b200_bootstrap.argtypes = [_vp, _vp, _vp, ctypes.c_int32, _i, _vp]
+        L.tfhe_b200_keyswitch.argtypes = [_vp, _vp, _vp, _i, _vp]
+        L.tfhe_b200_blind_rotate.argtypes = [_vp, _vp, _vp, _i, _i, _vp]
+        L.tfhe_b200_blind_rotate_and_extract.argtypes = [_vp, _vp, _vp, _vp, _vp, _i, _i, _vp]
+        L.tfhe_b200_extern_mul.argtypes = [_vp, _vp, _i, _i, _vp]
+        L.tfhe_b200_gate_host.argtypes = [_vp, _i, _vp, _vp, _vp, _i]
+        L.tfhe_b200_mux_host.argtypes = [_vp, _vp, _vp, _vp, _vp, _i]
+        _lib = L
+    return _lib
+
+
+def default_params():
+    p = Params()
+    lib().tfhe_b200_default_params(ctypes.byref(p))
+    return p
+
+
+def device_count():
+    return int(lib().tfhe_b200_device_count())
+
+
+def _np_i32(a):
+    return np.ascontiguousarray(a, dtype=np.int32)
+
+
+class Engine:
+    """One engine context = one GPU + one key set."""
+
+    def __init__(self, params=None, device=0):
+        self.L = lib()
+        self.p = params or default_params()
+        self.device = device
+        h = _vp()
+        if self.L.tfhe_b200_ctx_create(ctypes.byref(h), ctypes.byref(self.p), device):
+            raise EngineError(self.L.tfhe_b200_last_error().decode())
+        self.h = h
+        self.words = self.p.n + 1
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.tfhe_b200_ctx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc):
+        if rc:
+            raise EngineError(self.L.tfhe_b200_last_error().decode())
+
+    # -- keys ----------------------------------------------------------------
+    def load_keys(self, bk_coef=None, ks=None):
+        bk = _np_i32(bk_coef) if bk_coef is not None else None
+        k = _np_i32(ks) if ks is not None else None
+        self._ck(self.L.tfhe_b200_load_keys(self.h, bk.ctypes.data if bk is not None else None,
+                                            k.ctypes.data if k is not None else None))
+
+    def load_keys_device(self, d_bk_coef=None, d_ks=None, stream=None):
+        self._ck(self.L.tfhe_b200_load_keys_device(
+            self.h, d_bk_coef.data_ptr() if d_bk_coef is not None else None,
+            d_ks.data_ptr() if d_ks is not None else None, self._stream(stream)))
+
+    def load_bk_fourier(self, bkfft_ref):
+        a = np.ascontiguousarray(bkfft_ref, dtype=np.complex128)
+        self._ck(self.L.tfhe_b200_load_bk_fourier(self.h, a.ctypes.data))
+
+    @property
+    def key_bytes(self):
+        return int(self.L.tfhe_b200_key_bytes(self.h))
+
+    @property
+    def launch_count(self):
+        return int(self.L.tfhe_b200_launch_count(self.h))
+
+    @property
+    def sm_count(self):
+        return int(self.L.tfhe_b200_sm_count(self.h))
+
+    # -- helpers ---------------------------------------------------------------
+    def _stream(self, stream):
+        import torch
+
+        s = stream if stream is not None else torch.cuda.current_stream(self.device)
+        return _vp(s.cuda_stream)
+
+    def _dev(self):
+        import torch
+
+        return torch.device("cuda", self.device)
+
+    def _chk(self, t, words=None):
+        import torch
+
+        assert t.is_cuda and t.dtype == torch.int32 and t.is_contiguous(), "need contiguous int32 CUDA tensor"
+        if words is not None:
+            assert t.shape[-1] == words, "last dimension must be %d" % words
+        return t
+
+    def empty(self, count, words=None):
+        import torch
+
+        return torch.empty((count, words or self.words), dtype=torch.int32, device=self._dev())
+
+    def to_device(self, a):
+        import torch
+
+        return torch.from_numpy(_np_i32(a)).to(self._dev())
+
+    # -- gates (device tensors [count, n+1] int32) -------------------------------
+    def gate(self, name, ca, cb, out=None, stream=None):
+        self._chk(ca, self.words), self._chk(cb, self.words)
+        count = ca.shape[0]
+        out = self.empty(count) if out is None else out
+        self._ck(self.L.tfhe_b200_gate(self.h, GATE_ID[name], out.data_ptr(), ca.data_ptr(), cb.data_ptr(), count,
+                                       self._stream(stream)))
+        return out
+
+    def gate2(self, g0, g1, ca, cb, out=None, stream=None):
+        count = ca.shape[0]
+        out = self.empty(2 * count) if out is None else out
+        self._ck(self.L.tfhe_b200_gate2(self.h, GATE_ID[g0], GATE_ID[g1], out.data_ptr(), ca.data_ptr(),
+                                        cb.data_ptr(), count, self._stream(stream)))
+        return out
+
+    def gate_pair(self, g0, a0, b0, g1, a1, b1, out=None, stream=None):
+        count = a0.shape[0]
+        out = self.empty(2 * count) if out is None else out
+        self._ck(self.L.tfhe_b200_gate_pair(self.h, GATE_ID[g0], a0.data_ptr(), b0.data_ptr(), GATE_ID[g1],
+                                            a1.data_ptr(), b1.data_ptr(), out.data_ptr(), count,
+                                            self._stream(stream)))
+        return out
+
+    def mux(self, a, b, c, out=None, stream=None):
+        count = a.shape[0]
+        out = self.empty(count) if out is None else out
+        self._ck(self.L.tfhe_b200_mux(self.h, out.data_ptr(), a.data_ptr(), b.data_ptr(), c.data_ptr(), count,
+                                      self._stream(stream)))
+        return out
+
+    def not_(self, ca, out=None, stream=None):
+        out = self.empty(ca.shape[0]) if out is None else out
+        self._ck(self.L.tfhe_b200_not(self.h, out.data_ptr(), ca.data_ptr(), ca.shape[0], self._stream(stream)))
+        return out
+
+    def copy(self, ca, out=None, stream=None):
+        out = self.empty(ca.shape[0]) if out is None else out
+        self._ck(self.L.tfhe_b200_copy(self.h, out.data_ptr(), ca.data_ptr(), ca.shape[0], self._stream(stream)))
+        return out
+
+    def constant(self, value, count, out=None, stream=None):
+        out = self.empty(count) if out is None else out
+        self._ck(self.L.tfhe_b200_constant(self.h, out.data_ptr(), int(value), count, self._stream(stream)))
+        return out
+
+    # -- building blocks ---------------------------------------------------------
+    def bootstrap_woks(self, x, mu=MU, stream=None):
+        count = x.shape[0]
+        u = self.empty(count, self.p.N * self.p.k + 1)
+        self._ck(self.L.tfhe_b200_bootstrap_woks(self.h, u.data_ptr(), x.data_ptr(), mu, count, self._stream(stream)))
+        return u
+
+    def bootstrap(self, x, mu=MU, stream=None):
+        count = x.shape[0]
+        out = self.empty(count)
+        self._ck(self.L.tfhe_b200_bootstrap(self.h, out.data_ptr(), x.data_ptr(), mu, count, self._stream(stream)))
+        return out
+
+    def keyswitch(self, u, stream=None):
+        count = u.shape[0]
+        out = self.empty(count)
+        self._ck(self.L.tfhe_b200_keyswitch(self.h, out.data_ptr(), u.data_ptr(), count, self._stream(stream)))
+        return out
+
+    def blind_rotate(self, acc, bara, stream=None):
+        """acc [count, k+1, N] (modified in place and returned), bara [count, n_iter]."""
+        count, n_iter = bara.shape
+        self._ck(self.L.tfhe_b200_blind_rotate(self.h, acc.data_ptr(), bara.data_ptr(), n_iter, count,
+                                               self._stream(stream)))
+        return acc
+
+    def blind_rotate_and_extract(self, testvect, barb, bara, stream=None):
+        count, n_iter = bara.shape
+        u = self.empty(count, self.p.N * self.p.k + 1)
+        self._ck(self.L.tfhe_b200_blind_rotate_and_extract(self.h, u.data_ptr(), testvect.data_ptr(),
+                                                           barb.data_ptr(), bara.data_ptr(), n_iter, count,
+                                                           self._stream(stream)))
+        return u
+
+    def extern_mul(self, acc, bk_index, stream=None):
+        count = acc.shape[0]
+        self._ck(self.L.tfhe_b200_extern_mul(self.h, acc.data_ptr(), int(bk_index), count, self._stream(stream)))
+        return acc
+
+    # -- host buffers (numpy in, numpy out; copies inside the call) -----------------
+    def gate_host(self, name, ca, cb, out=None):
+        ca, cb = _np_i32(ca), _np_i32(cb)
+        out = np.empty_like(ca) if out is None else out
+        self._ck(self.L.tfhe_b200_gate_host(self.h, GATE_ID[name], out.ctypes.data, ca.ctypes.data, cb.ctypes.data,
+                                            ca.shape[0]))
+        return out
+
+    def mux_host(self, a, b, c):
+        a, b, c = _np_i32(a), _np_i32(b), _np_i32(c)
+        out = np.empty_like(a)
+        self._ck(self.L.tfhe_b200_mux_host(self.h, out.ctypes.data, a.ctypes.data, b.ctypes.data, c.ctypes.data,
+                                           a.shape[0]))
+        return out

@@ -1,0 +1,292 @@
+// Persistent blind-rotation + sample-extraction kernel for sm_100a.
+//
+// Replaces the reference's host-driven loop of 2500 launches + 1000 cuFFT calls
+// per gate batch (bootstrapAndKeySwitch_n_Bit, boot-gates.cu:2481-2629, kernels
+// :2127-2362) and implements tfhe_blindRotateAndExtract_FFT
+// (lwe-bootstrapping-functions-fft.cu:1408-1456) for a whole batch:
+//
+//   * one warp owns one ciphertext; its TLWE accumulator (8 KB) and the FFT
+//     exchange buffers stay in shared memory for all n iterations; the
+//     transforms run in registers (br_core.cuh) and only warp-level barriers
+//     are needed between phases;
+//   * 4 ciphertext warps per CTA share each 16 KiB row of the bootstrapping key,
+//     streamed from L2/HBM by a producer lane with 1-D TMA bulk copies
+//     (cp.async.bulk + mbarrier expect_tx) into a 3-stage ring;
+//   * the gate's linear prologue and the mod-switch are computed on the fly
+//     from the input samples (no temporaries in global memory);
+//   * grid = min(#groups, #SMs) CTAs, each looping over groups of 4 ciphertexts.
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "br_core.cuh"
+#include "kernels.h"
+
+namespace tfhe_b200 {
+
+namespace {
+
+constexpr int kCtWarps = 4;                       // ciphertexts (consumer warps) per CTA
+constexpr int kThreads = (kCtWarps + 1) * 32;     // + 1 producer warp
+constexpr int kStages = 3;                        // BK ring depth (rows of 16 KiB)
+constexpr uint32_t kStageBytes = kBkRowCplx * sizeof(cpx);
+
+struct __align__(128) CtaSmem {
+    WarpSmem w[kCtWarps];
+    cpx e2[32 * kE2Row];
+    cpx ring[kStages][kBkRowCplx];
+    unsigned long long full[kStages];
+    unsigned long long empty[kStages];
+};
+
+static_assert(sizeof(WarpSmem) % 16 == 0, "warp working set must keep 16 B alignment");
+static_assert(offsetof(CtaSmem, ring) % 128 == 0, "TMA destination alignment");
+static_assert(sizeof(CtaSmem) <= 227 * 1024, "shared memory budget");
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+
+__device__ __forceinline__ void mbar_arrive(unsigned long long *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+__device__ __forceinline__ void mbar_arrive_expect_tx(unsigned long long *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "LAB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE;\n"
+        "bra LAB_WAIT;\n"
+        "DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+
+// 1-D bulk copy global -> shared, completion signalled on an mbarrier (TMA unit).
+__device__ __forceinline__ void tma_load_1d(void *dst, const void *src, uint32_t bytes, unsigned long long *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+struct RingPos {
+    uint32_t stage = 0, phase = 0;
+    __device__ __forceinline__ void advance() {
+        if (++stage == kStages) {
+            stage = 0;
+            phase ^= 1;
+        }
+    }
+};
+
+__device__ __forceinline__ void build_e2(cpx *e2) {
+    for (int t = threadIdx.x; t < 32 * 15; t += blockDim.x) {
+        const int m1 = t / 15, idx = t % 15;
+        double s, c;
+        sincospi(e2_shift(m1, idx), &s, &c);
+        e2[m1 * kE2Row + idx].x = c;
+        e2[m1 * kE2Row + idx].y = s;
+    }
+}
+
+// modSwitchFromTorus32(x, 2N), numeric-functions.cu:60-66  ==  ((uint32)x + 2^20) >> 21
+__device__ __forceinline__ int modswitch_2N(uint32_t x) { return (int) ((x + (1u << 20)) >> 21); }
+
+__global__ void __launch_bounds__(kThreads, 1) blind_rotate_kernel(const BrLaunch L) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    CtaSmem &S = *reinterpret_cast<CtaSmem *>(smem_raw);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    build_e2(S.e2);
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kStages; s++) {
+            mbar_init(&S.full[s], 1);
+            mbar_init(&S.empty[s], kCtWarps);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    const int ngroups = (L.total + kCtWarps - 1) / kCtWarps;
+    const int n_iter = L.n_iter;
+
+    if (warp == kCtWarps) {
+        // ---------------- producer: stream BK rows through the ring -----------
+        if (lane == 0) {
+            RingPos rp;
+            for (int grp = blockIdx.x; grp < ngroups; grp += gridDim.x) {
+                const cpx *src = L.bk + (size_t) L.bk_first * kBkIterCplx;
+                for (int it = 0; it < n_iter; it++) {
+#pragma unroll 1
+                    for (int row = 0; row < kKpl; row++) {
+                        mbar_wait(&S.empty[rp.stage], rp.phase ^ 1);
+                        mbar_arrive_expect_tx(&S.full[rp.stage], kStageBytes);
+                        tma_load_1d(S.ring[rp.stage], src, kStageBytes, &S.full[rp.stage]);
+                        src += kBkRowCplx;
+                        rp.advance();
+                    }
+                }
+            }
+        }
+        return;
+    }
+
+    // -------------------- consumers: one ciphertext per warp ------------------
+    WarpSmem &W = S.w[warp];
+    RingPos rp;
+    for (int grp = blockIdx.x; grp < ngroups; grp += gridDim.x) {
+        int g = grp * kCtWarps + warp;
+        const bool valid = g < L.total;
+        if (!valid) g = L.total - 1;
+
+        // which gate prologue does this bootstrap belong to
+        const int32_t *in0 = nullptr, *in1 = nullptr;
+        uint32_t sa = 0, sb = 0, cst = 0;
+        if (L.explicit_inputs == 0) {
+            int local = g;
+            int si = 0;
+            while (si + 1 < L.nseg && local >= L.seg[si].count) {
+                local -= L.seg[si].count;
+                si++;
+            }
+            in0 = L.seg[si].in0 + (size_t) local * L.seg[si].stride0;
+            in1 = L.seg[si].in1 + (size_t) local * L.seg[si].stride1;
+            sa = (uint32_t) L.seg[si].sa;
+            sb = (uint32_t) L.seg[si].sb;
+            cst = (uint32_t) L.seg[si].cst;
+        }
+
+        int barb;
+        if (L.explicit_inputs != 0) barb = L.barb ? (L.barb[g] & (2 * kN - 1)) : 0;
+        else barb = modswitch_2N(cst + sa * (uint32_t) __ldg(in0 + L.n) + sb * (uint32_t) __ldg(in1 + L.n));
+
+        if (L.acc_in != nullptr) {
+            phase_load_acc(lane, W, L.acc_in + (size_t) g * (kK + 1) * kN);
+        } else if (L.testvect != nullptr) {
+            // ACC = (0, X^{2N-barb} * testvect)
+            for (int j = lane; j < kN; j += 32) {
+                const int s = (j + barb) & (2 * kN - 1);
+                const uint32_t v = (uint32_t) __ldg(L.testvect + (s & (kN - 1)));
+                W.acc[0][(j & 15) * kAccRow + (j >> 4)] = 0;
+                W.acc[kK][(j & 15) * kAccRow + (j >> 4)] = (int32_t) (s < kN ? v : 0u - v);
+            }
+        } else {
+            phase_init(lane, W, barb, L.mu);
+        }
+        __syncwarp();
+
+        int a_blk = 0;  // lane l holds bara of iteration (it & ~31) + l
+        for (int it = 0; it < n_iter; it++) {
+            if ((it & 31) == 0) {
+                const int idx = it + lane;
+                a_blk = 0;
+                if (idx < n_iter && L.extern_only == 0) {
+                    if (L.explicit_inputs != 0) a_blk = __ldg(L.bara + (size_t) g * n_iter + idx) & (2 * kN - 1);
+                    else a_blk = modswitch_2N(sa * (uint32_t) __ldg(in0 + idx) + sb * (uint32_t) __ldg(in1 + idx));
+                }
+            }
+            const int a = __shfl_sync(0xffffffffu, a_blk, it & 31);
+            const bool rotate = (L.extern_only == 0);
+            const bool active = (a != 0) || !rotate;  // tfhe_blindRotate_FFT :705 skips barai == 0 (no-op)
+
+            if (active) {
+                phase_f1(lane, W, a, rotate);
+                __syncwarp();
+            }
+            cpx acc_a[16], acc_b[16];
+#pragma unroll
+            for (int i = 0; i < 16; i++) {
+                acc_a[i].x = 0.0; acc_a[i].y = 0.0;
+                acc_b[i].x = 0.0; acc_b[i].y = 0.0;
+            }
+#pragma unroll 1
+            for (int row = 0; row < kKpl; row++) {
+                mbar_wait(&S.full[rp.stage], rp.phase);
+                if (active) phase_f2_row(lane, W, S.e2, row, S.ring[rp.stage], acc_a, acc_b);
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&S.empty[rp.stage]);
+                rp.advance();
+            }
+            if (active) {
+                phase_f2_end(lane, W, S.e2, acc_a, acc_b);
+                __syncwarp();
+                phase_i2(lane, W, rotate);
+                __syncwarp();
+            }
+        }
+
+        if (valid) {
+            if (L.u_out != nullptr) phase_extract(lane, W, L.u_out + (size_t) g * (kN + 1));
+            if (L.acc_out != nullptr) phase_dump_acc(lane, W, L.acc_out + (size_t) g * (kK + 1) * kN);
+        }
+        __syncwarp();
+    }
+}
+
+// ------------------------------------------------------------ key conversion
+
+struct __align__(128) FwdSmem {
+    WarpSmem w[kCtWarps];
+    cpx e2[32 * kE2Row];
+};
+
+__global__ void __launch_bounds__(kCtWarps * 32, 1)
+forward_polys_kernel(const int32_t *__restrict__ coef, cpx *__restrict__ out, int ngroups, double scale) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    FwdSmem &S = *reinterpret_cast<FwdSmem *>(smem_raw);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    build_e2(S.e2);
+    __syncthreads();
+    WarpSmem &W = S.w[warp];
+    for (int grp = blockIdx.x * kCtWarps + warp; grp < ngroups; grp += gridDim.x * kCtWarps) {
+        const int32_t *src = coef + (size_t) grp * 4 * kN;
+        fwd4_pass1(lane, W, [&](int p, int j) { return (double) __ldg(src + p * kN + j) * scale; });
+        __syncwarp();
+        fwd4_pass2(lane, W, S.e2, out + (size_t) grp * 4 * kM);
+        __syncwarp();
+    }
+}
+
+}  // namespace
+
+size_t blind_rotate_smem_bytes() { return sizeof(CtaSmem); }
+
+cudaError_t blind_rotate_configure() {
+    cudaError_t e = cudaFuncSetAttribute(blind_rotate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int) sizeof(CtaSmem));
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(forward_polys_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int) sizeof(FwdSmem));
+}
+
+cudaError_t launch_blind_rotate(const BrLaunch &L, int sm_count, cudaStream_t stream) {
+    if (L.total <= 0) return cudaSuccess;
+    const int ngroups = (L.total + kCtWarps - 1) / kCtWarps;
+    const int grid = ngroups < sm_count ? ngroups : sm_count;
+    blind_rotate_kernel<<<grid, kThreads, sizeof(CtaSmem), stream>>>(L);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_forward_polys(const int32_t *coef, cpx *out, int npolys, double scale, cudaStream_t stream) {
+    if (npolys <= 0) return cudaSuccess;
+    if (npolys % 4 != 0) return cudaErrorInvalidValue;
+    const int ngroups = npolys / 4;
+    int grid = (ngroups + kCtWarps - 1) / kCtWarps;
+    if (grid > 4 * 148) grid = 4 * 148;
+    forward_polys_kernel<<<grid, kCtWarps * 32, sizeof(FwdSmem), stream>>>(coef, out, ngroups, scale);
+    return cudaGetLastError();
+}
+
+}  // namespace tfhe_b200

@@ -1,0 +1,348 @@
+// Blind-rotation core: per-lane phase functions of the warp-per-ciphertext
+// persistent kernel (blind_rotate.cu).  Everything here is __host__ __device__
+// so that tests/host_emul.cu can run the exact same index math lane by lane on
+// the CPU (there is no GPU in the build container).
+//
+// One warp owns one ciphertext for all n iterations of
+//   ACC <- ACC + BK_i (.) ((X^{a_i} - 1) * ACC)
+// (reference: tfhe_MuxRotate_FFT, lwe-bootstrapping-functions-fft.cu:105-185;
+//  tGswFFTExternMulToTLwe, tgsw-fft-operations.cu:124-264).
+//
+// Number representation.  A real polynomial P mod X^N+1 (N = 1024) is held in
+// the Fourier domain as the M = N/2 = 512 values
+//     V_m = P(zeta^(4m+1)),  zeta = exp(i*pi/N),  m = 0..511
+//         = sum_{j<512} (p_j + i*p_{j+512}) * exp(2*pi*i * j*(m + 1/4)/512)
+// i.e. the reference's "lagrangehalfc" values (fft_processor_fftw.cu:148-181,
+// lagrangehalfc_impl.h:45-52) at the conjugate half of the odd roots and in a
+// different order.  Any consistent pair of transforms gives the same negacyclic
+// product; the key is converted with the same forward transform, so ordering
+// never needs to be undone.
+//
+// Transform.  9 radix-2 stages with the 1/4 frequency shift carried through the
+// recursion (a size-L block with shift d: u = a + e*b -> shift d/2,
+// v = a - e*b -> shift (d+1)/2, e = exp(i*pi*d)), so there is no separate twist
+// or twiddle pass and every butterfly is 6 FMA-class fp64 instructions.
+// Index split j = 16*j1 + j2, m = m1 + 32*m2:
+//   pass 1 (stages 0-4): lane (o, j2) holds the 32 elements j1 = 0..31 of
+//           polynomial o's slice j2; multipliers are compile-time constants.
+//   exchange through shared memory (rows of 17 complex -> conflict free).
+//   pass 2 (stages 5-8): lane m1 holds the 16 elements j2 = 0..15 of frequency
+//           class m1; multipliers depend on the lane (table e2).
+// The inverse is the exact conjugate transpose (pass 2 then pass 1 reversed),
+// unnormalised (factor 512 is folded into the key's scale 2^-9).
+#pragma once
+
+#include <stdint.h>
+
+#include "fft_consts.h"
+
+#ifndef __CUDACC__
+#define __host__
+#define __device__
+#define __forceinline__ inline
+#endif
+
+#define TFHE_HD __host__ __device__ __forceinline__
+
+namespace tfhe_b200 {
+
+constexpr int kN = 1024;          // ring degree
+constexpr int kM = 512;           // complex points per polynomial
+constexpr int kK = 1;             // TLWE mask polynomials
+constexpr int kL = 2;             // gadget length
+constexpr int kBgbit = 10;        // log2 gadget base
+constexpr int kKpl = (kK + 1) * kL;
+// offset = Bg/2 * sum_i 2^(32-(i+1)*Bgbit) = 512*(2^22+2^12)   (tgsw.cu:19-27)
+constexpr uint32_t kDecompOffset = 0x80200000u;
+constexpr int kExchRow = 17;      // complex per exchange row (16 used)
+constexpr int kExchPoly = 32 * kExchRow;
+constexpr int kAccRow = 65;       // words per accumulator row (64 used)
+constexpr int kAccPoly = 16 * kAccRow;
+constexpr int kE2Row = 17;        // complex per pass-2 constant row (15 used)
+constexpr int kBkRowCplx = 2 * 16 * 32;            // one TGSW row: [o][pos][m1]
+constexpr int kBkIterCplx = kKpl * kBkRowCplx;     // one BK_i: 4096 complex = 64 KiB
+
+struct cpx {
+    double x, y;
+};
+
+// Per-warp shared-memory working set.
+struct WarpSmem {
+    cpx exch[kKpl][kExchPoly];     // 4 * 8704 B
+    int32_t acc[kK + 1][kAccPoly]; // 2 * 4160 B
+};
+
+TFHE_HD constexpr int bitrev5(int v) {
+    return ((v & 1) << 4) | ((v & 2) << 2) | (v & 4) | ((v & 8) >> 2) | ((v & 16) >> 4);
+}
+
+// (a, b) <- (a + e*b, a - e*b)
+TFHE_HD void bf_fwd(cpx &a, cpx &b, double er, double ei) {
+    double ur = fma(er, b.x, a.x);
+    double ui = fma(er, b.y, a.y);
+    ur = fma(-ei, b.y, ur);
+    ui = fma(ei, b.x, ui);
+    b.x = fma(2.0, a.x, -ur);
+    b.y = fma(2.0, a.y, -ui);
+    a.x = ur;
+    a.y = ui;
+}
+
+// (u, v) <- (u + v, conj(e)*(u - v))
+TFHE_HD void bf_inv(cpx &a, cpx &b, double er, double ei) {
+    const double tr = a.x - b.x, ti = a.y - b.y;
+    a.x += b.x;
+    a.y += b.y;
+    b.x = fma(er, tr, ei * ti);
+    b.y = fma(er, ti, -(ei * tr));
+}
+
+// acc += z * w
+TFHE_HD void cmac(cpx &acc, const cpx &z, const cpx &w) {
+    acc.x = fma(z.x, w.x, acc.x);
+    acc.y = fma(z.x, w.y, acc.y);
+    acc.x = fma(-z.y, w.y, acc.x);
+    acc.y = fma(z.y, w.x, acc.y);
+}
+
+// Stages 0-4 on the 32 in-register elements (natural j1 in, bit-reversed m1 out).
+TFHE_HD void fwd32(cpx (&x)[32]) {
+#pragma unroll
+    for (int s = 0; s < 5; s++) {
+        const int half = 16 >> s;
+#pragma unroll
+        for (int b = 0; b < (1 << s); b++) {
+            const int ci = (1 << s) - 1 + b;
+#pragma unroll
+            for (int i = 0; i < half; i++)
+                bf_fwd(x[b * 2 * half + i], x[b * 2 * half + i + half], c1_re(ci), c1_im(ci));
+        }
+    }
+}
+
+TFHE_HD void inv32(cpx (&x)[32]) {
+#pragma unroll
+    for (int s = 4; s >= 0; s--) {
+        const int half = 16 >> s;
+#pragma unroll
+        for (int b = 0; b < (1 << s); b++) {
+            const int ci = (1 << s) - 1 + b;
+#pragma unroll
+            for (int i = 0; i < half; i++)
+                bf_inv(x[b * 2 * half + i], x[b * 2 * half + i + half], c1_re(ci), c1_im(ci));
+        }
+    }
+}
+
+// Stages 5-8 on the 16 in-register elements of frequency class m1; e points at
+// this lane's 15 multipliers (natural j2 in, bit-reversed m2 out).
+TFHE_HD void fwd16(cpx (&z)[16], const cpx *e) {
+#pragma unroll
+    for (int s = 0; s < 4; s++) {
+        const int half = 8 >> s;
+#pragma unroll
+        for (int b = 0; b < (1 << s); b++) {
+            const cpx c = e[(1 << s) - 1 + b];
+#pragma unroll
+            for (int i = 0; i < half; i++) bf_fwd(z[b * 2 * half + i], z[b * 2 * half + i + half], c.x, c.y);
+        }
+    }
+}
+
+TFHE_HD void inv16(cpx (&z)[16], const cpx *e) {
+#pragma unroll
+    for (int s = 3; s >= 0; s--) {
+        const int half = 8 >> s;
+#pragma unroll
+        for (int b = 0; b < (1 << s); b++) {
+            const cpx c = e[(1 << s) - 1 + b];
+#pragma unroll
+            for (int i = 0; i < half; i++) bf_inv(z[b * 2 * half + i], z[b * 2 * half + i + half], c.x, c.y);
+        }
+    }
+}
+
+// Shift of pass-2 block `idx` (= (1<<stage)-1+block) for frequency class m1.
+TFHE_HD double e2_shift(int m1, int idx) {
+    double d = ((double) m1 + 0.25) / 32.0;
+    // walk down the tree: idx+1 in binary, below the leading one, MSB first
+    const int v = idx + 1;
+    int top = 0;
+    while ((v >> (top + 1)) != 0) top++;
+    for (int bit = top - 1; bit >= 0; bit--) d = (d + (double) ((v >> bit) & 1)) * 0.5;
+    return d;
+}
+
+// ---------------------------------------------------------------- phases ---
+
+// ACC = (0, X^{2N-barb} * (mu, ..., mu))   tfhe_blindRotateAndExtract_FFT,
+// lwe-bootstrapping-functions-fft.cu:1425-1431 ; torusPolynomialMulByXai :492-519
+TFHE_HD void phase_init(int lane, WarpSmem &ws, int barb, int32_t mu) {
+    const int o = lane >> 4, j2 = lane & 15;
+    int32_t *row = ws.acc[o] + j2 * kAccRow;
+#pragma unroll 8
+    for (int e = 0; e < 64; e++) {
+        const int j = 16 * e + j2;
+        int32_t v = 0;
+        if (o == kK) v = (((j + barb) & (2 * kN - 1)) < kN) ? mu : (int32_t) (0u - (uint32_t) mu);
+        row[e] = v;
+    }
+}
+
+// Pass 1 of the four forward transforms, fused with the rotation
+// (torusPolynomialMulByXaiMinusOne, toruspolynomial-functions.cu:191-213) and the
+// gadget decomposition (tGswTorus32PolynomialDecompH, tgsw-functions.cu:301-352).
+// rotate == false: plain decomposition of ACC (stand-alone external product).
+TFHE_HD void phase_f1(int lane, WarpSmem &ws, int a, bool rotate = true) {
+    const int o = lane >> 4, j2 = lane & 15;
+    const int a_lo = a & 15, a_hi = a >> 4;
+    const int j2p = (j2 - a_lo) & 15;
+    const int sh = a_hi + (j2 < a_lo ? 1 : 0);
+    const int32_t *own = ws.acc[o] + j2 * kAccRow;
+    const int32_t *rot = ws.acc[o] + j2p * kAccRow;
+    uint32_t t[64];
+#pragma unroll
+    for (int e = 0; e < 64; e++) {
+        const int idx = (e - sh) & 127;
+        uint32_t v = (uint32_t) rot[idx & 63];
+        if (idx & 64) v = 0u - v;
+        t[e] = (rotate ? v - (uint32_t) own[e] : (uint32_t) own[e]) + kDecompOffset;
+    }
+#pragma unroll
+    for (int q = 0; q < kL; q++) {
+        const int shift = 32 - (q + 1) * kBgbit;
+        cpx x[32];
+#pragma unroll
+        for (int j1 = 0; j1 < 32; j1++) {
+            x[j1].x = (double) ((int) ((t[j1] >> shift) & 1023u) - 512);
+            x[j1].y = (double) ((int) ((t[j1 + 32] >> shift) & 1023u) - 512);
+        }
+        fwd32(x);
+        cpx *dst = ws.exch[o * kL + q] + j2;
+#pragma unroll
+        for (int pos = 0; pos < 32; pos++) dst[bitrev5(pos) * kExchRow] = x[pos];
+    }
+}
+
+// Pass 2 of forward transform of decomposed polynomial `row` + Fourier MAC
+// against that TGSW row (tLweFFTAddMulRTo, tlwe-fft-operations.cu:286 ->
+// LagrangeHalfCPolynomialAddMul, lagrangehalfc_impl.cu:95-117).
+// bkrow: [o][pos][m1] complex, 16 KiB.
+TFHE_HD void phase_f2_row(int lane, WarpSmem &ws, const cpx *e2, int row, const cpx *bkrow,
+                          cpx (&acc_a)[16], cpx (&acc_b)[16]) {
+    cpx z[16];
+    const cpx *src = ws.exch[row] + lane * kExchRow;
+#pragma unroll
+    for (int j2 = 0; j2 < 16; j2++) z[j2] = src[j2];
+    fwd16(z, e2 + lane * kE2Row);
+#pragma unroll
+    for (int pos = 0; pos < 16; pos++) {
+        cmac(acc_a[pos], z[pos], bkrow[pos * 32 + lane]);
+        cmac(acc_b[pos], z[pos], bkrow[(16 + pos) * 32 + lane]);
+    }
+}
+
+// Inverse pass 2 (pass "I1") of both result polynomials, in place in the
+// exchange rows this lane owns.
+TFHE_HD void phase_f2_end(int lane, WarpSmem &ws, const cpx *e2, cpx (&acc_a)[16], cpx (&acc_b)[16]) {
+    inv16(acc_a, e2 + lane * kE2Row);
+    cpx *d0 = ws.exch[0] + lane * kExchRow;
+#pragma unroll
+    for (int j2 = 0; j2 < 16; j2++) d0[j2] = acc_a[j2];
+    inv16(acc_b, e2 + lane * kE2Row);
+    cpx *d1 = ws.exch[1] + lane * kExchRow;
+#pragma unroll
+    for (int j2 = 0; j2 < 16; j2++) d1[j2] = acc_b[j2];
+}
+
+// Inverse pass 1 + conversion to Torus32 (execute_direct_Torus32,
+// fft_processor_fftw.cu:168-181: double -> int64 truncation -> int32 wrap) +
+// the tLweAddTo of MuxRotate (tlwe-functions.cu:170).
+// accumulate == false: the result replaces ACC (stand-alone external product).
+TFHE_HD void phase_i2(int lane, WarpSmem &ws, bool accumulate = true) {
+    const int o = lane >> 4, j2 = lane & 15;
+    cpx x[32];
+    const cpx *src = ws.exch[o] + j2;
+#pragma unroll
+    for (int pos = 0; pos < 32; pos++) x[pos] = src[bitrev5(pos) * kExchRow];
+    inv32(x);
+    int32_t *row = ws.acc[o] + j2 * kAccRow;
+#pragma unroll
+    for (int j1 = 0; j1 < 32; j1++) {
+        const uint32_t re = (uint32_t) (int32_t) (long long) x[j1].x;
+        const uint32_t im = (uint32_t) (int32_t) (long long) x[j1].y;
+        row[j1] = (int32_t) ((accumulate ? (uint32_t) row[j1] : 0u) + re);
+        row[j1 + 32] = (int32_t) ((accumulate ? (uint32_t) row[j1 + 32] : 0u) + im);
+    }
+}
+
+TFHE_HD int32_t acc_coef(const WarpSmem &ws, int o, int j) {
+    return ws.acc[o][(j & 15) * kAccRow + (j >> 4)];
+}
+
+// Sample extraction at index 0 (tLweExtractLweSampleIndex, lwe.cu:41-56):
+// u.a[0] = ACC.a[0], u.a[j] = -ACC.a[N-j], u.b = ACC.b[0].  u: int32[N+1].
+TFHE_HD void phase_extract(int lane, const WarpSmem &ws, int32_t *u) {
+    for (int j = lane; j < kN; j += 32) {
+        const int32_t v = (j == 0) ? acc_coef(ws, 0, 0) : (int32_t) (0u - (uint32_t) acc_coef(ws, 0, kN - j));
+        u[j] = v;
+    }
+    if (lane == 0) u[kN] = acc_coef(ws, kK, 0);
+}
+
+// Raw accumulator dump, natural coefficient order: int32[2][N].
+TFHE_HD void phase_dump_acc(int lane, const WarpSmem &ws, int32_t *out) {
+    for (int j = lane; j < (kK + 1) * kN; j += 32) out[j] = acc_coef(ws, j >> 10, j & (kN - 1));
+}
+
+TFHE_HD void phase_load_acc(int lane, WarpSmem &ws, const int32_t *in) {
+    for (int j = lane; j < (kK + 1) * kN; j += 32) {
+        const int o = j >> 10, c = j & (kN - 1);
+        ws.acc[o][(c & 15) * kAccRow + (c >> 4)] = in[j];
+    }
+}
+
+// ------------------------------------------------ generic forward transform -
+// Forward transform of 4 polynomials given as doubles via `fetch(p, j)`; used
+// for the key (TorusPolynomial_ifft in tGswToFFTConvert, tgsw-fft-operations.cu:84)
+// and for the standalone IntPolynomial_ifft entry point.  Pass 1: lane (o, j2)
+// handles polynomials 2o and 2o+1.
+template <typename Fetch>
+TFHE_HD void fwd4_pass1(int lane, WarpSmem &ws, Fetch fetch) {
+    const int o = lane >> 4, j2 = lane & 15;
+#pragma unroll
+    for (int q = 0; q < 2; q++) {
+        const int p = o * 2 + q;
+        cpx x[32];
+#pragma unroll
+        for (int j1 = 0; j1 < 32; j1++) {
+            x[j1].x = fetch(p, 16 * j1 + j2);
+            x[j1].y = fetch(p, 16 * j1 + j2 + kM);
+        }
+        fwd32(x);
+        cpx *dst = ws.exch[p] + j2;
+#pragma unroll
+        for (int pos = 0; pos < 32; pos++) dst[bitrev5(pos) * kExchRow] = x[pos];
+    }
+}
+
+// Pass 2: writes polynomial p's 512 values to out[p*512 + pos*32 + m1].
+TFHE_HD void fwd4_pass2(int lane, WarpSmem &ws, const cpx *e2, cpx *out) {
+#pragma unroll 1
+    for (int p = 0; p < 4; p++) {
+        cpx z[16];
+        const cpx *src = ws.exch[p] + lane * kExchRow;
+#pragma unroll
+        for (int j2 = 0; j2 < 16; j2++) z[j2] = src[j2];
+        fwd16(z, e2 + lane * kE2Row);
+#pragma unroll
+        for (int pos = 0; pos < 16; pos++) out[p * kM + pos * 32 + lane] = z[pos];
+    }
+}
+
+// Frequency index m held at (pos, m1) of the device layout.
+TFHE_HD constexpr int freq_of(int pos, int m1) {
+    return m1 + 32 * (((pos & 1) << 3) | ((pos & 2) << 1) | ((pos & 4) >> 1) | ((pos & 8) >> 3));
+}
+
+}  // namespace tfhe_b200

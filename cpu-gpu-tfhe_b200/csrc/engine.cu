@@ -1,0 +1,522 @@
+// Host side of the C ABI declared in include/tfhe_b200.h: context, key upload /
+// conversion, and the gate-level launch sequences (blind-rotate kernel followed
+// by the key-switch kernel).  No CPU arithmetic on the data path and no
+// fallback: every entry point fails loudly if CUDA is unavailable.
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include "../../include/tfhe_b200.h"
+#include "br_core.cuh"
+#include "kernels.h"
+
+using namespace tfhe_b200;
+
+struct tfhe_b200_ctx {
+    tfhe_b200_params p;
+    int device;
+    int sm_count;
+    cpx *d_bk;        // [n][4][2][16][32] complex
+    int32_t *d_ks;    // [N][t][base-1][512]
+    size_t bk_bytes, ks_bytes;
+    cudaStream_t stream;  // used by the host-buffer entry points
+    std::atomic<unsigned long long> launches;
+};
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+int fail(const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return 1;
+}
+
+#define CU(expr)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (expr);                                                                   \
+        if (e_ != cudaSuccess) return fail("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e_), \
+                                           __FILE__, __LINE__);                                    \
+    } while (0)
+
+struct GateDef {
+    int32_t cst;
+    int sa, sb;
+};
+
+// modSwitchToTorus32(+-1, 8) = +-0x20000000, (+-1, 4) = +-0x40000000 (numeric-functions.cu:72-77)
+constexpr int32_t kMu = 0x20000000;
+const GateDef kGates[TFHE_B200_NUM_GATES] = {
+    /* NAND  boot-gates.cu:106-109 */ {kMu, -1, -1},
+    /* OR    :132-135 */ {kMu, 1, 1},
+    /* AND   :158-162 */ {-kMu, 1, 1},
+    /* XOR   :198-201 */ {2 * kMu, 2, 2},
+    /* XNOR  :224-227 */ {-2 * kMu, -2, -2},
+    /* NOR   :283-286 */ {-kMu, -1, -1},
+    /* ANDNY :309-312 */ {-kMu, -1, 1},
+    /* ANDYN :335-338 */ {-kMu, 1, -1},
+    /* ORNY  :361-364 */ {kMu, -1, 1},
+    /* ORYN  :387-390 */ {kMu, 1, -1},
+};
+
+BrLaunch base_launch(const tfhe_b200_ctx *c) {
+    BrLaunch L;
+    memset(&L, 0, sizeof(L));
+    L.n = c->p.n;
+    L.n_iter = c->p.n;
+    L.mu = kMu;
+    L.bk = c->d_bk;
+    return L;
+}
+
+void set_segment(BrSegment &s, const GateDef &g, const int32_t *a, const int32_t *b, int n, int count) {
+    s.in0 = a;
+    s.in1 = b;
+    s.stride0 = n + 1;
+    s.stride1 = n + 1;
+    s.sa = g.sa;
+    s.sb = g.sb;
+    s.cst = g.cst;
+    s.count = count;
+}
+
+int check_ctx(const tfhe_b200_ctx *c, bool need_bk, bool need_ks) {
+    if (!c) return fail("null context");
+    if (need_bk && !c->d_bk) return fail("bootstrapping key not loaded");
+    if (need_ks && !c->d_ks) return fail("key-switch key not loaded");
+    return 0;
+}
+
+// blind rotate (segments) -> u scratch -> key switch -> out
+int run_bootstrap_ks(tfhe_b200_ctx *c, BrLaunch &L, int nsrc, int32_t ks_cst, int32_t *d_out, int out_count,
+                     cudaStream_t st) {
+    CU(cudaSetDevice(c->device));
+    int32_t *d_u = nullptr;
+    const size_t ubytes = (size_t) L.total * (kN + 1) * sizeof(int32_t);
+    CU(cudaMallocAsync(&d_u, ubytes, st));
+    L.u_out = d_u;
+    CU(launch_blind_rotate(L, c->sm_count, st));
+    c->launches += 1;
+    KsLaunch K;
+    memset(&K, 0, sizeof(K));
+    K.ks = c->d_ks;
+    K.u = d_u;
+    K.nsrc = nsrc;
+    K.cst = ks_cst;
+    K.out = d_out;
+    K.out_stride = c->p.n + 1;
+    K.count = out_count;
+    K.n = c->p.n;
+    K.N = c->p.N * c->p.k;
+    K.t = c->p.ks_t;
+    K.basebit = c->p.ks_basebit;
+    CU(launch_keyswitch(K, c->sm_count, st));
+    c->launches += (out_count > 0 && ((out_count + 15) / 16) < 2 * c->sm_count) ? 2 : 1;
+    CU(cudaFreeAsync(d_u, st));
+    return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char *tfhe_b200_last_error(void) { return g_err; }
+
+void tfhe_b200_default_params(tfhe_b200_params *p) {
+    p->n = 500;
+    p->N = 1024;
+    p->k = 1;
+    p->l = 2;
+    p->Bgbit = 10;
+    p->ks_t = 8;
+    p->ks_basebit = 2;
+}
+
+int tfhe_b200_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+int tfhe_b200_ctx_create(tfhe_b200_ctx **out, const tfhe_b200_params *p, int device) {
+    if (!out || !p) return fail("null argument");
+    *out = nullptr;
+    if (p->N != kN || p->k != kK || p->l != kL || p->Bgbit != kBgbit)
+        return fail("unsupported TGSW parameters (N=%d k=%d l=%d Bgbit=%d): this build instantiates "
+                    "N=1024 k=1 l=2 Bgbit=10", p->N, p->k, p->l, p->Bgbit);
+    if (p->ks_basebit != 2 || p->ks_t < 1 || p->ks_t > 15 || p->n < 1 || p->n > 511)
+        return fail("unsupported LWE / key-switch parameters (n=%d t=%d basebit=%d)", p->n, p->ks_t, p->ks_basebit);
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail("no CUDA device available (%s): the engine has no CPU fallback", cudaGetErrorString(e));
+    if (device < 0 || device >= ndev) return fail("device %d out of range (%d devices)", device, ndev);
+    CU(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 9) return fail("device %d is sm_%d%d; sm_100a required", device, prop.major, prop.minor);
+    if ((size_t) prop.sharedMemPerBlockOptin < blind_rotate_smem_bytes())
+        return fail("device offers %zu B of shared memory per block, kernel needs %zu",
+                    (size_t) prop.sharedMemPerBlockOptin, blind_rotate_smem_bytes());
+    CU(blind_rotate_configure());
+    tfhe_b200_ctx *c = new (std::nothrow) tfhe_b200_ctx();
+    if (!c) return fail("out of host memory");
+    c->p = *p;
+    c->device = device;
+    c->sm_count = prop.multiProcessorCount;
+    c->d_bk = nullptr;
+    c->d_ks = nullptr;
+    c->bk_bytes = c->ks_bytes = 0;
+    c->launches = 0;
+    if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) {
+        delete c;
+        return fail("cudaStreamCreate failed");
+    }
+    *out = c;
+    return 0;
+}
+
+void tfhe_b200_ctx_destroy(tfhe_b200_ctx *c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    if (c->d_bk) cudaFree(c->d_bk);
+    if (c->d_ks) cudaFree(c->d_ks);
+    cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+size_t tfhe_b200_key_bytes(const tfhe_b200_ctx *c) { return c ? c->bk_bytes + c->ks_bytes : 0; }
+unsigned long long tfhe_b200_launch_count(const tfhe_b200_ctx *c) { return c ? c->launches.load() : 0; }
+int tfhe_b200_sm_count(const tfhe_b200_ctx *c) { return c ? c->sm_count : 0; }
+
+int tfhe_b200_load_keys_device(tfhe_b200_ctx *c, const int32_t *d_bk_coef, const int32_t *d_ks, void *stream) {
+    if (!c) return fail("null context");
+    cudaStream_t st = (cudaStream_t) stream;
+    CU(cudaSetDevice(c->device));
+    const int n = c->p.n;
+    if (d_bk_coef) {
+        const size_t npolys = (size_t) n * kKpl * (kK + 1);
+        if (!c->d_bk) {
+            c->bk_bytes = npolys * kM * sizeof(cpx);
+            CU(cudaMalloc(&c->d_bk, c->bk_bytes));
+        }
+        // Fourier(bk * 2^-32) * 2^32 / (N/2): the inverse transform is unnormalised
+        CU(launch_forward_polys(d_bk_coef, c->d_bk, (int) npolys, 1.0 / 512.0, st));
+        c->launches += 1;
+    }
+    if (d_ks) {
+        const int N = c->p.N * c->p.k, t = c->p.ks_t, base = 1 << c->p.ks_basebit;
+        if (!c->d_ks) {
+            c->ks_bytes = (size_t) N * t * (base - 1) * kKsRowWords * sizeof(int32_t);
+            CU(cudaMalloc(&c->d_ks, c->ks_bytes));
+        }
+        CU(launch_ks_relayout(d_ks, c->d_ks, N, t, base, n, st));
+        c->launches += 1;
+    }
+    return 0;
+}
+
+int tfhe_b200_load_keys(tfhe_b200_ctx *c, const int32_t *bk_coef, const int32_t *ks) {
+    if (!c) return fail("null context");
+    CU(cudaSetDevice(c->device));
+    const int n = c->p.n;
+    int32_t *d_tmp_bk = nullptr, *d_tmp_ks = nullptr;
+    if (bk_coef) {
+        const size_t bytes = (size_t) n * kKpl * (kK + 1) * kN * sizeof(int32_t);
+        CU(cudaMalloc(&d_tmp_bk, bytes));
+        CU(cudaMemcpyAsync(d_tmp_bk, bk_coef, bytes, cudaMemcpyHostToDevice, c->stream));
+    }
+    if (ks) {
+        const size_t bytes = (size_t) c->p.N * c->p.k * c->p.ks_t * (1 << c->p.ks_basebit) * (n + 1) * sizeof(int32_t);
+        CU(cudaMalloc(&d_tmp_ks, bytes));
+        CU(cudaMemcpyAsync(d_tmp_ks, ks, bytes, cudaMemcpyHostToDevice, c->stream));
+    }
+    int rc = tfhe_b200_load_keys_device(c, d_tmp_bk, d_tmp_ks, c->stream);
+    cudaError_t e = cudaStreamSynchronize(c->stream);
+    if (d_tmp_bk) cudaFree(d_tmp_bk);
+    if (d_tmp_ks) cudaFree(d_tmp_ks);
+    if (rc) return rc;
+    if (e != cudaSuccess) return fail("key upload failed: %s", cudaGetErrorString(e));
+    return 0;
+}
+
+int tfhe_b200_load_ks(tfhe_b200_ctx *c, const int32_t *ks) { return tfhe_b200_load_keys(c, nullptr, ks); }
+
+// Reference Fourier form -> device layout.  ref[j] = P(zeta^-(2j+1)); ours V_m = P(zeta^(4m+1)):
+// m < 256: V_m = conj(ref[2m]);  m >= 256: V_m = ref[1023 - 2m].  Scale: ref is in torus
+// units (int * 2^-32), ours in int * 2^-9  => factor 2^23.  Pure data re-layout.
+int tfhe_b200_load_bk_fourier(tfhe_b200_ctx *c, const double *ref) {
+    if (!c || !ref) return fail("null argument");
+    CU(cudaSetDevice(c->device));
+    const size_t npolys = (size_t) c->p.n * kKpl * (kK + 1);
+    std::vector<cpx> host(npolys * kM);
+    const double sc = 8388608.0;  // 2^23
+    for (size_t q = 0; q < npolys; q++) {
+        const double *src = ref + q * kM * 2;
+        cpx *dst = host.data() + q * kM;
+        for (int pos = 0; pos < 16; pos++)
+            for (int m1 = 0; m1 < 32; m1++) {
+                const int m = freq_of(pos, m1);
+                cpx v;
+                if (m < 256) {
+                    v.x = src[2 * (2 * m)] * sc;
+                    v.y = -src[2 * (2 * m) + 1] * sc;
+                } else {
+                    v.x = src[2 * (1023 - 2 * m)] * sc;
+                    v.y = src[2 * (1023 - 2 * m) + 1] * sc;
+                }
+                dst[pos * 32 + m1] = v;
+            }
+    }
+    if (!c->d_bk) {
+        c->bk_bytes = npolys * kM * sizeof(cpx);
+        CU(cudaMalloc(&c->d_bk, c->bk_bytes));
+    }
+    CU(cudaMemcpy(c->d_bk, host.data(), c->bk_bytes, cudaMemcpyHostToDevice));
+    return 0;
+}
+
+// ------------------------------------------------------------------- gates --
+
+int tfhe_b200_gate(tfhe_b200_ctx *c, int gate, int32_t *d_out, const int32_t *d_ca, const int32_t *d_cb,
+                   int count, void *stream) {
+    if (check_ctx(c, true, true)) return 1;
+    if (gate < 0 || gate >= TFHE_B200_NUM_GATES) return fail("bad gate id %d", gate);
+    if (count < 0) return fail("negative count");
+    if (count == 0) return 0;
+    BrLaunch L = base_launch(c);
+    L.nseg = 1;
+    L.total = count;
+    set_segment(L.seg[0], kGates[gate], d_ca, d_cb, c->p.n, count);
+    return run_bootstrap_ks(c, L, 1, 0, d_out, count, (cudaStream_t) stream);
+}
+
+int tfhe_b200_gate2(tfhe_b200_ctx *c, int gate0, int gate1, int32_t *d_out, const int32_t *d_ca,
+                    const int32_t *d_cb, int count, void *stream) {
+    return tfhe_b200_gate_pair(c, gate0, d_ca, d_cb, gate1, d_ca, d_cb, d_out, count, stream);
+}
+
+int tfhe_b200_gate_pair(tfhe_b200_ctx *c, int gate0, const int32_t *d_a0, const int32_t *d_b0, int gate1,
+                        const int32_t *d_a1, const int32_t *d_b1, int32_t *d_out, int count, void *stream) {
+    if (check_ctx(c, true, true)) return 1;
+    if (gate0 < 0 || gate0 >= TFHE_B200_NUM_GATES || gate1 < 0 || gate1 >= TFHE_B200_NUM_GATES)
+        return fail("bad gate id");
+    if (count < 0) return fail("negative count");
+    if (count == 0) return 0;
+    BrLaunch L = base_launch(c);
+    L.nseg = 2;
+    L.total = 2 * count;
+    set_segment(L.seg[0], kGates[gate0], d_a0, d_b0, c->p.n, count);
+    set_segment(L.seg[1], kGates[gate1], d_a1, d_b1, c->p.n, count);
+    return run_bootstrap_ks(c, L, 1, 0, d_out, 2 * count, (cudaStream_t) stream);
+}
+
+// bootsMUX (boot-gates.cu:407-448): u1 = BS(-1/8 + a + b), u2 = BS(-1/8 - a + c),
+// result = KS((0,1/8) + u1 + u2)
+int tfhe_b200_mux(tfhe_b200_ctx *c, int32_t *d_out, const int32_t *d_a, const int32_t *d_b,
+                  const int32_t *d_c, int count, void *stream) {
+    if (check_ctx(c, true, true)) return 1;
+    if (count < 0) return fail("negative count");
+    if (count == 0) return 0;
+    BrLaunch L = base_launch(c);
+    L.nseg = 2;
+    L.total = 2 * count;
+    const GateDef g1 = {-kMu, 1, 1}, g2 = {-kMu, -1, 1};
+    set_segment(L.seg[0], g1, d_a, d_b, c->p.n, count);
+    set_segment(L.seg[1], g2, d_a, d_c, c->p.n, count);
+    return run_bootstrap_ks(c, L, 2, kMu, d_out, count, (cudaStream_t) stream);
+}
+
+int tfhe_b200_not(tfhe_b200_ctx *c, int32_t *d_out, const int32_t *d_ca, int count, void *stream) {
+    if (check_ctx(c, false, false)) return 1;
+    CU(cudaSetDevice(c->device));
+    const int s = c->p.n + 1;
+    CU(launch_lwe_linear(d_out, s, d_ca, s, -1, nullptr, 0, 0, 0, count, c->p.n, (cudaStream_t) stream));
+    c->launches += 1;
+    return 0;
+}
+
+int tfhe_b200_copy(tfhe_b200_ctx *c, int32_t *d_out, const int32_t *d_ca, int count, void *stream) {
+    if (check_ctx(c, false, false)) return 1;
+    CU(cudaSetDevice(c->device));
+    if (d_out != d_ca)
+        CU(cudaMemcpyAsync(d_out, d_ca, (size_t) count * (c->p.n + 1) * sizeof(int32_t), cudaMemcpyDeviceToDevice,
+                           (cudaStream_t) stream));
+    return 0;
+}
+
+int tfhe_b200_constant(tfhe_b200_ctx *c, int32_t *d_out, int value, int count, void *stream) {
+    if (check_ctx(c, false, false)) return 1;
+    CU(cudaSetDevice(c->device));
+    const int s = c->p.n + 1;
+    CU(launch_lwe_linear(d_out, s, nullptr, 0, 0, nullptr, 0, 0, value ? kMu : -kMu, count, c->p.n,
+                         (cudaStream_t) stream));
+    c->launches += 1;
+    return 0;
+}
+
+// --------------------------------------------------------- building blocks --
+
+int tfhe_b200_bootstrap_woks(tfhe_b200_ctx *c, int32_t *d_u, const int32_t *d_x, int32_t mu, int count,
+                             void *stream) {
+    if (check_ctx(c, true, false)) return 1;
+    if (count <= 0) return count < 0 ? fail("negative count") : 0;
+    CU(cudaSetDevice(c->device));
+    BrLaunch L = base_launch(c);
+    L.nseg = 1;
+    L.total = count;
+    L.mu = mu;
+    const GateDef id = {0, 1, 0};
+    set_segment(L.seg[0], id, d_x, d_x, c->p.n, count);
+    L.u_out = d_u;
+    CU(launch_blind_rotate(L, c->sm_count, (cudaStream_t) stream));
+    c->launches += 1;
+    return 0;
+}
+
+int tfhe_b200_bootstrap(tfhe_b200_ctx *c, int32_t *d_out, const int32_t *d_x, int32_t mu, int count,
+                        void *stream) {
+    if (check_ctx(c, true, true)) return 1;
+    if (count <= 0) return count < 0 ? fail("negative count") : 0;
+    BrLaunch L = base_launch(c);
+    L.nseg = 1;
+    L.total = count;
+    L.mu = mu;
+    const GateDef id = {0, 1, 0};
+    set_segment(L.seg[0], id, d_x, d_x, c->p.n, count);
+    return run_bootstrap_ks(c, L, 1, 0, d_out, count, (cudaStream_t) stream);
+}
+
+int tfhe_b200_keyswitch(tfhe_b200_ctx *c, int32_t *d_out, const int32_t *d_u, int count, void *stream) {
+    if (check_ctx(c, false, true)) return 1;
+    if (count <= 0) return count < 0 ? fail("negative count") : 0;
+    CU(cudaSetDevice(c->device));
+    KsLaunch K;
+    memset(&K, 0, sizeof(K));
+    K.ks = c->d_ks;
+    K.u = d_u;
+    K.nsrc = 1;
+    K.out = d_out;
+    K.out_stride = c->p.n + 1;
+    K.count = count;
+    K.n = c->p.n;
+    K.N = c->p.N * c->p.k;
+    K.t = c->p.ks_t;
+    K.basebit = c->p.ks_basebit;
+    CU(launch_keyswitch(K, c->sm_count, (cudaStream_t) stream));
+    c->launches += 1;
+    return 0;
+}
+
+int tfhe_b200_blind_rotate(tfhe_b200_ctx *c, int32_t *d_acc, const int32_t *d_bara, int n_iter, int count,
+                           void *stream) {
+    if (check_ctx(c, true, false)) return 1;
+    if (n_iter < 0 || n_iter > c->p.n) return fail("n_iter %d out of range", n_iter);
+    if (count <= 0) return count < 0 ? fail("negative count") : 0;
+    CU(cudaSetDevice(c->device));
+    BrLaunch L = base_launch(c);
+    L.total = count;
+    L.n_iter = n_iter;
+    L.explicit_inputs = 1;
+    L.bara = d_bara;
+    L.acc_in = d_acc;
+    L.acc_out = d_acc;
+    CU(launch_blind_rotate(L, c->sm_count, (cudaStream_t) stream));
+    c->launches += 1;
+    return 0;
+}
+
+int tfhe_b200_blind_rotate_and_extract(tfhe_b200_ctx *c, int32_t *d_u, const int32_t *d_testvect,
+                                       const int32_t *d_barb, const int32_t *d_bara, int n_iter, int count,
+                                       void *stream) {
+    if (check_ctx(c, true, false)) return 1;
+    if (n_iter < 0 || n_iter > c->p.n) return fail("n_iter %d out of range", n_iter);
+    if (count <= 0) return count < 0 ? fail("negative count") : 0;
+    CU(cudaSetDevice(c->device));
+    BrLaunch L = base_launch(c);
+    L.total = count;
+    L.n_iter = n_iter;
+    L.explicit_inputs = 1;
+    L.bara = d_bara;
+    L.barb = d_barb;
+    L.testvect = d_testvect;
+    L.u_out = d_u;
+    CU(launch_blind_rotate(L, c->sm_count, (cudaStream_t) stream));
+    c->launches += 1;
+    return 0;
+}
+
+int tfhe_b200_extern_mul(tfhe_b200_ctx *c, int32_t *d_acc, int bk_index, int count, void *stream) {
+    if (check_ctx(c, true, false)) return 1;
+    if (bk_index < 0 || bk_index >= c->p.n) return fail("bk_index %d out of range", bk_index);
+    if (count <= 0) return count < 0 ? fail("negative count") : 0;
+    CU(cudaSetDevice(c->device));
+    BrLaunch L = base_launch(c);
+    L.total = count;
+    L.n_iter = 1;
+    L.extern_only = 1;
+    L.bk_first = bk_index;
+    L.explicit_inputs = 1;
+    L.acc_in = d_acc;
+    L.acc_out = d_acc;
+    CU(launch_blind_rotate(L, c->sm_count, (cudaStream_t) stream));
+    c->launches += 1;
+    return 0;
+}
+
+// ------------------------------------------------------ host-buffer variants --
+
+static int host_gate_common(tfhe_b200_ctx *c, int gate, bool mux, int32_t *out, const int32_t *a, const int32_t *b,
+                            const int32_t *cc, int count) {
+    if (check_ctx(c, true, true)) return 1;
+    if (count <= 0) return count < 0 ? fail("negative count") : 0;
+    CU(cudaSetDevice(c->device));
+    const size_t bytes = (size_t) count * (c->p.n + 1) * sizeof(int32_t);
+    int32_t *d_a = nullptr, *d_b = nullptr, *d_c = nullptr, *d_o = nullptr;
+    cudaStream_t st = c->stream;
+    CU(cudaMallocAsync(&d_a, bytes, st));
+    CU(cudaMallocAsync(&d_b, bytes, st));
+    CU(cudaMallocAsync(&d_o, bytes, st));
+    CU(cudaMemcpyAsync(d_a, a, bytes, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(d_b, b, bytes, cudaMemcpyHostToDevice, st));
+    if (mux) {
+        CU(cudaMallocAsync(&d_c, bytes, st));
+        CU(cudaMemcpyAsync(d_c, cc, bytes, cudaMemcpyHostToDevice, st));
+    }
+    int rc = mux ? tfhe_b200_mux(c, d_o, d_a, d_b, d_c, count, st) : tfhe_b200_gate(c, gate, d_o, d_a, d_b, count, st);
+    if (!rc) {
+        cudaError_t e = cudaMemcpyAsync(out, d_o, bytes, cudaMemcpyDeviceToHost, st);
+        if (e != cudaSuccess) rc = fail("D2H copy failed: %s", cudaGetErrorString(e));
+    }
+    cudaFreeAsync(d_a, st);
+    cudaFreeAsync(d_b, st);
+    cudaFreeAsync(d_o, st);
+    if (d_c) cudaFreeAsync(d_c, st);
+    cudaError_t e = cudaStreamSynchronize(st);
+    if (!rc && e != cudaSuccess) rc = fail("gate batch failed: %s", cudaGetErrorString(e));
+    return rc;
+}
+
+int tfhe_b200_gate_host(tfhe_b200_ctx *c, int gate, int32_t *out, const int32_t *ca, const int32_t *cb, int count) {
+    if (gate < 0 || gate >= TFHE_B200_NUM_GATES) return fail("bad gate id %d", gate);
+    return host_gate_common(c, gate, false, out, ca, cb, nullptr, count);
+}
+
+int tfhe_b200_mux_host(tfhe_b200_ctx *c, int32_t *out, const int32_t *a, const int32_t *b, const int32_t *cc,
+                       int count) {
+    return host_gate_common(c, 0, true, out, a, b, cc, count);
+}
+
+}  // extern "C"

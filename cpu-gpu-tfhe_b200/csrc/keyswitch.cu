@@ -1,0 +1,184 @@
+// LWE key switch for a batch of extracted samples, plus the small linear
+// kernels of the gate API (NOT / COPY / CONSTANT / linear combinations).
+//
+// lweKeySwitch (lwe-keyswitch-functions.cu:955-987) and
+// lweKeySwitchTranslate_fromArray (:101-127):
+//   res = (0, u.b);  for i < N, j < t:
+//     aij = (((uint32)u.a[i] + 2^(31 - basebit*t)) >> (32 - (j+1)*basebit)) & (base-1)
+//     if aij != 0: res -= ks[i][j][aij]
+// Integer arithmetic mod 2^32: bit-exact whatever the summation order.
+//
+// One CTA handles a tile of 16 gates for a range of i.  The digits of the tile
+// are precomputed into shared memory (2 bits per gate packed in one word per
+// (i, j)), then every thread owns two output columns for all 16 gates in
+// registers and streams the table rows (coalesced 2 KiB rows, L2 resident)
+// exactly once per tile instead of once per gate as the reference does
+// (lweKeySwitchVectorSubstraction_gpu_testing_coalesce_n_Bit, boot-gates.cu:2382-2421).
+// Small batches split the i range over several CTAs and combine with integer
+// atomics so that a single gate still uses the whole chip.
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "kernels.h"
+
+namespace tfhe_b200 {
+
+namespace {
+
+constexpr int kTile = 16;       // gates per CTA
+constexpr int kKsThreads = 256; // two columns per thread (c, c + 256)
+constexpr int kMaxT = 16;
+
+template <bool kAtomic>
+__global__ void __launch_bounds__(kKsThreads) keyswitch_kernel(const KsLaunch L, int nsplit) {
+    extern __shared__ uint32_t dig[];  // [i_per * t]
+    const int g0 = blockIdx.x * kTile;
+    const int ng = min(kTile, L.count - g0);
+    const int i_per = L.N / nsplit;
+    const int i0 = blockIdx.y * i_per;
+    const int t = L.t;
+    const size_t ustride = (size_t) L.N + 1;
+    const uint32_t prec_offset = 1u << (32 - (1 + L.basebit * t));
+
+    // ---- digits of this tile: dig[(i - i0) * t + j], gate g in bits [2g, 2g+2) ----
+    for (int i = i0 + (int) threadIdx.x; i < i0 + i_per; i += kKsThreads) {
+        uint32_t w[kMaxT];
+#pragma unroll
+        for (int j = 0; j < kMaxT; j++) w[j] = 0;
+        for (int g = 0; g < ng; g++) {
+            uint32_t a = (uint32_t) __ldg(L.u + (size_t) (g0 + g) * ustride + i);
+            if (L.nsrc == 2) a += (uint32_t) __ldg(L.u + (size_t) (g0 + g + L.count) * ustride + i);
+            const uint32_t aibar = a + prec_offset;
+#pragma unroll
+            for (int j = 0; j < kMaxT; j++)
+                if (j < t) w[j] |= ((aibar >> (32 - (j + 1) * 2)) & 3u) << (2 * g);
+        }
+#pragma unroll
+        for (int j = 0; j < kMaxT; j++)
+            if (j < t) dig[(i - i0) * t + j] = w[j];
+    }
+    __syncthreads();
+
+    // ---- accumulate table rows --------------------------------------------
+    const int c0 = threadIdx.x, c1 = threadIdx.x + kKsThreads;
+    uint32_t acc0[kTile], acc1[kTile];
+#pragma unroll
+    for (int g = 0; g < kTile; g++) {
+        acc0[g] = 0;
+        acc1[g] = 0;
+    }
+    const int32_t *tbl = L.ks + (size_t) i0 * t * 3 * kKsRowWords;
+    const int steps = i_per * t;
+#pragma unroll 4
+    for (int idx = 0; idx < steps; idx++) {
+        const uint32_t w = dig[idx];
+        const int32_t *r = tbl + (size_t) idx * 3 * kKsRowWords;
+        const uint32_t r1a = (uint32_t) __ldg(r + c0), r1b = (uint32_t) __ldg(r + c1);
+        const uint32_t r2a = (uint32_t) __ldg(r + kKsRowWords + c0), r2b = (uint32_t) __ldg(r + kKsRowWords + c1);
+        const uint32_t r3a = (uint32_t) __ldg(r + 2 * kKsRowWords + c0), r3b = (uint32_t) __ldg(r + 2 * kKsRowWords + c1);
+#pragma unroll
+        for (int g = 0; g < kTile; g++) {
+            const bool lo = (w >> (2 * g)) & 1u, hi = (w >> (2 * g + 1)) & 1u;
+            const uint32_t xa = lo ? r3a : r2a, ya = lo ? r1a : 0u;
+            const uint32_t xb = lo ? r3b : r2b, yb = lo ? r1b : 0u;
+            acc0[g] += hi ? xa : ya;
+            acc1[g] += hi ? xb : yb;
+        }
+    }
+
+    // ---- result = (0, u.b + cst) - acc -----------------------------------------
+    const int n = L.n;
+#pragma unroll
+    for (int g = 0; g < kTile; g++) {
+        if (g < ng) {
+            int32_t *row = L.out + (size_t) (g0 + g) * L.out_stride;
+            uint32_t v0 = 0u - acc0[g], v1 = 0u - acc1[g];
+            if ((c0 == n || c1 == n) && blockIdx.y == 0) {
+                uint32_t b = (uint32_t) __ldg(L.u + (size_t) (g0 + g) * ustride + L.N) + (uint32_t) L.cst;
+                if (L.nsrc == 2) b += (uint32_t) __ldg(L.u + (size_t) (g0 + g + L.count) * ustride + L.N);
+                if (c0 == n) v0 += b;
+                else v1 += b;
+            }
+            if (kAtomic) {
+                if (c0 <= n) atomicAdd(reinterpret_cast<unsigned int *>(row + c0), v0);
+                if (c1 <= n) atomicAdd(reinterpret_cast<unsigned int *>(row + c1), v1);
+            } else {
+                if (c0 <= n) row[c0] = (int32_t) v0;
+                if (c1 <= n) row[c1] = (int32_t) v1;
+            }
+        }
+    }
+}
+
+__global__ void ks_zero_kernel(int32_t *out, long long stride, int count, int words) {
+    const long long t = (long long) blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (long long) count * words) return;
+    out[(t / words) * stride + (t % words)] = 0;
+}
+
+// src [N][t][base][n+1] -> dst [N][t][base-1][512] (row h = 0 is the noiseless zero sample,
+// lwe-keyswitch-functions.cu:919, and is dropped; columns > n are zero padding)
+__global__ void ks_relayout_kernel(const int32_t *__restrict__ src, int32_t *__restrict__ dst, long long rows_out,
+                                   int base, int n) {
+    const long long t = (long long) blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= rows_out * kKsRowWords) return;
+    const long long row = t / kKsRowWords;
+    const int c = (int) (t % kKsRowWords);
+    const long long ij = row / (base - 1);
+    const int h = (int) (row % (base - 1)) + 1;
+    dst[t] = (c <= n) ? src[(ij * base + h) * (n + 1) + c] : 0;
+}
+
+// out = c0*in0 + c1*in1 + (0, cst) on rows of n+1 words
+__global__ void lwe_linear_kernel(int32_t *out, long long so, const int32_t *in0, long long s0, int c0,
+                                  const int32_t *in1, long long s1, int c1, int32_t cst, int count, int n) {
+    const long long t = (long long) blockIdx.x * blockDim.x + threadIdx.x;
+    const int words = n + 1;
+    if (t >= (long long) count * words) return;
+    const long long g = t / words;
+    const int c = (int) (t % words);
+    uint32_t v = 0;
+    if (in0) v += (uint32_t) c0 * (uint32_t) in0[g * s0 + c];
+    if (in1) v += (uint32_t) c1 * (uint32_t) in1[g * s1 + c];
+    if (c == n) v += (uint32_t) cst;
+    out[g * so + c] = (int32_t) v;
+}
+
+}  // namespace
+
+cudaError_t launch_keyswitch(const KsLaunch &L, int sm_count, cudaStream_t stream) {
+    if (L.count <= 0) return cudaSuccess;
+    if (L.basebit != 2 || L.t > kMaxT || L.n + 1 > 2 * kKsThreads) return cudaErrorInvalidValue;
+    const int tiles = (L.count + kTile - 1) / kTile;
+    int nsplit = 1;
+    while (tiles * nsplit < 2 * sm_count && nsplit < 64 && (L.N / (nsplit * 2)) >= 8) nsplit *= 2;
+    const size_t smem = (size_t) (L.N / nsplit) * L.t * sizeof(uint32_t);
+    dim3 grid(tiles, nsplit);
+    if (nsplit > 1) {
+        const long long total = (long long) L.count * (L.n + 1);
+        ks_zero_kernel<<<(unsigned) ((total + 255) / 256), 256, 0, stream>>>(L.out, L.out_stride, L.count, L.n + 1);
+        keyswitch_kernel<true><<<grid, kKsThreads, smem, stream>>>(L, nsplit);
+    } else {
+        keyswitch_kernel<false><<<grid, kKsThreads, smem, stream>>>(L, nsplit);
+    }
+    return cudaGetLastError();
+}
+
+cudaError_t launch_ks_relayout(const int32_t *src, int32_t *dst, int N, int t, int base, int n, cudaStream_t stream) {
+    const long long rows_out = (long long) N * t * (base - 1);
+    const long long total = rows_out * kKsRowWords;
+    ks_relayout_kernel<<<(unsigned) ((total + 255) / 256), 256, 0, stream>>>(src, dst, rows_out, base, n);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_lwe_linear(int32_t *out, long long out_stride, const int32_t *in0, long long s0, int c0,
+                              const int32_t *in1, long long s1, int c1, int32_t cst, int count, int n,
+                              cudaStream_t stream) {
+    if (count <= 0) return cudaSuccess;
+    const long long total = (long long) count * (n + 1);
+    lwe_linear_kernel<<<(unsigned) ((total + 255) / 256), 256, 0, stream>>>(out, out_stride, in0, s0, c0, in1, s1, c1,
+                                                                            cst, count, n);
+    return cudaGetLastError();
+}
+
+}  // namespace tfhe_b200

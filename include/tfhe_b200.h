@@ -1,0 +1,141 @@
+/*
+ * tfhe_b200.h — C ABI of the B200-native TFHE gate-bootstrapping engine.
+ *
+ * Plain C, plain pointers and sizes; no CUDA or torch types in the signatures
+ * (streams are passed as void* holding a cudaStream_t, 0 = default stream).
+ * Library: cpu-gpu-tfhe_b200/libtfhe_b200.so.
+ *
+ * This header is the batch ("flat") interface.  The drop-in replacements for
+ * the reference's own entry points (bootsNAND ... bootsMUX,
+ * tfhe_blindRotateAndExtract_FFT, tGswFFTExternMulToTLwe, lweKeySwitch, with
+ * the reference's struct layouts) are declared in tfhe_compat.h and are thin
+ * wrappers over the functions below.
+ *
+ * Data formats (int32 = Torus32, reference: gpuParallel/tfhe_core.h:28):
+ *   sample       int32[n+1]              a[0..n) then b     (LweSample, lwesamples.h:18-29)
+ *   extracted    int32[N+1]              a[0..N) then b     (LweSample of dimension N)
+ *   accumulator  int32[k+1][N]           TLweSample polynomials (tlwe.h:47-52)
+ *   bk (coef)    int32[n][kpl][k+1][N]   LweBootstrappingKey->bk[i].all_sample[r].a[j]
+ *                                        (lwebootstrappingkey.h:10-16, tgsw.h:60-70)
+ *   ks           int32[N][t][base][n+1]  LweKeySwitchKey->ks[i][j][h] (lwekeyswitch.h:11-28)
+ * Batches are contiguous rows unless a stride (in words) is given.
+ *
+ * Every function returns 0 on success, non-zero on failure;
+ * tfhe_b200_last_error() describes the last failure of the calling thread.
+ * There is no CPU fallback: without a CUDA device every compute call fails.
+ */
+#ifndef TFHE_B200_H
+#define TFHE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct tfhe_b200_ctx tfhe_b200_ctx;
+
+/* reference: new_default_gate_bootstrapping_parameters, tfhe_gate_bootstrapping.cu:25-49 */
+typedef struct {
+    int32_t n;          /* LWE dimension (500)            */
+    int32_t N;          /* ring degree (1024, fixed)      */
+    int32_t k;          /* TLWE mask size (1, fixed)      */
+    int32_t l;          /* gadget length (2, fixed)       */
+    int32_t Bgbit;      /* log2 gadget base (10, fixed)   */
+    int32_t ks_t;       /* key-switch length (8)          */
+    int32_t ks_basebit; /* key-switch log2 base (2)       */
+} tfhe_b200_params;
+
+/* gate ids: x = (0, c) + sa*ca + sb*cb, then bootstrap to +-1/8 (boot-gates.cu:98-397) */
+enum {
+    TFHE_B200_NAND = 0, /* boot-gates.cu:98  */
+    TFHE_B200_OR = 1,   /* :124 */
+    TFHE_B200_AND = 2,  /* :150 */
+    TFHE_B200_XOR = 3,  /* :190 */
+    TFHE_B200_XNOR = 4, /* :216 */
+    TFHE_B200_NOR = 5,  /* :275 */
+    TFHE_B200_ANDNY = 6,/* :301 */
+    TFHE_B200_ANDYN = 7,/* :327 */
+    TFHE_B200_ORNY = 8, /* :353 */
+    TFHE_B200_ORYN = 9, /* :379 */
+    TFHE_B200_NUM_GATES = 10
+};
+
+const char *tfhe_b200_last_error(void);
+void tfhe_b200_default_params(tfhe_b200_params *p);
+/* number of CUDA devices visible (0 if none / no driver) */
+int tfhe_b200_device_count(void);
+
+/* ---- context and keys -------------------------------------------------- */
+int tfhe_b200_ctx_create(tfhe_b200_ctx **ctx, const tfhe_b200_params *p, int device);
+void tfhe_b200_ctx_destroy(tfhe_b200_ctx *ctx);
+/* Upload + convert keys from HOST flat arrays.  Replaces sendBootstrappingKeyToGPUCoalesceExt /
+ * sendKeySwitchKeyToGPU_extendedOnePointer / sendKeySwitchBtoGPUOnePtr (main.cu:165,364,236)
+ * and init_LweBootstrappingKeyFFT (lwe-bootstrapping-functions-fft.cu:60-89). */
+int tfhe_b200_load_keys(tfhe_b200_ctx *ctx, const int32_t *bk_coef, const int32_t *ks);
+/* Same, from DEVICE arrays (e.g. after an NCCL broadcast). */
+int tfhe_b200_load_keys_device(tfhe_b200_ctx *ctx, const int32_t *d_bk_coef, const int32_t *d_ks, void *stream);
+/* Bootstrapping key given in the reference's Fourier form: complex double
+ * [n][kpl][k+1][N/2], value j = P(exp(-i*pi*(2j+1)/N)) of the torus polynomial scaled to
+ * [-1/2,1/2) (TGswSampleFFT, tgsw.h:78-96; fft_processor_fftw.cu:158-167). Host pointer. */
+int tfhe_b200_load_bk_fourier(tfhe_b200_ctx *ctx, const double *bkfft_ref);
+int tfhe_b200_load_ks(tfhe_b200_ctx *ctx, const int32_t *ks);
+/* bytes of device memory held by the keys */
+size_t tfhe_b200_key_bytes(const tfhe_b200_ctx *ctx);
+
+/* ---- batched gates on DEVICE buffers (asynchronous on `stream`) ----------
+ * out may alias an input (the reference's callers do this, Cipher.cu:373). */
+int tfhe_b200_gate(tfhe_b200_ctx *ctx, int gate, int32_t *d_out, const int32_t *d_ca, const int32_t *d_cb,
+                   int count, void *stream);
+/* compound gate: out[0..count) = gate0(ca,cb), out[count..2count) = gate1(ca,cb) in ONE
+ * bootstrap batch (bootsANDXOR_fullGPU_n_Bit_vector, boot-gates.cu:3027-3060) */
+int tfhe_b200_gate2(tfhe_b200_ctx *ctx, int gate0, int gate1, int32_t *d_out, const int32_t *d_ca,
+                    const int32_t *d_cb, int count, void *stream);
+/* two independent gate batches in one launch: out[0..count) = gate0(a0,b0),
+ * out[count..2count) = gate1(a1,b1) (bootsXORXOR_fullGPU_n_Bit_vector, boot-gates.cu:3062-3098) */
+int tfhe_b200_gate_pair(tfhe_b200_ctx *ctx, int gate0, const int32_t *d_a0, const int32_t *d_b0, int gate1,
+                        const int32_t *d_a1, const int32_t *d_b1, int32_t *d_out, int count, void *stream);
+/* MUX(a,b,c) = a ? b : c  (bootsMUX, boot-gates.cu:407-448; bootsMUX_fullGPU_n_Bit :2987) */
+int tfhe_b200_mux(tfhe_b200_ctx *ctx, int32_t *d_out, const int32_t *d_a, const int32_t *d_b,
+                  const int32_t *d_c, int count, void *stream);
+/* bootsNOT :242, bootsCOPY :253, bootsCONSTANT :263 — no bootstrap */
+int tfhe_b200_not(tfhe_b200_ctx *ctx, int32_t *d_out, const int32_t *d_ca, int count, void *stream);
+int tfhe_b200_copy(tfhe_b200_ctx *ctx, int32_t *d_out, const int32_t *d_ca, int count, void *stream);
+int tfhe_b200_constant(tfhe_b200_ctx *ctx, int32_t *d_out, int value, int count, void *stream);
+
+/* ---- building blocks (DEVICE buffers) ------------------------------------ */
+/* tfhe_bootstrap_woKS_FFT (lwe-bootstrapping-functions-fft.cu:1834): x[count][n+1] -> u[count][N+1] */
+int tfhe_b200_bootstrap_woks(tfhe_b200_ctx *ctx, int32_t *d_u, const int32_t *d_x, int32_t mu, int count,
+                             void *stream);
+/* tfhe_bootstrap_FFT (:1884) */
+int tfhe_b200_bootstrap(tfhe_b200_ctx *ctx, int32_t *d_out, const int32_t *d_x, int32_t mu, int count,
+                        void *stream);
+/* lweKeySwitch (lwe-keyswitch-functions.cu:955): u[count][N+1] -> out[count][n+1] */
+int tfhe_b200_keyswitch(tfhe_b200_ctx *ctx, int32_t *d_out, const int32_t *d_u, int count, void *stream);
+/* tfhe_blindRotate_FFT (:676): acc[count][k+1][N] in place, bara[count][n_iter] in [0,2N) */
+int tfhe_b200_blind_rotate(tfhe_b200_ctx *ctx, int32_t *d_acc, const int32_t *d_bara, int n_iter, int count,
+                           void *stream);
+/* tfhe_blindRotateAndExtract_FFT (:1408): testvect[N] shared, barb[count], bara[count][n_iter] */
+int tfhe_b200_blind_rotate_and_extract(tfhe_b200_ctx *ctx, int32_t *d_u, const int32_t *d_testvect,
+                                       const int32_t *d_barb, const int32_t *d_bara, int n_iter, int count,
+                                       void *stream);
+/* tGswFFTExternMulToTLwe (tgsw-fft-operations.cu:124) with BK_{bk_index}: acc[count][k+1][N] in place */
+int tfhe_b200_extern_mul(tfhe_b200_ctx *ctx, int32_t *d_acc, int bk_index, int count, void *stream);
+
+/* ---- HOST-buffer convenience (synchronous; copies in and out) ------------- */
+int tfhe_b200_gate_host(tfhe_b200_ctx *ctx, int gate, int32_t *out, const int32_t *ca, const int32_t *cb,
+                        int count);
+int tfhe_b200_mux_host(tfhe_b200_ctx *ctx, int32_t *out, const int32_t *a, const int32_t *b, const int32_t *c,
+                       int count);
+
+/* ---- introspection (tests, bench) ---------------------------------------- */
+/* kernels launched by this context so far (each = one launch of one of this library's kernels) */
+unsigned long long tfhe_b200_launch_count(const tfhe_b200_ctx *ctx);
+int tfhe_b200_sm_count(const tfhe_b200_ctx *ctx);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif /* TFHE_B200_H */

@@ -1,0 +1,145 @@
+// CPU lane-by-lane emulation of the blind-rotation kernel's phase functions
+// (cpu-gpu-tfhe_b200/csrc/br_core.cuh are __host__ __device__).  Checks, with no
+// GPU: the twisted FFT against the defining sum, the key layout, and one
+// MuxRotate step (rotation + decomposition + external product + add) against
+// the oracle's exact-integer path, plus init and extraction.
+// Built and run by tests/test_host_emulation.py.  Links oracle/liboracle.so
+// (allowed: this is a test).
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#include "../cpu-gpu-tfhe_b200/csrc/br_core.cuh"
+#include "../oracle/tfhe_oracle.h"
+
+using namespace tfhe_b200;
+
+static std::vector<cpx> make_e2() {
+    std::vector<cpx> e2(32 * kE2Row);
+    for (int m1 = 0; m1 < 32; m1++)
+        for (int idx = 0; idx < 15; idx++) {
+            const double d = e2_shift(m1, idx);
+            e2[m1 * kE2Row + idx].x = cos(M_PI * d);
+            e2[m1 * kE2Row + idx].y = sin(M_PI * d);
+        }
+    return e2;
+}
+
+static int fails = 0;
+#define CHECK(cond, ...) do { if (!(cond)) { printf("FAIL: " __VA_ARGS__); printf("\n"); fails++; } } while (0)
+
+int main() {
+    std::vector<cpx> e2 = make_e2();
+    WarpSmem *ws = new WarpSmem();
+    srand(12345);
+
+    // ---- A. forward transform vs the defining sum -------------------------
+    {
+        std::vector<double> polys(4 * kN);
+        for (auto &v : polys) v = (double) ((rand() % 1024) - 512);
+        auto fetch = [&](int p, int j) { return polys[p * kN + j]; };
+        for (int lane = 0; lane < 32; lane++) fwd4_pass1(lane, *ws, fetch);
+        std::vector<cpx> out(4 * kM);
+        for (int lane = 0; lane < 32; lane++) fwd4_pass2(lane, *ws, e2.data(), out.data());
+        double maxerr = 0;
+        for (int p = 0; p < 4; p++)
+            for (int pos = 0; pos < 16; pos++)
+                for (int m1 = 0; m1 < 32; m1 += 7) {
+                    const int m = freq_of(pos, m1);
+                    long double re = 0, im = 0;
+                    for (int j = 0; j < kM; j++) {
+                        const long double ang = 2.0L * M_PIl * (long double) j * ((long double) m + 0.25L) / 512.0L;
+                        const long double c = cosl(ang), s = sinl(ang);
+                        const long double a = polys[p * kN + j], b = polys[p * kN + j + kM];
+                        re += a * c - b * s;
+                        im += a * s + b * c;
+                    }
+                    const cpx g = out[p * kM + pos * 32 + m1];
+                    maxerr = fmax(maxerr, fmax(fabs((double) (re - g.x)), fabs((double) (im - g.y))));
+                }
+        printf("A. forward transform max abs err %.3e\n", maxerr);
+        CHECK(maxerr < 1e-8, "forward transform mismatch");
+    }
+
+    // ---- B. one MuxRotate step vs exact integer arithmetic -----------------
+    OracleParams P;
+    oracle_default_params(&P);
+    P.n = 6;
+    std::vector<int32_t> lwe_key(P.n), tlwe_key(P.N), bk(oracle_bk_words(&P)), ks(oracle_ks_words(&P));
+    oracle_keygen(&P, 99, lwe_key.data(), tlwe_key.data(), bk.data(), ks.data());
+
+    // key -> device layout [i][row][o][pos][m1], scale 2^-9 (= 2^-32 * 2^32 / 512)
+    std::vector<cpx> bkdev((size_t) P.n * kBkIterCplx);
+    for (int g = 0; g < P.n * kKpl * 2 / 4; g++) {
+        const int32_t *src = bk.data() + (size_t) g * 4 * kN;
+        auto fetch = [&](int p, int j) { return (double) src[p * kN + j] * (1.0 / 512.0); };
+        for (int lane = 0; lane < 32; lane++) fwd4_pass1(lane, *ws, fetch);
+        for (int lane = 0; lane < 32; lane++) fwd4_pass2(lane, *ws, e2.data(), bkdev.data() + (size_t) g * 4 * kM);
+    }
+
+    // init
+    const int32_t mu = oracle_modswitch_to(1, 8);
+    for (int barb : {0, 1, 17, 1023, 1024, 1500, 2047}) {
+        for (int lane = 0; lane < 32; lane++) phase_init(lane, *ws, barb, mu);
+        std::vector<int32_t> got(2 * kN), tv(kN, mu), exp_b(kN);
+        for (int lane = 0; lane < 32; lane++) phase_dump_acc(lane, *ws, got.data());
+        if (barb) oracle_mul_by_xai(2 * kN - barb, kN, tv.data(), exp_b.data());
+        else exp_b = tv;
+        bool ok = true;
+        for (int j = 0; j < kN; j++) ok = ok && got[j] == 0 && got[kN + j] == exp_b[j];
+        CHECK(ok, "phase_init barb=%d", barb);
+    }
+
+    // random accumulator, several rotations, teacher forcing against the exact path
+    std::vector<int32_t> acc(2 * kN);
+    for (auto &v : acc) v = (int32_t) ((((uint32_t) rand()) << 16) ^ (uint32_t) rand() ^ (((uint32_t) rand()) << 31));
+    int maxdiff = 0, ndiff = 0;
+    const int rots[] = {1, 2047, 1024, 15, 16, 17, 1023, 1025, 777, 1300, 31, 2032};
+    for (int it = 0; it < 12; it++) {
+        const int i = it % P.n;
+        const int a = rots[it];
+        for (int lane = 0; lane < 32; lane++) phase_load_acc(lane, *ws, acc.data());
+        for (int lane = 0; lane < 32; lane++) phase_f1(lane, *ws, a);
+        cpx acc_a[32][16], acc_b[32][16];
+        memset(acc_a, 0, sizeof(acc_a));
+        memset(acc_b, 0, sizeof(acc_b));
+        for (int row = 0; row < kKpl; row++)
+            for (int lane = 0; lane < 32; lane++)
+                phase_f2_row(lane, *ws, e2.data(), row, bkdev.data() + ((size_t) i * kKpl + row) * kBkRowCplx,
+                             acc_a[lane], acc_b[lane]);
+        for (int lane = 0; lane < 32; lane++) phase_f2_end(lane, *ws, e2.data(), acc_a[lane], acc_b[lane]);
+        for (int lane = 0; lane < 32; lane++) phase_i2(lane, *ws);
+        std::vector<int32_t> got(2 * kN);
+        for (int lane = 0; lane < 32; lane++) phase_dump_acc(lane, *ws, got.data());
+        // expected: acc + BK_i (.) ((X^a - 1) acc), exact
+        std::vector<int32_t> tmp(2 * kN);
+        for (int o = 0; o < 2; o++) oracle_mul_by_xai_minus_one(a, kN, acc.data() + o * kN, tmp.data() + o * kN);
+        oracle_extern_mul_exact(&P, bk.data() + (size_t) i * kKpl * 2 * kN, tmp.data());
+        for (int j = 0; j < 2 * kN; j++) {
+            const int32_t e = (int32_t) ((uint32_t) acc[j] + (uint32_t) tmp[j]);
+            const int d = (int) ((uint32_t) got[j] - (uint32_t) e);
+            if (d != 0) ndiff++;
+            if (abs(d) > maxdiff) maxdiff = abs(d);
+        }
+        acc = got;  // keep going from the emulator's own state
+    }
+    printf("B. MuxRotate vs exact: max |diff| = %d LSB, %d of %d words differ\n", maxdiff, ndiff, 12 * 2 * kN);
+    CHECK(maxdiff <= 1, "MuxRotate step differs from exact result by more than truncation");
+
+    // ---- C. extraction ----------------------------------------------------
+    {
+        for (int lane = 0; lane < 32; lane++) phase_load_acc(lane, *ws, acc.data());
+        std::vector<int32_t> u(kN + 1);
+        for (int lane = 0; lane < 32; lane++) phase_extract(lane, *ws, u.data());
+        bool ok = u[0] == acc[0] && u[kN] == acc[kN];
+        for (int j = 1; j < kN; j++) ok = ok && u[j] == (int32_t) (0u - (uint32_t) acc[kN - j]);
+        CHECK(ok, "extraction");
+        printf("C. extraction %s\n", ok ? "ok" : "BAD");
+    }
+
+    delete ws;
+    printf(fails ? "HOST EMULATION FAILED (%d)\n" : "HOST EMULATION OK\n", fails);
+    return fails ? 1 : 0;
+}
