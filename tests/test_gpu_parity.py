@@ -75,8 +75,10 @@ def test_mux_rotate_step_teacher_forced(engine, oracle, keys):
 
 
 def test_blind_rotate_short_run_tracks_oracle(engine, oracle, keys, ctx_ref):
-    """A few consecutive iterations from the same accumulator: phases agree to a few LSB
-    of bootstrapping-key noise; masks may differ after a decomposition-boundary flip."""
+    """A few consecutive iterations from the same accumulator.  Masks may differ entirely
+    after the first decomposition-boundary flip (about 2 % of iterations), after which the
+    two runs draw independent key noise (1.4e-4 per iteration): 12 iterations stay below
+    2^-7; a wrong coefficient anywhere would show up as a phase error of order 2^-2."""
     rng = np.random.default_rng(13)
     count, n_iter = 4, 12
     acc = np.zeros((count, 2, 1024), np.int32)
@@ -86,7 +88,7 @@ def test_blind_rotate_short_run_tracks_oracle(engine, oracle, keys, ctx_ref):
     for r in range(count):
         ref = ctx_ref.blind_rotate(acc[r], bara[r])
         dph = wrap32(_tlwe_phase(got[r], keys.tlwe_key) - _tlwe_phase(ref, keys.tlwe_key)) / 2.0 ** 32
-        assert np.abs(dph).max() < 2.0 ** -9, np.abs(dph).max()
+        assert np.abs(dph).max() < 2.0 ** -7, np.abs(dph).max()
 
 
 def test_init_and_extract_exact(engine, oracle, ctx_ref):
