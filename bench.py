@@ -1,0 +1,386 @@
+#!/usr/bin/env python3
+"""Headline benchmark: bootstrapped gates/s on B200 (BASELINE.json).
+
+    python bench.py --gpus N --steps K --warmup W            # this engine
+    python bench.py --impl reference --gpus N --steps K ...  # reference CPU path (oracle/_ref)
+
+A step = one batch of independent bootstrapped NAND gates per GPU (BASELINE.json
+configs[2]: 65536 gates; each rank processes its own 65536, scaling "weak": the
+gates are independent and nothing is exchanged on the data path; keys are
+generated on rank 0 and broadcast once over NCCL before timing).
+
+Prints ONE JSON line (rank 0): metric/value/unit, ms_per_step, e2e (host buffers,
+copies inside the timed region, through the C ABI), roofline of the dominant kernel
+(fp64 blind rotation, live CUDA-event kernel time / measured fp64 peak), cpu_baseline
+(reference host path on this box's cores), clocks, gpu_launches.
+"""
+import argparse
+import json
+import multiprocessing as mp
+import os
+import statistics
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "bootstrapped_gates_per_sec"
+UNIT = "gates/s"
+FLOP_PER_BOOTSTRAP = 500 * (6 * 26112 + 32768)  # 94.72 MFLOP (algorithmic, folded FFT)
+BATCH = 65536
+
+
+# ----------------------------------------------------------------- CPU side ---
+
+def _load_keys(path):
+    from oracle.pyoracle import Keys, Oracle
+
+    o = Oracle()
+    z = {k: np.load(os.path.join(path, k + ".npy"), mmap_mode="r") for k in ("lwe", "tlwe", "bk", "ks", "ca", "cb")}
+    return o, Keys(o.params, np.array(z["lwe"]), np.array(z["tlwe"]), z["bk"], z["ks"]), np.array(z["ca"]), np.array(z["cb"])
+
+
+def _ref_worker(args):
+    """One process per core: the reference's own host path (oracle/_ref) on `count` NAND gates."""
+    path, count = args
+    from oracle.pyoracle import Ref
+
+    o, keys, ca, cb = _load_keys(path)
+    r = Ref().import_keys(keys)
+    secs, last = r.time_nand(ca, cb, count)
+    return secs, int(r.phase(last) > 0)
+
+
+def _port_worker(args):
+    path, count = args
+    from oracle.pyoracle import FFT_FOLDED
+
+    o, keys, ca, cb = _load_keys(path)
+    cx = o.ctx(keys, FFT_FOLDED)
+    t0 = time.perf_counter()
+    for g in range(count):
+        cx.gate("NAND", ca[g % len(ca)], cb[g % len(cb)])
+    return time.perf_counter() - t0, 0
+
+
+_KEY_DIR = None
+
+
+def _dump_keys(sk, pkg):
+    """Keys + 16 input pairs written once to a temp dir; workers mmap them."""
+    global _KEY_DIR
+    if _KEY_DIR is None:
+        import tempfile
+
+        _KEY_DIR = tempfile.mkdtemp(prefix="tfhe_b200_bench_")
+        bits_a, bits_b = np.arange(16) % 2, (np.arange(16) // 2) % 2
+        for name, arr in (("lwe", sk.lwe_key), ("tlwe", sk.tlwe_key), ("bk", sk.bk), ("ks", sk.ks),
+                          ("ca", pkg.encrypt_bits(sk, bits_a, 11)), ("cb", pkg.encrypt_bits(sk, bits_b, 12))):
+            np.save(os.path.join(_KEY_DIR, name + ".npy"), np.ascontiguousarray(arr))
+    return _KEY_DIR
+
+
+def cpu_reference_run(sk, pkg, gates_per_core, cores=None):
+    """Times the reference CPU implementation on `cores` processes x gates_per_core NANDs
+    (the reference host path is not re-entrant -- global FFT scratch, lagrangehalfc_impl.cu:4 --
+    so parallelism is one process per core).  Returns dict(value gates/s, cores, kind, sample)."""
+    from oracle.pyoracle import have_ref
+
+    cores = cores or os.cpu_count() or 1
+    kind = "reference" if have_ref() else "port"
+    path = _dump_keys(sk, pkg)
+    worker = _ref_worker if kind == "reference" else _port_worker
+    ctx = mp.get_context("spawn")
+    t0 = time.perf_counter()
+    with ctx.Pool(cores) as pool:
+        res = pool.map(worker, [(path, gates_per_core)] * cores, chunksize=1)
+    wall = time.perf_counter() - t0
+    busy = max(r[0] for r in res)  # slowest worker's gate loop (excludes process start / key import)
+    total = cores * gates_per_core
+    return {
+        "value": total / busy, "unit": UNIT, "cores": cores, "kind": kind,
+        "sample": "%d bootsNAND per core on %d cores (%s host path, FFTW-shim FFT), %.1f s gate time, %.1f s wall"
+                  % (gates_per_core, cores, "reference oracle/_ref" if kind == "reference" else "C port", busy, wall),
+        "ms_per_gate_per_core": 1e3 * busy / gates_per_core,
+    }
+
+
+# ------------------------------------------------------------- clock sampler ---
+
+class ClockSampler(threading.Thread):
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.stop_flag, self.sm, self.reasons, self.max_mhz = index, False, [], set(), None
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        if self.nv is None:
+            return
+        nv = self.nv
+        names = {
+            getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8): "hw_slowdown",
+            getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4): "sw_power_cap",
+        }
+        while not self.stop_flag:
+            try:
+                self.sm.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    mask = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in names.items():
+                    if mask & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def result(self):
+        return {"sm_mhz": statistics.median(self.sm) if self.sm else None, "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.sm)}
+
+
+# -------------------------------------------------------------------- arms ---
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import __graft_entry__ as ge
+
+    pkg = ge.load_package()
+    sk = pkg.keygen(2026)
+    cores = os.cpu_count() or 1
+    # size the per-step sample from a one-gate probe so that K+W steps stay within a few minutes
+    probe = cpu_reference_run(sk, pkg, 2, cores)
+    per_gate = probe["ms_per_gate_per_core"] / 1e3
+    budget = 120.0 / max(1, args.steps + args.warmup)
+    gpc = max(2, min(64, int(budget / per_gate)))
+    vals = []
+    for step in range(args.warmup + args.steps):
+        r = cpu_reference_run(sk, pkg, gpc, cores)
+        if step >= args.warmup:
+            vals.append(r)
+    gates = gpc * cores * len(vals)
+    secs = sum(gpc * cores / v["value"] for v in vals)
+    value = gates / secs
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * secs / len(vals),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "independent bootstrapped NAND gates, default TFHE gate params (n=500,N=1024,k=1,l=2)",
+                   "gates_per_step": gpc * cores, "note": "bounded sample of the 65536-gate batch"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": vals[0]["kind"],
+                         "sample": vals[0]["sample"]},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+
+    import __graft_entry__ as ge
+
+    pkg = ge.load_package()
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    p = pkg.default_params()
+    n = p.n
+    batch = args.batch
+
+    # ---- keys: generated on rank 0, broadcast once over NCCL (NVLink), converted on each GPU
+    t0 = time.perf_counter()
+    if rank == 0:
+        sk = pkg.keygen(2026)
+        d_bk = torch.from_numpy(sk.bk).to(dev)
+        d_ks = torch.from_numpy(sk.ks).to(dev)
+        d_key = torch.from_numpy(sk.lwe_key).to(dev)
+    else:
+        sk = None
+        kpl = (p.k + 1) * p.l
+        d_bk = torch.empty((p.n, kpl, p.k + 1, p.N), dtype=torch.int32, device=dev)
+        d_ks = torch.empty((p.N * p.k, p.ks_t, 1 << p.ks_basebit, p.n + 1), dtype=torch.int32, device=dev)
+        d_key = torch.empty(p.n, dtype=torch.int32, device=dev)
+    if world > 1:
+        for t in (d_bk, d_ks, d_key):
+            dist.broadcast(t, 0)
+    eng = pkg.Engine(device=local)
+    eng.load_keys_device(d_bk, d_ks)
+    torch.cuda.synchronize()
+    key_secs = time.perf_counter() - t0
+    lwe_key = d_key.cpu().numpy()
+    del d_bk, d_ks
+
+    # ---- synthetic inputs: valid encryptions of random bits under the broadcast key,
+    #      generated on the device from a recorded seed
+    g = torch.Generator(device=dev)
+    g.manual_seed(1234 + rank)
+    alpha = 2.0 ** -15 * (2.0 / np.pi) ** 0.5
+    keyt = d_key.to(torch.int64)
+
+    def make_inputs():
+        bits = torch.randint(0, 2, (batch,), generator=g, device=dev, dtype=torch.int64)
+        a = torch.randint(-2 ** 31, 2 ** 31, (batch, n), generator=g, device=dev, dtype=torch.int64)
+        e = torch.round(torch.randn(batch, generator=g, device=dev, dtype=torch.float64) * alpha * 2.0 ** 32).to(torch.int64)
+        b = (a * keyt).sum(1) + (2 * bits - 1) * (1 << 29) + e
+        s = torch.cat([a, b[:, None]], 1)
+        s = ((s + 2 ** 31) % 2 ** 32 - 2 ** 31).to(torch.int32).contiguous()
+        return bits, s
+
+    bits_a, ca = make_inputs()
+    bits_b, cb = make_inputs()
+    out = eng.empty(batch)
+    expect = 1 - (bits_a & bits_b)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident steps (value) ------------------------------------------------
+    for _ in range(args.warmup):
+        eng.gate("NAND", ca, cb, out=out)
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    eng.set_timing(True)
+    launches0 = eng.launch_count
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    for _ in range(args.steps):
+        eng.gate("NAND", ca, cb, out=out)
+    ev1.record()
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    launches = eng.launch_count - launches0
+    br_ms, ks_ms, calls = eng.get_timing()
+    eng.set_timing(False)
+    sampler.stop_flag = True
+    sampler.join()
+
+    # correctness of the timed output (outside the timed region): decrypt on the device
+    ph = (out[:, -1].to(torch.int64) - (out[:, :-1].to(torch.int64) * keyt).sum(1))
+    ph = (ph + 2 ** 31) % 2 ** 32 - 2 ** 31
+    bits_ok = bool(torch.equal((ph > 0).to(torch.int64), expect))
+
+    # ---- end to end through the C ABI with HOST buffers (pinned), copies inside the timed region
+    h_ca, h_cb = ca.cpu().pin_memory(), cb.cpu().pin_memory()
+    h_out = torch.empty((batch, n + 1), dtype=torch.int32).pin_memory()
+    np_ca, np_cb, np_out = h_ca.numpy(), h_cb.numpy(), h_out.numpy()
+    e2e_steps = max(1, min(args.steps, 3))
+    eng.gate_host("NAND", np_ca, np_cb, out=np_out)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        eng.gate_host("NAND", np_ca, np_cb, out=np_out)
+    torch.cuda.synchronize()
+    e2e_ms = (time.perf_counter() - t0) * 1e3
+    ph = np_out[:, -1].astype(np.int64) - (np_out[:, :-1].astype(np.int64) * lwe_key.astype(np.int64)).sum(1)
+    ph = (ph + 2 ** 31) % 2 ** 32 - 2 ** 31
+    bits_ok = bits_ok and bool(np.array_equal((ph > 0).astype(np.int64), expect.cpu().numpy()))
+
+    # ---- reduce over ranks: max time ---------------------------------------------------
+    tt = torch.tensor([ms, e2e_ms, br_ms, ks_ms, 0.0 if bits_ok else 1.0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    ms, e2e_ms, br_ms, ks_ms, bad = tt.tolist()
+
+    if rank == 0:
+        peak_burst, peak_sust = pkg.measure_fp64_peak(local)
+        total_gates = batch * world * args.steps
+        value = total_gates / (ms * 1e-3)
+        e2e_value = batch * world * e2e_steps / (e2e_ms * 1e-3)
+        # roofline of the dominant kernel (blind rotation), per launch: algorithmic flops / event time
+        br_ms_per_launch = br_ms / max(1, calls)
+        achieved = batch * FLOP_PER_BOOTSTRAP / (br_ms_per_launch * 1e-3) / 1e12
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "dram_traffic.json")
+        if os.path.exists(tpath):
+            try:
+                traffic = json.load(open(tpath)).get("blind_rotate_kernel_bytes_per_launch_65536")
+            except Exception:
+                traffic = None
+        cpu = None
+        if not args.no_cpu_baseline and sk is not None:
+            probe = cpu_reference_run(sk, pkg, 2)
+            gpc = max(4, min(256, int(12.0 / (probe["ms_per_gate_per_core"] / 1e3))))
+            cpu = cpu_reference_run(sk, pkg, gpc)
+            cpu.pop("ms_per_gate_per_core", None)
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {
+                "workload": "%d independent bootstrapped NAND gates per GPU (BASELINE configs[2]), default TFHE gate "
+                            "params n=500 N=1024 k=1 l=2 Bgbit=10 ks_t=8 ks_basebit=2" % batch,
+                "gates_per_gpu_per_step": batch, "parallelism": "gates sharded over %d GPU(s), no data-path collective; "
+                "keys broadcast once over NCCL (%.2f s incl. keygen)" % (world, key_secs),
+                "l2": "inputs+outputs 393 MB per step > 126 MB L2 (no flush needed); keys (32.8 MB Fourier BK + 50.3 MB KS) "
+                      "are meant to stay L2-resident",
+                "bits_decrypt_ok": bool(bad == 0.0),
+            },
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(2 * batch * (n + 1) * 4),
+                    "d2h_bytes_per_step": int(batch * (n + 1) * 4), "ms_per_step": e2e_ms / e2e_steps,
+                    "api": "tfhe_b200_gate_host (C ABI, pinned host buffers)"},
+            "gpu_launches": int(launches),
+            "roofline": {
+                "bound": "fp64", "kernel": "blind_rotate_kernel", "achieved": achieved, "peak": peak_sust,
+                "unit": "TFLOP/s", "frac": achieved / peak_sust, "traffic": traffic,
+                "peak_burst": peak_burst, "peak_source": "measured live (DFMA micro-benchmark, sustained 0.4 s)",
+                "kernel_ms_per_launch": br_ms_per_launch,
+                "flop_per_launch": batch * FLOP_PER_BOOTSTRAP,
+                "share_of_step": br_ms / ms, "keyswitch_ms_per_launch": ks_ms / max(1, calls),
+            },
+            "clocks": sampler.result(),
+            "cpu_baseline": cpu,
+        }
+        print(json.dumps(line), flush=True)
+    eng.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=BATCH, help="gates per GPU per step")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 0)
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        if args.warmup < 3:
+            args.warmup = 3  # timing rule: at least 3 warm-up steps
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -15,8 +15,14 @@ from .binding import (  # noqa: F401
     Engine,
     EngineError,
     Params,
+    SecretKeys,
+    decrypt_bits,
+    encrypt_bits,
+    keygen,
+    phases,
     default_params,
     device_count,
     lib,
     lib_path,
+    measure_fp64_peak,
 )

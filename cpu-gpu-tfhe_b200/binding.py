@@ -70,8 +70,84 @@ def lib():
         L.tfhe_b200_extern_mul.argtypes = [_vp, _vp, _i, _i, _vp]
         L.tfhe_b200_gate_host.argtypes = [_vp, _i, _vp, _vp, _vp, _i]
         L.tfhe_b200_mux_host.argtypes = [_vp, _vp, _vp, _vp, _vp, _i]
+        L.tfhe_b200_bk_words.restype = ctypes.c_size_t
+        L.tfhe_b200_ks_words.restype = ctypes.c_size_t
+        L.tfhe_b200_bk_words.argtypes = [ctypes.POINTER(Params)]
+        L.tfhe_b200_ks_words.argtypes = [ctypes.POINTER(Params)]
+        L.tfhe_b200_keygen.argtypes = [ctypes.POINTER(Params), ctypes.c_uint64, ctypes.c_double, ctypes.c_double,
+                                       _vp, _vp, _vp, _vp]
+        L.tfhe_b200_encrypt_bits.argtypes = [ctypes.POINTER(Params), _vp, ctypes.c_uint64, ctypes.c_double, _vp, _i,
+                                             _vp]
+        L.tfhe_b200_decrypt_bits.argtypes = [ctypes.POINTER(Params), _vp, _vp, _i, _vp]
+        L.tfhe_b200_phases.argtypes = [_vp, _i, _vp, _i, _vp]
+        L.tfhe_b200_set_timing.argtypes = [_vp, _i]
+        L.tfhe_b200_get_timing.argtypes = [_vp, _vp, _vp, _vp]
+        L.tfhe_b200_measure_fp64_peak.argtypes = [_i, _vp, _vp]
         _lib = L
     return _lib
+
+
+class SecretKeys:
+    """Client-side key material in the flat formats of include/tfhe_b200.h."""
+
+    def __init__(self, params, lwe_key, tlwe_key, bk, ks, alpha_lwe, alpha_bk):
+        self.params, self.lwe_key, self.tlwe_key, self.bk, self.ks = params, lwe_key, tlwe_key, bk, ks
+        self.alpha_lwe, self.alpha_bk = alpha_lwe, alpha_bk
+
+
+def keygen(seed, params=None):
+    """new_random_gate_bootstrapping_secret_keyset (tfhe_gate_bootstrapping.cu:57-68), host side."""
+    L = lib()
+    p = params or default_params()
+    a, b = ctypes.c_double(), ctypes.c_double()
+    L.tfhe_b200_default_noise(ctypes.byref(a), ctypes.byref(b))
+    kpl = (p.k + 1) * p.l
+    lwe = np.zeros(p.n, np.int32)
+    tlwe = np.zeros(p.k * p.N, np.int32)
+    bk = np.zeros((p.n, kpl, p.k + 1, p.N), np.int32)
+    ks = np.zeros((p.N * p.k, p.ks_t, 1 << p.ks_basebit, p.n + 1), np.int32)
+    if L.tfhe_b200_keygen(ctypes.byref(p), seed, a.value, b.value, lwe.ctypes.data, tlwe.ctypes.data,
+                          bk.ctypes.data, ks.ctypes.data):
+        raise EngineError("keygen failed")
+    return SecretKeys(p, lwe, tlwe, bk, ks, a.value, b.value)
+
+
+def encrypt_bits(sk, bits, seed):
+    """bootsSymEncrypt (tfhe_gate_bootstrapping.cu:114) for an array of bits."""
+    bits = _np_i32(bits).reshape(-1)
+    out = np.empty((bits.size, sk.params.n + 1), np.int32)
+    if lib().tfhe_b200_encrypt_bits(ctypes.byref(sk.params), sk.lwe_key.ctypes.data, seed, sk.alpha_lwe,
+                                    bits.ctypes.data, bits.size, out.ctypes.data):
+        raise EngineError("encrypt failed")
+    return out
+
+
+def decrypt_bits(sk, samples):
+    """bootsSymDecrypt (tfhe_gate_bootstrapping.cu:122)."""
+    samples = _np_i32(samples)
+    flat = samples.reshape(-1, sk.params.n + 1)
+    out = np.empty(flat.shape[0], np.int32)
+    if lib().tfhe_b200_decrypt_bits(ctypes.byref(sk.params), sk.lwe_key.ctypes.data, flat.ctypes.data,
+                                    flat.shape[0], out.ctypes.data):
+        raise EngineError("decrypt failed")
+    return out.reshape(samples.shape[:-1])
+
+
+def phases(key, samples):
+    samples = _np_i32(samples)
+    key = _np_i32(key)
+    flat = samples.reshape(-1, key.size + 1)
+    out = np.empty(flat.shape[0], np.int32)
+    lib().tfhe_b200_phases(key.ctypes.data, key.size, flat.ctypes.data, flat.shape[0], out.ctypes.data)
+    return out.reshape(samples.shape[:-1])
+
+
+def measure_fp64_peak(device=0):
+    """(burst, sustained) fp64 FMA TFLOP/s measured live on `device`."""
+    a, b = ctypes.c_double(), ctypes.c_double()
+    if lib().tfhe_b200_measure_fp64_peak(device, ctypes.byref(a), ctypes.byref(b)):
+        raise EngineError("fp64 peak measurement failed")
+    return a.value, b.value
 
 
 def default_params():
@@ -143,6 +219,15 @@ class Engine:
     @property
     def sm_count(self):
         return int(self.L.tfhe_b200_sm_count(self.h))
+
+    def set_timing(self, enable):
+        self._ck(self.L.tfhe_b200_set_timing(self.h, int(bool(enable))))
+
+    def get_timing(self):
+        """(blind_rotate_ms, keyswitch_ms, calls) accumulated since set_timing(True)."""
+        a, b, n = ctypes.c_double(), ctypes.c_double(), ctypes.c_int()
+        self._ck(self.L.tfhe_b200_get_timing(self.h, ctypes.byref(a), ctypes.byref(b), ctypes.byref(n)))
+        return a.value, b.value, n.value
 
     # -- helpers ---------------------------------------------------------------
     def _stream(self, stream):

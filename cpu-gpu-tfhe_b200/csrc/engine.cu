@@ -26,6 +26,9 @@ struct tfhe_b200_ctx {
     size_t bk_bytes, ks_bytes;
     cudaStream_t stream;  // used by the host-buffer entry points
     std::atomic<unsigned long long> launches;
+    // optional per-kernel timing (bench roofline): event triples around blind-rotate / key-switch
+    bool timing;
+    std::vector<cudaEvent_t> ev;
 };
 
 namespace {
@@ -103,8 +106,16 @@ int run_bootstrap_ks(tfhe_b200_ctx *c, BrLaunch &L, int nsrc, int32_t ks_cst, in
     const size_t ubytes = (size_t) L.total * (kN + 1) * sizeof(int32_t);
     CU(cudaMallocAsync(&d_u, ubytes, st));
     L.u_out = d_u;
+    cudaEvent_t e0 = nullptr, e1 = nullptr, e2 = nullptr;
+    if (c->timing) {
+        CU(cudaEventCreate(&e0));
+        CU(cudaEventCreate(&e1));
+        CU(cudaEventCreate(&e2));
+        CU(cudaEventRecord(e0, st));
+    }
     CU(launch_blind_rotate(L, c->sm_count, st));
     c->launches += 1;
+    if (c->timing) CU(cudaEventRecord(e1, st));
     KsLaunch K;
     memset(&K, 0, sizeof(K));
     K.ks = c->d_ks;
@@ -120,6 +131,12 @@ int run_bootstrap_ks(tfhe_b200_ctx *c, BrLaunch &L, int nsrc, int32_t ks_cst, in
     K.basebit = c->p.ks_basebit;
     CU(launch_keyswitch(K, c->sm_count, st));
     c->launches += (out_count > 0 && ((out_count + 15) / 16) < 2 * c->sm_count) ? 2 : 1;
+    if (c->timing) {
+        CU(cudaEventRecord(e2, st));
+        c->ev.push_back(e0);
+        c->ev.push_back(e1);
+        c->ev.push_back(e2);
+    }
     CU(cudaFreeAsync(d_u, st));
     return 0;
 }
@@ -179,6 +196,7 @@ int tfhe_b200_ctx_create(tfhe_b200_ctx **out, const tfhe_b200_params *p, int dev
     c->d_ks = nullptr;
     c->bk_bytes = c->ks_bytes = 0;
     c->launches = 0;
+    c->timing = false;
     if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) {
         delete c;
         return fail("cudaStreamCreate failed");
@@ -193,8 +211,37 @@ void tfhe_b200_ctx_destroy(tfhe_b200_ctx *c) {
     cudaStreamSynchronize(c->stream);
     if (c->d_bk) cudaFree(c->d_bk);
     if (c->d_ks) cudaFree(c->d_ks);
+    for (cudaEvent_t e : c->ev) cudaEventDestroy(e);
     cudaStreamDestroy(c->stream);
     delete c;
+}
+
+// Per-kernel device time of the gate calls issued since timing was enabled: sums of the
+// blind-rotate and key-switch kernel durations (CUDA events on the launching stream).
+int tfhe_b200_set_timing(tfhe_b200_ctx *c, int enable) {
+    if (!c) return fail("null context");
+    for (cudaEvent_t e : c->ev) cudaEventDestroy(e);
+    c->ev.clear();
+    c->timing = enable != 0;
+    return 0;
+}
+
+int tfhe_b200_get_timing(tfhe_b200_ctx *c, double *blind_rotate_ms, double *keyswitch_ms, int *calls) {
+    if (!c) return fail("null context");
+    double br = 0, ks = 0;
+    const int n = (int) c->ev.size() / 3;
+    for (int i = 0; i < n; i++) {
+        CU(cudaEventSynchronize(c->ev[3 * i + 2]));
+        float a = 0, b = 0;
+        CU(cudaEventElapsedTime(&a, c->ev[3 * i], c->ev[3 * i + 1]));
+        CU(cudaEventElapsedTime(&b, c->ev[3 * i + 1], c->ev[3 * i + 2]));
+        br += a;
+        ks += b;
+    }
+    if (blind_rotate_ms) *blind_rotate_ms = br;
+    if (keyswitch_ms) *keyswitch_ms = ks;
+    if (calls) *calls = n;
+    return 0;
 }
 
 size_t tfhe_b200_key_bytes(const tfhe_b200_ctx *c) { return c ? c->bk_bytes + c->ks_bytes : 0; }

@@ -129,10 +129,32 @@ int tfhe_b200_gate_host(tfhe_b200_ctx *ctx, int gate, int32_t *out, const int32_
 int tfhe_b200_mux_host(tfhe_b200_ctx *ctx, int32_t *out, const int32_t *a, const int32_t *b, const int32_t *c,
                        int count);
 
+/* ---- client side: key generation, encryption, decryption (HOST, CPU) -------
+ * These belong to the key owner, not to the evaluation path; the reference runs them on
+ * the host as well (new_random_gate_bootstrapping_secret_keyset tfhe_gate_bootstrapping.cu:57-68,
+ * bootsSymEncrypt :114, bootsSymDecrypt :122, lwePhase lwe-functions.cu:72). */
+size_t tfhe_b200_bk_words(const tfhe_b200_params *p);
+size_t tfhe_b200_ks_words(const tfhe_b200_params *p);
+void tfhe_b200_default_noise(double *alpha_lwe, double *alpha_bk);
+int tfhe_b200_keygen(const tfhe_b200_params *p, uint64_t seed, double alpha_lwe, double alpha_bk,
+                     int32_t *lwe_key, int32_t *tlwe_key, int32_t *bk, int32_t *ks);
+int tfhe_b200_encrypt_bits(const tfhe_b200_params *p, const int32_t *lwe_key, uint64_t seed, double alpha,
+                           const int32_t *bits, int count, int32_t *out);
+int tfhe_b200_decrypt_bits(const tfhe_b200_params *p, const int32_t *lwe_key, const int32_t *samples,
+                           int count, int32_t *bits_out);
+int tfhe_b200_phases(const int32_t *key, int n, const int32_t *samples, int count, int32_t *phases_out);
+
 /* ---- introspection (tests, bench) ---------------------------------------- */
 /* kernels launched by this context so far (each = one launch of one of this library's kernels) */
 unsigned long long tfhe_b200_launch_count(const tfhe_b200_ctx *ctx);
 int tfhe_b200_sm_count(const tfhe_b200_ctx *ctx);
+/* per-kernel device time (CUDA events on the launching stream) of the gate calls issued while
+ * timing is enabled: total blind-rotate ms, total key-switch ms, number of gate calls */
+int tfhe_b200_set_timing(tfhe_b200_ctx *ctx, int enable);
+int tfhe_b200_get_timing(tfhe_b200_ctx *ctx, double *blind_rotate_ms, double *keyswitch_ms, int *calls);
+/* fp64 FMA peak of `device` in TFLOP/s, measured live: best single launch and the mean over
+ * ~0.4 s of back-to-back launches (roofline denominator of the blind-rotation kernel) */
+int tfhe_b200_measure_fp64_peak(int device, double *burst_tflops, double *sustained_tflops);
 
 #ifdef __cplusplus
 }
