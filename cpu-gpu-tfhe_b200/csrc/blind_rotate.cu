@@ -5,13 +5,16 @@
 // :2127-2362) and implements tfhe_blindRotateAndExtract_FFT
 // (lwe-bootstrapping-functions-fft.cu:1408-1456) for a whole batch:
 //
-//   * one warp owns one ciphertext; its TLWE accumulator (8 KB) and the FFT
+//   * a pair of warps owns one ciphertext; its TLWE accumulator (8 KB) and the FFT
 //     exchange buffers stay in shared memory for all n iterations; the
-//     transforms run in registers (br_core.cuh) and only warp-level barriers
-//     are needed between phases;
-//   * 4 ciphertext warps per CTA share each 16 KiB row of the bootstrapping key,
-//     streamed from L2/HBM by a producer lane with 1-D TMA bulk copies
-//     (cp.async.bulk + mbarrier expect_tx) into a 3-stage ring;
+//     transforms run in registers (br_core.cuh) and only pair-level named
+//     barriers are needed between phases; both warps do identical work between
+//     barriers (two warps per SM sub-partition hide each other's latencies: ncu of
+//     the one-warp-per-ciphertext version showed 43 % fp64 pipe use);
+//   * 4 ciphertexts per CTA share each 16 KiB row of the bootstrapping key,
+//     streamed from L2/HBM with 1-D TMA bulk copies (cp.async.bulk + mbarrier
+//     expect_tx) into a 3-stage ring; the last warp to finish with a stage
+//     issues the refill, so there is no producer warp;
 //   * the gate's linear prologue and the mod-switch are computed on the fly
 //     from the input samples (no temporaries in global memory);
 //   * grid = min(#groups, #SMs) CTAs, each looping over groups of 4 ciphertexts.
@@ -25,17 +28,25 @@ namespace tfhe_b200 {
 
 namespace {
 
-constexpr int kCtWarps = 4;                       // ciphertexts (consumer warps) per CTA
-constexpr int kThreads = (kCtWarps + 1) * 32;     // + 1 producer warp
-constexpr int kStages = 3;                        // BK ring depth (rows of 16 KiB)
-constexpr uint32_t kStageBytes = kBkRowCplx * sizeof(cpx);
+constexpr int kCtWarps = 4;                       // ciphertexts per CTA
+constexpr int kPairWarps = 2 * kCtWarps;          // two warps per ciphertext
+constexpr int kThreads = kPairWarps * 32;         // 2 warps per SM sub-partition, 255 registers each
+// Key ring: 8 KiB chunks = one result-polynomial half of one TGSW row.  Each role has its
+// own ring so that every consumer of a ring takes every chunk in order (a warp skipping
+// chunks could get two mbarrier phases ahead on a stage: parity aliasing).  Role r
+// multiplies rows r and 2+r; chunk order per iteration:
+//   (row r, half r), (row r, half 1-r), (row 2+r, half r), (row 2+r, half 1-r)
+// i.e. always the half this role KEEPS first, then the half it GIVES to its partner.
+constexpr int kRingStages = 3, kStages = 2 * kRingStages;
+constexpr uint32_t kChunksPerIter = 4;
+constexpr uint32_t kStageBytes = kBkHalfCplx * sizeof(cpx);
 
 struct __align__(128) CtaSmem {
     WarpSmem w[kCtWarps];
     cpx e2[32 * kE2Row];
-    cpx ring[kStages][kBkRowCplx];
-    unsigned long long full[kStages];
-    unsigned long long empty[kStages];
+    cpx ring[kStages][kBkHalfCplx];
+    unsigned long long full[kStages];   // mbarriers: TMA completion of a ring stage
+    unsigned int drained[kStages];      // warps that have finished with the stage's current row
 };
 
 static_assert(sizeof(WarpSmem) % 16 == 0, "warp working set must keep 16 B alignment");
@@ -48,10 +59,6 @@ __device__ __forceinline__ uint32_t smem_u32(const void *p) {
 
 __device__ __forceinline__ void mbar_init(unsigned long long *bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-
-__device__ __forceinline__ void mbar_arrive(unsigned long long *bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
 __device__ __forceinline__ void mbar_arrive_expect_tx(unsigned long long *bar, uint32_t bytes) {
@@ -81,10 +88,12 @@ __device__ __forceinline__ void tma_load_1d(void *dst, const void *src, uint32_t
                  : "memory");
 }
 
+// Position of one warp in its role's ring: ring-local chunk number, stage and phase parity.
 struct RingPos {
-    uint32_t stage = 0, phase = 0;
-    __device__ __forceinline__ void advance() {
-        if (++stage == kStages) {
+    uint32_t stage = 0, phase = 0, chunk = 0;
+    __device__ __forceinline__ void advance(uint32_t nstages) {
+        chunk++;
+        if (++stage == nstages) {
             stage = 0;
             phase ^= 1;
         }
@@ -104,50 +113,54 @@ __device__ __forceinline__ void build_e2(cpx *e2) {
 // modSwitchFromTorus32(x, 2N), numeric-functions.cu:60-66  ==  ((uint32)x + 2^20) >> 21
 __device__ __forceinline__ int modswitch_2N(uint32_t x) { return (int) ((x + (1u << 20)) >> 21); }
 
+// Issue the TMA copy of chunk `chunk` of role `role`'s ring into absolute stage `stage`
+// (one elected lane).
+__device__ __forceinline__ void ring_fill(CtaSmem &S, const BrLaunch &L, int role, uint32_t chunk, uint32_t stage) {
+    uint32_t it = chunk >> 2;
+    const uint32_t sub = chunk & 3u;
+    const uint32_t row = (uint32_t) role + 2u * (sub >> 1);
+    const uint32_t out = (sub & 1u) ? 1u - (uint32_t) role : (uint32_t) role;
+    it %= (uint32_t) L.n_iter;
+    const cpx *src = L.bk + ((size_t) (L.bk_first + it) * kKpl + row) * kBkRowCplx + out * kBkHalfCplx;
+    mbar_arrive_expect_tx(&S.full[stage], kStageBytes);
+    tma_load_1d(S.ring[stage], src, kStageBytes, &S.full[stage]);
+}
+
 __global__ void __launch_bounds__(kThreads, 1) blind_rotate_kernel(const BrLaunch L) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     CtaSmem &S = *reinterpret_cast<CtaSmem *>(smem_raw);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
+    const int ngroups = (L.total + kCtWarps - 1) / kCtWarps;
+    const int n_iter = L.n_iter;
+    const int my_groups = (ngroups - (int) blockIdx.x + (int) gridDim.x - 1) / (int) gridDim.x;
+    const uint32_t iters_total = (uint32_t) my_groups * (uint32_t) n_iter;
+
     build_e2(S.e2);
     if (threadIdx.x == 0) {
         for (int s = 0; s < kStages; s++) {
             mbar_init(&S.full[s], 1);
-            mbar_init(&S.empty[s], kCtWarps);
+            S.drained[s] = 0;
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        // prime the ring; afterwards the last warp to drain a stage refills it (no producer warp:
+        // a ninth warp would cap the kernel at 168 registers per thread)
+        for (int r = 0; r < 2; r++)
+            for (uint32_t c = 0; c < (uint32_t) kRingStages && c < kChunksPerIter * iters_total; c++)
+                ring_fill(S, L, r, c, r * kRingStages + c);
     }
     __syncthreads();
 
-    const int ngroups = (L.total + kCtWarps - 1) / kCtWarps;
-    const int n_iter = L.n_iter;
-
-    if (warp == kCtWarps) {
-        // ---------------- producer: stream BK rows through the ring -----------
-        if (lane == 0) {
-            RingPos rp;
-            for (int grp = blockIdx.x; grp < ngroups; grp += gridDim.x) {
-                const cpx *src = L.bk + (size_t) L.bk_first * kBkIterCplx;
-                for (int it = 0; it < n_iter; it++) {
-#pragma unroll 1
-                    for (int row = 0; row < kKpl; row++) {
-                        mbar_wait(&S.empty[rp.stage], rp.phase ^ 1);
-                        mbar_arrive_expect_tx(&S.full[rp.stage], kStageBytes);
-                        tma_load_1d(S.ring[rp.stage], src, kStageBytes, &S.full[rp.stage]);
-                        src += kBkRowCplx;
-                        rp.advance();
-                    }
-                }
-            }
-        }
-        return;
-    }
-
-    // -------------------- consumers: one ciphertext per warp ------------------
-    WarpSmem &W = S.w[warp];
+    // -------------------- consumers: a pair of warps per ciphertext -----------
+    const int ct = warp >> 1, role = warp & 1;
+    WarpSmem &W = S.w[ct];
+    const int bar_id = 1 + ct;
+    auto pair_sync = [bar_id]() { asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory"); };
+    const uint32_t ring_base = role * kRingStages, ring_stages = kRingStages;
+    const uint32_t ring_chunks = kChunksPerIter * iters_total;
     RingPos rp;
     for (int grp = blockIdx.x; grp < ngroups; grp += gridDim.x) {
-        int g = grp * kCtWarps + warp;
+        int g = grp * kCtWarps + ct;
         const bool valid = g < L.total;
         if (!valid) g = L.total - 1;
 
@@ -168,70 +181,96 @@ __global__ void __launch_bounds__(kThreads, 1) blind_rotate_kernel(const BrLaunc
             cst = (uint32_t) L.seg[si].cst;
         }
 
-        int barb;
-        if (L.explicit_inputs != 0) barb = L.barb ? (L.barb[g] & (2 * kN - 1)) : 0;
-        else barb = modswitch_2N(cst + sa * (uint32_t) __ldg(in0 + L.n) + sb * (uint32_t) __ldg(in1 + L.n));
-
-        if (L.acc_in != nullptr) {
-            phase_load_acc(lane, W, L.acc_in + (size_t) g * (kK + 1) * kN);
-        } else if (L.testvect != nullptr) {
-            // ACC = (0, X^{2N-barb} * testvect)
-            for (int j = lane; j < kN; j += 32) {
-                const int s = (j + barb) & (2 * kN - 1);
-                const uint32_t v = (uint32_t) __ldg(L.testvect + (s & (kN - 1)));
-                W.acc[0][(j & 15) * kAccRow + (j >> 4)] = 0;
-                W.acc[kK][(j & 15) * kAccRow + (j >> 4)] = (int32_t) (s < kN ? v : 0u - v);
+        if (role == 0) {
+            int barb;
+            if (L.explicit_inputs != 0) barb = L.barb ? (L.barb[g] & (2 * kN - 1)) : 0;
+            else barb = modswitch_2N(cst + sa * (uint32_t) __ldg(in0 + L.n) + sb * (uint32_t) __ldg(in1 + L.n));
+            if (L.acc_in != nullptr) {
+                phase_load_acc(lane, W, L.acc_in + (size_t) g * (kK + 1) * kN);
+            } else if (L.testvect != nullptr) {
+                // ACC = (0, X^{2N-barb} * testvect)
+                for (int j = lane; j < kN; j += 32) {
+                    const int s = (j + barb) & (2 * kN - 1);
+                    const uint32_t v = (uint32_t) __ldg(L.testvect + (s & (kN - 1)));
+                    W.acc[0][(j & 15) * kAccRow + (j >> 4)] = 0;
+                    W.acc[kK][(j & 15) * kAccRow + (j >> 4)] = (int32_t) (s < kN ? v : 0u - v);
+                }
+            } else {
+                phase_init(lane, W, barb, L.mu);
             }
-        } else {
-            phase_init(lane, W, barb, L.mu);
         }
-        __syncwarp();
+        pair_sync();
 
+        const bool rotate = (L.extern_only == 0);
         int a_blk = 0;  // lane l holds bara of iteration (it & ~31) + l
         for (int it = 0; it < n_iter; it++) {
             if ((it & 31) == 0) {
                 const int idx = it + lane;
                 a_blk = 0;
-                if (idx < n_iter && L.extern_only == 0) {
+                if (idx < n_iter && rotate) {
                     if (L.explicit_inputs != 0) a_blk = __ldg(L.bara + (size_t) g * n_iter + idx) & (2 * kN - 1);
                     else a_blk = modswitch_2N(sa * (uint32_t) __ldg(in0 + idx) + sb * (uint32_t) __ldg(in1 + idx));
                 }
             }
             const int a = __shfl_sync(0xffffffffu, a_blk, it & 31);
-            const bool rotate = (L.extern_only == 0);
             const bool active = (a != 0) || !rotate;  // tfhe_blindRotate_FFT :705 skips barai == 0 (no-op)
 
             if (active) {
-                phase_f1(lane, W, a, rotate);
-                __syncwarp();
+                phase_f1q(lane, W, a, role, rotate);
+                __syncwarp();  // this warp multiplies exactly the rows it has just transformed
             }
-            cpx acc_a[16], acc_b[16];
+            cpx keep[16], give[16];
 #pragma unroll
             for (int i = 0; i < 16; i++) {
-                acc_a[i].x = 0.0; acc_a[i].y = 0.0;
-                acc_b[i].x = 0.0; acc_b[i].y = 0.0;
+                keep[i].x = 0.0; keep[i].y = 0.0;
+                give[i].x = 0.0; give[i].y = 0.0;
             }
+            // MAC rows of this role; per row the kept half arrives first, then the given half
 #pragma unroll 1
-            for (int row = 0; row < kKpl; row++) {
-                mbar_wait(&S.full[rp.stage], rp.phase);
-                if (active) phase_f2_row(lane, W, S.e2, row, S.ring[rp.stage], acc_a, acc_b);
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&S.empty[rp.stage]);
-                rp.advance();
+            for (int row = role; row < kKpl; row += 2) {
+                cpx z[16];
+                if (active) phase_f2_fft(lane, W, S.e2, row, z);
+#pragma unroll
+                for (int half = 0; half < 2; half++) {
+                    const uint32_t st = ring_base + rp.stage;
+                    mbar_wait(&S.full[st], rp.phase);
+                    if (active) {
+                        if (half == 0) phase_mac_half(lane, z, S.ring[st], keep);
+                        else phase_mac_half(lane, z, S.ring[st], give);
+                    }
+                    __syncwarp();
+                    if (lane == 0) {
+                        // 4 warps (one per ciphertext) read every chunk; the last one refills the stage
+                        const unsigned int seen = atomicAdd(&S.drained[st], 1u);
+                        if ((seen & (kCtWarps - 1)) == kCtWarps - 1) {
+                            const uint32_t next = rp.chunk + ring_stages;
+                            if (next < ring_chunks) {
+                                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                                ring_fill(S, L, role, next, st);
+                            }
+                        }
+                    }
+                    rp.advance(ring_stages);
+                }
             }
             if (active) {
-                phase_f2_end(lane, W, S.e2, acc_a, acc_b);
-                __syncwarp();
-                phase_i2(lane, W, rotate);
-                __syncwarp();
+                phase_xchg_store(lane, W, role, give);
+                pair_sync();
+                phase_xchg_load_inv(lane, W, S.e2, role, keep);
+                pair_sync();
+                cpx x[16];
+                phase_i2_half(lane, W, role, x);
+                pair_sync();
+                phase_i2_final(lane, W, role, x, rotate);
+                pair_sync();
             }
         }
 
-        if (valid) {
+        if (valid && role == 0) {
             if (L.u_out != nullptr) phase_extract(lane, W, L.u_out + (size_t) g * (kN + 1));
             if (L.acc_out != nullptr) phase_dump_acc(lane, W, L.acc_out + (size_t) g * (kK + 1) * kN);
         }
-        __syncwarp();
+        pair_sync();
     }
 }
 

@@ -3,7 +3,7 @@
 // so that tests/host_emul.cu can run the exact same index math lane by lane on
 // the CPU (there is no GPU in the build container).
 //
-// One warp owns one ciphertext for all n iterations of
+// A pair of warps owns one ciphertext for all n iterations of
 //   ACC <- ACC + BK_i (.) ((X^{a_i} - 1) * ACC)
 // (reference: tfhe_MuxRotate_FFT, lwe-bootstrapping-functions-fft.cu:105-185;
 //  tGswFFTExternMulToTLwe, tgsw-fft-operations.cu:124-264).
@@ -59,7 +59,8 @@ constexpr int kExchPoly = 32 * kExchRow;
 constexpr int kAccRow = 65;       // words per accumulator row (64 used)
 constexpr int kAccPoly = 16 * kAccRow;
 constexpr int kE2Row = 17;        // complex per pass-2 constant row (15 used)
-constexpr int kBkRowCplx = 2 * 16 * 32;            // one TGSW row: [o][pos][m1]
+constexpr int kBkHalfCplx = 16 * 32;                // one result polynomial of a TGSW row: [pos][m1]
+constexpr int kBkRowCplx = 2 * kBkHalfCplx;         // one TGSW row: [o][pos][m1]
 constexpr int kBkIterCplx = kKpl * kBkRowCplx;     // one BK_i: 4096 complex = 64 KiB
 
 struct cpx {
@@ -95,6 +96,19 @@ TFHE_HD void bf_inv(cpx &a, cpx &b, double er, double ei) {
     a.y += b.y;
     b.x = fma(er, tr, ei * ti);
     b.y = fma(er, ti, -(ei * tr));
+}
+
+// Gadget digit in offset form (0..1023) -> double(digit - 512) without an I2F on the XU
+// pipe: the word 0x43300000:dig is the double 2^52 + dig, and the subtraction is exact.
+TFHE_HD double digit_to_double(uint32_t dig) {
+#ifdef __CUDA_ARCH__
+    return __hiloint2double(0x43300000, (int) dig) - 4503599627371008.0;  // 2^52 + 512
+#else
+    const uint64_t bits = (UINT64_C(0x43300000) << 32) | dig;
+    double d;
+    __builtin_memcpy(&d, &bits, sizeof(d));
+    return d - 4503599627371008.0;
+#endif
 }
 
 // acc += z * w
@@ -189,90 +203,161 @@ TFHE_HD void phase_init(int lane, WarpSmem &ws, int barb, int32_t mu) {
     }
 }
 
-// Pass 1 of the four forward transforms, fused with the rotation
-// (torusPolynomialMulByXaiMinusOne, toruspolynomial-functions.cu:191-213) and the
-// gadget decomposition (tGswTorus32PolynomialDecompH, tgsw-functions.cu:301-352).
+// ---- two warps per ciphertext -------------------------------------------------
+// The work of one MuxRotate iteration is split over a PAIR of warps so that every SM
+// sub-partition holds two warps (latency hiding) while a ciphertext still needs only one
+// shared-memory working set.  Both warps do the same amount of work between pair barriers:
+//   warp r (role r = 0, 1):
+//     pass 1 of digit level q = r (decomposed rows r and 2+r)          480 fp64 instr + 64 conversions
+//     pass 2 + MAC of those two rows against BK rows r, 2+r            2 x 320
+//     | barrier | partial sums exchanged; I1 of result polynomial r    288
+//     | barrier | half of the 32-point inverse pass (positions 16r..)  256
+//     | barrier | last butterfly stage for 16 of the outputs, to Torus32, += ACC
+//     | barrier |
+// Partial Fourier sums and the half-pass values are exchanged through exchange rows that
+// are free at that point.
+
+TFHE_HD double c1_re_rt(int i) {
+#ifdef __CUDA_ARCH__
+    return d_c1_tab_re[i];
+#else
+    return h_c1_tab_re[i];
+#endif
+}
+
+TFHE_HD double c1_im_rt(int i) {
+#ifdef __CUDA_ARCH__
+    return d_c1_tab_im[i];
+#else
+    return h_c1_tab_im[i];
+#endif
+}
+
+// Pass 1 of the two forward transforms of digit level q (decomposed rows (o, q), o = 0..k),
+// fused with the rotation (torusPolynomialMulByXaiMinusOne, toruspolynomial-functions.cu:191-213)
+// and the gadget decomposition (tGswTorus32PolynomialDecompH, tgsw-functions.cu:301-352).
 // rotate == false: plain decomposition of ACC (stand-alone external product).
-TFHE_HD void phase_f1(int lane, WarpSmem &ws, int a, bool rotate = true) {
+TFHE_HD void phase_f1q(int lane, WarpSmem &ws, int a, int q, bool rotate = true) {
     const int o = lane >> 4, j2 = lane & 15;
     const int a_lo = a & 15, a_hi = a >> 4;
     const int j2p = (j2 - a_lo) & 15;
     const int sh = a_hi + (j2 < a_lo ? 1 : 0);
     const int32_t *own = ws.acc[o] + j2 * kAccRow;
     const int32_t *rot = ws.acc[o] + j2p * kAccRow;
-    uint32_t t[64];
+    const int shift = 32 - (q + 1) * kBgbit;
+    cpx x[32];
 #pragma unroll
     for (int e = 0; e < 64; e++) {
         const int idx = (e - sh) & 127;
         uint32_t v = (uint32_t) rot[idx & 63];
         if (idx & 64) v = 0u - v;
-        t[e] = (rotate ? v - (uint32_t) own[e] : (uint32_t) own[e]) + kDecompOffset;
+        const uint32_t t = (rotate ? v - (uint32_t) own[e] : (uint32_t) own[e]) + kDecompOffset;
+        const double d = digit_to_double((t >> shift) & 1023u);
+        if (e < 32) x[e & 31].x = d;
+        else x[e & 31].y = d;
     }
+    fwd32(x);
+    cpx *dst = ws.exch[o * kL + q] + j2;
 #pragma unroll
-    for (int q = 0; q < kL; q++) {
-        const int shift = 32 - (q + 1) * kBgbit;
-        cpx x[32];
-#pragma unroll
-        for (int j1 = 0; j1 < 32; j1++) {
-            x[j1].x = (double) ((int) ((t[j1] >> shift) & 1023u) - 512);
-            x[j1].y = (double) ((int) ((t[j1 + 32] >> shift) & 1023u) - 512);
-        }
-        fwd32(x);
-        cpx *dst = ws.exch[o * kL + q] + j2;
-#pragma unroll
-        for (int pos = 0; pos < 32; pos++) dst[bitrev5(pos) * kExchRow] = x[pos];
-    }
+    for (int pos = 0; pos < 32; pos++) dst[bitrev5(pos) * kExchRow] = x[pos];
 }
 
-// Pass 2 of forward transform of decomposed polynomial `row` + Fourier MAC
-// against that TGSW row (tLweFFTAddMulRTo, tlwe-fft-operations.cu:286 ->
-// LagrangeHalfCPolynomialAddMul, lagrangehalfc_impl.cu:95-117).
-// bkrow: [o][pos][m1] complex, 16 KiB.
-TFHE_HD void phase_f2_row(int lane, WarpSmem &ws, const cpx *e2, int row, const cpx *bkrow,
-                          cpx (&acc_a)[16], cpx (&acc_b)[16]) {
-    cpx z[16];
+// Pass 2 of the forward transform of decomposed polynomial `row` (lane m1: 16 values).
+TFHE_HD void phase_f2_fft(int lane, WarpSmem &ws, const cpx *e2, int row, cpx (&z)[16]) {
     const cpx *src = ws.exch[row] + lane * kExchRow;
 #pragma unroll
     for (int j2 = 0; j2 < 16; j2++) z[j2] = src[j2];
     fwd16(z, e2 + lane * kE2Row);
+}
+
+// Fourier MAC against one result-polynomial half of a TGSW row (tLweFFTAddMulRTo,
+// tlwe-fft-operations.cu:286 -> LagrangeHalfCPolynomialAddMul, lagrangehalfc_impl.cu:95-117).
+// half: [pos][m1] complex, 8 KiB.
+TFHE_HD void phase_mac_half(int lane, const cpx (&z)[16], const cpx *half, cpx (&acc)[16]) {
 #pragma unroll
-    for (int pos = 0; pos < 16; pos++) {
-        cmac(acc_a[pos], z[pos], bkrow[pos * 32 + lane]);
-        cmac(acc_b[pos], z[pos], bkrow[(16 + pos) * 32 + lane]);
+    for (int pos = 0; pos < 16; pos++) cmac(acc[pos], z[pos], half[pos * 32 + lane]);
+}
+
+// Hand the partial sum of the result polynomial the OTHER warp finishes to that warp:
+// role 0 parks its partial b-sum in exchange buffer 0, role 1 its partial a-sum in buffer 1
+// (rows this lane owns; both buffers have been consumed by then).
+TFHE_HD void phase_xchg_store(int lane, WarpSmem &ws, int role, const cpx (&give)[16]) {
+    cpx *d = ws.exch[role] + lane * kExchRow;
+#pragma unroll
+    for (int i = 0; i < 16; i++) d[i] = give[i];
+}
+
+// keep += partner's partial; inverse pass 2 ("I1") of that result polynomial; the 16
+// outputs go to exchange buffer 2 (result a, role 0) or 3 (result b, role 1).
+TFHE_HD void phase_xchg_load_inv(int lane, WarpSmem &ws, const cpx *e2, int role, cpx (&keep)[16]) {
+    const cpx *s = ws.exch[1 - role] + lane * kExchRow;
+#pragma unroll
+    for (int i = 0; i < 16; i++) {
+        const cpx v = s[i];
+        keep[i].x += v.x;
+        keep[i].y += v.y;
     }
+    inv16(keep, e2 + lane * kE2Row);
+    cpx *d = ws.exch[2 + role] + lane * kExchRow;
+#pragma unroll
+    for (int j2 = 0; j2 < 16; j2++) d[j2] = keep[j2];
 }
 
-// Inverse pass 2 (pass "I1") of both result polynomials, in place in the
-// exchange rows this lane owns.
-TFHE_HD void phase_f2_end(int lane, WarpSmem &ws, const cpx *e2, cpx (&acc_a)[16], cpx (&acc_b)[16]) {
-    inv16(acc_a, e2 + lane * kE2Row);
-    cpx *d0 = ws.exch[0] + lane * kExchRow;
-#pragma unroll
-    for (int j2 = 0; j2 < 16; j2++) d0[j2] = acc_a[j2];
-    inv16(acc_b, e2 + lane * kE2Row);
-    cpx *d1 = ws.exch[1] + lane * kExchRow;
-#pragma unroll
-    for (int j2 = 0; j2 < 16; j2++) d1[j2] = acc_b[j2];
-}
-
-// Inverse pass 1 + conversion to Torus32 (execute_direct_Torus32,
-// fft_processor_fftw.cu:168-181: double -> int64 truncation -> int32 wrap) +
-// the tLweAddTo of MuxRotate (tlwe-functions.cu:170).
-// accumulate == false: the result replaces ACC (stand-alone external product).
-TFHE_HD void phase_i2(int lane, WarpSmem &ws, bool accumulate = true) {
+// Inverse pass 1, first part: the four inner stages on positions [16*role, 16*role+16) of
+// both result polynomials (lane (o, j2)); the 16 values are parked in exchange buffer `role`
+// ([i][lane], conflict free) for the partner.
+TFHE_HD void phase_i2_half(int lane, WarpSmem &ws, int role, cpx (&x)[16]) {
     const int o = lane >> 4, j2 = lane & 15;
-    cpx x[32];
-    const cpx *src = ws.exch[o] + j2;
+    const cpx *src = ws.exch[2 + o] + j2;
 #pragma unroll
-    for (int pos = 0; pos < 32; pos++) x[pos] = src[bitrev5(pos) * kExchRow];
-    inv32(x);
-    int32_t *row = ws.acc[o] + j2 * kAccRow;
+    for (int p = 0; p < 16; p++) {
+        // position 16*role + p holds frequency class m1 = bitrev5(16*role + p) = 2*bitrev4(p) + role
+        const int m1 = bitrev5(p) + role;  // bitrev5(p) for p < 16 is even
+        x[p] = src[m1 * kExchRow];
+    }
 #pragma unroll
-    for (int j1 = 0; j1 < 32; j1++) {
-        const uint32_t re = (uint32_t) (int32_t) (long long) x[j1].x;
-        const uint32_t im = (uint32_t) (int32_t) (long long) x[j1].y;
-        row[j1] = (int32_t) ((accumulate ? (uint32_t) row[j1] : 0u) + re);
-        row[j1 + 32] = (int32_t) ((accumulate ? (uint32_t) row[j1 + 32] : 0u) + im);
+    for (int s = 4; s >= 1; s--) {
+        const int half = 16 >> s;
+#pragma unroll
+        for (int b = 0; b < (1 << (s - 1)); b++) {
+            const int ci = (1 << s) - 1 + role * (1 << (s - 1)) + b;
+            const double er = c1_re_rt(ci), ei = c1_im_rt(ci);
+#pragma unroll
+            for (int i = 0; i < half; i++) bf_inv(x[b * 2 * half + i], x[b * 2 * half + i + half], er, ei);
+        }
+    }
+    cpx *dst = ws.exch[role] + lane;
+#pragma unroll
+    for (int i = 0; i < 16; i++) dst[i * 32] = x[i];
+}
+
+// Inverse pass 1, last stage (pairs position i of role 0 with position i of role 1) for the
+// 16 outputs of this role, conversion to Torus32 (execute_direct_Torus32,
+// fft_processor_fftw.cu:168-181: double -> int64 truncation -> int32 wrap) and the tLweAddTo
+// of MuxRotate (tlwe-functions.cu:170).  Role 0 produces coefficients j1 = 0..15, role 1
+// j1 = 16..31 (and the matching upper-half coefficients from the imaginary parts).
+// accumulate == false: the result replaces ACC (stand-alone external product).
+TFHE_HD void phase_i2_final(int lane, WarpSmem &ws, int role, const cpx (&x)[16], bool accumulate = true) {
+    const int o = lane >> 4, j2 = lane & 15;
+    const cpx *other = ws.exch[1 - role] + lane;
+    int32_t *row = ws.acc[o] + j2 * kAccRow + 16 * role;
+    const double er = c1_re(0), ei = c1_im(0);
+#pragma unroll
+    for (int i = 0; i < 16; i++) {
+        const cpx v = other[i * 32];
+        double re, im;
+        if (role == 0) {  // u + v
+            re = x[i].x + v.x;
+            im = x[i].y + v.y;
+        } else {          // conj(e) * (u - v), u = partner's value
+            const double tr = v.x - x[i].x, ti = v.y - x[i].y;
+            re = fma(er, tr, ei * ti);
+            im = fma(er, ti, -(ei * tr));
+        }
+        const uint32_t ure = (uint32_t) (int32_t) (long long) re;
+        const uint32_t uim = (uint32_t) (int32_t) (long long) im;
+        row[i] = (int32_t) ((accumulate ? (uint32_t) row[i] : 0u) + ure);
+        row[i + 32] = (int32_t) ((accumulate ? (uint32_t) row[i + 32] : 0u) + uim);
     }
 }
 

@@ -187,6 +187,14 @@ int tfhe_b200_ctx_create(tfhe_b200_ctx **out, const tfhe_b200_params *p, int dev
         return fail("device offers %zu B of shared memory per block, kernel needs %zu",
                     (size_t) prop.sharedMemPerBlockOptin, blind_rotate_smem_bytes());
     CU(blind_rotate_configure());
+    {
+        // scratch comes from the stream-ordered allocator: keep freed blocks cached instead of
+        // returning them to the driver at every synchronisation
+        cudaMemPool_t pool;
+        CU(cudaDeviceGetDefaultMemPool(&pool, device));
+        unsigned long long threshold = ~0ull;
+        CU(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &threshold));
+    }
     tfhe_b200_ctx *c = new (std::nothrow) tfhe_b200_ctx();
     if (!c) return fail("out of host memory");
     c->p = *p;

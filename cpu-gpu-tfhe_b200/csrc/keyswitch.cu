@@ -76,13 +76,18 @@ __global__ void __launch_bounds__(kKsThreads) keyswitch_kernel(const KsLaunch L,
         const uint32_t r1a = (uint32_t) __ldg(r + c0), r1b = (uint32_t) __ldg(r + c1);
         const uint32_t r2a = (uint32_t) __ldg(r + kKsRowWords + c0), r2b = (uint32_t) __ldg(r + kKsRowWords + c1);
         const uint32_t r3a = (uint32_t) __ldg(r + 2 * kKsRowWords + c0), r3b = (uint32_t) __ldg(r + 2 * kKsRowWords + c1);
+        // value(d) = lo*r1 + hi*r2 + (lo&hi)*(r3 - r1 - r2) for d = lo + 2*hi: three integer
+        // multiply-adds on the FMA pipe per column instead of selects on the (saturated) ALU pipe
+        const uint32_t ca = r3a - r1a - r2a, cb = r3b - r1b - r2b;
 #pragma unroll
         for (int g = 0; g < kTile; g++) {
-            const bool lo = (w >> (2 * g)) & 1u, hi = (w >> (2 * g + 1)) & 1u;
-            const uint32_t xa = lo ? r3a : r2a, ya = lo ? r1a : 0u;
-            const uint32_t xb = lo ? r3b : r2b, yb = lo ? r1b : 0u;
-            acc0[g] += hi ? xa : ya;
-            acc1[g] += hi ? xb : yb;
+            const uint32_t lo = (w >> (2 * g)) & 1u, hi = (w >> (2 * g + 1)) & 1u, lh = lo & hi;
+            asm("mad.lo.u32 %0, %1, %2, %0;" : "+r"(acc0[g]) : "r"(lo), "r"(r1a));
+            asm("mad.lo.u32 %0, %1, %2, %0;" : "+r"(acc1[g]) : "r"(lo), "r"(r1b));
+            asm("mad.lo.u32 %0, %1, %2, %0;" : "+r"(acc0[g]) : "r"(hi), "r"(r2a));
+            asm("mad.lo.u32 %0, %1, %2, %0;" : "+r"(acc1[g]) : "r"(hi), "r"(r2b));
+            asm("mad.lo.u32 %0, %1, %2, %0;" : "+r"(acc0[g]) : "r"(lh), "r"(ca));
+            asm("mad.lo.u32 %0, %1, %2, %0;" : "+r"(acc1[g]) : "r"(lh), "r"(cb));
         }
     }
 

@@ -101,16 +101,31 @@ int main() {
         const int i = it % P.n;
         const int a = rots[it];
         for (int lane = 0; lane < 32; lane++) phase_load_acc(lane, *ws, acc.data());
-        for (int lane = 0; lane < 32; lane++) phase_f1(lane, *ws, a);
-        cpx acc_a[32][16], acc_b[32][16];
-        memset(acc_a, 0, sizeof(acc_a));
-        memset(acc_b, 0, sizeof(acc_b));
-        for (int row = 0; row < kKpl; row++)
-            for (int lane = 0; lane < 32; lane++)
-                phase_f2_row(lane, *ws, e2.data(), row, bkdev.data() + ((size_t) i * kKpl + row) * kBkRowCplx,
-                             acc_a[lane], acc_b[lane]);
-        for (int lane = 0; lane < 32; lane++) phase_f2_end(lane, *ws, e2.data(), acc_a[lane], acc_b[lane]);
-        for (int lane = 0; lane < 32; lane++) phase_i2(lane, *ws);
+        // warp pair: role 0 transforms digit level 0 and multiplies row 0, role 1 level 1 and rows 1..3
+        for (int role = 0; role < 2; role++)
+            for (int lane = 0; lane < 32; lane++) phase_f1q(lane, *ws, a, role);
+        cpx keep[2][32][16], give[2][32][16];
+        memset(keep, 0, sizeof(keep));
+        memset(give, 0, sizeof(give));
+        for (int row = 0; row < kKpl; row++) {
+            const int role = row & 1;  // role r owns rows r and 2+r; keep = result polynomial r
+            const cpx *bkrow = bkdev.data() + ((size_t) i * kKpl + row) * kBkRowCplx;
+            for (int lane = 0; lane < 32; lane++) {
+                cpx z[16];
+                phase_f2_fft(lane, *ws, e2.data(), row, z);
+                phase_mac_half(lane, z, bkrow + role * kBkHalfCplx, keep[role][lane]);
+                phase_mac_half(lane, z, bkrow + (1 - role) * kBkHalfCplx, give[role][lane]);
+            }
+        }
+        for (int role = 0; role < 2; role++)
+            for (int lane = 0; lane < 32; lane++) phase_xchg_store(lane, *ws, role, give[role][lane]);
+        for (int role = 0; role < 2; role++)
+            for (int lane = 0; lane < 32; lane++) phase_xchg_load_inv(lane, *ws, e2.data(), role, keep[role][lane]);
+        cpx xh[2][32][16];
+        for (int role = 0; role < 2; role++)
+            for (int lane = 0; lane < 32; lane++) phase_i2_half(lane, *ws, role, xh[role][lane]);
+        for (int role = 0; role < 2; role++)
+            for (int lane = 0; lane < 32; lane++) phase_i2_final(lane, *ws, role, xh[role][lane]);
         std::vector<int32_t> got(2 * kN);
         for (int lane = 0; lane < 32; lane++) phase_dump_acc(lane, *ws, got.data());
         // expected: acc + BK_i (.) ((X^a - 1) acc), exact
