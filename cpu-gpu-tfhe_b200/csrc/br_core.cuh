@@ -111,6 +111,10 @@ TFHE_HD double digit_to_double(uint32_t dig) {
 #endif
 }
 
+// double -> Torus32 exactly as the reference does it: Torus32(int64_t(x)), i.e. truncation
+// toward zero, then wrap (fft_processor_fftw.cu:177).
+TFHE_HD uint32_t double_to_torus32(double x) { return (uint32_t) (int32_t) (long long) x; }
+
 // acc += z * w
 TFHE_HD void cmac(cpx &acc, const cpx &z, const cpx &w) {
     acc.x = fma(z.x, w.x, acc.x);
@@ -245,16 +249,31 @@ TFHE_HD void phase_f1q(int lane, WarpSmem &ws, int a, int q, bool rotate = true)
     const int32_t *own = ws.acc[o] + j2 * kAccRow;
     const int32_t *rot = ws.acc[o] + j2p * kAccRow;
     const int shift = 32 - (q + 1) * kBgbit;
+    const uint32_t rmask = rotate ? 0xffffffffu : 0u;  // rotate == false: T = ACC
     cpx x[32];
+    // blocks of 16 coefficients: all shared-memory loads of a block are issued before its
+    // integer work so that their latencies overlap
 #pragma unroll
-    for (int e = 0; e < 64; e++) {
-        const int idx = (e - sh) & 127;
-        uint32_t v = (uint32_t) rot[idx & 63];
-        if (idx & 64) v = 0u - v;
-        const uint32_t t = (rotate ? v - (uint32_t) own[e] : (uint32_t) own[e]) + kDecompOffset;
-        const double d = digit_to_double((t >> shift) & 1023u);
-        if (e < 32) x[e & 31].x = d;
-        else x[e & 31].y = d;
+    for (int blk = 0; blk < 64; blk += 16) {
+        uint32_t vr[16], vo[16];
+#pragma unroll
+        for (int i = 0; i < 16; i++) {
+            const int idx = (blk + i - sh) & 127;
+            vr[i] = (uint32_t) rot[idx & 63];
+            vo[i] = (uint32_t) own[blk + i];
+        }
+#pragma unroll
+        for (int i = 0; i < 16; i++) {
+            const int e = blk + i;
+            const int idx = (e - sh) & 127;
+            const uint32_t neg = 0u - (uint32_t) ((idx >> 6) & 1);  // branch-free negacyclic sign
+            const uint32_t v = ((vr[i] ^ neg) - neg) & rmask;
+            // rotate: X^a*ACC - ACC ; otherwise +ACC
+            const uint32_t t = (rotate ? v - vo[i] : vo[i]) + kDecompOffset;
+            const double d = digit_to_double((t >> shift) & 1023u);
+            if (e < 32) x[e & 31].x = d;
+            else x[e & 31].y = d;
+        }
     }
     fwd32(x);
     cpx *dst = ws.exch[o * kL + q] + j2;
@@ -342,22 +361,106 @@ TFHE_HD void phase_i2_final(int lane, WarpSmem &ws, int role, const cpx (&x)[16]
     const cpx *other = ws.exch[1 - role] + lane;
     int32_t *row = ws.acc[o] + j2 * kAccRow + 16 * role;
     const double er = c1_re(0), ei = c1_im(0);
+    // blocks of 8 outputs: all loads, then all butterflies and conversions, then the updates
+    // (keeps the XU conversions and the shared-memory round trips overlapped)
 #pragma unroll
-    for (int i = 0; i < 16; i++) {
-        const cpx v = other[i * 32];
-        double re, im;
-        if (role == 0) {  // u + v
-            re = x[i].x + v.x;
-            im = x[i].y + v.y;
-        } else {          // conj(e) * (u - v), u = partner's value
-            const double tr = v.x - x[i].x, ti = v.y - x[i].y;
-            re = fma(er, tr, ei * ti);
-            im = fma(er, ti, -(ei * tr));
+    for (int blk = 0; blk < 16; blk += 8) {
+        cpx v[8];
+        uint32_t old_lo[8], old_hi[8];
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            v[i] = other[(blk + i) * 32];
+            old_lo[i] = accumulate ? (uint32_t) row[blk + i] : 0u;
+            old_hi[i] = accumulate ? (uint32_t) row[blk + i + 32] : 0u;
         }
-        const uint32_t ure = (uint32_t) (int32_t) (long long) re;
-        const uint32_t uim = (uint32_t) (int32_t) (long long) im;
-        row[i] = (int32_t) ((accumulate ? (uint32_t) row[i] : 0u) + ure);
-        row[i + 32] = (int32_t) ((accumulate ? (uint32_t) row[i + 32] : 0u) + uim);
+        uint32_t ure[8], uim[8];
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            double re, im;
+            if (role == 0) {  // u + v
+                re = x[blk + i].x + v[i].x;
+                im = x[blk + i].y + v[i].y;
+            } else {          // conj(e) * (u - v), u = partner's value
+                const double tr = v[i].x - x[blk + i].x, ti = v[i].y - x[blk + i].y;
+                re = fma(er, tr, ei * ti);
+                im = fma(er, ti, -(ei * tr));
+            }
+            ure[i] = double_to_torus32(re);
+            uim[i] = double_to_torus32(im);
+        }
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            row[blk + i] = (int32_t) (old_lo[i] + ure[i]);
+            row[blk + i + 32] = (int32_t) (old_hi[i] + uim[i]);
+        }
+    }
+}
+
+// ---- one warp per ciphertext ---------------------------------------------------
+// Same mathematics with a single warp doing every step (fewer shared-memory bytes per
+// iteration: no partial-sum or half-pass exchange; used for large throughput batches).
+
+// Pass 1 of all four forward transforms (both digit levels share the rotated difference).
+TFHE_HD void phase1w_f1(int lane, WarpSmem &ws, int a, bool rotate = true) {
+    const int o = lane >> 4, j2 = lane & 15;
+    const int a_lo = a & 15, a_hi = a >> 4;
+    const int j2p = (j2 - a_lo) & 15;
+    const int sh = a_hi + (j2 < a_lo ? 1 : 0);
+    const int32_t *own = ws.acc[o] + j2 * kAccRow;
+    const int32_t *rot = ws.acc[o] + j2p * kAccRow;
+    uint32_t t[64];
+#pragma unroll
+    for (int e = 0; e < 64; e++) {
+        const int idx = (e - sh) & 127;
+        uint32_t v = (uint32_t) rot[idx & 63];
+        const uint32_t neg = 0u - (uint32_t) ((idx >> 6) & 1);  // branch-free negacyclic sign
+        v = (v ^ neg) - neg;
+        t[e] = (rotate ? v - (uint32_t) own[e] : (uint32_t) own[e]) + kDecompOffset;
+    }
+    // the two digit levels reuse one copy of the 32-point network (instruction-cache footprint)
+#pragma unroll 1
+    for (int q = 0; q < kL; q++) {
+        const int shift = 32 - (q + 1) * kBgbit;
+        cpx x[32];
+#pragma unroll
+        for (int j1 = 0; j1 < 32; j1++) {
+            x[j1].x = digit_to_double((t[j1] >> shift) & 1023u);
+            x[j1].y = digit_to_double((t[j1 + 32] >> shift) & 1023u);
+        }
+        fwd32(x);
+        cpx *dst = ws.exch[o * kL + q] + j2;
+#pragma unroll
+        for (int pos = 0; pos < 32; pos++) dst[bitrev5(pos) * kExchRow] = x[pos];
+    }
+}
+
+// Inverse pass 2 ("I1") of both result polynomials into exchange buffers 2 and 3.
+TFHE_HD void phase1w_f2_end(int lane, WarpSmem &ws, const cpx *e2, cpx (&acc_a)[16], cpx (&acc_b)[16]) {
+    inv16(acc_a, e2 + lane * kE2Row);
+    cpx *d0 = ws.exch[2] + lane * kExchRow;
+#pragma unroll
+    for (int j2 = 0; j2 < 16; j2++) d0[j2] = acc_a[j2];
+    inv16(acc_b, e2 + lane * kE2Row);
+    cpx *d1 = ws.exch[3] + lane * kExchRow;
+#pragma unroll
+    for (int j2 = 0; j2 < 16; j2++) d1[j2] = acc_b[j2];
+}
+
+// Inverse pass 1 (all five stages) + conversion to Torus32 + tLweAddTo, see phase_i2_final.
+TFHE_HD void phase1w_i2(int lane, WarpSmem &ws, bool accumulate = true) {
+    const int o = lane >> 4, j2 = lane & 15;
+    cpx x[32];
+    const cpx *src = ws.exch[2 + o] + j2;
+#pragma unroll
+    for (int pos = 0; pos < 32; pos++) x[pos] = src[bitrev5(pos) * kExchRow];
+    inv32(x);
+    int32_t *row = ws.acc[o] + j2 * kAccRow;
+#pragma unroll
+    for (int j1 = 0; j1 < 32; j1++) {
+        const uint32_t re = double_to_torus32(x[j1].x);
+        const uint32_t im = double_to_torus32(x[j1].y);
+        row[j1] = (int32_t) ((accumulate ? (uint32_t) row[j1] : 0u) + re);
+        row[j1 + 32] = (int32_t) ((accumulate ? (uint32_t) row[j1 + 32] : 0u) + im);
     }
 }
 
