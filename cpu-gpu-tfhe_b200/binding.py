@@ -81,7 +81,6 @@ def lib():
         L.tfhe_b200_decrypt_bits.argtypes = [ctypes.POINTER(Params), _vp, _vp, _i, _vp]
         L.tfhe_b200_phases.argtypes = [_vp, _i, _vp, _i, _vp]
         L.tfhe_b200_set_timing.argtypes = [_vp, _i]
-        L.tfhe_b200_set_schedule.argtypes = [_vp, _i]
         L.tfhe_b200_get_timing.argtypes = [_vp, _vp, _vp, _vp]
         L.tfhe_b200_measure_fp64_peak.argtypes = [_i, _vp, _vp]
         _lib = L
@@ -220,10 +219,6 @@ class Engine:
     @property
     def sm_count(self):
         return int(self.L.tfhe_b200_sm_count(self.h))
-
-    def set_schedule(self, schedule):
-        """0 auto, 1 one warp per ciphertext (throughput), 2 two warps per ciphertext (latency)."""
-        self._ck(self.L.tfhe_b200_set_schedule(self.h, int(schedule)))
 
     def set_timing(self, enable):
         self._ck(self.L.tfhe_b200_set_timing(self.h, int(bool(enable))))

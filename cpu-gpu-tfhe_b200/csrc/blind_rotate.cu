@@ -29,26 +29,20 @@ namespace tfhe_b200 {
 namespace {
 
 constexpr int kCtWarps = 4;                       // ciphertexts per CTA
-// Two schedules of the same per-iteration mathematics (template parameter kPair):
-//   kPair = true : two warps per ciphertext (8 warps per CTA).  Shortest critical path per
-//                  iteration -> used for small batches / circuit latency.
-//   kPair = false: one warp per ciphertext (4 warps per CTA), fewer shared-memory bytes per
-//                  iteration (no partial-sum / half-pass exchange) -> used for large batches.
-//                  The four warps re-align once per iteration so that they run through the same
-//                  88 KB of straight-line code together (instruction-cache misses were 19 % of
-//                  the stall samples when they drifted apart).
-template <bool kPair> __host__ __device__ constexpr int threads_of() { return (kPair ? 2 : 1) * kCtWarps * 32; }
+// Two warps per ciphertext (8 warps per CTA, 2 per SM sub-partition, 255 registers each).
+// A one-warp-per-ciphertext schedule (4 warps per CTA) was measured too: it moves fewer
+// shared-memory bytes per iteration but leaves every sub-partition with a single warp that
+// cannot hide its own latencies (profiles/README.md: 503 ms vs 455 ms per 65536 gates).
+constexpr int kThreads = 2 * kCtWarps * 32;
 // Key ring: 8 KiB chunks = one result-polynomial half of one TGSW row.  Each role has its
 // own ring so that every consumer of a ring takes every chunk in order (a warp skipping
 // chunks could get two mbarrier phases ahead on a stage: parity aliasing).  Role r
 // multiplies rows r and 2+r; chunk order per iteration:
 //   (row r, half r), (row r, half 1-r), (row 2+r, half r), (row 2+r, half 1-r)
 // i.e. always the half this role KEEPS first, then the half it GIVES to its partner.
-// With one warp per ciphertext there is a single ring of all 6 stages, chunk order
-// (row, half a), (row, half b) for row = 0..3.
 constexpr int kStages = 6;
-template <bool kPair> __host__ __device__ constexpr uint32_t ring_stages_of() { return kPair ? 3 : 6; }
-template <bool kPair> __host__ __device__ constexpr uint32_t chunks_per_iter_of() { return kPair ? 4 : 8; }
+constexpr uint32_t kRingStages = 3;     // per role
+constexpr uint32_t kChunksPerIter = 4;  // per role
 constexpr uint32_t kStageBytes = kBkHalfCplx * sizeof(cpx);
 
 struct __align__(128) CtaSmem {
@@ -111,8 +105,8 @@ struct RingPos {
 };
 
 __device__ __forceinline__ void build_e2(cpx *e2) {
-    for (int t = threadIdx.x; t < 32 * 15; t += blockDim.x) {
-        const int m1 = t / 15, idx = t % 15;
+    for (int t = threadIdx.x; t < 32 * 4; t += blockDim.x) {
+        const int m1 = t / 4, idx = t % 4;
         double s, c;
         sincospi(e2_shift(m1, idx), &s, &c);
         e2[m1 * kE2Row + idx].x = c;
@@ -125,20 +119,11 @@ __device__ __forceinline__ int modswitch_2N(uint32_t x) { return (int) ((x + (1u
 
 // Issue the TMA copy of chunk `chunk` of role `role`'s ring into absolute stage `stage`
 // (one elected lane).
-template <bool kPair>
 __device__ __forceinline__ void ring_fill(CtaSmem &S, const BrLaunch &L, int role, uint32_t chunk, uint32_t stage) {
-    uint32_t it, row, out;
-    if (kPair) {
-        it = chunk >> 2;
-        const uint32_t sub = chunk & 3u;
-        row = (uint32_t) role + 2u * (sub >> 1);
-        out = (sub & 1u) ? 1u - (uint32_t) role : (uint32_t) role;
-    } else {
-        it = chunk >> 3;
-        row = (chunk >> 1) & 3u;
-        out = chunk & 1u;
-    }
-    it %= (uint32_t) L.n_iter;
+    const uint32_t it = (chunk >> 2) % (uint32_t) L.n_iter;
+    const uint32_t sub = chunk & 3u;
+    const uint32_t row = (uint32_t) role + 2u * (sub >> 1);
+    const uint32_t out = (sub & 1u) ? 1u - (uint32_t) role : (uint32_t) role;
     const cpx *src = L.bk + ((size_t) (L.bk_first + it) * kKpl + row) * kBkRowCplx + out * kBkHalfCplx;
     mbar_arrive_expect_tx(&S.full[stage], kStageBytes);
     tma_load_1d(S.ring[stage], src, kStageBytes, &S.full[stage]);
@@ -146,7 +131,7 @@ __device__ __forceinline__ void ring_fill(CtaSmem &S, const BrLaunch &L, int rol
 
 // Consumer side of one chunk: wait for it, use it, and let the last of the 4 warps that read
 // it issue the refill of its stage.
-template <bool kPair, typename Use>
+template <typename Use>
 __device__ __forceinline__ void ring_consume(CtaSmem &S, const BrLaunch &L, int role, int lane, RingPos &rp,
                                              uint32_t ring_base, uint32_t ring_chunks, Use use) {
     const uint32_t st = ring_base + rp.stage;
@@ -156,18 +141,17 @@ __device__ __forceinline__ void ring_consume(CtaSmem &S, const BrLaunch &L, int 
     if (lane == 0) {
         const unsigned int seen = atomicAdd(&S.drained[st], 1u);
         if ((seen & (kCtWarps - 1)) == kCtWarps - 1) {
-            const uint32_t next = rp.chunk + ring_stages_of<kPair>();
+            const uint32_t next = rp.chunk + kRingStages;
             if (next < ring_chunks) {
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                ring_fill<kPair>(S, L, role, next, st);
+                ring_fill(S, L, role, next, st);
             }
         }
     }
-    rp.advance(ring_stages_of<kPair>());
+    rp.advance(kRingStages);
 }
 
-template <bool kPair>
-__global__ void __launch_bounds__(threads_of<kPair>(), 1) blind_rotate_kernel(const BrLaunch L) {
+__global__ void __launch_bounds__(kThreads, 1) blind_rotate_kernel(const BrLaunch L) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     CtaSmem &S = *reinterpret_cast<CtaSmem *>(smem_raw);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -186,23 +170,20 @@ __global__ void __launch_bounds__(threads_of<kPair>(), 1) blind_rotate_kernel(co
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         // prime the ring; afterwards the last warp to drain a stage refills it (no producer warp:
         // a ninth warp would cap the kernel at 168 registers per thread)
-        for (int r = 0; r < (kPair ? 2 : 1); r++)
-            for (uint32_t c = 0; c < ring_stages_of<kPair>() && c < chunks_per_iter_of<kPair>() * iters_total; c++)
-                ring_fill<kPair>(S, L, r, c, r * ring_stages_of<kPair>() + c);
+        for (int r = 0; r < 2; r++)
+            for (uint32_t c = 0; c < kRingStages && c < kChunksPerIter * iters_total; c++)
+                ring_fill(S, L, r, c, r * kRingStages + c);
     }
     __syncthreads();
 
     // -------------------- ciphertext warps ---------------------------------------
-    const int ct = kPair ? (warp >> 1) : warp, role = kPair ? (warp & 1) : 0;
+    const int ct = warp >> 1, role = warp & 1;
     WarpSmem &W = S.w[ct];
     const int bar_id = 1 + ct;
-    // pair barrier (two warps of one ciphertext) / plain warp barrier
-    auto pair_sync = [bar_id]() {
-        if (kPair) asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");
-        else __syncwarp();
-    };
-    const uint32_t ring_base = role * ring_stages_of<kPair>();
-    const uint32_t ring_chunks = chunks_per_iter_of<kPair>() * iters_total;
+    // barrier of the two warps of one ciphertext
+    auto pair_sync = [bar_id]() { asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory"); };
+    const uint32_t ring_base = role * kRingStages;
+    const uint32_t ring_chunks = kChunksPerIter * iters_total;
     RingPos rp;
     for (int grp = blockIdx.x; grp < ngroups; grp += gridDim.x) {
         int g = grp * kCtWarps + ct;
@@ -261,12 +242,10 @@ __global__ void __launch_bounds__(threads_of<kPair>(), 1) blind_rotate_kernel(co
             const bool active = (a != 0) || !rotate;  // tfhe_blindRotate_FFT :705 skips barai == 0 (no-op)
 
             if (active) {
-                if (kPair) phase_f1q(lane, W, a, role, rotate);
-                else phase1w_f1(lane, W, a, rotate);
+                phase_f1q(lane, W, a, role, rotate);
                 __syncwarp();  // a warp multiplies exactly the rows it has just transformed
             }
             // keep / give: partial sums of the result polynomial this warp finishes / hands over
-            // (one warp per ciphertext: keep = a, give = b)
             cpx keep[16], give[16];
 #pragma unroll
             for (int i = 0; i < 16; i++) {
@@ -274,37 +253,26 @@ __global__ void __launch_bounds__(threads_of<kPair>(), 1) blind_rotate_kernel(co
                 give[i].x = 0.0; give[i].y = 0.0;
             }
 #pragma unroll 1
-            for (int row = role; row < kKpl; row += (kPair ? 2 : 1)) {
+            for (int row = role; row < kKpl; row += 2) {
                 cpx z[16];
                 if (active) phase_f2_fft(lane, W, S.e2, row, z);
-                ring_consume<kPair>(S, L, role, lane, rp, ring_base, ring_chunks, [&](const cpx *half) {
+                ring_consume(S, L, role, lane, rp, ring_base, ring_chunks, [&](const cpx *half) {
                     if (active) phase_mac_half(lane, z, half, keep);
                 });
-                ring_consume<kPair>(S, L, role, lane, rp, ring_base, ring_chunks, [&](const cpx *half) {
+                ring_consume(S, L, role, lane, rp, ring_base, ring_chunks, [&](const cpx *half) {
                     if (active) phase_mac_half(lane, z, half, give);
                 });
             }
             if (active) {
-                if (kPair) {
-                    phase_xchg_store(lane, W, role, give);
-                    pair_sync();
-                    phase_xchg_load_inv(lane, W, S.e2, role, keep);
-                    pair_sync();
-                    cpx x[16];
-                    phase_i2_half(lane, W, role, x);
-                    pair_sync();
-                    phase_i2_final(lane, W, role, x, rotate);
-                    pair_sync();
-                } else {
-                    phase1w_f2_end(lane, W, S.e2, keep, give);
-                    __syncwarp();
-                    phase1w_i2(lane, W, rotate);
-                    __syncwarp();
-                }
-            }
-            if (!kPair) {
-                // keep the four independent ciphertext warps on the same stretch of code
-                asm volatile("bar.sync 1, 128;" ::: "memory");
+                phase_xchg_store(lane, W, role, give);
+                pair_sync();
+                phase_xchg_load_inv(lane, W, S.e2, role, keep);
+                pair_sync();
+                cpx x[16];
+                phase_i2_half(lane, W, role, x);
+                pair_sync();
+                phase_i2_final(lane, W, role, x, rotate);
+                pair_sync();
             }
         }
 
@@ -345,11 +313,8 @@ forward_polys_kernel(const int32_t *__restrict__ coef, cpx *__restrict__ out, in
 size_t blind_rotate_smem_bytes() { return sizeof(CtaSmem); }
 
 cudaError_t blind_rotate_configure() {
-    cudaError_t e = cudaFuncSetAttribute(blind_rotate_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(blind_rotate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int) sizeof(CtaSmem));
-    if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(blind_rotate_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             (int) sizeof(CtaSmem));
     if (e != cudaSuccess) return e;
     return cudaFuncSetAttribute(forward_polys_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 (int) sizeof(FwdSmem));
@@ -359,13 +324,7 @@ cudaError_t launch_blind_rotate(const BrLaunch &L, int sm_count, cudaStream_t st
     if (L.total <= 0) return cudaSuccess;
     const int ngroups = (L.total + kCtWarps - 1) / kCtWarps;
     const int grid = ngroups < sm_count ? ngroups : sm_count;
-    // schedule: more than two waves of ciphertexts -> throughput schedule (one warp per
-    // ciphertext); otherwise the latency schedule (two warps per ciphertext)
-    bool pair = ngroups <= 2 * sm_count;
-    if (L.schedule == 1) pair = false;
-    if (L.schedule == 2) pair = true;
-    if (pair) blind_rotate_kernel<true><<<grid, threads_of<true>(), sizeof(CtaSmem), stream>>>(L);
-    else blind_rotate_kernel<false><<<grid, threads_of<false>(), sizeof(CtaSmem), stream>>>(L);
+    blind_rotate_kernel<<<grid, kThreads, sizeof(CtaSmem), stream>>>(L);
     return cudaGetLastError();
 }
 

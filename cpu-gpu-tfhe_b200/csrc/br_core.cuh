@@ -58,7 +58,7 @@ constexpr int kExchRow = 17;      // complex per exchange row (16 used)
 constexpr int kExchPoly = 32 * kExchRow;
 constexpr int kAccRow = 65;       // words per accumulator row (64 used)
 constexpr int kAccPoly = 16 * kAccRow;
-constexpr int kE2Row = 17;        // complex per pass-2 constant row (15 used)
+constexpr int kE2Row = 5;         // complex per pass-2 constant row (4 used; 80 B stride is conflict free)
 constexpr int kBkHalfCplx = 16 * 32;                // one result polynomial of a TGSW row: [pos][m1]
 constexpr int kBkRowCplx = 2 * kBkHalfCplx;         // one TGSW row: [o][pos][m1]
 constexpr int kBkIterCplx = kKpl * kBkRowCplx;     // one BK_i: 4096 complex = 64 KiB
@@ -154,40 +154,88 @@ TFHE_HD void inv32(cpx (&x)[32]) {
 
 // Stages 5-8 on the 16 in-register elements of frequency class m1; e points at
 // this lane's 15 multipliers (natural j2 in, bit-reversed m2 out).
-TFHE_HD void fwd16(cpx (&z)[16], const cpx *e) {
-#pragma unroll
-    for (int s = 0; s < 4; s++) {
-        const int half = 8 >> s;
-#pragma unroll
-        for (int b = 0; b < (1 << s); b++) {
-            const cpx c = e[(1 << s) - 1 + b];
-#pragma unroll
-            for (int i = 0; i < half; i++) bf_fwd(z[b * 2 * half + i], z[b * 2 * half + i + half], c.x, c.y);
-        }
+// Stage constants of pass 2.  Block b of stage s has shift (d0 + rev_s(b)) / 2^s with
+// d0 = (m1 + 1/4)/32, so its multiplier is g_s * exp(i*pi*rev_s(b)/2^s) with the
+// lane-dependent g_s = exp(i*pi*d0/2^s).  Only g_0..g_3 are kept per lane (table e, 4 complex
+// instead of 15: shared-memory wavefronts were the busiest resource of the kernel); the other
+// factors are exp(i*pi/2) = i (free), exp(i*pi/4), exp(i*pi/8), exp(3i*pi/8) (16 fp64
+// instructions per transform).
+struct Stage3Consts {
+    cpx g, h4, h8, h38;  // g_3, g_3*e^{i pi/4}, g_3*e^{i pi/8}, g_3*e^{3 i pi/8}
+};
+
+TFHE_HD cpx cmul_const(const cpx &g, double cr, double ci) {
+    cpx r;
+    r.x = fma(g.x, cr, -(g.y * ci));
+    r.y = fma(g.x, ci, g.y * cr);
+    return r;
+}
+
+constexpr double kSqrtHalf = 0.70710678118654752440;
+constexpr double kCosPi8 = 0.92387953251128675613, kSinPi8 = 0.38268343236508977173;
+
+// constant of (stage s, block b) given the stage's base values; odd blocks are i * (even block)
+template <int S, int B>
+TFHE_HD cpx pass2_const(const cpx &g, const cpx &h4, const cpx &h8, const cpx &h38) {
+    constexpr int base = B >> 1;
+    cpx c = (S <= 1 || base == 0) ? g : (base == 1 ? h4 : (base == 2 ? h8 : h38));
+    if (B & 1) {
+        const double t = c.x;
+        c.x = -c.y;
+        c.y = t;
     }
+    return c;
+}
+
+template <int S, bool kInv, int B = 0>
+struct Pass2Stage {
+    TFHE_HD static void run(cpx (&z)[16], const cpx &g, const cpx &h4, const cpx &h8, const cpx &h38) {
+        constexpr int half = 8 >> S;
+        const cpx c = pass2_const<S, B>(g, h4, h8, h38);
+#pragma unroll
+        for (int i = 0; i < half; i++) {
+            if (kInv) bf_inv(z[B * 2 * half + i], z[B * 2 * half + i + half], c.x, c.y);
+            else bf_fwd(z[B * 2 * half + i], z[B * 2 * half + i + half], c.x, c.y);
+        }
+        if constexpr (B + 1 < (1 << S)) Pass2Stage<S, kInv, B + 1>::run(z, g, h4, h8, h38);
+    }
+};
+
+template <int S, bool kInv>
+TFHE_HD void pass2_stage(cpx (&z)[16], const cpx *e) {
+    const cpx g = e[S];
+    cpx h4 = g, h8 = g, h38 = g;
+    if (S >= 2) {
+        h4.x = (g.x - g.y) * kSqrtHalf;
+        h4.y = (g.x + g.y) * kSqrtHalf;
+    }
+    if (S >= 3) {
+        h8 = cmul_const(g, kCosPi8, kSinPi8);
+        h38 = cmul_const(g, kSinPi8, kCosPi8);
+    }
+    Pass2Stage<S, kInv>::run(z, g, h4, h8, h38);
+}
+
+// Stages 5-8 on the 16 in-register elements of frequency class m1; e points at
+// this lane's 4 base multipliers (natural j2 in, bit-reversed m2 out).
+TFHE_HD void fwd16(cpx (&z)[16], const cpx *e) {
+    pass2_stage<0, false>(z, e);
+    pass2_stage<1, false>(z, e);
+    pass2_stage<2, false>(z, e);
+    pass2_stage<3, false>(z, e);
 }
 
 TFHE_HD void inv16(cpx (&z)[16], const cpx *e) {
-#pragma unroll
-    for (int s = 3; s >= 0; s--) {
-        const int half = 8 >> s;
-#pragma unroll
-        for (int b = 0; b < (1 << s); b++) {
-            const cpx c = e[(1 << s) - 1 + b];
-#pragma unroll
-            for (int i = 0; i < half; i++) bf_inv(z[b * 2 * half + i], z[b * 2 * half + i + half], c.x, c.y);
-        }
-    }
+    pass2_stage<3, true>(z, e);
+    pass2_stage<2, true>(z, e);
+    pass2_stage<1, true>(z, e);
+    pass2_stage<0, true>(z, e);
 }
 
-// Shift of pass-2 block `idx` (= (1<<stage)-1+block) for frequency class m1.
-TFHE_HD double e2_shift(int m1, int idx) {
+// Shift of the lane-dependent base multiplier g_s of pass-2 stage s for frequency class m1.
+TFHE_HD double e2_shift(int m1, int s) {
     double d = ((double) m1 + 0.25) / 32.0;
-    // walk down the tree: idx+1 in binary, below the leading one, MSB first
-    const int v = idx + 1;
-    int top = 0;
-    while ((v >> (top + 1)) != 0) top++;
-    for (int bit = top - 1; bit >= 0; bit--) d = (d + (double) ((v >> bit) & 1)) * 0.5;
+    for (int i = 0; i < s; i++) d *= 0.5;
     return d;
 }
 
@@ -393,74 +441,6 @@ TFHE_HD void phase_i2_final(int lane, WarpSmem &ws, int role, const cpx (&x)[16]
             row[blk + i] = (int32_t) (old_lo[i] + ure[i]);
             row[blk + i + 32] = (int32_t) (old_hi[i] + uim[i]);
         }
-    }
-}
-
-// ---- one warp per ciphertext ---------------------------------------------------
-// Same mathematics with a single warp doing every step (fewer shared-memory bytes per
-// iteration: no partial-sum or half-pass exchange; used for large throughput batches).
-
-// Pass 1 of all four forward transforms (both digit levels share the rotated difference).
-TFHE_HD void phase1w_f1(int lane, WarpSmem &ws, int a, bool rotate = true) {
-    const int o = lane >> 4, j2 = lane & 15;
-    const int a_lo = a & 15, a_hi = a >> 4;
-    const int j2p = (j2 - a_lo) & 15;
-    const int sh = a_hi + (j2 < a_lo ? 1 : 0);
-    const int32_t *own = ws.acc[o] + j2 * kAccRow;
-    const int32_t *rot = ws.acc[o] + j2p * kAccRow;
-    uint32_t t[64];
-#pragma unroll
-    for (int e = 0; e < 64; e++) {
-        const int idx = (e - sh) & 127;
-        uint32_t v = (uint32_t) rot[idx & 63];
-        const uint32_t neg = 0u - (uint32_t) ((idx >> 6) & 1);  // branch-free negacyclic sign
-        v = (v ^ neg) - neg;
-        t[e] = (rotate ? v - (uint32_t) own[e] : (uint32_t) own[e]) + kDecompOffset;
-    }
-    // the two digit levels reuse one copy of the 32-point network (instruction-cache footprint)
-#pragma unroll 1
-    for (int q = 0; q < kL; q++) {
-        const int shift = 32 - (q + 1) * kBgbit;
-        cpx x[32];
-#pragma unroll
-        for (int j1 = 0; j1 < 32; j1++) {
-            x[j1].x = digit_to_double((t[j1] >> shift) & 1023u);
-            x[j1].y = digit_to_double((t[j1 + 32] >> shift) & 1023u);
-        }
-        fwd32(x);
-        cpx *dst = ws.exch[o * kL + q] + j2;
-#pragma unroll
-        for (int pos = 0; pos < 32; pos++) dst[bitrev5(pos) * kExchRow] = x[pos];
-    }
-}
-
-// Inverse pass 2 ("I1") of both result polynomials into exchange buffers 2 and 3.
-TFHE_HD void phase1w_f2_end(int lane, WarpSmem &ws, const cpx *e2, cpx (&acc_a)[16], cpx (&acc_b)[16]) {
-    inv16(acc_a, e2 + lane * kE2Row);
-    cpx *d0 = ws.exch[2] + lane * kExchRow;
-#pragma unroll
-    for (int j2 = 0; j2 < 16; j2++) d0[j2] = acc_a[j2];
-    inv16(acc_b, e2 + lane * kE2Row);
-    cpx *d1 = ws.exch[3] + lane * kExchRow;
-#pragma unroll
-    for (int j2 = 0; j2 < 16; j2++) d1[j2] = acc_b[j2];
-}
-
-// Inverse pass 1 (all five stages) + conversion to Torus32 + tLweAddTo, see phase_i2_final.
-TFHE_HD void phase1w_i2(int lane, WarpSmem &ws, bool accumulate = true) {
-    const int o = lane >> 4, j2 = lane & 15;
-    cpx x[32];
-    const cpx *src = ws.exch[2 + o] + j2;
-#pragma unroll
-    for (int pos = 0; pos < 32; pos++) x[pos] = src[bitrev5(pos) * kExchRow];
-    inv32(x);
-    int32_t *row = ws.acc[o] + j2 * kAccRow;
-#pragma unroll
-    for (int j1 = 0; j1 < 32; j1++) {
-        const uint32_t re = double_to_torus32(x[j1].x);
-        const uint32_t im = double_to_torus32(x[j1].y);
-        row[j1] = (int32_t) ((accumulate ? (uint32_t) row[j1] : 0u) + re);
-        row[j1 + 32] = (int32_t) ((accumulate ? (uint32_t) row[j1 + 32] : 0u) + im);
     }
 }
 

@@ -30,7 +30,6 @@ struct tfhe_b200_ctx {
     // optional per-kernel timing (bench roofline): event triples around blind-rotate / key-switch
     bool timing;
     std::vector<cudaEvent_t> ev;
-    int schedule;  // 0 auto, 1 one warp per ciphertext, 2 two warps per ciphertext
 };
 
 namespace {
@@ -79,7 +78,6 @@ BrLaunch base_launch(const tfhe_b200_ctx *c) {
     L.n_iter = c->p.n;
     L.mu = kMu;
     L.bk = c->d_bk;
-    L.schedule = c->schedule;
     return L;
 }
 
@@ -208,8 +206,6 @@ int tfhe_b200_ctx_create(tfhe_b200_ctx **out, const tfhe_b200_params *p, int dev
     c->bk_bytes = c->ks_bytes = 0;
     c->launches = 0;
     c->timing = false;
-    c->schedule = 0;
-    if (const char *env = getenv("TFHE_B200_SCHEDULE")) c->schedule = atoi(env);
     if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) {
         delete c;
         return fail("cudaStreamCreate failed");
@@ -254,15 +250,6 @@ int tfhe_b200_get_timing(tfhe_b200_ctx *c, double *blind_rotate_ms, double *keys
     if (blind_rotate_ms) *blind_rotate_ms = br;
     if (keyswitch_ms) *keyswitch_ms = ks;
     if (calls) *calls = n;
-    return 0;
-}
-
-// Blind-rotation schedule: 0 = automatic (by batch size), 1 = one warp per ciphertext
-// (throughput), 2 = two warps per ciphertext (latency).  Results are identical.
-int tfhe_b200_set_schedule(tfhe_b200_ctx *c, int schedule) {
-    if (!c) return fail("null context");
-    if (schedule < 0 || schedule > 2) return fail("bad schedule %d", schedule);
-    c->schedule = schedule;
     return 0;
 }
 

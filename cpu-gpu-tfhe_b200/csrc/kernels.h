@@ -29,7 +29,6 @@ struct BrLaunch {
     int total;            // bootstraps in this launch
     int n;                // LWE dimension = blind-rotation iterations available in bk
     int n_iter;           // iterations to run (<= n)
-    int schedule;         // 0: auto, 1: one warp per ciphertext, 2: two warps per ciphertext
     int extern_only;      // 1: a single external product ACC <- BK_{bk_first} (.) ACC, no rotation
     int bk_first;         // first key element used (iteration it uses BK_{bk_first + it})
     int32_t mu;           // test-vector message

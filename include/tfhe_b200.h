@@ -81,9 +81,6 @@ int tfhe_b200_load_keys_device(tfhe_b200_ctx *ctx, const int32_t *d_bk_coef, con
  * [-1/2,1/2) (TGswSampleFFT, tgsw.h:78-96; fft_processor_fftw.cu:158-167). Host pointer. */
 int tfhe_b200_load_bk_fourier(tfhe_b200_ctx *ctx, const double *bkfft_ref);
 int tfhe_b200_load_ks(tfhe_b200_ctx *ctx, const int32_t *ks);
-/* Blind-rotation schedule: 0 = automatic (by batch size), 1 = one warp per ciphertext
- * (throughput), 2 = two warps per ciphertext (latency).  Results do not depend on it. */
-int tfhe_b200_set_schedule(tfhe_b200_ctx *ctx, int schedule);
 /* bytes of device memory held by the keys */
 size_t tfhe_b200_key_bytes(const tfhe_b200_ctx *ctx);
 
