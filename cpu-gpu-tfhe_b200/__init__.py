@@ -12,6 +12,7 @@ The directory name contains a hyphen, so import it through
 from .binding import (  # noqa: F401
     GATES,
     GATE_ID,
+    Circuit,
     Engine,
     EngineError,
     Params,

@@ -81,6 +81,19 @@ def lib():
         L.tfhe_b200_decrypt_bits.argtypes = [ctypes.POINTER(Params), _vp, _vp, _i, _vp]
         L.tfhe_b200_phases.argtypes = [_vp, _i, _vp, _i, _vp]
         L.tfhe_b200_set_timing.argtypes = [_vp, _i]
+        for f in ("add", "mul", "matmul"):
+            getattr(L, "tfhe_b200_circuit_" + f).restype = _vp
+        L.tfhe_b200_circuit_add.argtypes = [_vp, _i, _i, _i]
+        L.tfhe_b200_circuit_mul.argtypes = [_vp, _i, _i]
+        L.tfhe_b200_circuit_matmul.argtypes = [_vp, _i, _i, _i, _i]
+        L.tfhe_b200_circuit_destroy.argtypes = [_vp]
+        L.tfhe_b200_circuit_levels.argtypes = [_vp]
+        L.tfhe_b200_circuit_gates.argtypes = [_vp]
+        L.tfhe_b200_circuit_gates.restype = ctypes.c_longlong
+        L.tfhe_b200_circuit_operands.argtypes = [_vp]
+        L.tfhe_b200_circuit_operand_rows.argtypes = [_vp, _i]
+        L.tfhe_b200_circuit_output_rows.argtypes = [_vp]
+        L.tfhe_b200_circuit_run.argtypes = [_vp, _vp, _vp, _vp]
         L.tfhe_b200_get_timing.argtypes = [_vp, _vp, _vp, _vp]
         L.tfhe_b200_measure_fp64_peak.argtypes = [_i, _vp, _vp]
         _lib = L
@@ -358,3 +371,41 @@ class Engine:
         self._ck(self.L.tfhe_b200_mux_host(self.h, out.ctypes.data, a.ctypes.data, b.ctypes.data, c.ctypes.data,
                                            a.shape[0]))
         return out
+
+
+class Circuit:
+    """A compiled gate schedule (include/tfhe_b200.h, "Cipher-level circuits")."""
+
+    def __init__(self, engine, kind, *args):
+        self.eng, self.L = engine, engine.L
+        h = getattr(self.L, "tfhe_b200_circuit_" + kind)(engine.h, *[int(a) for a in args])
+        if not h:
+            raise EngineError("could not build circuit %s%r" % (kind, args))
+        self.h = _vp(h)
+        self.levels = int(self.L.tfhe_b200_circuit_levels(self.h))
+        self.gates = int(self.L.tfhe_b200_circuit_gates(self.h))
+        self.out_rows = int(self.L.tfhe_b200_circuit_output_rows(self.h))
+        self.operand_rows = [int(self.L.tfhe_b200_circuit_operand_rows(self.h, o))
+                             for o in range(int(self.L.tfhe_b200_circuit_operands(self.h)))]
+
+    def run(self, *operands, out=None, stream=None):
+        assert len(operands) == len(self.operand_rows)
+        for t, rows in zip(operands, self.operand_rows):
+            self.eng._chk(t, self.eng.words)
+            assert t.numel() == rows * self.eng.words, "operand has the wrong number of samples"
+        out = self.eng.empty(self.out_rows) if out is None else out
+        ptrs = (_vp * len(operands))(*[t.data_ptr() for t in operands])
+        if self.L.tfhe_b200_circuit_run(self.h, out.data_ptr(), ptrs, self.eng._stream(stream)):
+            raise EngineError(self.L.tfhe_b200_last_error().decode())
+        return out
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.tfhe_b200_circuit_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

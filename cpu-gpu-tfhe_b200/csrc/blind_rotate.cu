@@ -200,8 +200,10 @@ __global__ void __launch_bounds__(kThreads, 1) blind_rotate_kernel(const BrLaunc
                 local -= L.seg[si].count;
                 si++;
             }
-            in0 = L.seg[si].in0 + (size_t) local * L.seg[si].stride0;
-            in1 = L.seg[si].in1 + (size_t) local * L.seg[si].stride1;
+            const long long r0 = L.seg[si].idx0 ? (long long) __ldg(L.seg[si].idx0 + local) : (long long) local;
+            const long long r1 = L.seg[si].idx1 ? (long long) __ldg(L.seg[si].idx1 + local) : (long long) local;
+            in0 = L.seg[si].in0 + r0 * L.seg[si].stride0;
+            in1 = L.seg[si].in1 + r1 * L.seg[si].stride1;
             sa = (uint32_t) L.seg[si].sa;
             sb = (uint32_t) L.seg[si].sb;
             cst = (uint32_t) L.seg[si].cst;

@@ -101,7 +101,7 @@ int check_ctx(const tfhe_b200_ctx *c, bool need_bk, bool need_ks) {
 
 // blind rotate (segments) -> u scratch -> key switch -> out
 int run_bootstrap_ks(tfhe_b200_ctx *c, BrLaunch &L, int nsrc, int32_t ks_cst, int32_t *d_out, int out_count,
-                     cudaStream_t st) {
+                     cudaStream_t st, const KsLaunch::Out *dst = nullptr, int ndst = 0) {
     CU(cudaSetDevice(c->device));
     int32_t *d_u = nullptr;
     const size_t ubytes = (size_t) L.total * (kN + 1) * sizeof(int32_t);
@@ -123,8 +123,16 @@ int run_bootstrap_ks(tfhe_b200_ctx *c, BrLaunch &L, int nsrc, int32_t ks_cst, in
     K.u = d_u;
     K.nsrc = nsrc;
     K.cst = ks_cst;
-    K.out = d_out;
-    K.out_stride = c->p.n + 1;
+    if (ndst > 0) {
+        for (int i = 0; i < ndst; i++) K.dst[i] = dst[i];
+        K.ndst = ndst;
+    } else {
+        K.dst[0].out = d_out;
+        K.dst[0].stride = c->p.n + 1;
+        K.dst[0].count = out_count;
+        K.dst[0].idx = nullptr;
+        K.ndst = 1;
+    }
     K.count = out_count;
     K.n = c->p.n;
     K.N = c->p.N * c->p.k;
@@ -253,6 +261,8 @@ int tfhe_b200_get_timing(tfhe_b200_ctx *c, double *blind_rotate_ms, double *keys
     return 0;
 }
 
+int tfhe_b200_ctx_words(const tfhe_b200_ctx *c) { return c ? c->p.n + 1 : 0; }
+
 size_t tfhe_b200_key_bytes(const tfhe_b200_ctx *c) { return c ? c->bk_bytes + c->ks_bytes : 0; }
 unsigned long long tfhe_b200_launch_count(const tfhe_b200_ctx *c) { return c ? c->launches.load() : 0; }
 int tfhe_b200_sm_count(const tfhe_b200_ctx *c) { return c ? c->sm_count : 0; }
@@ -379,6 +389,45 @@ int tfhe_b200_gate_pair(tfhe_b200_ctx *c, int gate0, const int32_t *d_a0, const 
     return run_bootstrap_ks(c, L, 1, 0, d_out, 2 * count, (cudaStream_t) stream);
 }
 
+// Up to 4 independent runs of gates (each with its own gate type, strided inputs and strided
+// output) in ONE bootstrap batch.  Generalises the reference's compound gates
+// (bootsANDXOR / bootsXORXOR_fullGPU_n_Bit_vector, boot-gates.cu:3027-3098) and lets the
+// circuit schedules address bit i of every number of a vector without copies.
+int tfhe_b200_gate_multi(tfhe_b200_ctx *c, const tfhe_b200_gate_op *ops, int nops, void *stream) {
+    if (check_ctx(c, true, true)) return 1;
+    if (!ops || nops < 1 || nops > kMaxSegments) return fail("nops must be 1..%d", kMaxSegments);
+    BrLaunch L = base_launch(c);
+    KsLaunch::Out dst[kMaxSegments];
+    int total = 0, nseg = 0;
+    for (int i = 0; i < nops; i++) {
+        const tfhe_b200_gate_op &o = ops[i];
+        if (o.gate < 0 || o.gate >= TFHE_B200_NUM_GATES) return fail("bad gate id %d", o.gate);
+        if (o.count < 0) return fail("negative count");
+        if (o.count == 0) continue;
+        BrSegment &sg = L.seg[nseg];
+        sg.in0 = o.a;
+        sg.in1 = o.b;
+        sg.stride0 = o.stride_a;
+        sg.stride1 = o.stride_b;
+        sg.sa = kGates[o.gate].sa;
+        sg.sb = kGates[o.gate].sb;
+        sg.cst = kGates[o.gate].cst;
+        sg.count = o.count;
+        sg.idx0 = o.idx_a;
+        sg.idx1 = o.idx_b;
+        dst[nseg].out = o.out;
+        dst[nseg].stride = o.stride_out;
+        dst[nseg].count = o.count;
+        dst[nseg].idx = o.idx_out;
+        total += o.count;
+        nseg++;
+    }
+    if (total == 0) return 0;
+    L.nseg = nseg;
+    L.total = total;
+    return run_bootstrap_ks(c, L, 1, 0, nullptr, total, (cudaStream_t) stream, dst, nseg);
+}
+
 // bootsMUX (boot-gates.cu:407-448): u1 = BS(-1/8 + a + b), u2 = BS(-1/8 - a + c),
 // result = KS((0,1/8) + u1 + u2)
 int tfhe_b200_mux(tfhe_b200_ctx *c, int32_t *d_out, const int32_t *d_a, const int32_t *d_b,
@@ -464,8 +513,10 @@ int tfhe_b200_keyswitch(tfhe_b200_ctx *c, int32_t *d_out, const int32_t *d_u, in
     K.ks = c->d_ks;
     K.u = d_u;
     K.nsrc = 1;
-    K.out = d_out;
-    K.out_stride = c->p.n + 1;
+    K.dst[0].out = d_out;
+    K.dst[0].stride = c->p.n + 1;
+    K.dst[0].count = count;
+    K.ndst = 1;
     K.count = count;
     K.n = c->p.n;
     K.N = c->p.N * c->p.k;

@@ -16,6 +16,9 @@ struct BrSegment {
     const int32_t *in1;
     long long stride0;  // in words
     long long stride1;
+    // optional gather: operand row of local gate g is in + idx[g] * stride (instead of g * stride)
+    const int32_t *idx0;
+    const int32_t *idx1;
     int sa, sb;
     int32_t cst;
     int count;
@@ -59,8 +62,14 @@ struct KsLaunch {
     const int32_t *u;      // [*][N+1]
     int nsrc;              // 1: u[g]; 2: u[g] + u[g + count]  (MUX)
     int32_t cst;           // added to b
-    int32_t *out;          // [count][n+1]
-    long long out_stride;  // words
+    // outputs: up to kMaxSegments runs of rows (out + i*stride), in gate order
+    struct Out {
+        int32_t *out;
+        long long stride;  // words
+        int count;
+        const int32_t *idx;  // optional scatter: row of local gate g is out + idx[g] * stride
+    } dst[kMaxSegments];
+    int ndst;
     int count;
     int n;                 // 500
     int N;                 // 1024

@@ -96,7 +96,13 @@ __global__ void __launch_bounds__(kKsThreads) keyswitch_kernel(const KsLaunch L,
 #pragma unroll
     for (int g = 0; g < kTile; g++) {
         if (g < ng) {
-            int32_t *row = L.out + (size_t) (g0 + g) * L.out_stride;
+            int local = g0 + g, di = 0;
+            while (di + 1 < L.ndst && local >= L.dst[di].count) {
+                local -= L.dst[di].count;
+                di++;
+            }
+            const long long orow = L.dst[di].idx ? (long long) __ldg(L.dst[di].idx + local) : (long long) local;
+            int32_t *row = L.dst[di].out + orow * L.dst[di].stride;
             uint32_t v0 = 0u - acc0[g], v1 = 0u - acc1[g];
             if ((c0 == n || c1 == n) && blockIdx.y == 0) {
                 uint32_t b = (uint32_t) __ldg(L.u + (size_t) (g0 + g) * ustride + L.N) + (uint32_t) L.cst;
@@ -115,10 +121,16 @@ __global__ void __launch_bounds__(kKsThreads) keyswitch_kernel(const KsLaunch L,
     }
 }
 
-__global__ void ks_zero_kernel(int32_t *out, long long stride, int count, int words) {
+__global__ void ks_zero_kernel(const KsLaunch L, int words) {
     const long long t = (long long) blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= (long long) count * words) return;
-    out[(t / words) * stride + (t % words)] = 0;
+    if (t >= (long long) L.count * words) return;
+    int local = (int) (t / words), di = 0;
+    while (di + 1 < L.ndst && local >= L.dst[di].count) {
+        local -= L.dst[di].count;
+        di++;
+    }
+    const long long orow = L.dst[di].idx ? (long long) L.dst[di].idx[local] : (long long) local;
+    L.dst[di].out[orow * L.dst[di].stride + (t % words)] = 0;
 }
 
 // src [N][t][base][n+1] -> dst [N][t][base-1][512] (row h = 0 is the noiseless zero sample,
@@ -161,7 +173,7 @@ cudaError_t launch_keyswitch(const KsLaunch &L, int sm_count, cudaStream_t strea
     dim3 grid(tiles, nsplit);
     if (nsplit > 1) {
         const long long total = (long long) L.count * (L.n + 1);
-        ks_zero_kernel<<<(unsigned) ((total + 255) / 256), 256, 0, stream>>>(L.out, L.out_stride, L.count, L.n + 1);
+        ks_zero_kernel<<<(unsigned) ((total + 255) / 256), 256, 0, stream>>>(L, L.n + 1);
         keyswitch_kernel<true><<<grid, kKsThreads, smem, stream>>>(L, nsplit);
     } else {
         keyswitch_kernel<false><<<grid, kKsThreads, smem, stream>>>(L, nsplit);

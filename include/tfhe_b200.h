@@ -96,6 +96,20 @@ int tfhe_b200_gate2(tfhe_b200_ctx *ctx, int gate0, int gate1, int32_t *d_out, co
  * out[count..2count) = gate1(a1,b1) (bootsXORXOR_fullGPU_n_Bit_vector, boot-gates.cu:3062-3098) */
 int tfhe_b200_gate_pair(tfhe_b200_ctx *ctx, int gate0, const int32_t *d_a0, const int32_t *d_b0, int gate1,
                         const int32_t *d_a1, const int32_t *d_b1, int32_t *d_out, int count, void *stream);
+/* One run of `count` gates of one type.  Operand / result row of gate g is
+ * base + idx[g] * stride when the (device) index array is given, else base + g * stride
+ * (strides in int32 words; a stride of 0 broadcasts one sample).  out may alias a or b. */
+typedef struct {
+    int32_t gate;
+    int32_t count;
+    const int32_t *a;
+    const int32_t *b;
+    int32_t *out;
+    int64_t stride_a, stride_b, stride_out;
+    const int32_t *idx_a, *idx_b, *idx_out; /* optional, device memory */
+} tfhe_b200_gate_op;
+/* Up to 4 runs in ONE bootstrap batch (one blind-rotate launch + one key-switch launch). */
+int tfhe_b200_gate_multi(tfhe_b200_ctx *ctx, const tfhe_b200_gate_op *ops, int nops, void *stream);
 /* MUX(a,b,c) = a ? b : c  (bootsMUX, boot-gates.cu:407-448; bootsMUX_fullGPU_n_Bit :2987) */
 int tfhe_b200_mux(tfhe_b200_ctx *ctx, int32_t *d_out, const int32_t *d_a, const int32_t *d_b,
                   const int32_t *d_c, int count, void *stream);
@@ -122,6 +136,31 @@ int tfhe_b200_blind_rotate_and_extract(tfhe_b200_ctx *ctx, int32_t *d_u, const i
                                        void *stream);
 /* tGswFFTExternMulToTLwe (tgsw-fft-operations.cu:124) with BK_{bk_index}: acc[count][k+1][N] in place */
 int tfhe_b200_extern_mul(tfhe_b200_ctx *ctx, int32_t *d_acc, int bk_index, int count, void *stream);
+
+/* ---- Cipher-level circuits (DEVICE buffers) --------------------------------
+ * Integers are arrays of nbits samples, LSB first, two's complement (Cipher.cu:5-7); vectors
+ * of `count` integers are contiguous.  A circuit is compiled once into a plan (all levels,
+ * index tables and workspace on the device) and can be run any number of times. */
+typedef struct tfhe_b200_circuit tfhe_b200_circuit;
+/* a + b mod 2^nbits for count pairs.  mode 0: bit-wise ripple carry (taskLevelParallelAdd_bitwise
+ * main.cu:821, _vector_coalInput :1138, Cipher::operator+ Cipher.cu:334); mode 1: number-wise
+ * (taskLevelParallelAdd main.cu:619).  Operands: a[count][nbits], b[count][nbits]. */
+tfhe_b200_circuit *tfhe_b200_circuit_add(tfhe_b200_ctx *ctx, int nbits, int count, int mode);
+/* a * b mod 2^nbits for count pairs (multiplyLweSamples main.cu:1483, BOOTS_vectorMultiplication
+ * :1746, Cipher::operator* Cipher.cu:83) */
+tfhe_b200_circuit *tfhe_b200_circuit_mul(tfhe_b200_ctx *ctx, int nbits, int count);
+/* C[rows][cols] = A[rows][inner] * B[inner][cols], nbits-bit elements mod 2^nbits
+ * (BOOTS_matrixMultiplication main.cu:2342; cpu/cloud.cpp:390-408) */
+tfhe_b200_circuit *tfhe_b200_circuit_matmul(tfhe_b200_ctx *ctx, int rows, int inner, int cols, int nbits);
+void tfhe_b200_circuit_destroy(tfhe_b200_circuit *c);
+int tfhe_b200_circuit_levels(const tfhe_b200_circuit *c);      /* sequential bootstrap batches */
+long long tfhe_b200_circuit_gates(const tfhe_b200_circuit *c); /* bootstrapped gates per run   */
+int tfhe_b200_circuit_operands(const tfhe_b200_circuit *c);
+int tfhe_b200_circuit_operand_rows(const tfhe_b200_circuit *c, int operand);
+int tfhe_b200_circuit_output_rows(const tfhe_b200_circuit *c);
+/* operands[o]: device array of tfhe_b200_circuit_operand_rows(c, o) samples */
+int tfhe_b200_circuit_run(tfhe_b200_circuit *c, int32_t *d_out, const int32_t *const *operands, void *stream);
+int tfhe_b200_ctx_words(const tfhe_b200_ctx *ctx); /* n + 1 */
 
 /* ---- HOST-buffer convenience (synchronous; copies in and out) ------------- */
 int tfhe_b200_gate_host(tfhe_b200_ctx *ctx, int gate, int32_t *out, const int32_t *ca, const int32_t *cb,

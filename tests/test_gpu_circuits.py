@@ -1,0 +1,87 @@
+"""Cipher-level circuits on the GPU: decrypted integers must equal the plaintext results
+(bit-exact), for the reference's schedules (BASELINE.json configs 2, 4, 5)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def to_bits(vals, nbits):
+    vals = np.asarray(vals, dtype=np.int64).reshape(-1)
+    return ((vals[:, None] >> np.arange(nbits)) & 1).astype(np.int32)
+
+
+def from_bits(bits):
+    bits = np.asarray(bits, dtype=np.int64)
+    return (bits << np.arange(bits.shape[-1])).sum(-1)
+
+
+def enc_ints(pkg, engine, sk, vals, nbits, seed):
+    bits = to_bits(vals, nbits)
+    return engine.to_device(pkg.encrypt_bits(sk, bits.reshape(-1), seed))
+
+
+def dec_ints(pkg, sk, t, nbits):
+    return from_bits(pkg.decrypt_bits(sk, t.cpu().numpy()).reshape(-1, nbits))
+
+
+@pytest.fixture(scope="module")
+def sk_engine(pkg):
+    sk = pkg.keygen(99)
+    eng = pkg.Engine(device=0)
+    eng.load_keys(sk.bk, sk.ks)
+    yield sk, eng
+    eng.close()
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+def test_16_bit_addition(pkg, sk_engine, mode):
+    """./main 16 a b (BASELINE config 2): both reference schedules."""
+    sk, eng = sk_engine
+    nbits = 16
+    a = np.array([12345, 65535, 0, 40000])
+    b = np.array([(-6789) & 0xFFFF, 1, 0, 30000])
+    circ = pkg.Circuit(eng, "add", nbits, len(a), mode)
+    assert circ.levels == (45 if mode == 0 else 16)
+    out = circ.run(enc_ints(pkg, eng, sk, a, nbits, 1), enc_ints(pkg, eng, sk, b, nbits, 2))
+    assert np.array_equal(dec_ints(pkg, sk, out, nbits), (a + b) & 0xFFFF)
+    out2 = circ.run(enc_ints(pkg, eng, sk, b, nbits, 3), enc_ints(pkg, eng, sk, a, nbits, 4))  # plans are reusable
+    assert np.array_equal(dec_ints(pkg, sk, out2, nbits), (a + b) & 0xFFFF)
+    circ.close()
+
+
+def test_8_bit_multiplication_vector(pkg, sk_engine):
+    sk, eng = sk_engine
+    nbits = 8
+    a = np.array([13, 255, 0, 100, 7])
+    b = np.array([11, 255, 99, 3, 36])
+    circ = pkg.Circuit(eng, "mul", nbits, len(a))
+    out = circ.run(enc_ints(pkg, eng, sk, a, nbits, 5), enc_ints(pkg, eng, sk, b, nbits, 6))
+    assert np.array_equal(dec_ints(pkg, sk, out, nbits), (a * b) & 0xFF)
+    circ.close()
+
+
+def test_32_bit_multiplication(pkg, sk_engine):
+    """BASELINE config 4 (multiplyLweSamples schedule, single precision)."""
+    sk, eng = sk_engine
+    nbits = 32
+    a, b = np.array([40000]), np.array([50000])
+    circ = pkg.Circuit(eng, "mul", nbits, 1)
+    out = circ.run(enc_ints(pkg, eng, sk, a, nbits, 7), enc_ints(pkg, eng, sk, b, nbits, 8))
+    assert np.array_equal(dec_ints(pkg, sk, out, nbits), (a * b) & 0xFFFFFFFF)
+    circ.close()
+
+
+def test_matrix_multiply_4x4_of_8_bit(pkg, sk_engine):
+    """Reduced BASELINE config 5 (the reference's own test driver uses 4x4, main.cu:2471)."""
+    sk, eng = sk_engine
+    nbits, n = 8, 4
+    rng = np.random.default_rng(3)
+    A = rng.integers(-8, 8, (n, n))
+    Bm = rng.integers(-8, 8, (n, n))
+    circ = pkg.Circuit(eng, "matmul", n, n, n, nbits)
+    out = circ.run(enc_ints(pkg, eng, sk, A.reshape(-1) & 0xFF, nbits, 9),
+                   enc_ints(pkg, eng, sk, Bm.reshape(-1) & 0xFF, nbits, 10))
+    got = dec_ints(pkg, sk, out, nbits).reshape(n, n)
+    assert np.array_equal(got, (A @ Bm) & 0xFF)
+    circ.close()
