@@ -337,6 +337,45 @@ double ref_time_nand(const RefHandle *h, const int32_t *ca, const int32_t *cb, i
     return std::chrono::duration<double>(t1 - t0).count();
 }
 
+/* Raw reference objects, for ABI tests of the drop-in library: the pointers are handed to
+ * libtfhe_b200.so's bootsNAND / tfhe_bootstrap_FFT / lweKeySwitch ... unchanged. */
+const void *ref_cloud_keyset(const RefHandle *h) { return h->cloud; }
+const void *ref_bkfft(const RefHandle *h) { return h->bkFFT; }
+const void *ref_tgsw_fft_array(const RefHandle *h) { return h->bkFFT->bkFFT; }
+const void *ref_tgsw_params(const RefHandle *h) { return h->params->tgsw_params; }
+const void *ref_ks_key(const RefHandle *h) { return h->bkFFT->ks; }
+void *ref_sample_new(const RefHandle *h, int extracted) {
+    return new_LweSample(extracted ? &h->params->tgsw_params->tlwe_params->extracted_lweparams
+                                   : h->params->in_out_params);
+}
+void ref_sample_set(void *s, const int32_t *flat, int n) {
+    LweSample *p = (LweSample *) s;
+    memcpy(p->a, flat, sizeof(int32_t) * n);
+    p->b = flat[n];
+}
+void ref_sample_get(const void *s, int32_t *flat, int n) {
+    const LweSample *p = (const LweSample *) s;
+    memcpy(flat, p->a, sizeof(int32_t) * n);
+    flat[n] = p->b;
+}
+void ref_sample_free(void *s) { delete_LweSample((LweSample *) s); }
+void *ref_tlwe_new(const RefHandle *h) { return new_TLweSample(h->params->tgsw_params->tlwe_params); }
+void ref_tlwe_set(void *s, const int32_t *flat, int N, int k) {
+    TLweSample *p = (TLweSample *) s;
+    for (int j = 0; j <= k; j++) memcpy(p->a[j].coefsT, flat + j * N, sizeof(int32_t) * N);
+}
+void ref_tlwe_get(const void *s, int32_t *flat, int N, int k) {
+    const TLweSample *p = (const TLweSample *) s;
+    for (int j = 0; j <= k; j++) memcpy(flat + j * N, p->a[j].coefsT, sizeof(int32_t) * N);
+}
+void ref_tlwe_free(void *s) { delete_TLweSample((TLweSample *) s); }
+void *ref_torus_poly_new(int N, const int32_t *coefs) {
+    TorusPolynomial *p = new_TorusPolynomial(N);
+    memcpy(p->coefsT, coefs, sizeof(int32_t) * N);
+    return p;
+}
+void ref_torus_poly_free(void *p) { delete_TorusPolynomial((TorusPolynomial *) p); }
+
 void ref_free(RefHandle *h) {
     if (!h) return;
     if (h->sk) {

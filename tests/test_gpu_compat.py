@@ -1,0 +1,204 @@
+"""Drop-in boundary test: the REFERENCE'S OWN objects (key sets, LweSample, TLweSample,
+TorusPolynomial built by the reference's code in oracle/_ref) are handed, unchanged, to the
+same-named entry points of libtfhe_b200.so (include/tfhe_compat.h).  Proves the struct
+layouts and the calling conventions match; results are checked against the reference's own
+functions on the same objects.  Needs oracle/_ref (travels with the repo) and a GPU."""
+import ctypes
+
+import numpy as np
+import pytest
+
+from conftest import wrap32
+from oracle.pyoracle import GATES, Oracle, Ref, have_ref
+
+pytestmark = [pytest.mark.gpu, pytest.mark.skipif(not have_ref(), reason="oracle/_ref not built")]
+
+vp = ctypes.c_void_p
+MU = 0x20000000
+
+
+@pytest.fixture(scope="module")
+def world(pkg):
+    o = Oracle()
+    r = Ref().keygen((314, 1592, 657))
+    L = ctypes.CDLL(pkg.lib_path())  # RTLD_LOCAL: its bootsNAND does not clash with the reference's
+    R = r.L
+    for f in ("ref_cloud_keyset", "ref_bkfft", "ref_tgsw_fft_array", "ref_tgsw_params", "ref_ks_key",
+              "ref_sample_new", "ref_tlwe_new", "ref_torus_poly_new"):
+        getattr(R, f).restype = vp
+    L.tfhe_b200_keys_to_gpu.restype = vp
+    L.convertBitToNumberZero_GPU.restype = vp
+    keys = r.export_keys(o.params)
+    return o, r, R, L, keys
+
+
+class Sample:
+    """A reference LweSample object (allocated and freed by the reference)."""
+
+    def __init__(self, R, h, n, flat=None, extracted=0):
+        self.R, self.n = R, n
+        self.p = vp(R.ref_sample_new(h, extracted))
+        if flat is not None:
+            flat = np.ascontiguousarray(flat, np.int32)
+            R.ref_sample_set(self.p, flat.ctypes.data_as(vp), n)
+
+    def get(self):
+        out = np.zeros(self.n + 1, np.int32)
+        self.R.ref_sample_get(self.p, out.ctypes.data_as(vp), self.n)
+        return out
+
+    def __del__(self):
+        self.R.ref_sample_free(self.p)
+
+
+def test_classic_gates_on_reference_objects(world):
+    o, r, R, L, keys = world
+    cloud = vp(R.ref_cloud_keyset(r.h))
+    bits = [(0, 0), (0, 1), (1, 0), (1, 1)]
+    truth = {"NAND": lambda a, b: 1 - (a & b), "OR": lambda a, b: a | b, "AND": lambda a, b: a & b,
+             "XOR": lambda a, b: a ^ b, "XNOR": lambda a, b: 1 - (a ^ b), "NOR": lambda a, b: 1 - (a | b),
+             "ANDNY": lambda a, b: (1 - a) & b, "ANDYN": lambda a, b: a & (1 - b),
+             "ORNY": lambda a, b: (1 - a) | b, "ORYN": lambda a, b: a | (1 - b)}
+    for g in GATES:
+        for a, b in bits:
+            ca, cb = r.encrypt(a), r.encrypt(b)
+            sa, sb, res = Sample(R, r.h, 500, ca), Sample(R, r.h, 500, cb), Sample(R, r.h, 500)
+            getattr(L, "boots" + g)(res.p, sa.p, sb.p, cloud)
+            got = res.get()
+            ref = r.gate(g, ca, cb)  # the reference's own bootsXXX on the same inputs
+            assert int(r.phase(got) > 0) == truth[g](a, b) == int(r.phase(ref) > 0), (g, a, b)
+            assert abs(int(wrap32(r.phase(got) - r.phase(ref)))) / 2.0 ** 32 < 2.0 ** -5
+    # in-place: result aliases the first operand (Cipher.cu:373)
+    sa, sb = Sample(R, r.h, 500, r.encrypt(1)), Sample(R, r.h, 500, r.encrypt(0))
+    L.bootsAND(sa.p, sa.p, sb.p, cloud)
+    assert r.phase(sa.get()) < 0
+    # MUX, NOT, COPY, CONSTANT
+    for a in (0, 1):
+        sa, sb, sc, res = (Sample(R, r.h, 500, r.encrypt(x)) for x in (a, 1, 0, 0))
+        L.bootsMUX(res.p, sa.p, sb.p, sc.p, cloud)
+        assert int(r.phase(res.get()) > 0) == (1 if a else 0)
+    s1, res = Sample(R, r.h, 500, r.encrypt(1)), Sample(R, r.h, 500)
+    L.bootsNOT(res.p, s1.p, cloud)
+    assert np.array_equal(res.get(), (-s1.get().astype(np.int64)).astype(np.int32))
+    L.bootsCOPY(res.p, s1.p, cloud)
+    assert np.array_equal(res.get(), s1.get())
+    L.bootsCONSTANT(res.p, 1, cloud)
+    assert res.get()[-1] == MU and not res.get()[:-1].any()
+
+
+def test_bootstrap_and_keyswitch_on_reference_objects(world):
+    o, r, R, L, keys = world
+    bkfft = vp(R.ref_bkfft(r.h))
+    x = o.gate_prologue("NAND", r.encrypt(1), r.encrypt(1))
+    sx, u = Sample(R, r.h, 500, x), Sample(R, r.h, 1024, extracted=1)
+    L.tfhe_bootstrap_woKS_FFT(u.p, bkfft, ctypes.c_int32(MU), sx.p)
+    ref_u = r.bootstrap_woks(MU, x)
+    ph_g, ph_r = o.phase(keys.tlwe_key, u.get()), o.phase(keys.tlwe_key, ref_u)
+    assert ph_g < 0 and ph_r < 0 and abs(int(wrap32(ph_g - ph_r))) / 2.0 ** 32 < 2.0 ** -5
+    # key switch of the reference's own u: integer arithmetic, must be bit-exact
+    su, res = Sample(R, r.h, 1024, ref_u, extracted=1), Sample(R, r.h, 500)
+    L.lweKeySwitch(res.p, vp(R.ref_ks_key(r.h)), su.p)
+    assert np.array_equal(res.get(), r.keyswitch(ref_u))
+    # bootstrap with key switch
+    L.tfhe_bootstrap_FFT(res.p, bkfft, ctypes.c_int32(MU), sx.p)
+    assert r.phase(res.get()) < 0
+
+
+def test_extern_mul_and_blind_rotate_on_reference_objects(world):
+    o, r, R, L, keys = world
+    rng = np.random.default_rng(8)
+    acc = rng.integers(-2 ** 31, 2 ** 31, (2, 1024), dtype=np.int64).astype(np.int32)
+    params = vp(R.ref_tgsw_params(r.h))
+    base = R.ref_tgsw_fft_array(r.h)
+    # sizeof(TGswSampleFFT) = 2 pointers + 2 ints = 24 bytes (tgsw.h:78-84)
+    idx = 7
+    t = vp(R.ref_tlwe_new(r.h))
+    R.ref_tlwe_set(t, acc.ctypes.data_as(vp), 1024, 1)
+    L.tGswFFTExternMulToTLwe(t, vp(base + 24 * idx), params)
+    got = np.zeros_like(acc)
+    R.ref_tlwe_get(t, got.ctypes.data_as(vp), 1024, 1)
+    exact = o.extern_mul_exact(keys.bk[idx], acc)
+    assert np.abs(wrap32(got.astype(np.int64) - exact.astype(np.int64))).max() <= 1
+    assert np.abs(wrap32(got.astype(np.int64) - r.extern_mul(idx, acc).astype(np.int64))).max() <= 2
+    # tfhe_blindRotateAndExtract_FFT with n = 0 iterations is pure integer work: bit-exact
+    tv = rng.integers(-2 ** 31, 2 ** 31, 1024, dtype=np.int64).astype(np.int32)
+    pv = vp(R.ref_torus_poly_new(1024, tv.ctypes.data_as(vp)))
+    u = Sample(R, r.h, 1024, extracted=1)
+    bara = (ctypes.c_int * 1)(0)
+    L.tfhe_blindRotateAndExtract_FFT(u.p, pv, vp(base), 1500, bara, 0, params)
+    expect = o.ctx(keys).blind_rotate_and_extract(tv, 1500, np.zeros(0, np.int32))
+    assert np.array_equal(u.get(), expect)
+    # a short blind rotation of a reference accumulator
+    acc0 = np.zeros((2, 1024), np.int32)
+    acc0[1] = MU
+    R.ref_tlwe_set(t, acc0.ctypes.data_as(vp), 1024, 1)
+    bara = np.array([3, 2047, 0, 1024, 77], np.int32)
+    L.tfhe_blindRotate_FFT(t, vp(base), bara.ctypes.data_as(vp), 5, params)
+    R.ref_tlwe_get(t, got.ctypes.data_as(vp), 1024, 1)
+    ref_acc = r.blind_rotate(acc0, bara)
+
+    def phase(a):
+        full = np.convolve(a[0].astype(np.int64), keys.tlwe_key.astype(np.int64))
+        rr = full[:1024].copy()
+        rr[:1023] -= full[1024:]
+        return wrap32(a[1].astype(np.int64) - rr)
+
+    assert np.abs(wrap32(phase(got) - phase(ref_acc))).max() / 2.0 ** 32 < 2.0 ** -8
+    R.ref_tlwe_free(t)
+    R.ref_torus_poly_free(pv)
+
+
+def test_batched_fullgpu_family(world):
+    """LweSample_16 convention: a on the device, b on the host (boot-gates.cu:462-476)."""
+    import torch
+
+    o, r, R, L, keys = world
+
+    class S16(ctypes.Structure):
+        _fields_ = [("a", vp), ("b", ctypes.POINTER(ctypes.c_int)), ("cv", ctypes.POINTER(ctypes.c_double))]
+
+    cloud = vp(R.ref_cloud_keyset(r.h))
+    handle = vp(L.tfhe_b200_keys_to_gpu(cloud))
+    nb = 6
+    rng = np.random.default_rng(5)
+    bits = [rng.integers(0, 2, nb) for _ in range(4)]
+
+    torch.zeros(1, device="cuda")
+    cudart = ctypes.CDLL("libcudart.so.12")  # the runtime torch has already loaded
+    cudart.cudaMemcpy.argtypes = [vp, vp, ctypes.c_size_t, ctypes.c_int]
+
+    def make(bitvec):
+        s = ctypes.cast(L.convertBitToNumberZero_GPU(nb, cloud), ctypes.POINTER(S16))
+        flat = np.stack([r.encrypt(int(b)) for b in bitvec])
+        a = np.ascontiguousarray(flat[:, :-1])
+        assert cudart.cudaMemcpy(s.contents.a, a.ctypes.data_as(vp), a.nbytes, 1) == 0
+        for i in range(nb):
+            s.contents.b[i] = int(flat[i, -1])
+        return s, flat
+
+    def read(s, count):
+        a = np.zeros((count, 500), np.int32)
+        assert cudart.cudaMemcpy(a.ctypes.data_as(vp), s.contents.a, a.nbytes, 2) == 0
+        b = np.array([s.contents.b[i] for i in range(count)], np.int32)
+        return np.concatenate([a, b[:, None]], 1)
+
+    sa, fa = make(bits[0])
+    sb, fb = make(bits[1])
+    sc, fc = make(bits[2])
+    res = ctypes.cast(L.convertBitToNumberZero_GPU(2 * nb, cloud), ctypes.POINTER(S16))
+    L.bootsAND_fullGPU_n_Bit(res, sa, sb, nb, handle, None, None)
+    dec = (o.phases(keys.lwe_key, read(res, nb)) > 0).astype(int)
+    assert np.array_equal(dec, bits[0] & bits[1])
+    L.bootsXOR_fullGPU_n_Bit(res, sa, sb, nb, handle, None, None)
+    assert np.array_equal((o.phases(keys.lwe_key, read(res, nb)) > 0).astype(int), bits[0] ^ bits[1])
+    L.bootsMUX_fullGPU_n_Bit(res, sa, sb, sc, nb, handle, None, None)
+    assert np.array_equal((o.phases(keys.lwe_key, read(res, nb)) > 0).astype(int),
+                          np.where(bits[0] == 1, bits[1], bits[2]))
+    L.bootsANDXOR_fullGPU_n_Bit_vector(res, sa, sb, 1, nb, handle, None, None)
+    dec = (o.phases(keys.lwe_key, read(res, 2 * nb)) > 0).astype(int)
+    assert np.array_equal(dec[:nb], bits[0] & bits[1]) and np.array_equal(dec[nb:], bits[0] ^ bits[1])
+    L.bootsXORXOR_fullGPU_n_Bit_vector(res, sa, sb, sc, sb, 1, nb, handle, None, None)
+    dec = (o.phases(keys.lwe_key, read(res, 2 * nb)) > 0).astype(int)
+    assert np.array_equal(dec[:nb], bits[0] ^ bits[1]) and np.array_equal(dec[nb:], bits[2] ^ bits[1])
+    for s in (sa, sb, sc, res):
+        L.freeLweSample_16_gpu(s)
