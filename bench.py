@@ -213,20 +213,12 @@ def run_b200(args):
 
     # ---- keys: generated on rank 0, broadcast once over NCCL (NVLink), converted on each GPU
     t0 = time.perf_counter()
-    if rank == 0:
-        sk = pkg.keygen(2026)
-        d_bk = torch.from_numpy(sk.bk).to(dev)
-        d_ks = torch.from_numpy(sk.ks).to(dev)
-        d_key = torch.from_numpy(sk.lwe_key).to(dev)
-    else:
-        sk = None
-        kpl = (p.k + 1) * p.l
-        d_bk = torch.empty((p.n, kpl, p.k + 1, p.N), dtype=torch.int32, device=dev)
-        d_ks = torch.empty((p.N * p.k, p.ks_t, 1 << p.ks_basebit, p.n + 1), dtype=torch.int32, device=dev)
-        d_key = torch.empty(p.n, dtype=torch.int32, device=dev)
-    if world > 1:
-        for t in (d_bk, d_ks, d_key):
-            dist.broadcast(t, 0)
+    from importlib import import_module
+
+    tdist = import_module("cpu_gpu_tfhe_b200.dist")
+    sk = pkg.keygen(2026) if rank == 0 else None
+    kt = tdist.broadcast_cloud_keys(p, sk, dev)  # NCCL broadcast from rank 0 (no-op at N=1)
+    d_bk, d_ks, d_key = kt["bk"], kt["ks"], kt["lwe_key"]
     eng = pkg.Engine(device=local)
     eng.load_keys_device(d_bk, d_ks)
     torch.cuda.synchronize()
