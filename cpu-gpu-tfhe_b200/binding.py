@@ -20,8 +20,20 @@ _vp = ctypes.c_void_p
 _i = ctypes.c_int
 
 
+GPC = 10      # TFHE_B200_GPC: carry operator g | (p & c) for mutually exclusive g, p (extension)
+
+
 class EngineError(RuntimeError):
     pass
+
+
+class GateOp(ctypes.Structure):
+    """tfhe_b200_gate_op (include/tfhe_b200.h)."""
+    _fields_ = [("gate", ctypes.c_int32), ("count", ctypes.c_int32), ("a", ctypes.c_void_p), ("b", ctypes.c_void_p),
+                ("out", ctypes.c_void_p), ("stride_a", ctypes.c_int64), ("stride_b", ctypes.c_int64),
+                ("stride_out", ctypes.c_int64), ("idx_a", ctypes.c_void_p), ("idx_b", ctypes.c_void_p),
+                ("idx_out", ctypes.c_void_p), ("c", ctypes.c_void_p), ("stride_c", ctypes.c_int64),
+                ("idx_c", ctypes.c_void_p)]
 
 
 class Params(ctypes.Structure):
@@ -59,6 +71,7 @@ def lib():
         L.tfhe_b200_gate2.argtypes = [_vp, _i, _i, _vp, _vp, _vp, _i, _vp]
         L.tfhe_b200_gate_pair.argtypes = [_vp, _i, _vp, _vp, _i, _vp, _vp, _vp, _i, _vp]
         L.tfhe_b200_mux.argtypes = [_vp, _vp, _vp, _vp, _vp, _i, _vp]
+        L.tfhe_b200_gate_multi.argtypes = [_vp, _vp, _i, _vp]
         L.tfhe_b200_not.argtypes = [_vp, _vp, _vp, _i, _vp]
         L.tfhe_b200_copy.argtypes = [_vp, _vp, _vp, _i, _vp]
         L.tfhe_b200_constant.argtypes = [_vp, _vp, _i, _i, _vp]
@@ -81,11 +94,14 @@ def lib():
         L.tfhe_b200_decrypt_bits.argtypes = [ctypes.POINTER(Params), _vp, _vp, _i, _vp]
         L.tfhe_b200_phases.argtypes = [_vp, _i, _vp, _i, _vp]
         L.tfhe_b200_set_timing.argtypes = [_vp, _i]
-        for f in ("add", "mul", "matmul"):
+        for f in ("add", "mul", "matmul", "mul_ex", "matmul_ex"):
             getattr(L, "tfhe_b200_circuit_" + f).restype = _vp
         L.tfhe_b200_circuit_add.argtypes = [_vp, _i, _i, _i]
         L.tfhe_b200_circuit_mul.argtypes = [_vp, _i, _i]
+        L.tfhe_b200_circuit_mul_ex.argtypes = [_vp, _i, _i, _i]
         L.tfhe_b200_circuit_matmul.argtypes = [_vp, _i, _i, _i, _i]
+        L.tfhe_b200_circuit_matmul_ex.argtypes = [_vp, _i, _i, _i, _i, _i]
+        L.tfhe_b200_circuit_simulate.argtypes = [_vp, _vp, _vp]
         L.tfhe_b200_circuit_destroy.argtypes = [_vp]
         L.tfhe_b200_circuit_levels.argtypes = [_vp]
         L.tfhe_b200_circuit_gates.argtypes = [_vp]
@@ -281,6 +297,17 @@ class Engine:
                                        self._stream(stream)))
         return out
 
+    def carry_gate(self, g, p, c, out=None, stream=None):
+        """out = g | (p & c) in ONE bootstrap (TFHE_B200_GPC; g and p must be mutually exclusive)."""
+        for t in (g, p, c):
+            self._chk(t, self.words)
+        count = g.shape[0]
+        out = self.empty(count) if out is None else out
+        op = GateOp(GPC, count, g.data_ptr(), p.data_ptr(), out.data_ptr(), self.words, self.words, self.words,
+                    None, None, None, c.data_ptr(), self.words, None)
+        self._ck(self.L.tfhe_b200_gate_multi(self.h, ctypes.byref(op), 1, self._stream(stream)))
+        return out
+
     def gate2(self, g0, g1, ca, cb, out=None, stream=None):
         count = ca.shape[0]
         out = self.empty(2 * count) if out is None else out
@@ -377,8 +404,10 @@ class Circuit:
     """A compiled gate schedule (include/tfhe_b200.h, "Cipher-level circuits")."""
 
     def __init__(self, engine, kind, *args):
-        self.eng, self.L = engine, engine.L
-        h = getattr(self.L, "tfhe_b200_circuit_" + kind)(engine.h, *[int(a) for a in args])
+        """engine may be None: the plan can then only be inspected and simulated on plaintext bits."""
+        self.eng, self.L = engine, (engine.L if engine is not None else lib())
+        h = getattr(self.L, "tfhe_b200_circuit_" + kind)(engine.h if engine is not None else None,
+                                                         *[int(a) for a in args])
         if not h:
             raise EngineError("could not build circuit %s%r" % (kind, args))
         self.h = _vp(h)
@@ -397,6 +426,18 @@ class Circuit:
         ptrs = (_vp * len(operands))(*[t.data_ptr() for t in operands])
         if self.L.tfhe_b200_circuit_run(self.h, out.data_ptr(), ptrs, self.eng._stream(stream)):
             raise EngineError(self.L.tfhe_b200_last_error().decode())
+        return out
+
+    def simulate(self, *operand_bits):
+        """Plaintext evaluation of the schedule on the host (schedule check; not a compute path)."""
+        assert len(operand_bits) == len(self.operand_rows)
+        arrs = [np.ascontiguousarray(np.asarray(b, dtype=np.int32).reshape(-1)) for b in operand_bits]
+        for a, rows in zip(arrs, self.operand_rows):
+            assert a.size == rows
+        out = np.zeros(self.out_rows, np.int32)
+        ptrs = (_vp * len(arrs))(*[a.ctypes.data for a in arrs])
+        if self.L.tfhe_b200_circuit_simulate(self.h, out.ctypes.data, ptrs):
+            raise EngineError("circuit simulation failed")
         return out
 
     def close(self):

@@ -191,8 +191,8 @@ __global__ void __launch_bounds__(kThreads, 1) blind_rotate_kernel(const BrLaunc
         if (!valid) g = L.total - 1;
 
         // which gate prologue does this bootstrap belong to
-        const int32_t *in0 = nullptr, *in1 = nullptr;
-        uint32_t sa = 0, sb = 0, cst = 0;
+        const int32_t *in0 = nullptr, *in1 = nullptr, *in2 = nullptr;
+        uint32_t sa = 0, sb = 0, sc = 0, cst = 0;
         if (L.explicit_inputs == 0) {
             int local = g;
             int si = 0;
@@ -206,13 +206,22 @@ __global__ void __launch_bounds__(kThreads, 1) blind_rotate_kernel(const BrLaunc
             in1 = L.seg[si].in1 + r1 * L.seg[si].stride1;
             sa = (uint32_t) L.seg[si].sa;
             sb = (uint32_t) L.seg[si].sb;
+            if (L.seg[si].in2 != nullptr) {
+                const long long r2 = L.seg[si].idx2 ? (long long) __ldg(L.seg[si].idx2 + local) : (long long) local;
+                in2 = L.seg[si].in2 + r2 * L.seg[si].stride2;
+                sc = (uint32_t) L.seg[si].sc;
+            }
             cst = (uint32_t) L.seg[si].cst;
         }
 
         if (role == 0) {
             int barb;
             if (L.explicit_inputs != 0) barb = L.barb ? (L.barb[g] & (2 * kN - 1)) : 0;
-            else barb = modswitch_2N(cst + sa * (uint32_t) __ldg(in0 + L.n) + sb * (uint32_t) __ldg(in1 + L.n));
+            else {
+                uint32_t xb = cst + sa * (uint32_t) __ldg(in0 + L.n) + sb * (uint32_t) __ldg(in1 + L.n);
+                if (in2 != nullptr) xb += sc * (uint32_t) __ldg(in2 + L.n);
+                barb = modswitch_2N(xb);
+            }
             if (L.acc_in != nullptr) {
                 phase_load_acc(lane, W, L.acc_in + (size_t) g * (kK + 1) * kN);
             } else if (L.testvect != nullptr) {
@@ -237,7 +246,11 @@ __global__ void __launch_bounds__(kThreads, 1) blind_rotate_kernel(const BrLaunc
                 a_blk = 0;
                 if (idx < n_iter && rotate) {
                     if (L.explicit_inputs != 0) a_blk = __ldg(L.bara + (size_t) g * n_iter + idx) & (2 * kN - 1);
-                    else a_blk = modswitch_2N(sa * (uint32_t) __ldg(in0 + idx) + sb * (uint32_t) __ldg(in1 + idx));
+                    else {
+                        uint32_t xa = sa * (uint32_t) __ldg(in0 + idx) + sb * (uint32_t) __ldg(in1 + idx);
+                        if (in2 != nullptr) xa += sc * (uint32_t) __ldg(in2 + idx);
+                        a_blk = modswitch_2N(xa);
+                    }
                 }
             }
             const int a = __shfl_sync(0xffffffffu, a_blk, it & 31);

@@ -9,7 +9,7 @@ namespace tfhe_b200 {
 
 struct cpx;
 
-// One homogeneous run of bootstraps inside a batch: x = (0,cst) + sa*in0 + sb*in1
+// One homogeneous run of bootstraps inside a batch: x = (0,cst) + sa*in0 + sb*in1 [+ sc*in2]
 // (gate prologues, boot-gates.cu:98-448).  Samples are int32[n+1] rows.
 struct BrSegment {
     const int32_t *in0;
@@ -19,6 +19,11 @@ struct BrSegment {
     // optional gather: operand row of local gate g is in + idx[g] * stride (instead of g * stride)
     const int32_t *idx0;
     const int32_t *idx1;
+    // optional third operand (three-input threshold gates, e.g. the carry operator)
+    const int32_t *in2;
+    long long stride2;
+    const int32_t *idx2;
+    int sc;
     int sa, sb;
     int32_t cst;
     int count;

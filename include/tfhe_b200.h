@@ -59,7 +59,11 @@ enum {
     TFHE_B200_ANDYN = 7,/* :327 */
     TFHE_B200_ORNY = 8, /* :353 */
     TFHE_B200_ORYN = 9, /* :379 */
-    TFHE_B200_NUM_GATES = 10
+    TFHE_B200_NUM_GATES = 10,
+    /* extension (not in the reference): carry operator g | (p & c) for mutually exclusive g, p,
+     * one bootstrap of (1/8) + 2g + p + c; operands a = g, b = p, c = c (tfhe_b200_gate_op.c) */
+    TFHE_B200_GPC = 10,
+    TFHE_B200_NUM_GATES_EXT = 11
 };
 
 const char *tfhe_b200_last_error(void);
@@ -107,6 +111,9 @@ typedef struct {
     int32_t *out;
     int64_t stride_a, stride_b, stride_out;
     const int32_t *idx_a, *idx_b, *idx_out; /* optional, device memory */
+    const int32_t *c;                       /* third operand, only for three-input gates (else NULL) */
+    int64_t stride_c;
+    const int32_t *idx_c;
 } tfhe_b200_gate_op;
 /* Up to 4 runs in ONE bootstrap batch (one blind-rotate launch + one key-switch launch). */
 int tfhe_b200_gate_multi(tfhe_b200_ctx *ctx, const tfhe_b200_gate_op *ops, int nops, void *stream);
@@ -146,12 +153,20 @@ typedef struct tfhe_b200_circuit tfhe_b200_circuit;
  * main.cu:821, _vector_coalInput :1138, Cipher::operator+ Cipher.cu:334); mode 1: number-wise
  * (taskLevelParallelAdd main.cu:619).  Operands: a[count][nbits], b[count][nbits]. */
 tfhe_b200_circuit *tfhe_b200_circuit_add(tfhe_b200_ctx *ctx, int nbits, int count, int mode);
+/* Adder used inside the multiplier / matrix-multiply trees.  RIPPLE is the reference's schedule
+ * (3*nbits-3 levels per addition); PREFIX is a Kogge-Stone adder whose carry operator is one
+ * three-input bootstrap (TFHE_B200_GPC): 2 + ceil(log2(nbits-1)) levels per addition (SURVEY
+ * 8f rank 4, not in the reference).  tfhe_b200_circuit_add mode 2 is the PREFIX adder. */
+enum { TFHE_B200_ADDER_RIPPLE = 0, TFHE_B200_ADDER_PREFIX = 1 };
 /* a * b mod 2^nbits for count pairs (multiplyLweSamples main.cu:1483, BOOTS_vectorMultiplication
  * :1746, Cipher::operator* Cipher.cu:83) */
 tfhe_b200_circuit *tfhe_b200_circuit_mul(tfhe_b200_ctx *ctx, int nbits, int count);
+tfhe_b200_circuit *tfhe_b200_circuit_mul_ex(tfhe_b200_ctx *ctx, int nbits, int count, int adder);
 /* C[rows][cols] = A[rows][inner] * B[inner][cols], nbits-bit elements mod 2^nbits
  * (BOOTS_matrixMultiplication main.cu:2342; cpu/cloud.cpp:390-408) */
 tfhe_b200_circuit *tfhe_b200_circuit_matmul(tfhe_b200_ctx *ctx, int rows, int inner, int cols, int nbits);
+tfhe_b200_circuit *tfhe_b200_circuit_matmul_ex(tfhe_b200_ctx *ctx, int rows, int inner, int cols, int nbits,
+                                               int adder);
 void tfhe_b200_circuit_destroy(tfhe_b200_circuit *c);
 int tfhe_b200_circuit_levels(const tfhe_b200_circuit *c);      /* sequential bootstrap batches */
 long long tfhe_b200_circuit_gates(const tfhe_b200_circuit *c); /* bootstrapped gates per run   */
@@ -160,6 +175,9 @@ int tfhe_b200_circuit_operand_rows(const tfhe_b200_circuit *c, int operand);
 int tfhe_b200_circuit_output_rows(const tfhe_b200_circuit *c);
 /* operands[o]: device array of tfhe_b200_circuit_operand_rows(c, o) samples */
 int tfhe_b200_circuit_run(tfhe_b200_circuit *c, int32_t *d_out, const int32_t *const *operands, void *stream);
+/* Host-only check of a plan on PLAINTEXT bits (one int per sample row); needs no GPU and accepts
+ * plans built with ctx == NULL.  This is schedule verification, not a compute path. */
+int tfhe_b200_circuit_simulate(const tfhe_b200_circuit *c, int32_t *out_bits, const int32_t *const *operand_bits);
 int tfhe_b200_ctx_words(const tfhe_b200_ctx *ctx); /* n + 1 */
 
 /* ---- HOST-buffer convenience (synchronous; copies in and out) ------------- */

@@ -34,15 +34,26 @@ def sk_engine(pkg):
     eng.close()
 
 
-@pytest.mark.parametrize("mode", [0, 1])
+def test_carry_operator_gate(pkg, sk_engine):
+    """TFHE_B200_GPC = g | (p & c) in one bootstrap, every admissible input (g, p exclusive)."""
+    sk, eng = sk_engine
+    combos = [(g, p, c) for g in (0, 1) for p in (0, 1) for c in (0, 1) if not (g and p)]
+    reps = 40
+    g, p, c = [np.repeat(np.array([x[i] for x in combos], np.int32), reps) for i in range(3)]
+    out = eng.carry_gate(eng.to_device(pkg.encrypt_bits(sk, g, 21)), eng.to_device(pkg.encrypt_bits(sk, p, 22)),
+                         eng.to_device(pkg.encrypt_bits(sk, c, 23)))
+    assert np.array_equal(pkg.decrypt_bits(sk, out.cpu().numpy()), g | (p & c))
+
+
+@pytest.mark.parametrize("mode", [0, 1, 2])
 def test_16_bit_addition(pkg, sk_engine, mode):
-    """./main 16 a b (BASELINE config 2): both reference schedules."""
+    """./main 16 a b (BASELINE config 2): both reference schedules, and the prefix adder."""
     sk, eng = sk_engine
     nbits = 16
     a = np.array([12345, 65535, 0, 40000])
     b = np.array([(-6789) & 0xFFFF, 1, 0, 30000])
     circ = pkg.Circuit(eng, "add", nbits, len(a), mode)
-    assert circ.levels == (45 if mode == 0 else 16)
+    assert circ.levels == {0: 45, 1: 16, 2: 6}[mode]
     out = circ.run(enc_ints(pkg, eng, sk, a, nbits, 1), enc_ints(pkg, eng, sk, b, nbits, 2))
     assert np.array_equal(dec_ints(pkg, sk, out, nbits), (a + b) & 0xFFFF)
     out2 = circ.run(enc_ints(pkg, eng, sk, b, nbits, 3), enc_ints(pkg, eng, sk, a, nbits, 4))  # plans are reusable
@@ -61,25 +72,28 @@ def test_8_bit_multiplication_vector(pkg, sk_engine):
     circ.close()
 
 
-def test_32_bit_multiplication(pkg, sk_engine):
-    """BASELINE config 4 (multiplyLweSamples schedule, single precision)."""
+@pytest.mark.parametrize("adder", [0, 1])
+def test_32_bit_multiplication(pkg, sk_engine, adder):
+    """BASELINE config 4 (multiplyLweSamples schedule, single precision); adder 1 = prefix tree."""
     sk, eng = sk_engine
     nbits = 32
     a, b = np.array([40000]), np.array([50000])
-    circ = pkg.Circuit(eng, "mul", nbits, 1)
+    circ = pkg.Circuit(eng, "mul_ex", nbits, 1, adder)
+    assert circ.levels == (466 if adder == 0 else 36)
     out = circ.run(enc_ints(pkg, eng, sk, a, nbits, 7), enc_ints(pkg, eng, sk, b, nbits, 8))
     assert np.array_equal(dec_ints(pkg, sk, out, nbits), (a * b) & 0xFFFFFFFF)
     circ.close()
 
 
-def test_matrix_multiply_4x4_of_8_bit(pkg, sk_engine):
+@pytest.mark.parametrize("adder", [0, 1])
+def test_matrix_multiply_4x4_of_8_bit(pkg, sk_engine, adder):
     """Reduced BASELINE config 5 (the reference's own test driver uses 4x4, main.cu:2471)."""
     sk, eng = sk_engine
     nbits, n = 8, 4
     rng = np.random.default_rng(3)
     A = rng.integers(-8, 8, (n, n))
     Bm = rng.integers(-8, 8, (n, n))
-    circ = pkg.Circuit(eng, "matmul", n, n, n, nbits)
+    circ = pkg.Circuit(eng, "matmul_ex", n, n, n, nbits, adder)
     out = circ.run(enc_ints(pkg, eng, sk, A.reshape(-1) & 0xFF, nbits, 9),
                    enc_ints(pkg, eng, sk, Bm.reshape(-1) & 0xFF, nbits, 10))
     got = dec_ints(pkg, sk, out, nbits).reshape(n, n)
