@@ -41,7 +41,9 @@ class Params(ctypes.Structure):
 
 
 def lib_path():
-    return os.path.join(_HERE, "libtfhe_b200.so")
+    # TFHE_B200_LIB: development override used to A/B differently compiled builds of the SAME
+    # library on the GPU box (tools/build_variant.py); there is no other implementation to fall back to
+    return os.environ.get("TFHE_B200_LIB") or os.path.join(_HERE, "libtfhe_b200.so")
 
 
 _lib = None

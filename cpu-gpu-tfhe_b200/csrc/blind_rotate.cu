@@ -20,8 +20,12 @@
 //   * grid = min(#groups, #SMs) CTAs, each looping over groups of 4 ciphertexts.
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
-#include "br_core.cuh"
+#ifndef TFHE_B200_EXPERIMENTAL_WARP_KERNEL
+#define TFHE_B200_EXPERIMENTAL_WARP_KERNEL 0
+#endif
+#include "brw_core.cuh"
 #include "kernels.h"
 
 namespace tfhe_b200 {
@@ -112,6 +116,13 @@ __device__ __forceinline__ void build_e2(cpx *e2) {
         e2[m1 * kE2Row + idx].x = c;
         e2[m1 * kE2Row + idx].y = s;
     }
+    // entry 4: stage-4 multiplier of the one-warp-per-ciphertext kernel (brw_core.cuh)
+    for (int m1 = threadIdx.x; m1 < 32; m1 += blockDim.x) {
+        double s, c;
+        sincospi(w_stage4_shift(m1), &s, &c);
+        e2[m1 * kE2Row + 4].x = m1 < 16 ? c : -c;
+        e2[m1 * kE2Row + 4].y = m1 < 16 ? s : -s;
+    }
 }
 
 // modSwitchFromTorus32(x, 2N), numeric-functions.cu:60-66  ==  ((uint32)x + 2^20) >> 21
@@ -151,6 +162,49 @@ __device__ __forceinline__ void ring_consume(CtaSmem &S, const BrLaunch &L, int 
     rp.advance(kRingStages);
 }
 
+// Operands of the gate prologue of bootstrap g (x = (0,cst) + sa*in0 + sb*in1 [+ sc*in2]).
+struct GateIn {
+    const int32_t *in0 = nullptr, *in1 = nullptr, *in2 = nullptr;
+    uint32_t sa = 0, sb = 0, sc = 0, cst = 0;
+};
+
+__device__ __forceinline__ GateIn resolve_inputs(const BrLaunch &L, int g) {
+    GateIn I;
+    if (L.explicit_inputs != 0) return I;
+    int local = g;
+    int si = 0;
+    while (si + 1 < L.nseg && local >= L.seg[si].count) {
+        local -= L.seg[si].count;
+        si++;
+    }
+    const long long r0 = L.seg[si].idx0 ? (long long) __ldg(L.seg[si].idx0 + local) : (long long) local;
+    const long long r1 = L.seg[si].idx1 ? (long long) __ldg(L.seg[si].idx1 + local) : (long long) local;
+    I.in0 = L.seg[si].in0 + r0 * L.seg[si].stride0;
+    I.in1 = L.seg[si].in1 + r1 * L.seg[si].stride1;
+    I.sa = (uint32_t) L.seg[si].sa;
+    I.sb = (uint32_t) L.seg[si].sb;
+    if (L.seg[si].in2 != nullptr) {
+        const long long r2 = L.seg[si].idx2 ? (long long) __ldg(L.seg[si].idx2 + local) : (long long) local;
+        I.in2 = L.seg[si].in2 + r2 * L.seg[si].stride2;
+        I.sc = (uint32_t) L.seg[si].sc;
+    }
+    I.cst = (uint32_t) L.seg[si].cst;
+    return I;
+}
+
+// bara of iteration idx (mod-switched mask word of the prologue's linear combination)
+__device__ __forceinline__ int load_bara(const BrLaunch &L, const GateIn &I, int g, int idx, int n_iter, bool rotate) {
+    if (idx >= n_iter || !rotate) return 0;
+    if (L.explicit_inputs != 0) return __ldg(L.bara + (size_t) g * n_iter + idx) & (2 * kN - 1);
+    uint32_t xa = I.sa * (uint32_t) __ldg(I.in0 + idx) + I.sb * (uint32_t) __ldg(I.in1 + idx);
+    if (I.in2 != nullptr) xa += I.sc * (uint32_t) __ldg(I.in2 + idx);
+    return modswitch_2N(xa);
+}
+
+__device__ __forceinline__ void named_sync(int id, int nthreads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
 __global__ void __launch_bounds__(kThreads, 1) blind_rotate_kernel(const BrLaunch L) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     CtaSmem &S = *reinterpret_cast<CtaSmem *>(smem_raw);
@@ -175,13 +229,14 @@ __global__ void __launch_bounds__(kThreads, 1) blind_rotate_kernel(const BrLaunc
                 ring_fill(S, L, r, c, r * kRingStages + c);
     }
     __syncthreads();
+    const bool rotate = (L.extern_only == 0);
 
-    // -------------------- ciphertext warps ---------------------------------------
+    // -------------------- ciphertext warps ------------------------------------------
     const int ct = warp >> 1, role = warp & 1;
     WarpSmem &W = S.w[ct];
     const int bar_id = 1 + ct;
     // barrier of the two warps of one ciphertext
-    auto pair_sync = [bar_id]() { asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory"); };
+    auto pair_sync = [bar_id]() { named_sync(bar_id, 64); };
     const uint32_t ring_base = role * kRingStages;
     const uint32_t ring_chunks = kChunksPerIter * iters_total;
     RingPos rp;
@@ -189,37 +244,14 @@ __global__ void __launch_bounds__(kThreads, 1) blind_rotate_kernel(const BrLaunc
         int g = grp * kCtWarps + ct;
         const bool valid = g < L.total;
         if (!valid) g = L.total - 1;
-
-        // which gate prologue does this bootstrap belong to
-        const int32_t *in0 = nullptr, *in1 = nullptr, *in2 = nullptr;
-        uint32_t sa = 0, sb = 0, sc = 0, cst = 0;
-        if (L.explicit_inputs == 0) {
-            int local = g;
-            int si = 0;
-            while (si + 1 < L.nseg && local >= L.seg[si].count) {
-                local -= L.seg[si].count;
-                si++;
-            }
-            const long long r0 = L.seg[si].idx0 ? (long long) __ldg(L.seg[si].idx0 + local) : (long long) local;
-            const long long r1 = L.seg[si].idx1 ? (long long) __ldg(L.seg[si].idx1 + local) : (long long) local;
-            in0 = L.seg[si].in0 + r0 * L.seg[si].stride0;
-            in1 = L.seg[si].in1 + r1 * L.seg[si].stride1;
-            sa = (uint32_t) L.seg[si].sa;
-            sb = (uint32_t) L.seg[si].sb;
-            if (L.seg[si].in2 != nullptr) {
-                const long long r2 = L.seg[si].idx2 ? (long long) __ldg(L.seg[si].idx2 + local) : (long long) local;
-                in2 = L.seg[si].in2 + r2 * L.seg[si].stride2;
-                sc = (uint32_t) L.seg[si].sc;
-            }
-            cst = (uint32_t) L.seg[si].cst;
-        }
+        const GateIn I = resolve_inputs(L, g);
 
         if (role == 0) {
             int barb;
             if (L.explicit_inputs != 0) barb = L.barb ? (L.barb[g] & (2 * kN - 1)) : 0;
             else {
-                uint32_t xb = cst + sa * (uint32_t) __ldg(in0 + L.n) + sb * (uint32_t) __ldg(in1 + L.n);
-                if (in2 != nullptr) xb += sc * (uint32_t) __ldg(in2 + L.n);
+                uint32_t xb = I.cst + I.sa * (uint32_t) __ldg(I.in0 + L.n) + I.sb * (uint32_t) __ldg(I.in1 + L.n);
+                if (I.in2 != nullptr) xb += I.sc * (uint32_t) __ldg(I.in2 + L.n);
                 barb = modswitch_2N(xb);
             }
             if (L.acc_in != nullptr) {
@@ -238,21 +270,9 @@ __global__ void __launch_bounds__(kThreads, 1) blind_rotate_kernel(const BrLaunc
         }
         pair_sync();
 
-        const bool rotate = (L.extern_only == 0);
         int a_blk = 0;  // lane l holds bara of iteration (it & ~31) + l
         for (int it = 0; it < n_iter; it++) {
-            if ((it & 31) == 0) {
-                const int idx = it + lane;
-                a_blk = 0;
-                if (idx < n_iter && rotate) {
-                    if (L.explicit_inputs != 0) a_blk = __ldg(L.bara + (size_t) g * n_iter + idx) & (2 * kN - 1);
-                    else {
-                        uint32_t xa = sa * (uint32_t) __ldg(in0 + idx) + sb * (uint32_t) __ldg(in1 + idx);
-                        if (in2 != nullptr) xa += sc * (uint32_t) __ldg(in2 + idx);
-                        a_blk = modswitch_2N(xa);
-                    }
-                }
-            }
+            if ((it & 31) == 0) a_blk = load_bara(L, I, g, it + lane, n_iter, rotate);
             const int a = __shfl_sync(0xffffffffu, a_blk, it & 31);
             const bool active = (a != 0) || !rotate;  // tfhe_blindRotate_FFT :705 skips barai == 0 (no-op)
 
@@ -299,6 +319,174 @@ __global__ void __launch_bounds__(kThreads, 1) blind_rotate_kernel(const BrLaunc
     }
 }
 
+// =================================================================================
+// EXPERIMENTAL (compiled only with -DTFHE_B200_EXPERIMENTAL_WARP_KERNEL=1, selected with
+// TFHE_B200_BR_VARIANT=2): ONE warp per ciphertext, 8 ciphertexts per SM (brw_core.cuh),
+// 24 KB of shared memory and one 255-register warp each, no cross-warp synchronisation.
+// Bit-identical results (all GPU tests pass), but measured 16 % SLOWER than the pair kernel
+// (20.4 vs 2 x 8.6 us per iteration of 8 ciphertexts per SM, profiles/README.md): the two
+// Fourier-domain sums (128 registers) stay live across pass 1 of the second digit level, and
+// ptxas spills around it.  Kept for round 2 (the sums could be parked in tensor memory).
+// One key ring for the whole CTA: every warp consumes all 8 chunks of an iteration in the
+// order (q, o, result polynomial); the last of the 8 warps to finish with a stage refills it.
+#if TFHE_B200_EXPERIMENTAL_WARP_KERNEL
+
+#ifndef TFHE_B200_WARP_CTS
+#define TFHE_B200_WARP_CTS 8
+#endif
+constexpr int kWarpCts = TFHE_B200_WARP_CTS;
+constexpr uint32_t kWRingStages = 3;
+constexpr uint32_t kWChunksPerIter = 2 * kKpl;
+
+struct __align__(128) CtaSmemW {
+    CtSmem w[kWarpCts];
+    cpx e2[32 * kE2Row];
+    cpx ring[kWRingStages][kBkHalfCplx];
+    unsigned long long full[kWRingStages];
+    unsigned int drained[kWRingStages];
+};
+static_assert(sizeof(CtSmem) % 128 == 0, "ciphertext working set must keep 128 B alignment");
+static_assert(offsetof(CtaSmemW, ring) % 128 == 0, "TMA destination alignment");
+static_assert(sizeof(CtaSmemW) <= 227 * 1024, "shared memory budget");
+
+__device__ __forceinline__ void ring_fill_w(CtaSmemW &S, const BrLaunch &L, uint32_t chunk, uint32_t stage) {
+    const uint32_t it = (chunk / kWChunksPerIter) % (uint32_t) L.n_iter;
+    const uint32_t sub = chunk % kWChunksPerIter;
+    const uint32_t q = sub >> 2, o = (sub >> 1) & 1u, out = sub & 1u;
+    const uint32_t row = o * kL + q;
+    const cpx *src = L.bk + ((size_t) (L.bk_first + it) * kKpl + row) * kBkRowCplx + out * kBkHalfCplx;
+    mbar_arrive_expect_tx(&S.full[stage], kStageBytes);
+    tma_load_1d(S.ring[stage], src, kStageBytes, &S.full[stage]);
+}
+
+template <typename Use>
+__device__ __forceinline__ void ring_consume_w(CtaSmemW &S, const BrLaunch &L, int lane, RingPos &rp,
+                                               uint32_t ring_chunks, Use use) {
+    const uint32_t st = rp.stage;
+    mbar_wait(&S.full[st], rp.phase);
+    use(S.ring[st]);
+    __syncwarp();
+    if (lane == 0) {
+        const unsigned int seen = atomicAdd(&S.drained[st], 1u);
+        if ((seen & (kWarpCts - 1)) == kWarpCts - 1) {
+            const uint32_t next = rp.chunk + kWRingStages;
+            if (next < ring_chunks) {
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                ring_fill_w(S, L, next, st);
+            }
+        }
+    }
+    rp.advance(kWRingStages);
+}
+
+// Pass 1 as a real call: inlined, ptxas schedules it as aggressively as if it had the whole
+// register file (178 registers stand-alone) and then spills the 128 live accumulator registers
+// around it; as a separate function it is allocated on its own (it needs fewer than 100).
+template <int O>
+__device__ __noinline__ void w_f1_call(int lane, CtSmem *W, int a, int q, bool rotate) {
+    w_phase_f1(lane, *W, a, O, q, rotate);
+}
+
+__global__ void __launch_bounds__(kWarpCts * 32, 1) blind_rotate_warp_kernel(const BrLaunch L) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    CtaSmemW &S = *reinterpret_cast<CtaSmemW *>(smem_raw);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    const int ngroups = (L.total + kWarpCts - 1) / kWarpCts;
+    const int n_iter = L.n_iter;
+    const int my_groups = (ngroups - (int) blockIdx.x + (int) gridDim.x - 1) / (int) gridDim.x;
+    const uint32_t ring_chunks = kWChunksPerIter * (uint32_t) my_groups * (uint32_t) n_iter;
+
+    build_e2(S.e2);
+    if (threadIdx.x == 0) {
+        for (uint32_t s = 0; s < kWRingStages; s++) {
+            mbar_init(&S.full[s], 1);
+            S.drained[s] = 0;
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        for (uint32_t c = 0; c < kWRingStages && c < ring_chunks; c++) ring_fill_w(S, L, c, c);
+    }
+    __syncthreads();
+    const bool rotate = (L.extern_only == 0);
+    CtSmem &W0 = S.w[warp];
+    RingPos rp;
+    for (int grp = blockIdx.x; grp < ngroups; grp += gridDim.x) {
+        int g = grp * kWarpCts + warp;
+        const bool valid = g < L.total;
+        if (!valid) g = L.total - 1;
+        const GateIn I = resolve_inputs(L, g);
+        {
+            int barb;
+            if (L.explicit_inputs != 0) barb = L.barb ? (L.barb[g] & (2 * kN - 1)) : 0;
+            else {
+                uint32_t xb = I.cst + I.sa * (uint32_t) __ldg(I.in0 + L.n) + I.sb * (uint32_t) __ldg(I.in1 + L.n);
+                if (I.in2 != nullptr) xb += I.sc * (uint32_t) __ldg(I.in2 + L.n);
+                barb = modswitch_2N(xb);
+            }
+            if (L.acc_in != nullptr) w_phase_load_acc(lane, W0, L.acc_in + (size_t) g * (kK + 1) * kN);
+            else if (L.testvect != nullptr) w_phase_init_testvect(lane, W0, barb, L.testvect);
+            else w_phase_init(lane, W0, barb, L.mu);
+        }
+        __syncwarp();
+
+        int a_blk = 0;  // lane l holds bara of iteration (it & ~31) + l
+        for (int it = 0; it < n_iter; it++) {
+            if ((it & 31) == 0) a_blk = load_bara(L, I, g, it + lane, n_iter, rotate);
+            const int a = __shfl_sync(0xffffffffu, a_blk, it & 31);
+            const bool active = (a != 0) || !rotate;  // tfhe_blindRotate_FFT :705 skips barai == 0 (no-op)
+            // The phases below derive all their shared-memory addresses from the lane index.
+            // Laundering it once per iteration keeps the compiler from hoisting ~100 loop-invariant
+            // addresses out of the iteration loop (they were spilled: 776 B of stack per thread).
+            int ln = lane;
+            asm volatile("" : "+r"(ln));
+            CtSmem &W = W0;
+
+            cpx acc0[16], acc1[16];  // Fourier-domain sums of the two result polynomials
+#pragma unroll
+            for (int i = 0; i < 16; i++) {
+                acc0[i].x = 0.0; acc0[i].y = 0.0;
+                acc1[i].x = 0.0; acc1[i].y = 0.0;
+            }
+#pragma unroll 1
+            for (int q = 0; q < kL; q++) {
+                if (active) {
+                    w_f1_call<0>(ln, &W, a, q, rotate);
+                    __syncwarp();
+                    w_f1_call<1>(ln, &W, a, q, rotate);
+                }
+                __syncwarp();
+#pragma unroll 1
+                for (int o = 0; o <= kK; o++) {
+                    cpx z[16];
+                    if (active) w_phase_f2(ln, W.x[o], S.e2, z);
+                    ring_consume_w(S, L, lane, rp, ring_chunks, [&](const cpx *half) {
+                        if (active) phase_mac_half(ln, z, half, acc0);
+                    });
+                    ring_consume_w(S, L, lane, rp, ring_chunks, [&](const cpx *half) {
+                        if (active) phase_mac_half(ln, z, half, acc1);
+                    });
+                }
+                __syncwarp();  // pass 1 of the next digit level overwrites the exchange buffers
+            }
+            if (active) {
+                w_phase_i1(ln, W.x[0], S.e2, acc0);
+                w_phase_i1(ln, W.x[1], S.e2, acc1);
+                __syncwarp();
+                w_phase_i2<0>(ln, W, rotate);
+                w_phase_i2<1>(ln, W, rotate);
+                __syncwarp();
+            }
+        }
+
+        if (valid) {
+            if (L.u_out != nullptr) w_phase_extract(lane, W0, L.u_out + (size_t) g * (kN + 1));
+            if (L.acc_out != nullptr) w_phase_dump_acc(lane, W0, L.acc_out + (size_t) g * (kK + 1) * kN);
+        }
+        __syncwarp();
+    }
+}
+#endif  // TFHE_B200_EXPERIMENTAL_WARP_KERNEL
+
 // ------------------------------------------------------------ key conversion
 
 struct __align__(128) FwdSmem {
@@ -331,6 +519,11 @@ cudaError_t blind_rotate_configure() {
     cudaError_t e = cudaFuncSetAttribute(blind_rotate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int) sizeof(CtaSmem));
     if (e != cudaSuccess) return e;
+#if TFHE_B200_EXPERIMENTAL_WARP_KERNEL
+    e = cudaFuncSetAttribute(blind_rotate_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int) sizeof(CtaSmemW));
+    if (e != cudaSuccess) return e;
+#endif
     return cudaFuncSetAttribute(forward_polys_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 (int) sizeof(FwdSmem));
 }
@@ -339,6 +532,17 @@ cudaError_t launch_blind_rotate(const BrLaunch &L, int sm_count, cudaStream_t st
     if (L.total <= 0) return cudaSuccess;
     const int ngroups = (L.total + kCtWarps - 1) / kCtWarps;
     const int grid = ngroups < sm_count ? ngroups : sm_count;
+#if TFHE_B200_EXPERIMENTAL_WARP_KERNEL
+    static const int variant = [] {
+        const char *v = getenv("TFHE_B200_BR_VARIANT");
+        return v ? atoi(v) : 0;
+    }();
+    if (variant == 2) {
+        const int ng = (L.total + kWarpCts - 1) / kWarpCts;
+        blind_rotate_warp_kernel<<<ng < sm_count ? ng : sm_count, kWarpCts * 32, sizeof(CtaSmemW), stream>>>(L);
+        return cudaGetLastError();
+    }
+#endif
     blind_rotate_kernel<<<grid, kThreads, sizeof(CtaSmem), stream>>>(L);
     return cudaGetLastError();
 }

@@ -123,6 +123,25 @@ TFHE_HD void cmac(cpx &acc, const cpx &z, const cpx &w) {
     acc.y = fma(z.y, w.x, acc.y);
 }
 
+// Butterfly multipliers of pass 1 read from the __constant__ table: with a compile-time index
+// they become constant-bank operands of the DFMAs (as immediates every one of them costs two
+// UMOVs per use: 259 extra instructions per iteration in the first version).
+TFHE_HD double c1_re_rt(int i) {
+#ifdef __CUDA_ARCH__
+    return d_c1_tab_re[i];
+#else
+    return h_c1_tab_re[i];
+#endif
+}
+
+TFHE_HD double c1_im_rt(int i) {
+#ifdef __CUDA_ARCH__
+    return d_c1_tab_im[i];
+#else
+    return h_c1_tab_im[i];
+#endif
+}
+
 // Stages 0-4 on the 32 in-register elements (natural j1 in, bit-reversed m1 out).
 TFHE_HD void fwd32(cpx (&x)[32]) {
 #pragma unroll
@@ -133,7 +152,7 @@ TFHE_HD void fwd32(cpx (&x)[32]) {
             const int ci = (1 << s) - 1 + b;
 #pragma unroll
             for (int i = 0; i < half; i++)
-                bf_fwd(x[b * 2 * half + i], x[b * 2 * half + i + half], c1_re(ci), c1_im(ci));
+                bf_fwd(x[b * 2 * half + i], x[b * 2 * half + i + half], c1_re_rt(ci), c1_im_rt(ci));
         }
     }
 }
@@ -147,7 +166,7 @@ TFHE_HD void inv32(cpx (&x)[32]) {
             const int ci = (1 << s) - 1 + b;
 #pragma unroll
             for (int i = 0; i < half; i++)
-                bf_inv(x[b * 2 * half + i], x[b * 2 * half + i + half], c1_re(ci), c1_im(ci));
+                bf_inv(x[b * 2 * half + i], x[b * 2 * half + i + half], c1_re_rt(ci), c1_im_rt(ci));
         }
     }
 }
@@ -268,22 +287,6 @@ TFHE_HD void phase_init(int lane, WarpSmem &ws, int barb, int32_t mu) {
 //     | barrier |
 // Partial Fourier sums and the half-pass values are exchanged through exchange rows that
 // are free at that point.
-
-TFHE_HD double c1_re_rt(int i) {
-#ifdef __CUDA_ARCH__
-    return d_c1_tab_re[i];
-#else
-    return h_c1_tab_re[i];
-#endif
-}
-
-TFHE_HD double c1_im_rt(int i) {
-#ifdef __CUDA_ARCH__
-    return d_c1_tab_im[i];
-#else
-    return h_c1_tab_im[i];
-#endif
-}
 
 // Pass 1 of the two forward transforms of digit level q (decomposed rows (o, q), o = 0..k),
 // fused with the rotation (torusPolynomialMulByXaiMinusOne, toruspolynomial-functions.cu:191-213)
@@ -408,7 +411,7 @@ TFHE_HD void phase_i2_final(int lane, WarpSmem &ws, int role, const cpx (&x)[16]
     const int o = lane >> 4, j2 = lane & 15;
     const cpx *other = ws.exch[1 - role] + lane;
     int32_t *row = ws.acc[o] + j2 * kAccRow + 16 * role;
-    const double er = c1_re(0), ei = c1_im(0);
+    const double er = c1_re_rt(0), ei = c1_im_rt(0);
     // blocks of 8 outputs: all loads, then all butterflies and conversions, then the updates
     // (keeps the XU conversions and the shared-memory round trips overlapped)
 #pragma unroll
