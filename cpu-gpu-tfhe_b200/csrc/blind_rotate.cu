@@ -210,7 +210,11 @@ __global__ void __launch_bounds__(kThreads, 1) blind_rotate_kernel(const BrLaunc
     CtaSmem &S = *reinterpret_cast<CtaSmem *>(smem_raw);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
-    const int ngroups = (L.total + kCtWarps - 1) / kCtWarps;
+    // Small batches are spread over the SMs: a group holds `cpg` <= 4 ciphertexts (the other
+    // warp pairs of the CTA only keep the key ring moving), so that a single gate or a narrow
+    // circuit level does not share its SM with copies of itself.
+    const int cpg = L.cts_per_group;
+    const int ngroups = (L.total + cpg - 1) / cpg;
     const int n_iter = L.n_iter;
     const int my_groups = (ngroups - (int) blockIdx.x + (int) gridDim.x - 1) / (int) gridDim.x;
     const uint32_t iters_total = (uint32_t) my_groups * (uint32_t) n_iter;
@@ -241,8 +245,8 @@ __global__ void __launch_bounds__(kThreads, 1) blind_rotate_kernel(const BrLaunc
     const uint32_t ring_chunks = kChunksPerIter * iters_total;
     RingPos rp;
     for (int grp = blockIdx.x; grp < ngroups; grp += gridDim.x) {
-        int g = grp * kCtWarps + ct;
-        const bool valid = g < L.total;
+        int g = grp * cpg + ct;
+        const bool valid = ct < cpg && g < L.total;
         if (!valid) g = L.total - 1;
         const GateIn I = resolve_inputs(L, g);
 
@@ -274,7 +278,8 @@ __global__ void __launch_bounds__(kThreads, 1) blind_rotate_kernel(const BrLaunc
         for (int it = 0; it < n_iter; it++) {
             if ((it & 31) == 0) a_blk = load_bara(L, I, g, it + lane, n_iter, rotate);
             const int a = __shfl_sync(0xffffffffu, a_blk, it & 31);
-            const bool active = (a != 0) || !rotate;  // tfhe_blindRotate_FFT :705 skips barai == 0 (no-op)
+            // tfhe_blindRotate_FFT :705 skips barai == 0 (no-op); idle slots do no arithmetic either
+            const bool active = valid && ((a != 0) || !rotate);
 
             if (active) {
                 phase_f1q(lane, W, a, role, rotate);
@@ -528,9 +533,12 @@ cudaError_t blind_rotate_configure() {
                                 (int) sizeof(FwdSmem));
 }
 
-cudaError_t launch_blind_rotate(const BrLaunch &L, int sm_count, cudaStream_t stream) {
-    if (L.total <= 0) return cudaSuccess;
-    const int ngroups = (L.total + kCtWarps - 1) / kCtWarps;
+cudaError_t launch_blind_rotate(const BrLaunch &L_in, int sm_count, cudaStream_t stream) {
+    if (L_in.total <= 0) return cudaSuccess;
+    BrLaunch L = L_in;
+    int cpg = (L.total + sm_count - 1) / sm_count;
+    L.cts_per_group = cpg < 1 ? 1 : (cpg > kCtWarps ? kCtWarps : cpg);
+    const int ngroups = (L.total + L.cts_per_group - 1) / L.cts_per_group;
     const int grid = ngroups < sm_count ? ngroups : sm_count;
 #if TFHE_B200_EXPERIMENTAL_WARP_KERNEL
     static const int variant = [] {

@@ -35,6 +35,7 @@ struct BrLaunch {
     BrSegment seg[kMaxSegments];
     int nseg;
     int total;            // bootstraps in this launch
+    int cts_per_group;    // set by launch_blind_rotate: ciphertexts per CTA pass (1..4)
     int n;                // LWE dimension = blind-rotation iterations available in bk
     int n_iter;           // iterations to run (<= n)
     int extern_only;      // 1: a single external product ACC <- BK_{bk_first} (.) ACC, no rotation
