@@ -10,7 +10,9 @@ The directory name contains a hyphen, so import it through
 ``__graft_entry__.load_package()`` (registers it as ``cpu_gpu_tfhe_b200``).
 """
 from .binding import (  # noqa: F401
+    CMP,
     GATES,
+    SHIFT,
     GATE_ID,
     Circuit,
     Engine,

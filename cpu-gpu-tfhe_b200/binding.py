@@ -20,6 +20,8 @@ _vp = ctypes.c_void_p
 _i = ctypes.c_int
 
 
+CMP = {"GT": 0, "LE": 1, "LT": 2, "GE": 3, "EQ": 4, "NE": 5}   # TFHE_B200_CMP_*
+SHIFT = {"LEFT": 0, "RIGHT_LOGICAL": 1, "RIGHT_ARITH": 2}         # TFHE_B200_SHIFT_*
 GPC = 10      # TFHE_B200_GPC: carry operator g | (p & c) for mutually exclusive g, p (extension)
 
 
@@ -96,8 +98,19 @@ def lib():
         L.tfhe_b200_decrypt_bits.argtypes = [ctypes.POINTER(Params), _vp, _vp, _i, _vp]
         L.tfhe_b200_phases.argtypes = [_vp, _i, _vp, _i, _vp]
         L.tfhe_b200_set_timing.argtypes = [_vp, _i]
-        for f in ("add", "mul", "matmul", "mul_ex", "matmul_ex"):
+        for f in ("add", "mul", "matmul", "mul_ex", "matmul_ex", "sub", "neg", "compare", "minmax", "select", "abs",
+                  "shift", "div"):
             getattr(L, "tfhe_b200_circuit_" + f).restype = _vp
+        L.tfhe_b200_circuit_sub.argtypes = [_vp, _i, _i, _i]
+        L.tfhe_b200_circuit_neg.argtypes = [_vp, _i, _i]
+        L.tfhe_b200_circuit_compare.argtypes = [_vp, _i, _i, _i, _i]
+        L.tfhe_b200_circuit_minmax.argtypes = [_vp, _i, _i, _i, _i]
+        L.tfhe_b200_circuit_select.argtypes = [_vp, _i, _i]
+        L.tfhe_b200_circuit_abs.argtypes = [_vp, _i, _i, _i]
+        L.tfhe_b200_circuit_shift.argtypes = [_vp, _i, _i, _i, _i]
+        L.tfhe_b200_circuit_div.argtypes = [_vp, _i, _i, _i, _i]
+        L.tfhe_b200_mux_gather.argtypes = [_vp, _vp, ctypes.c_int64, _vp, _vp, _vp, _vp, _i, _vp]
+        L.tfhe_b200_linear_gather.argtypes = [_vp, _vp, ctypes.c_int64, _vp, _vp, _i, ctypes.c_int32, _i, _vp]
         L.tfhe_b200_circuit_add.argtypes = [_vp, _i, _i, _i]
         L.tfhe_b200_circuit_mul.argtypes = [_vp, _i, _i]
         L.tfhe_b200_circuit_mul_ex.argtypes = [_vp, _i, _i, _i]

@@ -22,12 +22,20 @@
 
 namespace {
 
+// One launch group of a plan.
+//   GATES : up to 4 runs of two-/three-input bootstrapped gates (one blind-rotate + one key-switch launch)
+//   MUX   : bootsMUX gates (two bootstraps + one key switch each, boot-gates.cu:407-448), one launch pair
+//   LINEAR: bootstrap-free row operations (bootsCOPY / bootsNOT / bootsCONSTANT, boot-gates.cu:242-267)
+enum { LV_GATES = 0, LV_MUX = 1, LV_LINEAR = 2 };
+enum { LIN_COPY = 0, LIN_NOT = 1, LIN_ZERO = 2, LIN_ONE = 3, LIN_KINDS = 4 };
+
 struct Op {
     int gate, count, off_a, off_b, off_out, off_c;
 };
 
 struct Level {
-    Op ops[4];
+    int type = LV_GATES;
+    Op ops[4];   // GATES: runs; MUX: ops[0] (a = selector, b, c = off_c); LINEAR: ops[0] (gate = LIN_*, a = source)
     int nops = 0;
 };
 
@@ -41,6 +49,7 @@ struct tfhe_b200_circuit {
     int out_row0 = 0, out_rows = 0;
     int row_zero = -1;                  // trivial encryption of 0 (bootsCONSTANT, boot-gates.cu:263)
     std::vector<Level> levels;
+    int depth = 0;                      // sequential bootstrap batches (GATES and MUX groups)
     std::vector<int32_t> h_idx;
     int32_t *d_idx = nullptr;
     int32_t *d_ws = nullptr;
@@ -49,13 +58,20 @@ struct tfhe_b200_circuit {
 
 namespace {
 
+typedef std::vector<int> Bits;  // rows of the bits of one integer, LSB first
+
 // ---- plan builder -----------------------------------------------------------------------
+// Ops are collected per LEVEL.  Inside a level the groups run in the order GATES, MUX, LINEAR;
+// gates of one group read the state before the group (a group may overwrite its own operands),
+// later groups of the same level see the results of earlier ones.
 
 struct Builder {
     tfhe_b200_circuit *c;
     // gates of the level under construction, grouped by gate type
     std::vector<int> ga[TFHE_B200_NUM_GATES_EXT], gb[TFHE_B200_NUM_GATES_EXT], go[TFHE_B200_NUM_GATES_EXT],
         gc[TFHE_B200_NUM_GATES_EXT];
+    std::vector<int> ms, mb, mc, mo;                  // MUX: selector, then-value, else-value, out
+    std::vector<int> li[LIN_KINDS], lo[LIN_KINDS];    // LINEAR
 
     explicit Builder(tfhe_b200_circuit *circ) : c(circ) {}
 
@@ -65,6 +81,19 @@ struct Builder {
         return r;
     }
 
+    Bits alloc_bits(int n) {
+        Bits v(n);
+        const int r = alloc(n);
+        for (int i = 0; i < n; i++) v[i] = r + i;
+        return v;
+    }
+
+    static Bits bits_at(int row0, int n) {
+        Bits v(n);
+        for (int i = 0; i < n; i++) v[i] = row0 + i;
+        return v;
+    }
+
     int operand(int rows) {
         const int r = alloc(rows);
         c->in_row0.push_back(r);
@@ -72,63 +101,115 @@ struct Builder {
         return r;
     }
 
-    // schedule out = gate(a, b) in the current level
+    // schedule out = gate(a, b [, c3]) in the current level
     void gate(int g, int a, int b, int out, int c3 = -1) {
         ga[g].push_back(a);
         gb[g].push_back(b);
         go[g].push_back(out);
         if (c3 >= 0) gc[g].push_back(c3);
     }
+    void mux(int sel, int b, int cc, int out) {  // out = sel ? b : cc
+        ms.push_back(sel);
+        mb.push_back(b);
+        mc.push_back(cc);
+        mo.push_back(out);
+    }
+    void lin(int kind, int in, int out) {
+        li[kind].push_back(in);
+        lo[kind].push_back(out);
+    }
+    void copy(int in, int out) { lin(LIN_COPY, in, out); }
+    void not_(int in, int out) { lin(LIN_NOT, in, out); }
+    void constant(int value, int out) { lin(value ? LIN_ONE : LIN_ZERO, 0, out); }
 
-    // close the level: one bootstrap batch per (up to) 4 gate types
+    int push_idx(const std::vector<int> &v) {
+        const int off = (int) c->h_idx.size();
+        c->h_idx.insert(c->h_idx.end(), v.begin(), v.end());
+        return off;
+    }
+
+    // close the level
     void end_level() {
         Level lv;
         for (int g = 0; g < TFHE_B200_NUM_GATES_EXT; g++) {
             if (ga[g].empty()) continue;
             if (lv.nops == 4) {
                 c->levels.push_back(lv);
+                c->depth++;
                 lv = Level();
             }
             Op &op = lv.ops[lv.nops++];
             op.gate = g;
             op.count = (int) ga[g].size();
-            op.off_a = (int) c->h_idx.size();
-            c->h_idx.insert(c->h_idx.end(), ga[g].begin(), ga[g].end());
-            op.off_b = (int) c->h_idx.size();
-            c->h_idx.insert(c->h_idx.end(), gb[g].begin(), gb[g].end());
-            op.off_out = (int) c->h_idx.size();
-            c->h_idx.insert(c->h_idx.end(), go[g].begin(), go[g].end());
-            op.off_c = -1;
-            if (!gc[g].empty()) {
-                op.off_c = (int) c->h_idx.size();
-                c->h_idx.insert(c->h_idx.end(), gc[g].begin(), gc[g].end());
-            }
-            gc[g].clear();
+            op.off_a = push_idx(ga[g]);
+            op.off_b = push_idx(gb[g]);
+            op.off_out = push_idx(go[g]);
+            op.off_c = gc[g].empty() ? -1 : push_idx(gc[g]);
             c->n_gates += op.count;
             ga[g].clear();
             gb[g].clear();
             go[g].clear();
+            gc[g].clear();
         }
-        if (lv.nops) c->levels.push_back(lv);
+        if (lv.nops) {
+            c->levels.push_back(lv);
+            c->depth++;
+        }
+        if (!ms.empty()) {
+            Level m;
+            m.type = LV_MUX;
+            m.nops = 1;
+            m.ops[0].gate = -1;
+            m.ops[0].count = (int) ms.size();
+            m.ops[0].off_a = push_idx(ms);
+            m.ops[0].off_b = push_idx(mb);
+            m.ops[0].off_c = push_idx(mc);
+            m.ops[0].off_out = push_idx(mo);
+            c->n_gates += m.ops[0].count;
+            c->levels.push_back(m);
+            c->depth++;
+            ms.clear();
+            mb.clear();
+            mc.clear();
+            mo.clear();
+        }
+        for (int k = 0; k < LIN_KINDS; k++) {
+            if (lo[k].empty()) continue;
+            Level l;
+            l.type = LV_LINEAR;
+            l.nops = 1;
+            l.ops[0].gate = k;
+            l.ops[0].count = (int) lo[k].size();
+            l.ops[0].off_a = push_idx(li[k]);
+            l.ops[0].off_b = -1;
+            l.ops[0].off_c = -1;
+            l.ops[0].off_out = push_idx(lo[k]);
+            c->levels.push_back(l);
+            li[k].clear();
+            lo[k].clear();
+        }
     }
 
-    // Ripple-carry addition of `m` pairs of nbits-bit numbers in lock-step
-    // (taskLevelParallelAdd_bitwise[_vector_coalInput], main.cu:821-890 / 1138-1302; the
-    // 5-gate full adder of Cipher::addBits, Cipher.cu:367-378, as 3 levels of 2/1/2 gates).
-    // a[i], b[i], out[i]: rows of bit 0 of number i (bits are consecutive rows; -1 marks an
-    // absent operand handled by the caller).  Result truncated to nbits.
-    void ripple_add(const std::vector<int> &a, const std::vector<int> &b, const std::vector<int> &out, int nbits) {
+    // ---- adders ---------------------------------------------------------------------------
+    // All adders work on m independent pairs in lock-step; a[i], b[i], out[i] are the bit rows of
+    // pair i.  cin1: carry-in 1 (used for a - b = a + ~b + 1).  Result truncated to nbits.
+
+    // Ripple-carry addition (taskLevelParallelAdd_bitwise[_vector_coalInput], main.cu:821-890 /
+    // 1138-1302; the 5-gate full adder of Cipher::addBits, Cipher.cu:367-378, as 3 levels of
+    // 2/1/2 gates).
+    void ripple_add(const std::vector<Bits> &a, const std::vector<Bits> &b, const std::vector<Bits> &out, int nbits,
+                    bool cin1 = false) {
         const int m = (int) a.size();
         const int carry = alloc(m), t0 = alloc(m), t1 = alloc(m);
         for (int i = 0; i < m; i++) {  // bit 0: (carry, sum) = (AND, XOR), bootsANDXOR main.cu:849
-            if (nbits > 1) gate(TFHE_B200_AND, a[i], b[i], carry + i);
-            gate(TFHE_B200_XOR, a[i], b[i], out[i]);
+            if (nbits > 1) gate(cin1 ? TFHE_B200_OR : TFHE_B200_AND, a[i][0], b[i][0], carry + i);
+            gate(cin1 ? TFHE_B200_XNOR : TFHE_B200_XOR, a[i][0], b[i][0], out[i][0]);
         }
         end_level();
         for (int bit = 1; bit < nbits; bit++) {
             for (int i = 0; i < m; i++) {  // t0 = a ^ c, t1 = b ^ c  (bootsXORXOR main.cu:869)
-                gate(TFHE_B200_XOR, a[i] + bit, carry + i, t0 + i);
-                gate(TFHE_B200_XOR, b[i] + bit, carry + i, t1 + i);
+                gate(TFHE_B200_XOR, a[i][bit], carry + i, t0 + i);
+                gate(TFHE_B200_XOR, b[i][bit], carry + i, t1 + i);
             }
             end_level();
             const bool last = (bit == nbits - 1);
@@ -137,64 +218,191 @@ struct Builder {
                 end_level();
             }
             for (int i = 0; i < m; i++) {  // sum = a ^ t1, carry' = t0 ^ c  (main.cu:878)
-                gate(TFHE_B200_XOR, a[i] + bit, t1 + i, out[i] + bit);
+                gate(TFHE_B200_XOR, a[i][bit], t1 + i, out[i][bit]);
                 if (!last) gate(TFHE_B200_XOR, t0 + i, carry + i, carry + i);
             }
             end_level();
         }
     }
 
-    // Parallel-prefix (Kogge-Stone) addition of m pairs: 2 + ceil(log2(nbits-1)) levels instead of
-    // 3*nbits - 3 (the ripple schedules are bound by sequential depth).
-    // The generate / propagate signals of a bit group are mutually exclusive, so the carry
-    // operator G' = G | (P & G_prev) is ONE three-input threshold bootstrap (TFHE_B200_GPC).
-    // Carry into bit i+1 = group generate of bits [0, i]; sum_i = p_i ^ carry_i.
-    void prefix_add(const std::vector<int> &a, const std::vector<int> &b, const std::vector<int> &out, int nbits) {
-        const int m = (int) a.size();
-        const int np = nbits - 1;  // carry positions 0..nbits-2 (the carry out of the top bit is unused)
-        const int p0 = alloc(m * nbits);
-        const int g0 = alloc(m * (np > 0 ? np : 1));
-        std::vector<int> G(m * (np > 0 ? np : 1)), P(m * (np > 0 ? np : 1));
-        for (int i = 0; i < m; i++)
-            for (int bit = 0; bit < nbits; bit++) {
-                const int prow = (bit == 0) ? out[i] : p0 + i * nbits + bit;  // sum bit 0 is p_0 itself
-                gate(TFHE_B200_XOR, a[i] + bit, b[i] + bit, prow);
-                if (bit < np) {
-                    gate(TFHE_B200_AND, a[i] + bit, b[i] + bit, g0 + i * np + bit);
-                    G[i * np + bit] = g0 + i * np + bit;
-                    P[i * np + bit] = prow;
-                }
-            }
-        end_level();
+    // Kogge-Stone scan of (generate, propagate) pairs, LSB first: on return G[i][k] is the
+    // generate signal of bits [0, k] (the carry into bit k+1).  The generate / propagate signals
+    // of a bit group are mutually exclusive, so the carry operator G' = G | (P & G_prev) is ONE
+    // three-input threshold bootstrap (TFHE_B200_GPC).  np positions per number.
+    void prefix_scan(std::vector<Bits> &G, std::vector<Bits> &P, int np) {
+        const int m = (int) G.size();
         for (int d = 1; d < np; d *= 2) {
-            // position `bit` holds the signals of bits [max(0, bit-d+1), bit]; after this level 2d bits
-            std::vector<int> G2 = G, P2 = P;
+            // position k holds the signals of bits [max(0, k-d+1), k]; after this level 2d bits
+            std::vector<Bits> G2 = G, P2 = P;
             const bool more = 2 * d < np;
             for (int i = 0; i < m; i++)
-                for (int bit = d; bit < np; bit++) {
-                    const int r = i * np + bit;
-                    G2[r] = alloc(1);
-                    gate(TFHE_B200_GPC, G[r], P[r], G2[r], G[r - d]);
-                    if (more && bit >= 2 * d) {  // groups that already reach bit 0 need no propagate
-                        P2[r] = alloc(1);
-                        gate(TFHE_B200_AND, P[r], P[r - d], P2[r]);
+                for (int k = d; k < np; k++) {
+                    G2[i][k] = alloc(1);
+                    gate(TFHE_B200_GPC, G[i][k], P[i][k], G2[i][k], G[i][k - d]);
+                    if (more && k >= 2 * d) {  // groups that already reach bit 0 need no propagate
+                        P2[i][k] = alloc(1);
+                        gate(TFHE_B200_AND, P[i][k], P[i][k - d], P2[i][k]);
                     }
                 }
             end_level();
             G.swap(G2);
             P.swap(P2);
         }
+    }
+
+    // Parallel-prefix addition: 2 + ceil(log2(nbits-1)) levels instead of 3*nbits - 3
+    // (the ripple schedules are bound by sequential depth).
+    void prefix_add(const std::vector<Bits> &a, const std::vector<Bits> &b, const std::vector<Bits> &out, int nbits,
+                    bool cin1 = false) {
+        const int m = (int) a.size();
+        const int np = nbits - 1;  // carries into bits 1..nbits-1 (the carry out of the top bit is unused)
+        std::vector<Bits> G(m), P(m), prop(m);
+        for (int i = 0; i < m; i++) {
+            prop[i] = alloc_bits(nbits);
+            G[i] = alloc_bits(np > 0 ? np : 1);
+            P[i].assign(np > 0 ? np : 1, -1);
+            for (int bit = 0; bit < nbits; bit++) {
+                // sum bit 0 is p_0 itself (carry-in 0) or its complement (carry-in 1)
+                const int prow = (bit == 0) ? out[i][0] : prop[i][bit];
+                gate((bit == 0 && cin1) ? TFHE_B200_XNOR : TFHE_B200_XOR, a[i][bit], b[i][bit], prow);
+                if (bit < np) {
+                    // with carry-in 1 bit 0 generates whenever it generates or propagates: a | b
+                    gate((bit == 0 && cin1) ? TFHE_B200_OR : TFHE_B200_AND, a[i][bit], b[i][bit], G[i][bit]);
+                    P[i][bit] = prow;  // P[i][0] is never read
+                }
+            }
+        }
+        end_level();
+        if (np > 0) prefix_scan(G, P, np);
         if (nbits > 1) {
             for (int i = 0; i < m; i++)
-                for (int bit = 1; bit < nbits; bit++)
-                    gate(TFHE_B200_XOR, p0 + i * nbits + bit, G[i * np + bit - 1], out[i] + bit);
+                for (int bit = 1; bit < nbits; bit++) gate(TFHE_B200_XOR, prop[i][bit], G[i][bit - 1], out[i][bit]);
             end_level();
         }
     }
 
-    void add(int adder, const std::vector<int> &a, const std::vector<int> &b, const std::vector<int> &out, int nbits) {
-        if (adder == TFHE_B200_ADDER_PREFIX) prefix_add(a, b, out, nbits);
-        else ripple_add(a, b, out, nbits);
+    void add(int adder, const std::vector<Bits> &a, const std::vector<Bits> &b, const std::vector<Bits> &out,
+             int nbits, bool cin1 = false) {
+        if (adder == TFHE_B200_ADDER_PREFIX) prefix_add(a, b, out, nbits, cin1);
+        else ripple_add(a, b, out, nbits, cin1);
+    }
+
+    // out = a - b = a + ~b + 1 (the reference: a + twosComplement(b), Cipher.cu:329-332)
+    void sub(int adder, const std::vector<Bits> &a, const std::vector<Bits> &b, const std::vector<Bits> &out,
+             int nbits) {
+        const int m = (int) a.size();
+        std::vector<Bits> nb(m);
+        for (int i = 0; i < m; i++) {
+            nb[i] = alloc_bits(nbits);
+            for (int bit = 0; bit < nbits; bit++) not_(b[i][bit], nb[i][bit]);
+        }
+        end_level();
+        add(adder, a, nb, out, nbits, true);
+    }
+
+    // Binary tree reduction of per-bit signals with a two-input gate; returns the row of the result.
+    std::vector<int> reduce_tree(int g, std::vector<Bits> cur) {
+        const int m = (int) cur.size();
+        while (cur[0].size() > 1) {
+            std::vector<Bits> next(m);
+            for (int i = 0; i < m; i++) {
+                const int n = (int) cur[i].size();
+                for (int k = 0; k + 1 < n; k += 2) {
+                    const int r = alloc(1);
+                    gate(g, cur[i][k], cur[i][k + 1], r);
+                    next[i].push_back(r);
+                }
+                if (n & 1) next[i].push_back(cur[i][n - 1]);
+            }
+            end_level();
+            cur.swap(next);
+        }
+        std::vector<int> res(m);
+        for (int i = 0; i < m; i++) res[i] = cur[i][0];
+        return res;
+    }
+
+    // a > b (row per pair).  a > b  <=>  a + ~b carries out; the carry is the group generate of all
+    // bits with g = a & ~b, p = a XNOR b, reduced in a tree with the same three-input carry operator.
+    // Signed operands: comparing with the sign bits flipped, i.e. g = ~a & b at the top bit
+    // (the reference chains compareBit_g over the bits and XORs the sign difference in,
+    // Cipher.cu:574-584; same truth table, depth nbits instead of 1 + log2).
+    std::vector<int> greater(const std::vector<Bits> &a, const std::vector<Bits> &b, int nbits, bool is_signed) {
+        const int m = (int) a.size();
+        std::vector<Bits> G(m), P(m);
+        for (int i = 0; i < m; i++) {
+            G[i] = alloc_bits(nbits);
+            P[i] = alloc_bits(nbits);
+            for (int bit = 0; bit < nbits; bit++) {
+                const bool top = is_signed && bit == nbits - 1;
+                gate(top ? TFHE_B200_ANDNY : TFHE_B200_ANDYN, a[i][bit], b[i][bit], G[i][bit]);
+                if (bit > 0) gate(TFHE_B200_XNOR, a[i][bit], b[i][bit], P[i][bit]);  // P of bit 0 is never used
+            }
+        }
+        end_level();
+        // (G, P)[k] covers a group of bits; neighbours merge as hi o lo = (G_hi | P_hi & G_lo, P_hi & P_lo)
+        while (G[0].size() > 1) {
+            std::vector<Bits> G2(m), P2(m);
+            for (int i = 0; i < m; i++) {
+                const int n = (int) G[i].size();
+                for (int k = 0; k + 1 < n; k += 2) {
+                    const int g = alloc(1);
+                    gate(TFHE_B200_GPC, G[i][k + 1], P[i][k + 1], g, G[i][k]);
+                    G2[i].push_back(g);
+                    if (k > 0) {  // the group containing bit 0 never needs its propagate
+                        const int pr = alloc(1);
+                        gate(TFHE_B200_AND, P[i][k + 1], P[i][k], pr);
+                        P2[i].push_back(pr);
+                    } else {
+                        P2[i].push_back(-1);
+                    }
+                }
+                if (n & 1) {
+                    G2[i].push_back(G[i][n - 1]);
+                    P2[i].push_back(P[i][n - 1]);
+                }
+            }
+            end_level();
+            G.swap(G2);
+            P.swap(P2);
+        }
+        std::vector<int> res(m);
+        for (int i = 0; i < m; i++) res[i] = G[i][0];
+        return res;
+    }
+
+    // a == b: AND over the bits of a XNOR b (the reference ORs the XORs serially, Cipher.cu:600-616)
+    std::vector<int> equal(const std::vector<Bits> &a, const std::vector<Bits> &b, int nbits) {
+        const int m = (int) a.size();
+        std::vector<Bits> e(m);
+        for (int i = 0; i < m; i++) {
+            e[i] = alloc_bits(nbits);
+            for (int bit = 0; bit < nbits; bit++) gate(TFHE_B200_XNOR, a[i][bit], b[i][bit], e[i][bit]);
+        }
+        end_level();
+        return reduce_tree(TFHE_B200_AND, e);
+    }
+
+    // out = -a (twosComplement, Cipher.cu:286-298: out_i = a_i ^ (a_0 | ... | a_{i-1})), with the
+    // running OR computed as a Kogge-Stone scan instead of a serial chain.
+    void negate(const std::vector<Bits> &a, const std::vector<Bits> &out, int nbits) {
+        const int m = (int) a.size();
+        std::vector<Bits> r = a;  // r[k] = OR of bits [max(0, k-d+1), k]
+        for (int d = 1; d < nbits - 1; d *= 2) {
+            std::vector<Bits> r2 = r;
+            for (int i = 0; i < m; i++)
+                for (int k = d; k < nbits - 1; k++) {
+                    r2[i][k] = alloc(1);
+                    gate(TFHE_B200_OR, r[i][k], r[i][k - d], r2[i][k]);
+                }
+            end_level();
+            r.swap(r2);
+        }
+        for (int i = 0; i < m; i++) {
+            copy(a[i][0], out[i][0]);
+            for (int bit = 1; bit < nbits; bit++) gate(TFHE_B200_XOR, a[i][bit], r[i][bit - 1], out[i][bit]);
+        }
+        end_level();
     }
 };
 
@@ -247,6 +455,13 @@ tfhe_b200_circuit *new_plan(tfhe_b200_ctx *ctx) {
     return c;
 }
 
+// operand / result rows of `count` nbits-bit integers stored contiguously from row0
+std::vector<Bits> numbers_at(int row0, int count, int nbits) {
+    std::vector<Bits> v(count);
+    for (int i = 0; i < count; i++) v[i] = Builder::bits_at(row0 + i * nbits, nbits);
+    return v;
+}
+
 }  // namespace
 
 extern "C" {
@@ -263,13 +478,8 @@ tfhe_b200_circuit *tfhe_b200_circuit_add(tfhe_b200_ctx *ctx, int nbits, int coun
     c->out_rows = count * nbits;
     if (mode != 1) {
         c->out_row0 = B.alloc(count * nbits);
-        std::vector<int> va, vb, vo;
-        for (int i = 0; i < count; i++) {
-            va.push_back(a + i * nbits);
-            vb.push_back(b + i * nbits);
-            vo.push_back(c->out_row0 + i * nbits);
-        }
-        B.add(mode == 2 ? TFHE_B200_ADDER_PREFIX : TFHE_B200_ADDER_RIPPLE, va, vb, vo, nbits);
+        B.add(mode == 2 ? TFHE_B200_ADDER_PREFIX : TFHE_B200_ADDER_RIPPLE, numbers_at(a, count, nbits),
+              numbers_at(b, count, nbits), numbers_at(c->out_row0, count, nbits), nbits);
     } else {
         c->row_zero = B.alloc(1);
         // ping-pong sets: (x = running sum, y = shifted carries)
@@ -301,30 +511,28 @@ tfhe_b200_circuit *tfhe_b200_circuit_add(tfhe_b200_ctx *ctx, int nbits, int coun
 // a * b mod 2^nbits for `count` pairs (multiplyLweSamples main.cu:1483-1579, single precision;
 // BOOTS_vectorMultiplication :1746): one AND level over the partial-product matrix, then a
 // binary tree of lock-step adders (ripple carry as in the reference, or parallel prefix).
-static void build_mul(Builder &B, const std::vector<int> &a, const std::vector<int> &b, const std::vector<int> &out,
-                      int nbits, int adder) {
+static void build_mul(Builder &B, const std::vector<Bits> &a, const std::vector<Bits> &b,
+                      const std::vector<Bits> &out, int nbits, int adder) {
     const int m = (int) a.size();
     // addend rows R[i][p]: (a << i) & b_i ; bits below i are the constant 0 (the whole workspace
     // is initialised to the constant at run time, those rows are never written)
-    std::vector<std::vector<int>> R(nbits, std::vector<int>(m));
+    std::vector<std::vector<Bits>> R(nbits, std::vector<Bits>(m));
     for (int i = 0; i < nbits; i++)
-        for (int p = 0; p < m; p++) R[i][p] = B.alloc(nbits);
+        for (int p = 0; p < m; p++) R[i][p] = B.alloc_bits(nbits);
     for (int i = 0; i < nbits; i++)
         for (int p = 0; p < m; p++)
-            for (int k = 0; k < nbits; k++) {
-                if (k >= i) B.gate(TFHE_B200_AND, a[p] + (k - i), b[p] + i, R[i][p] + k);  // main.cu:1524
-            }
+            for (int k = i; k < nbits; k++) B.gate(TFHE_B200_AND, a[p][k - i], b[p][i], R[i][p][k]);  // main.cu:1524
     B.end_level();
     int live = nbits;
-    std::vector<std::vector<int>> cur = R;
+    std::vector<std::vector<Bits>> cur = R;
     while (live > 1) {
         const int half = live / 2;
-        std::vector<int> va, vb, vo;
-        std::vector<std::vector<int>> next;
+        std::vector<Bits> va, vb, vo;
+        std::vector<std::vector<Bits>> next;
         for (int i = 0; i < half; i++) {
-            std::vector<int> dst(m);
+            std::vector<Bits> dst(m);
             for (int p = 0; p < m; p++) {
-                dst[p] = (live == 2) ? out[p] : B.alloc(nbits);
+                dst[p] = (live == 2) ? out[p] : B.alloc_bits(nbits);
                 va.push_back(cur[i][p]);
                 vb.push_back(cur[i + half][p]);
                 vo.push_back(dst[p]);
@@ -346,13 +554,8 @@ tfhe_b200_circuit *tfhe_b200_circuit_mul_ex(tfhe_b200_ctx *ctx, int nbits, int c
     c->out_row0 = B.alloc(count * nbits);
     c->out_rows = count * nbits;
     c->row_zero = -2;  // whole workspace is initialised to the constant 0 at run time
-    std::vector<int> va, vb, vo;
-    for (int i = 0; i < count; i++) {
-        va.push_back(a + i * nbits);
-        vb.push_back(b + i * nbits);
-        vo.push_back(c->out_row0 + i * nbits);
-    }
-    build_mul(B, va, vb, vo, nbits, adder);
+    build_mul(B, numbers_at(a, count, nbits), numbers_at(b, count, nbits), numbers_at(c->out_row0, count, nbits), nbits,
+              adder);
     return finish(c);
 }
 
@@ -372,14 +575,15 @@ tfhe_b200_circuit *tfhe_b200_circuit_matmul_ex(tfhe_b200_ctx *ctx, int rows, int
     c->out_row0 = B.alloc(rows * cols * nbits);
     c->out_rows = rows * cols * nbits;
     c->row_zero = -2;
-    std::vector<int> va, vb, vo;
-    std::vector<std::vector<int>> prod(inner);
+    std::vector<Bits> va, vb, vo;
+    std::vector<std::vector<Bits>> prod(inner);
     for (int k = 0; k < inner; k++)
         for (int r = 0; r < rows; r++)
             for (int q = 0; q < cols; q++) {
-                va.push_back(A + (r * inner + k) * nbits);      // matMul_prepareLeftMat matrixUtility.cu:65
-                vb.push_back(Bm + (k * cols + q) * nbits);      // matMul_prepareRightMat :82
-                const int dst = (inner == 1) ? c->out_row0 + (r * cols + q) * nbits : B.alloc(nbits);
+                va.push_back(Builder::bits_at(A + (r * inner + k) * nbits, nbits));   // matMul_prepareLeftMat matrixUtility.cu:65
+                vb.push_back(Builder::bits_at(Bm + (k * cols + q) * nbits, nbits));   // matMul_prepareRightMat :82
+                const Bits dst = (inner == 1) ? Builder::bits_at(c->out_row0 + (r * cols + q) * nbits, nbits)
+                                              : B.alloc_bits(nbits);
                 vo.push_back(dst);
                 prod[k].push_back(dst);
             }
@@ -387,12 +591,12 @@ tfhe_b200_circuit *tfhe_b200_circuit_matmul_ex(tfhe_b200_ctx *ctx, int rows, int
     int live = inner;
     while (live > 1) {
         const int half = live / 2;
-        std::vector<int> xa, xb, xo;
-        std::vector<std::vector<int>> next;
+        std::vector<Bits> xa, xb, xo;
+        std::vector<std::vector<Bits>> next;
         for (int k = 0; k < half; k++) {
-            std::vector<int> dst(rows * cols);
+            std::vector<Bits> dst(rows * cols);
             for (int e = 0; e < rows * cols; e++) {
-                dst[e] = (live == 2) ? c->out_row0 + e * nbits : B.alloc(nbits);
+                dst[e] = (live == 2) ? Builder::bits_at(c->out_row0 + e * nbits, nbits) : B.alloc_bits(nbits);
                 xa.push_back(prod[k][e]);
                 xb.push_back(prod[k + half][e]);
                 xo.push_back(dst[e]);
@@ -411,28 +615,223 @@ tfhe_b200_circuit *tfhe_b200_circuit_matmul(tfhe_b200_ctx *ctx, int rows, int in
     return tfhe_b200_circuit_matmul_ex(ctx, rows, inner, cols, nbits, TFHE_B200_ADDER_RIPPLE);
 }
 
-// Evaluates the plan on PLAINTEXT bits on the host (one int per sample row): the schedule's
-// logic can be checked without keys or a GPU.  operand_bits[o]: operand_rows(o) ints in {0,1}.
-int tfhe_b200_circuit_simulate(const tfhe_b200_circuit *c, int32_t *out_bits, const int32_t *const *operand_bits) {
-    if (!c || !out_bits || !operand_bits) return fail_msg("null argument");
-    std::vector<int32_t> ws((size_t) c->nrows, 0);
-    for (size_t o = 0; o < c->in_row0.size(); o++)
-        for (int r = 0; r < c->in_rows[o]; r++) ws[c->in_row0[o] + r] = operand_bits[o][r] & 1;
-    for (const Level &lv : c->levels) {
-        // all gates of a level read the state before the level (they run as one batch)
-        std::vector<std::pair<int, int32_t>> writes;
-        for (int i = 0; i < lv.nops; i++) {
-            const Op &op = lv.ops[i];
-            for (int g = 0; g < op.count; g++) {
-                const int a = ws[c->h_idx[op.off_a + g]], b = ws[c->h_idx[op.off_b + g]];
-                const int c3 = op.off_c >= 0 ? ws[c->h_idx[op.off_c + g]] : 0;
-                writes.emplace_back(c->h_idx[op.off_out + g], gate_truth(op.gate, a, b, c3));
-            }
-        }
-        for (const auto &w : writes) ws[w.first] = w.second;
+// ---- the rest of the Cipher arithmetic (Cipher.cu:237-630) as plans ------------------------
+
+// a - b mod 2^nbits (operator-, Cipher.cu:329-332)
+tfhe_b200_circuit *tfhe_b200_circuit_sub(tfhe_b200_ctx *ctx, int nbits, int count, int adder) {
+    if (nbits < 1 || count < 1 || adder < 0 || adder > 1) return nullptr;
+    tfhe_b200_circuit *c = new_plan(ctx);
+    Builder B(c);
+    const int a = B.operand(count * nbits), b = B.operand(count * nbits);
+    c->out_row0 = B.alloc(count * nbits);
+    c->out_rows = count * nbits;
+    B.sub(adder, numbers_at(a, count, nbits), numbers_at(b, count, nbits), numbers_at(c->out_row0, count, nbits), nbits);
+    return finish(c);
+}
+
+// -a mod 2^nbits (twosComplement, Cipher.cu:286-298)
+tfhe_b200_circuit *tfhe_b200_circuit_neg(tfhe_b200_ctx *ctx, int nbits, int count) {
+    if (nbits < 1 || count < 1) return nullptr;
+    tfhe_b200_circuit *c = new_plan(ctx);
+    Builder B(c);
+    const int a = B.operand(count * nbits);
+    c->out_row0 = B.alloc(count * nbits);
+    c->out_rows = count * nbits;
+    B.negate(numbers_at(a, count, nbits), numbers_at(c->out_row0, count, nbits), nbits);
+    return finish(c);
+}
+
+// One result bit per pair: op = TFHE_B200_CMP_* (operator>, operator<=, operator== of Cipher.cu:561-616
+// and their complements).
+tfhe_b200_circuit *tfhe_b200_circuit_compare(tfhe_b200_ctx *ctx, int nbits, int count, int op, int is_signed) {
+    if (nbits < 1 || count < 1 || op < 0 || op > TFHE_B200_CMP_NE) return nullptr;
+    tfhe_b200_circuit *c = new_plan(ctx);
+    Builder B(c);
+    const int a = B.operand(count * nbits), b = B.operand(count * nbits);
+    c->out_row0 = B.alloc(count);
+    c->out_rows = count;
+    const std::vector<Bits> va = numbers_at(a, count, nbits), vb = numbers_at(b, count, nbits);
+    std::vector<int> r;
+    bool invert = false;
+    switch (op) {
+        case TFHE_B200_CMP_GT: r = B.greater(va, vb, nbits, is_signed != 0); break;
+        case TFHE_B200_CMP_LE: r = B.greater(va, vb, nbits, is_signed != 0); invert = true; break;
+        case TFHE_B200_CMP_LT: r = B.greater(vb, va, nbits, is_signed != 0); break;
+        case TFHE_B200_CMP_GE: r = B.greater(vb, va, nbits, is_signed != 0); invert = true; break;
+        case TFHE_B200_CMP_EQ: r = B.equal(va, vb, nbits); break;
+        default: r = B.equal(va, vb, nbits); invert = true; break;
     }
-    for (int r = 0; r < c->out_rows; r++) out_bits[r] = ws[c->out_row0 + r];
-    return 0;
+    for (int i = 0; i < count; i++) {
+        if (invert) B.not_(r[i], c->out_row0 + i);
+        else B.copy(r[i], c->out_row0 + i);
+    }
+    B.end_level();
+    return finish(c);
+}
+
+// min(a, b) / max(a, b) (minimum, Cipher.cu:301-320: comparison, then one bootsMUX per bit)
+tfhe_b200_circuit *tfhe_b200_circuit_minmax(tfhe_b200_ctx *ctx, int nbits, int count, int want_max, int is_signed) {
+    if (nbits < 1 || count < 1) return nullptr;
+    tfhe_b200_circuit *c = new_plan(ctx);
+    Builder B(c);
+    const int a = B.operand(count * nbits), b = B.operand(count * nbits);
+    c->out_row0 = B.alloc(count * nbits);
+    c->out_rows = count * nbits;
+    const std::vector<Bits> va = numbers_at(a, count, nbits), vb = numbers_at(b, count, nbits);
+    const std::vector<int> gt = B.greater(va, vb, nbits, is_signed != 0);
+    for (int i = 0; i < count; i++)
+        for (int bit = 0; bit < nbits; bit++) {
+            const int out = c->out_row0 + i * nbits + bit;
+            if (want_max) B.mux(gt[i], va[i][bit], vb[i][bit], out);
+            else B.mux(gt[i], vb[i][bit], va[i][bit], out);
+        }
+    B.end_level();
+    return finish(c);
+}
+
+// sel ? a : b for count numbers (one selector bit per number; bootsMUX per bit, Cipher::mux)
+tfhe_b200_circuit *tfhe_b200_circuit_select(tfhe_b200_ctx *ctx, int nbits, int count) {
+    if (nbits < 1 || count < 1) return nullptr;
+    tfhe_b200_circuit *c = new_plan(ctx);
+    Builder B(c);
+    const int sel = B.operand(count), a = B.operand(count * nbits), b = B.operand(count * nbits);
+    c->out_row0 = B.alloc(count * nbits);
+    c->out_rows = count * nbits;
+    for (int i = 0; i < count; i++)
+        for (int bit = 0; bit < nbits; bit++)
+            B.mux(sel + i, a + i * nbits + bit, b + i * nbits + bit, c->out_row0 + i * nbits + bit);
+    B.end_level();
+    return finish(c);
+}
+
+// |a| for two's complement a (absolute, Cipher.cu:469-492: mask = sign bit replicated,
+// (a + mask) ^ mask)
+static void build_abs(Builder &B, const std::vector<Bits> &a, const std::vector<Bits> &out, int nbits, int adder) {
+    const int m = (int) a.size();
+    std::vector<Bits> mask(m), sum(m);
+    for (int i = 0; i < m; i++) {
+        mask[i].assign(nbits, a[i][nbits - 1]);  // every bit of the mask IS the sign row
+        sum[i] = B.alloc_bits(nbits);
+    }
+    B.add(adder, a, mask, sum, nbits);
+    for (int i = 0; i < m; i++)
+        for (int bit = 0; bit < nbits; bit++) B.gate(TFHE_B200_XOR, sum[i][bit], a[i][nbits - 1], out[i][bit]);
+    B.end_level();
+}
+
+tfhe_b200_circuit *tfhe_b200_circuit_abs(tfhe_b200_ctx *ctx, int nbits, int count, int adder) {
+    if (nbits < 2 || count < 1 || adder < 0 || adder > 1) return nullptr;
+    tfhe_b200_circuit *c = new_plan(ctx);
+    Builder B(c);
+    const int a = B.operand(count * nbits);
+    c->out_row0 = B.alloc(count * nbits);
+    c->out_rows = count * nbits;
+    build_abs(B, numbers_at(a, count, nbits), numbers_at(c->out_row0, count, nbits), nbits, adder);
+    return finish(c);
+}
+
+// Shifts by a public amount: kind = TFHE_B200_SHIFT_LEFT (innerLeftShift, Cipher.cu:215-228: zeros
+// come in), _RIGHT_LOGICAL, _RIGHT_ARITH (sign fill: the copy part of rightShift, Cipher.cu:237-246).
+// Bootstrap free.
+tfhe_b200_circuit *tfhe_b200_circuit_shift(tfhe_b200_ctx *ctx, int nbits, int count, int amount, int kind) {
+    if (nbits < 1 || count < 1 || amount < 0 || kind < 0 || kind > TFHE_B200_SHIFT_RIGHT_ARITH) return nullptr;
+    tfhe_b200_circuit *c = new_plan(ctx);
+    Builder B(c);
+    const int a = B.operand(count * nbits);
+    c->out_row0 = B.alloc(count * nbits);
+    c->out_rows = count * nbits;
+    for (int i = 0; i < count; i++)
+        for (int bit = 0; bit < nbits; bit++) {
+            const int out = c->out_row0 + i * nbits + bit;
+            const int src = (kind == TFHE_B200_SHIFT_LEFT) ? bit - amount : bit + amount;
+            if (src >= 0 && src < nbits) B.copy(a + i * nbits + src, out);
+            else if (kind == TFHE_B200_SHIFT_RIGHT_ARITH) B.copy(a + i * nbits + nbits - 1, out);
+            else B.constant(0, out);
+        }
+    B.end_level();
+    return finish(c);
+}
+
+// Division (operator/, divInternal, addSign; Cipher.cu:494-559): restoring division of the
+// absolute values, nbits rounds of shift / subtract / select, then the sign of the quotient.
+// Output per pair: quotient (nbits rows) followed by remainder (nbits rows; the remainder of
+// |a| / |b|, as divInternal leaves it).  is_signed = 0: operands are unsigned, no sign handling.
+// Division by zero gives the all-ones quotient pattern of the restoring algorithm (reference too).
+tfhe_b200_circuit *tfhe_b200_circuit_div(tfhe_b200_ctx *ctx, int nbits, int count, int is_signed, int adder) {
+    if (nbits < 2 || count < 1 || adder < 0 || adder > 1) return nullptr;
+    tfhe_b200_circuit *c = new_plan(ctx);
+    Builder B(c);
+    const int a = B.operand(count * nbits), b = B.operand(count * nbits);
+    c->out_row0 = B.alloc(count * 2 * nbits);
+    c->out_rows = count * 2 * nbits;
+    c->row_zero = B.alloc(1);
+    std::vector<Bits> ua = numbers_at(a, count, nbits), ub = numbers_at(b, count, nbits);
+    if (is_signed) {
+        std::vector<Bits> both, both_out;
+        for (int i = 0; i < count; i++) {
+            both.push_back(ua[i]);
+            both_out.push_back(B.alloc_bits(nbits));
+        }
+        for (int i = 0; i < count; i++) {
+            both.push_back(ub[i]);
+            both_out.push_back(B.alloc_bits(nbits));
+        }
+        build_abs(B, both, both_out, nbits, adder);
+        for (int i = 0; i < count; i++) {
+            ua[i] = both_out[i];
+            ub[i] = both_out[count + i];
+        }
+    }
+    // the subtraction runs on nbits + 1 bits (P can exceed nbits bits by one before the restore)
+    const int w = nbits + 1;
+    std::vector<Bits> P(count), A = ua, Bx(count);  // P: partial remainder (w bits), A: dividend bits still to shift in
+    for (int i = 0; i < count; i++) {
+        P[i].assign(w, c->row_zero);
+        Bx[i] = ub[i];
+        Bx[i].push_back(c->row_zero);  // zero-extended divisor
+    }
+    std::vector<Bits> quot(count, Bits(nbits, -1));
+    for (int step = 0; step < nbits; step++) {
+        // PA <<= 1 : P takes the top dividend bit (index renaming only)
+        std::vector<Bits> Ps(count), diff(count);
+        for (int i = 0; i < count; i++) {
+            Ps[i].resize(w);
+            Ps[i][0] = A[i][nbits - 1 - step];
+            for (int k = 1; k < w; k++) Ps[i][k] = P[i][k - 1];
+            diff[i] = B.alloc_bits(w);
+        }
+        B.sub(adder, Ps, Bx, diff, w);
+        // quotient bit = NOT sign(diff); P = sign ? Ps : diff   (divInternal, Cipher.cu:524-541)
+        for (int i = 0; i < count; i++) {
+            quot[i][nbits - 1 - step] = B.alloc(1);
+            B.not_(diff[i][w - 1], quot[i][nbits - 1 - step]);
+            Bits np = B.alloc_bits(w);
+            for (int k = 0; k < w; k++) B.mux(diff[i][w - 1], Ps[i][k], diff[i][k], np[k]);
+            P[i] = np;
+        }
+        B.end_level();
+    }
+    if (is_signed) {
+        // addSign (Cipher.cu:543-559): negate the quotient when the operand signs differ
+        std::vector<Bits> nq(count);
+        std::vector<int> sgn(count);
+        for (int i = 0; i < count; i++) {
+            nq[i] = B.alloc_bits(nbits);
+            sgn[i] = B.alloc(1);
+            B.gate(TFHE_B200_XOR, a + i * nbits + nbits - 1, b + i * nbits + nbits - 1, sgn[i]);
+        }
+        B.end_level();
+        B.negate(quot, nq, nbits);
+        for (int i = 0; i < count; i++)
+            for (int k = 0; k < nbits; k++) B.mux(sgn[i], nq[i][k], quot[i][k], c->out_row0 + i * 2 * nbits + k);
+    } else {
+        for (int i = 0; i < count; i++)
+            for (int k = 0; k < nbits; k++) B.copy(quot[i][k], c->out_row0 + i * 2 * nbits + k);
+    }
+    for (int i = 0; i < count; i++)
+        for (int k = 0; k < nbits; k++) B.copy(P[i][k], c->out_row0 + i * 2 * nbits + nbits + k);
+    B.end_level();
+    return finish(c);
 }
 
 void tfhe_b200_circuit_destroy(tfhe_b200_circuit *c) {
@@ -442,7 +841,7 @@ void tfhe_b200_circuit_destroy(tfhe_b200_circuit *c) {
     delete c;
 }
 
-int tfhe_b200_circuit_levels(const tfhe_b200_circuit *c) { return c ? (int) c->levels.size() : 0; }
+int tfhe_b200_circuit_levels(const tfhe_b200_circuit *c) { return c ? c->depth : 0; }
 long long tfhe_b200_circuit_gates(const tfhe_b200_circuit *c) { return c ? c->n_gates : 0; }
 int tfhe_b200_circuit_operands(const tfhe_b200_circuit *c) { return c ? (int) c->in_row0.size() : 0; }
 int tfhe_b200_circuit_operand_rows(const tfhe_b200_circuit *c, int o) {
@@ -467,26 +866,74 @@ int tfhe_b200_circuit_run(tfhe_b200_circuit *c, int32_t *d_out, const int32_t *c
                             cudaMemcpyDeviceToDevice, st) != cudaSuccess)
             return fail_msg("operand copy failed");
     for (const Level &lv : c->levels) {
-        tfhe_b200_gate_op ops[4];
-        for (int i = 0; i < lv.nops; i++) {
-            const Op &op = lv.ops[i];
-            ops[i].gate = op.gate;
-            ops[i].count = op.count;
-            ops[i].a = ops[i].b = c->d_ws;
-            ops[i].out = c->d_ws;
-            ops[i].stride_a = ops[i].stride_b = ops[i].stride_out = c->words;
-            ops[i].idx_a = c->d_idx + op.off_a;
-            ops[i].idx_b = c->d_idx + op.off_b;
-            ops[i].idx_out = c->d_idx + op.off_out;
-            ops[i].c = op.off_c >= 0 ? c->d_ws : nullptr;
-            ops[i].stride_c = c->words;
-            ops[i].idx_c = op.off_c >= 0 ? c->d_idx + op.off_c : nullptr;
+        if (lv.type == LV_GATES) {
+            tfhe_b200_gate_op ops[4];
+            for (int i = 0; i < lv.nops; i++) {
+                const Op &op = lv.ops[i];
+                ops[i].gate = op.gate;
+                ops[i].count = op.count;
+                ops[i].a = ops[i].b = c->d_ws;
+                ops[i].out = c->d_ws;
+                ops[i].stride_a = ops[i].stride_b = ops[i].stride_out = c->words;
+                ops[i].idx_a = c->d_idx + op.off_a;
+                ops[i].idx_b = c->d_idx + op.off_b;
+                ops[i].idx_out = c->d_idx + op.off_out;
+                ops[i].c = op.off_c >= 0 ? c->d_ws : nullptr;
+                ops[i].stride_c = c->words;
+                ops[i].idx_c = op.off_c >= 0 ? c->d_idx + op.off_c : nullptr;
+            }
+            if (tfhe_b200_gate_multi(c->ctx, ops, lv.nops, stream)) return 1;
+        } else if (lv.type == LV_MUX) {
+            const Op &op = lv.ops[0];
+            if (tfhe_b200_mux_gather(c->ctx, c->d_ws, c->words, c->d_idx + op.off_a, c->d_idx + op.off_b,
+                                     c->d_idx + op.off_c, c->d_idx + op.off_out, op.count, stream))
+                return 1;
+        } else {
+            const Op &op = lv.ops[0];
+            const int coef = op.gate == LIN_COPY ? 1 : (op.gate == LIN_NOT ? -1 : 0);
+            const int32_t cst = op.gate == LIN_ONE ? 0x20000000 : (op.gate == LIN_ZERO ? (int32_t) 0xE0000000 : 0);
+            if (tfhe_b200_linear_gather(c->ctx, c->d_ws, c->words, c->d_idx + op.off_a, c->d_idx + op.off_out, coef,
+                                        cst, op.count, stream))
+                return 1;
         }
-        if (tfhe_b200_gate_multi(c->ctx, ops, lv.nops, stream)) return 1;
     }
     if (cudaMemcpyAsync(d_out, c->d_ws + (size_t) c->out_row0 * c->words, rb * c->out_rows,
                         cudaMemcpyDeviceToDevice, st) != cudaSuccess)
         return fail_msg("result copy failed");
+    return 0;
+}
+
+// Evaluates the plan on PLAINTEXT bits on the host (one int per sample row), group by group
+// in the order the device runs them: the schedule's logic can be checked without keys or a GPU.
+// operand_bits[o]: operand_rows(o) ints in {0,1}.
+int tfhe_b200_circuit_simulate(const tfhe_b200_circuit *c, int32_t *out_bits, const int32_t *const *operand_bits) {
+    if (!c || !out_bits || !operand_bits) return fail_msg("null argument");
+    std::vector<int32_t> ws((size_t) c->nrows, 0);
+    for (size_t o = 0; o < c->in_row0.size(); o++)
+        for (int r = 0; r < c->in_rows[o]; r++) ws[c->in_row0[o] + r] = operand_bits[o][r] & 1;
+    for (const Level &lv : c->levels) {
+        // all gates of a group read the state before the group (they run as one batch)
+        std::vector<std::pair<int, int32_t>> writes;
+        for (int i = 0; i < lv.nops; i++) {
+            const Op &op = lv.ops[i];
+            for (int g = 0; g < op.count; g++) {
+                int v;
+                if (lv.type == LV_GATES) {
+                    const int a = ws[c->h_idx[op.off_a + g]], b = ws[c->h_idx[op.off_b + g]];
+                    const int c3 = op.off_c >= 0 ? ws[c->h_idx[op.off_c + g]] : 0;
+                    v = gate_truth(op.gate, a, b, c3);
+                } else if (lv.type == LV_MUX) {
+                    v = ws[c->h_idx[op.off_a + g]] ? ws[c->h_idx[op.off_b + g]] : ws[c->h_idx[op.off_c + g]];
+                } else {
+                    const int in = ws[c->h_idx[op.off_a + g]];
+                    v = op.gate == LIN_COPY ? in : (op.gate == LIN_NOT ? !in : (op.gate == LIN_ONE ? 1 : 0));
+                }
+                writes.emplace_back(c->h_idx[op.off_out + g], v);
+            }
+        }
+        for (const auto &w : writes) ws[w.first] = w.second;
+    }
+    for (int r = 0; r < c->out_rows; r++) out_bits[r] = ws[c->out_row0 + r];
     return 0;
 }
 

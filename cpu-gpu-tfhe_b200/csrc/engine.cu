@@ -455,6 +455,49 @@ int tfhe_b200_mux(tfhe_b200_ctx *c, int32_t *d_out, const int32_t *d_a, const in
     return run_bootstrap_ks(c, L, 2, kMu, d_out, count, (cudaStream_t) stream);
 }
 
+// bootsMUX on rows of one sample array: out row idx_out[g] = MUX(row idx_a[g], row idx_b[g], row idx_c[g])
+// (rows are `stride` words apart; index arrays in device memory).  Used by the circuit plans.
+int tfhe_b200_mux_gather(tfhe_b200_ctx *c, int32_t *d_rows, int64_t stride, const int32_t *idx_a,
+                         const int32_t *idx_b, const int32_t *idx_c, const int32_t *idx_out, int count,
+                         void *stream) {
+    if (check_ctx(c, true, true)) return 1;
+    if (count < 0) return fail("negative count");
+    if (count == 0) return 0;
+    if (!d_rows || !idx_a || !idx_b || !idx_c || !idx_out) return fail("null argument");
+    BrLaunch L = base_launch(c);
+    L.nseg = 2;
+    L.total = 2 * count;
+    const GateDef g1 = {-kMu, 1, 1}, g2 = {-kMu, -1, 1};
+    set_segment(L.seg[0], g1, d_rows, d_rows, c->p.n, count);
+    set_segment(L.seg[1], g2, d_rows, d_rows, c->p.n, count);
+    for (int s = 0; s < 2; s++) {
+        L.seg[s].stride0 = L.seg[s].stride1 = stride;
+        L.seg[s].idx0 = idx_a;
+    }
+    L.seg[0].idx1 = idx_b;
+    L.seg[1].idx1 = idx_c;
+    KsLaunch::Out dst;
+    dst.out = d_rows;
+    dst.stride = stride;
+    dst.count = count;
+    dst.idx = idx_out;
+    return run_bootstrap_ks(c, L, 2, kMu, nullptr, count, (cudaStream_t) stream, &dst, 1);
+}
+
+// Bootstrap-free ops on rows of one sample array: out row idx_out[g] = coef * (row idx_in[g]) + (0, cst)
+// (coef = 1: bootsCOPY, coef = -1: bootsNOT, coef = 0 and cst = +-1/8: bootsCONSTANT).
+int tfhe_b200_linear_gather(tfhe_b200_ctx *c, int32_t *d_rows, int64_t stride, const int32_t *idx_in,
+                            const int32_t *idx_out, int coef, int32_t cst, int count, void *stream) {
+    if (check_ctx(c, false, false)) return 1;
+    if (count < 0) return fail("negative count");
+    if (count == 0) return 0;
+    if (!d_rows || !idx_out || (coef != 0 && !idx_in)) return fail("null argument");
+    CU(cudaSetDevice(c->device));
+    CU(launch_lwe_linear_idx(d_rows, d_rows, stride, idx_out, idx_in, coef, cst, count, c->p.n, (cudaStream_t) stream));
+    c->launches += 1;
+    return 0;
+}
+
 int tfhe_b200_not(tfhe_b200_ctx *c, int32_t *d_out, const int32_t *d_ca, int count, void *stream) {
     if (check_ctx(c, false, false)) return 1;
     CU(cudaSetDevice(c->device));

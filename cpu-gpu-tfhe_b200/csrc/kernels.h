@@ -93,4 +93,7 @@ cudaError_t launch_lwe_linear(int32_t *out, long long out_stride, const int32_t 
                               const int32_t *in1, long long s1, int c1, int32_t cst, int count, int n,
                               cudaStream_t stream);
 
+cudaError_t launch_lwe_linear_idx(int32_t *out, const int32_t *in, long long stride, const int32_t *idx_out,
+                                  const int32_t *idx_in, int c0, int32_t cst, int count, int n, cudaStream_t stream);
+
 }  // namespace tfhe_b200

@@ -161,7 +161,30 @@ __global__ void lwe_linear_kernel(int32_t *out, long long so, const int32_t *in0
     out[g * so + c] = (int32_t) v;
 }
 
+// gather / scatter form: out row idx_out[g] = c0 * (in row idx_in[g]) + (0, cst)
+__global__ void lwe_linear_idx_kernel(int32_t *out, const int32_t *in, long long stride, const int32_t *idx_out,
+                                      const int32_t *idx_in, int c0, int32_t cst, int count, int n) {
+    const long long t = (long long) blockIdx.x * blockDim.x + threadIdx.x;
+    const int words = n + 1;
+    if (t >= (long long) count * words) return;
+    const int g = (int) (t / words);
+    const int c = (int) (t % words);
+    uint32_t v = 0;
+    if (c0 != 0) v = (uint32_t) c0 * (uint32_t) in[(long long) __ldg(idx_in + g) * stride + c];
+    if (c == n) v += (uint32_t) cst;
+    out[(long long) __ldg(idx_out + g) * stride + c] = (int32_t) v;
+}
+
 }  // namespace
+
+cudaError_t launch_lwe_linear_idx(int32_t *out, const int32_t *in, long long stride, const int32_t *idx_out,
+                                  const int32_t *idx_in, int c0, int32_t cst, int count, int n, cudaStream_t stream) {
+    if (count <= 0) return cudaSuccess;
+    const long long total = (long long) count * (n + 1);
+    lwe_linear_idx_kernel<<<(unsigned) ((total + 255) / 256), 256, 0, stream>>>(out, in, stride, idx_out, idx_in, c0,
+                                                                                cst, count, n);
+    return cudaGetLastError();
+}
 
 cudaError_t launch_keyswitch(const KsLaunch &L, int sm_count, cudaStream_t stream) {
     if (L.count <= 0) return cudaSuccess;

@@ -120,6 +120,14 @@ int tfhe_b200_gate_multi(tfhe_b200_ctx *ctx, const tfhe_b200_gate_op *ops, int n
 /* MUX(a,b,c) = a ? b : c  (bootsMUX, boot-gates.cu:407-448; bootsMUX_fullGPU_n_Bit :2987) */
 int tfhe_b200_mux(tfhe_b200_ctx *ctx, int32_t *d_out, const int32_t *d_a, const int32_t *d_b,
                   const int32_t *d_c, int count, void *stream);
+/* The same on rows of ONE sample array addressed through device index tables (circuit plans):
+ * row idx_out[g] = MUX(row idx_a[g], row idx_b[g], row idx_c[g]); rows are `stride` words apart */
+int tfhe_b200_mux_gather(tfhe_b200_ctx *ctx, int32_t *d_rows, int64_t stride, const int32_t *idx_a,
+                         const int32_t *idx_b, const int32_t *idx_c, const int32_t *idx_out, int count,
+                         void *stream);
+/* row idx_out[g] = coef * (row idx_in[g]) + (0, cst): coef 1 = COPY, -1 = NOT, 0 = CONSTANT (no bootstrap) */
+int tfhe_b200_linear_gather(tfhe_b200_ctx *ctx, int32_t *d_rows, int64_t stride, const int32_t *idx_in,
+                            const int32_t *idx_out, int coef, int32_t cst, int count, void *stream);
 /* bootsNOT :242, bootsCOPY :253, bootsCONSTANT :263 — no bootstrap */
 int tfhe_b200_not(tfhe_b200_ctx *ctx, int32_t *d_out, const int32_t *d_ca, int count, void *stream);
 int tfhe_b200_copy(tfhe_b200_ctx *ctx, int32_t *d_out, const int32_t *d_ca, int count, void *stream);
@@ -167,6 +175,29 @@ tfhe_b200_circuit *tfhe_b200_circuit_mul_ex(tfhe_b200_ctx *ctx, int nbits, int c
 tfhe_b200_circuit *tfhe_b200_circuit_matmul(tfhe_b200_ctx *ctx, int rows, int inner, int cols, int nbits);
 tfhe_b200_circuit *tfhe_b200_circuit_matmul_ex(tfhe_b200_ctx *ctx, int rows, int inner, int cols, int nbits,
                                                int adder);
+/* ---- the rest of the Cipher arithmetic (Cipher.cu:237-630) ------------------
+ * Same plan machinery; `adder` as above.  All operands have count numbers of nbits bits. */
+/* a - b (operator-, Cipher.cu:329) and -a (twosComplement, :286) */
+tfhe_b200_circuit *tfhe_b200_circuit_sub(tfhe_b200_ctx *ctx, int nbits, int count, int adder);
+tfhe_b200_circuit *tfhe_b200_circuit_neg(tfhe_b200_ctx *ctx, int nbits, int count);
+/* comparisons, ONE result bit per pair (operator> :561, operator<= :574, operator== :600) */
+enum {
+    TFHE_B200_CMP_GT = 0, TFHE_B200_CMP_LE = 1, TFHE_B200_CMP_LT = 2, TFHE_B200_CMP_GE = 3,
+    TFHE_B200_CMP_EQ = 4, TFHE_B200_CMP_NE = 5
+};
+tfhe_b200_circuit *tfhe_b200_circuit_compare(tfhe_b200_ctx *ctx, int nbits, int count, int op, int is_signed);
+/* min / max (minimum, :301) */
+tfhe_b200_circuit *tfhe_b200_circuit_minmax(tfhe_b200_ctx *ctx, int nbits, int count, int want_max, int is_signed);
+/* sel ? a : b; operands: sel[count] (one bit per number), a[count][nbits], b[count][nbits] */
+tfhe_b200_circuit *tfhe_b200_circuit_select(tfhe_b200_ctx *ctx, int nbits, int count);
+/* |a| for two's complement a (absolute, :469) */
+tfhe_b200_circuit *tfhe_b200_circuit_abs(tfhe_b200_ctx *ctx, int nbits, int count, int adder);
+/* shifts by a public amount (innerLeftShift :215, rightShift :237); no bootstrap */
+enum { TFHE_B200_SHIFT_LEFT = 0, TFHE_B200_SHIFT_RIGHT_LOGICAL = 1, TFHE_B200_SHIFT_RIGHT_ARITH = 2 };
+tfhe_b200_circuit *tfhe_b200_circuit_shift(tfhe_b200_ctx *ctx, int nbits, int count, int amount, int kind);
+/* a / b (operator/ :494, divInternal :515, addSign :543): output per pair = quotient[nbits] then
+ * remainder[nbits] of |a| / |b| (is_signed) or of a / b (unsigned) */
+tfhe_b200_circuit *tfhe_b200_circuit_div(tfhe_b200_ctx *ctx, int nbits, int count, int is_signed, int adder);
 void tfhe_b200_circuit_destroy(tfhe_b200_circuit *c);
 int tfhe_b200_circuit_levels(const tfhe_b200_circuit *c);      /* sequential bootstrap batches */
 long long tfhe_b200_circuit_gates(const tfhe_b200_circuit *c); /* bootstrapped gates per run   */

@@ -82,3 +82,131 @@ def test_matrix_multiply_schedule(pkg, adder):
 def test_plan_without_engine_cannot_run(pkg):
     circ = pkg.Circuit(None, "add", 4, 1, 2)
     assert circ.eng is None and circ.gates > 0
+
+
+# ---- the rest of the Cipher arithmetic (Cipher.cu:237-630) -------------------------------------
+
+def signed(v, nbits):
+    v = np.asarray(v, dtype=np.int64) % 2 ** nbits
+    return np.where(v >= 2 ** (nbits - 1), v - 2 ** nbits, v)
+
+
+def all_pairs(nbits):
+    v = np.arange(2 ** nbits)
+    a, b = np.meshgrid(v, v, indexing="ij")
+    return a.reshape(-1), b.reshape(-1)
+
+
+@pytest.mark.parametrize("adder", [0, 1])
+@pytest.mark.parametrize("nbits", [1, 2, 4, 5])
+def test_subtraction_exhaustive(pkg, nbits, adder):
+    a, b = all_pairs(nbits)
+    circ = pkg.Circuit(None, "sub", nbits, len(a), adder)
+    out = circ.simulate(to_bits(a, nbits), to_bits(b, nbits))
+    assert np.array_equal(from_bits(out, nbits), (a - b) % 2 ** nbits)
+
+
+@pytest.mark.parametrize("nbits", [1, 2, 3, 6, 9])
+def test_negation_exhaustive(pkg, nbits):
+    a = np.arange(2 ** nbits)
+    circ = pkg.Circuit(None, "neg", nbits, len(a))
+    assert np.array_equal(from_bits(circ.simulate(to_bits(a, nbits)), nbits), (-a) % 2 ** nbits)
+    if nbits == 9:
+        assert circ.levels == 1 + 3  # OR scan over 8 positions + the XOR level
+
+
+@pytest.mark.parametrize("is_signed", [0, 1])
+@pytest.mark.parametrize("nbits", [1, 2, 3, 5])
+def test_comparisons_exhaustive(pkg, nbits, is_signed):
+    a, b = all_pairs(nbits)
+    xa, xb = (signed(a, nbits), signed(b, nbits)) if is_signed else (a, b)
+    expect = {"GT": xa > xb, "LE": xa <= xb, "LT": xa < xb, "GE": xa >= xb, "EQ": xa == xb, "NE": xa != xb}
+    for name, code in pkg.CMP.items():
+        circ = pkg.Circuit(None, "compare", nbits, len(a), code, is_signed)
+        out = circ.simulate(to_bits(a, nbits), to_bits(b, nbits))
+        assert np.array_equal(out.astype(bool), expect[name]), name
+
+
+def test_comparison_depth(pkg):
+    """16-bit a > b: 1 + log2(16) bootstrap levels (the reference chains 16 x 4 gates, Cipher.cu:561-598)."""
+    assert pkg.Circuit(None, "compare", 16, 1, pkg.CMP["GT"], 1).levels == 5
+    assert pkg.Circuit(None, "compare", 16, 1, pkg.CMP["EQ"], 0).levels == 5
+
+
+@pytest.mark.parametrize("is_signed", [0, 1])
+@pytest.mark.parametrize("want_max", [0, 1])
+def test_min_max_exhaustive(pkg, want_max, is_signed):
+    nbits = 4
+    a, b = all_pairs(nbits)
+    xa, xb = (signed(a, nbits), signed(b, nbits)) if is_signed else (a, b)
+    circ = pkg.Circuit(None, "minmax", nbits, len(a), want_max, is_signed)
+    out = from_bits(circ.simulate(to_bits(a, nbits), to_bits(b, nbits)), nbits)
+    expect = np.where((xa > xb) == bool(want_max), a, b)
+    assert np.array_equal(out, expect)
+
+
+def test_select(pkg):
+    nbits, count = 6, 50
+    rng = np.random.default_rng(5)
+    sel = rng.integers(0, 2, count)
+    a, b = rng.integers(0, 64, count), rng.integers(0, 64, count)
+    circ = pkg.Circuit(None, "select", nbits, count)
+    out = from_bits(circ.simulate(sel, to_bits(a, nbits), to_bits(b, nbits)), nbits)
+    assert np.array_equal(out, np.where(sel == 1, a, b))
+    assert circ.levels == 1
+
+
+@pytest.mark.parametrize("adder", [0, 1])
+def test_absolute_exhaustive(pkg, adder):
+    nbits = 6
+    a = np.arange(2 ** nbits)
+    circ = pkg.Circuit(None, "abs", nbits, len(a), adder)
+    out = from_bits(circ.simulate(to_bits(a, nbits)), nbits)
+    assert np.array_equal(out, np.abs(signed(a, nbits)) % 2 ** nbits)
+
+
+@pytest.mark.parametrize("kind", ["LEFT", "RIGHT_LOGICAL", "RIGHT_ARITH"])
+@pytest.mark.parametrize("amount", [0, 1, 3, 8, 11])
+def test_shifts(pkg, kind, amount):
+    nbits = 8
+    a = np.arange(2 ** nbits)
+    circ = pkg.Circuit(None, "shift", nbits, len(a), amount, pkg.SHIFT[kind])
+    out = from_bits(circ.simulate(to_bits(a, nbits)), nbits)
+    if kind == "LEFT":
+        expect = (a << amount) % 2 ** nbits
+    elif kind == "RIGHT_LOGICAL":
+        expect = a >> amount
+    else:
+        expect = (signed(a, nbits) >> min(amount, 63)) % 2 ** nbits
+    assert np.array_equal(out, expect)
+    assert circ.levels == 0 and circ.gates == 0  # bootstrap free
+
+
+@pytest.mark.parametrize("adder", [0, 1])
+@pytest.mark.parametrize("is_signed", [0, 1])
+def test_division_exhaustive(pkg, is_signed, adder):
+    nbits = 4
+    a, b = all_pairs(nbits)
+    keep = b != 0
+    a, b = a[keep], b[keep]
+    circ = pkg.Circuit(None, "div", nbits, len(a), is_signed, adder)
+    out = from_bits(circ.simulate(to_bits(a, nbits), to_bits(b, nbits)), nbits).reshape(-1, 2)
+    if is_signed:
+        xa, xb = signed(a, nbits), signed(b, nbits)
+        q = np.sign(xa) * np.sign(xb) * (np.abs(xa) // np.abs(xb))
+        r = np.abs(xa) % np.abs(xb)
+    else:
+        q, r = a // b, a % b
+    assert np.array_equal(out[:, 0], q % 2 ** nbits)
+    assert np.array_equal(out[:, 1], r % 2 ** nbits)
+
+
+def test_division_16_bit_random(pkg):
+    nbits, count = 16, 40
+    rng = np.random.default_rng(8)
+    a = rng.integers(0, 2 ** nbits, count)
+    b = rng.integers(1, 2 ** nbits, count)
+    b[:10] = rng.integers(1, 40, 10)
+    circ = pkg.Circuit(None, "div", nbits, count, 0, 1)
+    out = from_bits(circ.simulate(to_bits(a, nbits), to_bits(b, nbits)), nbits).reshape(-1, 2)
+    assert np.array_equal(out[:, 0], a // b) and np.array_equal(out[:, 1], a % b)

@@ -99,3 +99,75 @@ def test_matrix_multiply_4x4_of_8_bit(pkg, sk_engine, adder):
     got = dec_ints(pkg, sk, out, nbits).reshape(n, n)
     assert np.array_equal(got, (A @ Bm) & 0xFF)
     circ.close()
+
+
+# ---- the rest of the Cipher arithmetic (Cipher.cu:237-630) on real ciphertexts --------------
+
+def sgn(v, nbits):
+    v = np.asarray(v, dtype=np.int64) % 2 ** nbits
+    return np.where(v >= 2 ** (nbits - 1), v - 2 ** nbits, v)
+
+
+@pytest.fixture(scope="module")
+def operands8():
+    a = np.array([100, 3, 255, 0, 128, 127, 77, 200, 13, 250])
+    b = np.array([27, 3, 1, 9, 127, 128, 78, 100, 240, 5])
+    return a, b
+
+
+@pytest.mark.parametrize("adder", [0, 1])
+def test_subtraction_and_negation(pkg, sk_engine, operands8, adder):
+    sk, eng = sk_engine
+    a, b = operands8
+    ea, eb = enc_ints(pkg, eng, sk, a, 8, 31), enc_ints(pkg, eng, sk, b, 8, 32)
+    out = pkg.Circuit(eng, "sub", 8, len(a), adder).run(ea, eb)
+    assert np.array_equal(dec_ints(pkg, sk, out, 8), (a - b) & 0xFF)
+    if adder == 0:
+        out = pkg.Circuit(eng, "neg", 8, len(a)).run(ea)
+        assert np.array_equal(dec_ints(pkg, sk, out, 8), (-a) & 0xFF)
+
+
+@pytest.mark.parametrize("is_signed", [0, 1])
+def test_comparisons_min_max(pkg, sk_engine, operands8, is_signed):
+    sk, eng = sk_engine
+    a, b = operands8
+    xa, xb = (sgn(a, 8), sgn(b, 8)) if is_signed else (a, b)
+    ea, eb = enc_ints(pkg, eng, sk, a, 8, 33), enc_ints(pkg, eng, sk, b, 8, 34)
+    expect = {"GT": xa > xb, "LE": xa <= xb, "LT": xa < xb, "GE": xa >= xb, "EQ": xa == xb, "NE": xa != xb}
+    for name, code in pkg.CMP.items():
+        out = pkg.Circuit(eng, "compare", 8, len(a), code, is_signed).run(ea, eb)
+        assert np.array_equal(pkg.decrypt_bits(sk, out.cpu().numpy()).astype(bool), expect[name]), name
+    for want_max in (0, 1):
+        out = pkg.Circuit(eng, "minmax", 8, len(a), want_max, is_signed).run(ea, eb)
+        assert np.array_equal(dec_ints(pkg, sk, out, 8), np.where((xa > xb) == bool(want_max), a, b))
+
+
+def test_select_abs_shift(pkg, sk_engine, operands8):
+    sk, eng = sk_engine
+    a, b = operands8
+    ea, eb = enc_ints(pkg, eng, sk, a, 8, 35), enc_ints(pkg, eng, sk, b, 8, 36)
+    sel = (np.arange(len(a)) % 2).astype(np.int32)
+    es = eng.to_device(pkg.encrypt_bits(sk, sel, 37))
+    out = pkg.Circuit(eng, "select", 8, len(a)).run(es, ea, eb)
+    assert np.array_equal(dec_ints(pkg, sk, out, 8), np.where(sel == 1, a, b))
+    out = pkg.Circuit(eng, "abs", 8, len(a), 1).run(ea)
+    assert np.array_equal(dec_ints(pkg, sk, out, 8), np.abs(sgn(a, 8)) & 0xFF)
+    out = pkg.Circuit(eng, "shift", 8, len(a), 3, pkg.SHIFT["RIGHT_ARITH"]).run(ea)
+    assert np.array_equal(dec_ints(pkg, sk, out, 8), (sgn(a, 8) >> 3) & 0xFF)
+    out = pkg.Circuit(eng, "shift", 8, len(a), 2, pkg.SHIFT["LEFT"]).run(ea)
+    assert np.array_equal(dec_ints(pkg, sk, out, 8), (a << 2) & 0xFF)
+
+
+@pytest.mark.parametrize("is_signed", [0, 1])
+def test_division(pkg, sk_engine, operands8, is_signed):
+    """operator/ (Cipher.cu:494): restoring division, quotient and remainder."""
+    sk, eng = sk_engine
+    a, b = operands8
+    ea, eb = enc_ints(pkg, eng, sk, a, 8, 38), enc_ints(pkg, eng, sk, b, 8, 39)
+    out = dec_ints(pkg, sk, pkg.Circuit(eng, "div", 8, len(a), is_signed, 1).run(ea, eb), 8).reshape(-1, 2)
+    if is_signed:
+        xa, xb = sgn(a, 8), sgn(b, 8)
+        q, r = np.sign(xa) * np.sign(xb) * (np.abs(xa) // np.abs(xb)), np.abs(xa) % np.abs(xb)
+    else:
+        q, r = a // b, a % b
+    assert np.array_equal(out[:, 0], q & 0xFF) and np.array_equal(out[:, 1], r & 0xFF)
