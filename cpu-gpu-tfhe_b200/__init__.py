@@ -28,4 +28,9 @@ from .binding import (  # noqa: F401
     lib,
     lib_path,
     measure_fp64_peak,
+    read_ciphertexts,
+    read_key_file,
+    write_ciphertexts,
+    write_cloud_key,
+    write_secret_key,
 )

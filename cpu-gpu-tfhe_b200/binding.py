@@ -125,6 +125,15 @@ def lib():
         L.tfhe_b200_circuit_operand_rows.argtypes = [_vp, _i]
         L.tfhe_b200_circuit_output_rows.argtypes = [_vp]
         L.tfhe_b200_circuit_run.argtypes = [_vp, _vp, _vp, _vp]
+        L.tfhe_b200_file_read_cloud_key.argtypes = [ctypes.c_char_p, _vp, _vp, _vp, _vp, _vp]
+        L.tfhe_b200_file_write_cloud_key.argtypes = [ctypes.c_char_p, _vp, _vp, _vp, _vp, _vp]
+        L.tfhe_b200_file_read_secret_key.argtypes = [ctypes.c_char_p, _vp, _vp, _vp, _vp, _vp, _vp, _vp]
+        L.tfhe_b200_file_write_secret_key.argtypes = [ctypes.c_char_p, _vp, _vp, _vp, _vp, _vp, _vp, _vp]
+        L.tfhe_b200_file_count_ciphertexts.argtypes = [ctypes.c_char_p, _i]
+        L.tfhe_b200_file_count_ciphertexts.restype = ctypes.c_long
+        L.tfhe_b200_file_read_ciphertexts.argtypes = [ctypes.c_char_p, _i, _vp, _vp, _i]
+        L.tfhe_b200_file_write_ciphertexts.argtypes = [ctypes.c_char_p, _i, _vp, _vp, _i, _i]
+        L.tfhe_b200_file_last_error.restype = ctypes.c_char_p
         L.tfhe_b200_get_timing.argtypes = [_vp, _vp, _vp, _vp]
         L.tfhe_b200_measure_fp64_peak.argtypes = [_i, _vp, _vp]
         _lib = L
@@ -154,6 +163,78 @@ def keygen(seed, params=None):
                           bk.ctypes.data, ks.ctypes.data):
         raise EngineError("keygen failed")
     return SecretKeys(p, lwe, tlwe, bk, ks, a.value, b.value)
+
+
+# ---- key / ciphertext files of stock TFHE clients (tfhe_io.cu formats) ------------------------
+
+def _file_ck(rc):
+    if rc:
+        raise EngineError(lib().tfhe_b200_file_last_error().decode())
+
+
+def _alphas(sk):
+    # new_default_gate_bootstrapping_parameters (tfhe_gate_bootstrapping.cu:36-38):
+    # max_stdev = sqrt(2/pi) * 2^-4 / 4 for both parameter sets
+    amax = (2.0 / np.pi) ** 0.5 * 2.0 ** -6
+    return (ctypes.c_double * 4)(sk.alpha_lwe, amax, sk.alpha_bk, amax)
+
+
+def write_cloud_key(path, sk, variances=None):
+    """cloud.key (export_tfheGateBootstrappingCloudKeySet_toFile, tfhe_io.cu:1109)."""
+    v = (ctypes.c_double * 2)(*(variances if variances is not None else (sk.alpha_bk ** 2, sk.alpha_lwe ** 2)))
+    _file_ck(lib().tfhe_b200_file_write_cloud_key(str(path).encode(), ctypes.byref(sk.params), _alphas(sk), v,
+                                                  sk.bk.ctypes.data, sk.ks.ctypes.data))
+
+
+def write_secret_key(path, sk, variances=None):
+    """secret.key (export_tfheGateBootstrappingSecretKeySet_toFile, tfhe_io.cu:1173)."""
+    v = (ctypes.c_double * 2)(*(variances if variances is not None else (sk.alpha_bk ** 2, sk.alpha_lwe ** 2)))
+    _file_ck(lib().tfhe_b200_file_write_secret_key(str(path).encode(), ctypes.byref(sk.params), _alphas(sk), v,
+                                                   sk.bk.ctypes.data, sk.ks.ctypes.data, sk.lwe_key.ctypes.data,
+                                                   sk.tlwe_key.ctypes.data))
+
+
+def read_key_file(path, secret=False):
+    """Reads cloud.key / secret.key; returns (SecretKeys [lwe_key / tlwe_key None for a cloud key], variances)."""
+    L = lib()
+    p = Params()
+    al, var = (ctypes.c_double * 4)(), (ctypes.c_double * 2)()
+    pb = str(path).encode()
+    _file_ck(L.tfhe_b200_file_read_cloud_key(pb, ctypes.byref(p), al, None, None, None))  # header
+    kpl = (p.k + 1) * p.l
+    bk = np.zeros((p.n, kpl, p.k + 1, p.N), np.int32)
+    ks = np.zeros((p.N * p.k, p.ks_t, 1 << p.ks_basebit, p.n + 1), np.int32)
+    lwe = tlwe = None
+    if secret:
+        lwe, tlwe = np.zeros(p.n, np.int32), np.zeros(p.k * p.N, np.int32)
+        _file_ck(L.tfhe_b200_file_read_secret_key(pb, ctypes.byref(p), al, var, bk.ctypes.data, ks.ctypes.data,
+                                                  lwe.ctypes.data, tlwe.ctypes.data))
+    else:
+        _file_ck(L.tfhe_b200_file_read_cloud_key(pb, ctypes.byref(p), al, var, bk.ctypes.data, ks.ctypes.data))
+    return SecretKeys(p, lwe, tlwe, bk, ks, al[0], al[2]), list(var)
+
+
+def write_ciphertexts(path, samples, variances=None, append=False):
+    """cloud.data / answer.data: one record per sample (export_gate_bootstrapping_ciphertext_toFile)."""
+    s = _np_i32(samples)
+    n = s.shape[-1] - 1
+    flat = s.reshape(-1, n + 1)
+    v = None if variances is None else np.ascontiguousarray(variances, np.float64)
+    _file_ck(lib().tfhe_b200_file_write_ciphertexts(str(path).encode(), n, flat.ctypes.data,
+                                                    None if v is None else v.ctypes.data, flat.shape[0],
+                                                    1 if append else 0))
+
+
+def read_ciphertexts(path, n, count=None):
+    L = lib()
+    if count is None:
+        count = int(L.tfhe_b200_file_count_ciphertexts(str(path).encode(), n))
+        if count < 0:
+            raise EngineError("%s is not a whole number of ciphertext records" % path)
+    out = np.zeros((count, n + 1), np.int32)
+    var = np.zeros(count, np.float64)
+    _file_ck(L.tfhe_b200_file_read_ciphertexts(str(path).encode(), n, out.ctypes.data, var.ctypes.data, count))
+    return out, var
 
 
 def encrypt_bits(sk, bits, seed):

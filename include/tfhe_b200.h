@@ -211,6 +211,30 @@ int tfhe_b200_circuit_run(tfhe_b200_circuit *c, int32_t *d_out, const int32_t *c
 int tfhe_b200_circuit_simulate(const tfhe_b200_circuit *c, int32_t *out_bits, const int32_t *const *operand_bits);
 int tfhe_b200_ctx_words(const tfhe_b200_ctx *ctx); /* n + 1 */
 
+/* ---- key and ciphertext FILES of stock TFHE clients (host only) -------------
+ * The serialisation of gpuParallel/tfhe_io.cu (text parameter sections + binary payloads):
+ * cloud.key / secret.key as written by export_tfheGateBootstrapping{Cloud,Secret}KeySet_toFile
+ * (tfhe_io.cu:1099-1103, 1160-1166; producer cpu/main.cpp:26-71, consumer cpu/cloud.cpp:138-161)
+ * and ciphertext records as written by export_gate_bootstrapping_ciphertext_toFile (:90-108).
+ * Payload order equals the flat formats above.  alphas4 = {lwe alpha_min, alpha_max, tlwe
+ * alpha_min, alpha_max}; variances2 = {bootstrapping key, key-switch key} (the single variance
+ * each section stores).  Any output pointer may be NULL (e.g. all NULL but p: read the header). */
+int tfhe_b200_file_read_cloud_key(const char *path, tfhe_b200_params *p, double *alphas4, double *variances2,
+                                  int32_t *bk_coef, int32_t *ks);
+int tfhe_b200_file_write_cloud_key(const char *path, const tfhe_b200_params *p, const double *alphas4,
+                                   const double *variances2, const int32_t *bk_coef, const int32_t *ks);
+int tfhe_b200_file_read_secret_key(const char *path, tfhe_b200_params *p, double *alphas4, double *variances2,
+                                   int32_t *bk_coef, int32_t *ks, int32_t *lwe_key, int32_t *tlwe_key);
+int tfhe_b200_file_write_secret_key(const char *path, const tfhe_b200_params *p, const double *alphas4,
+                                    const double *variances2, const int32_t *bk_coef, const int32_t *ks,
+                                    const int32_t *lwe_key, const int32_t *tlwe_key);
+/* ciphertext files: `count` records of dimension n into / from samples[count][n+1] */
+long tfhe_b200_file_count_ciphertexts(const char *path, int n);
+int tfhe_b200_file_read_ciphertexts(const char *path, int n, int32_t *samples, double *variances, int count);
+int tfhe_b200_file_write_ciphertexts(const char *path, int n, const int32_t *samples, const double *variances,
+                                     int count, int append);
+const char *tfhe_b200_file_last_error(void);
+
 /* ---- HOST-buffer convenience (synchronous; copies in and out) ------------- */
 int tfhe_b200_gate_host(tfhe_b200_ctx *ctx, int gate, int32_t *out, const int32_t *ca, const int32_t *cb,
                         int count);

@@ -153,6 +153,23 @@ typedef struct TFheGateBootstrappingCloudKeySet { /* tfhe_gate_bootstrapping_str
 
 #endif /* TFHE_CORE_H */
 
+/* ---- files and result buffers (tfhe_io.h, tfhe_gate_bootstrapping_functions.h) ----
+ * What cpu/cloud.cpp:138-161 needs besides the gates: read cloud.key, allocate / read / write
+ * ciphertexts.  A key set read here holds the coefficient-domain key (bkFFT == NULL; the gates
+ * convert it on the GPU at first use) and is released with tfhe_b200_delete_cloud_keyset_fromFile. */
+#include <stdio.h>
+TFheGateBootstrappingCloudKeySet *new_tfheGateBootstrappingCloudKeySet_fromFile(FILE *F); /* tfhe_io.cu:1117 */
+void tfhe_b200_delete_cloud_keyset_fromFile(TFheGateBootstrappingCloudKeySet *keyset);
+void export_tfheGateBootstrappingCloudKeySet_toFile(FILE *F, const TFheGateBootstrappingCloudKeySet *keyset); /* :1109 */
+void export_gate_bootstrapping_ciphertext_toFile(FILE *F, const LweSample *sample,
+                                                 const TFheGateBootstrappingParameterSet *params); /* :1214 */
+void import_gate_bootstrapping_ciphertext_fromFile(FILE *F, LweSample *sample,
+                                                   const TFheGateBootstrappingParameterSet *params); /* :1223 */
+LweSample *new_gate_bootstrapping_ciphertext(const TFheGateBootstrappingParameterSet *params);
+LweSample *new_gate_bootstrapping_ciphertext_array(int nbelems, const TFheGateBootstrappingParameterSet *params);
+void delete_gate_bootstrapping_ciphertext(LweSample *sample);
+void delete_gate_bootstrapping_ciphertext_array(int nbelems, LweSample *samples); /* tfhe_gate_bootstrapping.cu:93-108 */
+
 /* ---- classic gate API (tfhe_gate_bootstrapping_functions.h:40-87; boot-gates.cu:98-448) ---- */
 void bootsNAND(LweSample *result, const LweSample *ca, const LweSample *cb, const TFheGateBootstrappingCloudKeySet *bk);
 void bootsOR(LweSample *result, const LweSample *ca, const LweSample *cb, const TFheGateBootstrappingCloudKeySet *bk);

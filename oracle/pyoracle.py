@@ -323,6 +323,37 @@ class Ref:
         self.L.ref_export_bkfft(self.h, _p(out))
         return out
 
+    # ---- the reference's own file formats (tfhe_io.cu) ----
+    def write_cloud_key(self, path):
+        assert self.L.ref_write_cloud_key(self.h, str(path).encode()) == 0
+
+    def write_secret_key(self, path):
+        assert self.L.ref_write_secret_key(self.h, str(path).encode()) == 0
+
+    def read_cloud_key(self, path):
+        self.L.ref_read_cloud_key.restype = _vp
+        self.h = _vp(self.L.ref_read_cloud_key(str(path).encode()))
+        assert self.h
+        return self
+
+    def read_secret_key(self, path):
+        self.L.ref_read_secret_key.restype = _vp
+        self.h = _vp(self.L.ref_read_secret_key(str(path).encode()))
+        assert self.h
+        return self
+
+    def write_ciphertexts(self, path, samples, variances=None):
+        s = _i32(samples).reshape(-1, self.n + 1)
+        v = None if variances is None else np.ascontiguousarray(variances, np.float64)
+        assert self.L.ref_write_ciphertexts(self.h, str(path).encode(), _p(s), None if v is None else _p(v),
+                                            s.shape[0]) == 0
+
+    def read_ciphertexts(self, path, count):
+        out = np.zeros((count, self.n + 1), np.int32)
+        var = np.zeros(count, np.float64)
+        assert self.L.ref_read_ciphertexts(self.h, str(path).encode(), _p(out), _p(var), count) == 0
+        return out, var
+
     def encrypt(self, bit):
         out = np.zeros(self.n + 1, np.int32)
         self.L.ref_encrypt(self.h, int(bit), _p(out))

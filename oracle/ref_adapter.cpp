@@ -376,6 +376,82 @@ void *ref_torus_poly_new(int N, const int32_t *coefs) {
 }
 void ref_torus_poly_free(void *p) { delete_TorusPolynomial((TorusPolynomial *) p); }
 
+/* ---- the reference's own file formats (tfhe_io.cu) ------------------------------------ */
+int ref_write_cloud_key(const RefHandle *h, const char *path) {
+    FILE *f = fopen(path, "wb");
+    if (!f) return 1;
+    export_tfheGateBootstrappingCloudKeySet_toFile(f, h->cloud);
+    return fclose(f);
+}
+
+int ref_write_secret_key(const RefHandle *h, const char *path) {
+    if (!h->sk) return 2;
+    FILE *f = fopen(path, "wb");
+    if (!f) return 1;
+    export_tfheGateBootstrappingSecretKeySet_toFile(f, h->sk);
+    return fclose(f);
+}
+
+RefHandle *ref_read_cloud_key(const char *path) {
+    FILE *f = fopen(path, "rb");
+    if (!f) return nullptr;
+    TFheGateBootstrappingCloudKeySet *ck = new_tfheGateBootstrappingCloudKeySet_fromFile(f);
+    fclose(f);
+    RefHandle *h = new RefHandle();
+    memset(h, 0, sizeof(*h));
+    h->params = const_cast<TFheGateBootstrappingParameterSet *>(ck->params);
+    h->bk = const_cast<LweBootstrappingKey *>(ck->bk);
+    h->bkFFT = const_cast<LweBootstrappingKeyFFT *>(ck->bkFFT);
+    h->cloud = ck;
+    return h;
+}
+
+RefHandle *ref_read_secret_key(const char *path) {
+    FILE *f = fopen(path, "rb");
+    if (!f) return nullptr;
+    TFheGateBootstrappingSecretKeySet *sk = new_tfheGateBootstrappingSecretKeySet_fromFile(f);
+    fclose(f);
+    RefHandle *h = new RefHandle();
+    memset(h, 0, sizeof(*h));
+    h->params = const_cast<TFheGateBootstrappingParameterSet *>(sk->params);
+    h->sk = sk;
+    h->lwe_key = const_cast<LweKey *>(sk->lwe_key);
+    h->tgsw_key = const_cast<TGswKey *>(sk->tgsw_key);
+    h->bk = const_cast<LweBootstrappingKey *>(sk->cloud.bk);
+    h->bkFFT = const_cast<LweBootstrappingKeyFFT *>(sk->cloud.bkFFT);
+    h->cloud = const_cast<TFheGateBootstrappingCloudKeySet *>(&sk->cloud);
+    return h;
+}
+
+int ref_write_ciphertexts(const RefHandle *h, const char *path, const int32_t *flat, const double *variances,
+                          int count) {
+    FILE *f = fopen(path, "wb");
+    if (!f) return 1;
+    const int n = h->params->in_out_params->n;
+    for (int i = 0; i < count; i++) {
+        LweSample *s = mk(h->params->in_out_params, flat + (size_t) i * (n + 1));
+        s->current_variance = variances ? variances[i] : 0.;
+        export_gate_bootstrapping_ciphertext_toFile(f, s, h->params);
+        delete_LweSample(s);
+    }
+    return fclose(f);
+}
+
+int ref_read_ciphertexts(const RefHandle *h, const char *path, int32_t *flat, double *variances, int count) {
+    FILE *f = fopen(path, "rb");
+    if (!f) return 1;
+    const int n = h->params->in_out_params->n;
+    LweSample *s = new_LweSample(h->params->in_out_params);
+    for (int i = 0; i < count; i++) {
+        import_gate_bootstrapping_ciphertext_fromFile(f, s, h->params);
+        put(flat + (size_t) i * (n + 1), s, n);
+        if (variances) variances[i] = s->current_variance;
+    }
+    delete_LweSample(s);
+    fclose(f);
+    return 0;
+}
+
 void ref_free(RefHandle *h) {
     if (!h) return;
     if (h->sk) {

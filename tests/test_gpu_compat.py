@@ -202,3 +202,71 @@ def test_batched_fullgpu_family(world):
     assert np.array_equal(dec[:nb], bits[0] ^ bits[1]) and np.array_equal(dec[nb:], bits[2] ^ bits[1])
     for s in (sa, sb, sc, res):
         L.freeLweSample_16_gpu(s)
+
+
+def test_cloud_program_flow_through_files(pkg, tmp_path):
+    """cpu/cloud.cpp:138-161 + its gate loop, with THIS library's reference-named entry points only:
+    read cloud.key, read cloud.data, evaluate gates, write answer.data; the client (flat API)
+    wrote the inputs and decrypts the answer."""
+    sk = pkg.keygen(21)
+    bits_a = np.array([0, 0, 1, 1, 1, 0], np.int32)
+    bits_b = np.array([0, 1, 0, 1, 1, 1], np.int32)
+    pkg.write_cloud_key(tmp_path / "cloud.key", sk)
+    pkg.write_ciphertexts(tmp_path / "cloud.data", pkg.encrypt_bits(sk, bits_a, 1))
+    pkg.write_ciphertexts(tmp_path / "cloud.data", pkg.encrypt_bits(sk, bits_b, 2), append=True)
+
+    L = ctypes.CDLL(pkg.lib_path())
+    libc = ctypes.CDLL(None)
+    libc.fopen.restype = vp
+    libc.fopen.argtypes = [ctypes.c_char_p, ctypes.c_char_p]
+    libc.fclose.argtypes = [vp]
+    L.new_tfheGateBootstrappingCloudKeySet_fromFile.restype = vp
+    L.new_tfheGateBootstrappingCloudKeySet_fromFile.argtypes = [vp]
+    L.new_gate_bootstrapping_ciphertext_array.restype = vp
+    L.new_gate_bootstrapping_ciphertext_array.argtypes = [ctypes.c_int, vp]
+    for f in ("import_gate_bootstrapping_ciphertext_fromFile", "export_gate_bootstrapping_ciphertext_toFile"):
+        getattr(L, f).argtypes = [vp, vp, vp]
+    for f in ("bootsAND", "bootsXOR", "bootsNAND"):
+        getattr(L, f).argtypes = [vp, vp, vp, vp]
+    L.bootsMUX.argtypes = [vp, vp, vp, vp, vp]
+
+    F = libc.fopen(str(tmp_path / "cloud.key").encode(), b"rb")
+    bk = vp(L.new_tfheGateBootstrappingCloudKeySet_fromFile(F))
+    libc.fclose(F)
+    params = ctypes.cast(bk, ctypes.POINTER(vp))[0]  # TFheGateBootstrappingCloudKeySet::params (first member)
+    n = len(bits_a)
+    SZ = 24  # sizeof(LweSample): pointer, int32 (+pad), double
+    a = L.new_gate_bootstrapping_ciphertext_array(n, params)
+    b = L.new_gate_bootstrapping_ciphertext_array(n, params)
+    out = L.new_gate_bootstrapping_ciphertext_array(4 * n, params)
+    F = libc.fopen(str(tmp_path / "cloud.data").encode(), b"rb")
+    for arr in (a, b):
+        for i in range(n):
+            L.import_gate_bootstrapping_ciphertext_fromFile(F, arr + i * SZ, params)
+    libc.fclose(F)
+    for i in range(n):
+        L.bootsAND(out + i * SZ, a + i * SZ, b + i * SZ, bk)
+        L.bootsXOR(out + (n + i) * SZ, a + i * SZ, b + i * SZ, bk)
+        L.bootsNAND(out + (2 * n + i) * SZ, a + i * SZ, b + i * SZ, bk)
+        L.bootsMUX(out + (3 * n + i) * SZ, a + i * SZ, b + i * SZ, a + ((i + 1) % n) * SZ, bk)
+    F = libc.fopen(str(tmp_path / "answer.data").encode(), b"wb")
+    for i in range(4 * n):
+        L.export_gate_bootstrapping_ciphertext_toFile(F, out + i * SZ, params)
+    libc.fclose(F)
+    # re-export of the key set reproduces the file
+    F = libc.fopen(str(tmp_path / "cloud2.key").encode(), b"wb")
+    L.export_tfheGateBootstrappingCloudKeySet_toFile.argtypes = [vp, vp]
+    L.export_tfheGateBootstrappingCloudKeySet_toFile(F, bk)
+    libc.fclose(F)
+    import filecmp
+    assert filecmp.cmp(tmp_path / "cloud.key", tmp_path / "cloud2.key", shallow=False)
+    for arr, cnt in ((a, n), (b, n), (out, 4 * n)):
+        L.delete_gate_bootstrapping_ciphertext_array.argtypes = [ctypes.c_int, vp]
+        L.delete_gate_bootstrapping_ciphertext_array(cnt, arr)
+    L.tfhe_b200_delete_cloud_keyset_fromFile.argtypes = [vp]
+    L.tfhe_b200_delete_cloud_keyset_fromFile(bk)
+
+    ans, _ = pkg.read_ciphertexts(tmp_path / "answer.data", 500)
+    got = pkg.decrypt_bits(sk, ans)
+    mux = np.where(bits_a == 1, bits_b, np.roll(bits_a, -1))
+    assert np.array_equal(got, np.concatenate([bits_a & bits_b, bits_a ^ bits_b, 1 - (bits_a & bits_b), mux]))
