@@ -63,3 +63,62 @@ def gather_outputs(local, total, device=None):
     bufs = [torch.empty_like(pad) for _ in range(world)]
     dist.all_gather(bufs, pad)
     return torch.cat([b[: hi - lo] for b, (lo, hi) in zip(bufs, sizes)], 0)
+
+
+def gather_rows(local, sizes):
+    """All-gather of per-rank row blocks with the given sizes (rows per rank)."""
+    import torch
+    import torch.distributed as dist
+
+    if not (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1):
+        return local
+    maxlen = max(sizes)
+    pad = torch.zeros((maxlen,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    pad[: local.shape[0]] = local
+    bufs = [torch.empty_like(pad) for _ in sizes]
+    dist.all_gather(bufs, pad)
+    return torch.cat([b[:n] for b, n in zip(bufs, sizes)], 0)
+
+
+class ShardedMatmul:
+    """C = A (rows x inner) * B (inner x cols) of nbits-bit integers over the ranks (BASELINE config 5;
+    SURVEY.md 8e): the rows of C are split contiguously, every rank holds the whole encrypted A and B
+    (2*256*8 samples = 8 MB for the 16x16 case) and runs the plan of its own rows
+    (tfhe_b200_circuit_matmul_ex); the only exchange is the final gather of the result rows.
+    engine None: plaintext simulation of the same plans (CPU tests)."""
+
+    def __init__(self, pkg, engine, rows, inner, cols, nbits, adder=0, world=None, rank=None):
+        import torch.distributed as dist
+
+        multi = dist.is_available() and dist.is_initialized()
+        self.world = world if world is not None else (dist.get_world_size() if multi else 1)
+        self.rank = rank if rank is not None else (dist.get_rank() if multi else 0)
+        self.rows, self.inner, self.cols, self.nbits = rows, inner, cols, nbits
+        self.bounds = [shard_bounds(rows, self.world, r) for r in range(self.world)]
+        self.lo, self.hi = self.bounds[self.rank]
+        self.circ = pkg.Circuit(engine, "matmul_ex", self.hi - self.lo, inner, cols, nbits, adder) \
+            if self.hi > self.lo else None
+        self.sizes = [(hi - lo) * cols * nbits for lo, hi in self.bounds]
+
+    def local_rows_of_A(self, A):
+        """A: [rows*inner*nbits, ...] (samples or plaintext bits) -> this rank's rows."""
+        per = self.inner * self.nbits
+        return A[self.lo * per: self.hi * per]
+
+    def run(self, A_enc, B_enc, gather=True):
+        import torch
+
+        if self.circ is not None:
+            local = self.circ.run(self.local_rows_of_A(A_enc).contiguous(), B_enc)
+        else:
+            local = torch.empty((0, A_enc.shape[1]), dtype=A_enc.dtype, device=A_enc.device)
+        return gather_rows(local, self.sizes) if gather else local
+
+    def simulate(self, A_bits, B_bits):
+        import torch
+
+        A_bits, B_bits = np.asarray(A_bits).reshape(-1), np.asarray(B_bits).reshape(-1)
+        local = self.circ.simulate(self.local_rows_of_A(A_bits), B_bits) if self.circ is not None \
+            else np.zeros(0, np.int32)
+        return gather_rows(torch.from_numpy(np.ascontiguousarray(local, np.int32)).reshape(-1, 1), self.sizes) \
+            .reshape(-1).numpy()

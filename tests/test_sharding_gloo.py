@@ -66,3 +66,40 @@ def test_shard_bounds_cover_everything():
             assert all(b[i][1] == b[i + 1][0] for i in range(world - 1))
             sizes = [hi - lo for lo, hi in b]
             assert max(sizes) - min(sizes) <= 1
+
+
+def _matmul_worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    import __graft_entry__ as ge
+
+    pkg = ge.load_package()
+    from importlib import import_module
+
+    d = import_module("cpu_gpu_tfhe_b200.dist")
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    rows, inner, cols, nbits = 5, 3, 4, 6
+    rng = np.random.default_rng(1)
+    A, B = rng.integers(-8, 8, (rows, inner)), rng.integers(-8, 8, (inner, cols))
+    bits = lambda v: ((np.asarray(v).reshape(-1)[:, None] % 2 ** nbits >> np.arange(nbits)) & 1).astype(np.int32)
+    sm = d.ShardedMatmul(pkg, None, rows, inner, cols, nbits, adder=rank % 2)  # ranks may even differ in adder
+    out = sm.simulate(bits(A), bits(B)).reshape(-1, nbits)
+    got = (out.astype(np.int64) << np.arange(nbits)).sum(-1).reshape(rows, cols)
+    q.put((rank, sm.lo, sm.hi, bool(np.array_equal(got, (A @ B) % 2 ** nbits))))
+    dist.destroy_process_group()
+
+
+def test_two_rank_sharded_matrix_multiply_plan():
+    """BASELINE config 5 sharding (rows of C over the ranks, result gather) on plaintext plans."""
+    world, port = 2, 31500 + os.getpid() % 2000
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_matmul_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    assert [(r[1], r[2]) for r in res] == [(0, 3), (3, 5)]
+    assert all(r[3] for r in res)
