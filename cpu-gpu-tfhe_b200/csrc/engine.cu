@@ -145,7 +145,7 @@ int run_bootstrap_ks(tfhe_b200_ctx *c, BrLaunch &L, int nsrc, int32_t ks_cst, in
     K.t = c->p.ks_t;
     K.basebit = c->p.ks_basebit;
     CU(launch_keyswitch(K, c->sm_count, st));
-    c->launches += (out_count > 0 && ((out_count + 15) / 16) < 2 * c->sm_count) ? 2 : 1;
+    c->launches += (out_count > 0 && ((out_count + kKsTile - 1) / kKsTile) < 2 * c->sm_count) ? 2 : 1;
     if (c->timing) {
         CU(cudaEventRecord(e2, st));
         c->ev.push_back(e0);

@@ -84,6 +84,7 @@ struct KsLaunch {
 };
 cudaError_t launch_keyswitch(const KsLaunch &L, int sm_count, cudaStream_t stream);
 constexpr int kKsRowWords = 512;
+constexpr int kKsTile = 32;  // gates per key-switch CTA
 
 // KS table re-layout on device: src [N][t][base][n+1] -> dst [N][t][base-1][512]
 cudaError_t launch_ks_relayout(const int32_t *src, int32_t *dst, int N, int t, int base, int n, cudaStream_t stream);

@@ -8,10 +8,10 @@
 //     if aij != 0: res -= ks[i][j][aij]
 // Integer arithmetic mod 2^32: bit-exact whatever the summation order.
 //
-// One CTA handles a tile of 16 gates for a range of i.  The digits of the tile
-// are precomputed into shared memory (2 bits per gate packed in one word per
-// (i, j)), then every thread owns two output columns for all 16 gates in
-// registers and streams the table rows (coalesced 2 KiB rows, L2 resident)
+// One CTA handles a tile of 32 gates for a range of i.  The digits of the tile
+// are precomputed into shared memory (2 bits per gate, 16 gates per word, two
+// words per (i, j)), then every thread owns four output columns for 16 gates in
+// registers and streams the table rows (coalesced 128-bit loads, L2 resident)
 // exactly once per tile instead of once per gate as the reference does
 // (lweKeySwitchVectorSubstraction_gpu_testing_coalesce_n_Bit, boot-gates.cu:2382-2421).
 // Small batches split the i range over several CTAs and combine with integer
@@ -25,13 +25,14 @@ namespace tfhe_b200 {
 
 namespace {
 
-constexpr int kTile = 16;       // gates per CTA
-constexpr int kKsThreads = 256; // two columns per thread (c, c + 256)
+constexpr int kTile = kKsTile;  // gates per CTA: two groups of 16
+constexpr int kGrp = 16;        // gates per thread
+constexpr int kKsThreads = 256; // 128 column quads x 2 gate groups
 constexpr int kMaxT = 16;
 
 template <bool kAtomic>
-__global__ void __launch_bounds__(kKsThreads) keyswitch_kernel(const KsLaunch L, int nsplit) {
-    extern __shared__ uint32_t dig[];  // [i_per * t]
+__global__ void __launch_bounds__(kKsThreads, 2) keyswitch_kernel(const KsLaunch L, int nsplit) {
+    extern __shared__ uint32_t dig[];  // [i_per * t][2]: digits of gate group 0 / 1
     const int g0 = blockIdx.x * kTile;
     const int ng = min(kTile, L.count - g0);
     const int i_per = L.N / nsplit;
@@ -40,14 +41,17 @@ __global__ void __launch_bounds__(kKsThreads) keyswitch_kernel(const KsLaunch L,
     const size_t ustride = (size_t) L.N + 1;
     const uint32_t prec_offset = 1u << (32 - (1 + L.basebit * t));
 
-    // ---- digits of this tile: dig[(i - i0) * t + j], gate g in bits [2g, 2g+2) ----
-    for (int i = i0 + (int) threadIdx.x; i < i0 + i_per; i += kKsThreads) {
+    // ---- digits of this tile: dig[((i - i0) * t + j) * 2 + grp], gate g of the group in bits [2g, 2g+2) ----
+    for (int w0 = (int) threadIdx.x; w0 < 2 * i_per; w0 += kKsThreads) {
+        const int i = i0 + (w0 >> 1), grp = w0 & 1;
         uint32_t w[kMaxT];
 #pragma unroll
         for (int j = 0; j < kMaxT; j++) w[j] = 0;
-        for (int g = 0; g < ng; g++) {
-            uint32_t a = (uint32_t) __ldg(L.u + (size_t) (g0 + g) * ustride + i);
-            if (L.nsrc == 2) a += (uint32_t) __ldg(L.u + (size_t) (g0 + g + L.count) * ustride + i);
+        for (int g = 0; g < kGrp; g++) {
+            const int gg = grp * kGrp + g;
+            if (gg >= ng) break;
+            uint32_t a = (uint32_t) __ldg(L.u + (size_t) (g0 + gg) * ustride + i);
+            if (L.nsrc == 2) a += (uint32_t) __ldg(L.u + (size_t) (g0 + gg + L.count) * ustride + i);
             const uint32_t aibar = a + prec_offset;
 #pragma unroll
             for (int j = 0; j < kMaxT; j++)
@@ -55,67 +59,66 @@ __global__ void __launch_bounds__(kKsThreads) keyswitch_kernel(const KsLaunch L,
         }
 #pragma unroll
         for (int j = 0; j < kMaxT; j++)
-            if (j < t) dig[(i - i0) * t + j] = w[j];
+            if (j < t) dig[((i - i0) * t + j) * 2 + grp] = w[j];
     }
     __syncthreads();
 
-    // ---- accumulate table rows --------------------------------------------
-    const int c0 = threadIdx.x, c1 = threadIdx.x + kKsThreads;
-    uint32_t acc0[kTile], acc1[kTile];
+    // ---- accumulate table rows: 4 columns x 16 gates per thread ----------------
+    const int cq = (threadIdx.x & 127) * 4, grp = threadIdx.x >> 7;
+    uint32_t acc[4][kGrp];
 #pragma unroll
-    for (int g = 0; g < kTile; g++) {
-        acc0[g] = 0;
-        acc1[g] = 0;
-    }
-    const int32_t *tbl = L.ks + (size_t) i0 * t * 3 * kKsRowWords;
+    for (int c = 0; c < 4; c++)
+#pragma unroll
+        for (int g = 0; g < kGrp; g++) acc[c][g] = 0;
+    const int32_t *tbl = L.ks + (size_t) i0 * t * 3 * kKsRowWords + cq;
     const int steps = i_per * t;
-#pragma unroll 4
+#pragma unroll 2
     for (int idx = 0; idx < steps; idx++) {
-        const uint32_t w = dig[idx];
+        const uint32_t w = dig[idx * 2 + grp];
         const int32_t *r = tbl + (size_t) idx * 3 * kKsRowWords;
-        const uint32_t r1a = (uint32_t) __ldg(r + c0), r1b = (uint32_t) __ldg(r + c1);
-        const uint32_t r2a = (uint32_t) __ldg(r + kKsRowWords + c0), r2b = (uint32_t) __ldg(r + kKsRowWords + c1);
-        const uint32_t r3a = (uint32_t) __ldg(r + 2 * kKsRowWords + c0), r3b = (uint32_t) __ldg(r + 2 * kKsRowWords + c1);
+        const uint4 r1 = __ldg(reinterpret_cast<const uint4 *>(r));
+        const uint4 r2 = __ldg(reinterpret_cast<const uint4 *>(r + kKsRowWords));
+        const uint4 r3 = __ldg(reinterpret_cast<const uint4 *>(r + 2 * kKsRowWords));
         // value(d) = lo*r1 + hi*r2 + (lo&hi)*(r3 - r1 - r2) for d = lo + 2*hi: three integer
-        // multiply-adds on the FMA pipe per column instead of selects on the (saturated) ALU pipe
-        const uint32_t ca = r3a - r1a - r2a, cb = r3b - r1b - r2b;
+        // multiply-adds per cell; the digit bits are extracted once per gate for four columns
+        const uint32_t a1[4] = {r1.x, r1.y, r1.z, r1.w}, a2[4] = {r2.x, r2.y, r2.z, r2.w};
+        const uint32_t a3[4] = {r3.x - r1.x - r2.x, r3.y - r1.y - r2.y, r3.z - r1.z - r2.z, r3.w - r1.w - r2.w};
 #pragma unroll
-        for (int g = 0; g < kTile; g++) {
+        for (int g = 0; g < kGrp; g++) {
             const uint32_t lo = (w >> (2 * g)) & 1u, hi = (w >> (2 * g + 1)) & 1u, lh = lo & hi;
-            asm("mad.lo.u32 %0, %1, %2, %0;" : "+r"(acc0[g]) : "r"(lo), "r"(r1a));
-            asm("mad.lo.u32 %0, %1, %2, %0;" : "+r"(acc1[g]) : "r"(lo), "r"(r1b));
-            asm("mad.lo.u32 %0, %1, %2, %0;" : "+r"(acc0[g]) : "r"(hi), "r"(r2a));
-            asm("mad.lo.u32 %0, %1, %2, %0;" : "+r"(acc1[g]) : "r"(hi), "r"(r2b));
-            asm("mad.lo.u32 %0, %1, %2, %0;" : "+r"(acc0[g]) : "r"(lh), "r"(ca));
-            asm("mad.lo.u32 %0, %1, %2, %0;" : "+r"(acc1[g]) : "r"(lh), "r"(cb));
+#pragma unroll
+            for (int c = 0; c < 4; c++) {
+                asm("mad.lo.u32 %0, %1, %2, %0;" : "+r"(acc[c][g]) : "r"(lo), "r"(a1[c]));
+                asm("mad.lo.u32 %0, %1, %2, %0;" : "+r"(acc[c][g]) : "r"(hi), "r"(a2[c]));
+                asm("mad.lo.u32 %0, %1, %2, %0;" : "+r"(acc[c][g]) : "r"(lh), "r"(a3[c]));
+            }
         }
     }
 
     // ---- result = (0, u.b + cst) - acc -----------------------------------------
     const int n = L.n;
 #pragma unroll
-    for (int g = 0; g < kTile; g++) {
-        if (g < ng) {
-            int local = g0 + g, di = 0;
+    for (int g = 0; g < kGrp; g++) {
+        const int gg = grp * kGrp + g;
+        if (gg < ng) {
+            int local = g0 + gg, di = 0;
             while (di + 1 < L.ndst && local >= L.dst[di].count) {
                 local -= L.dst[di].count;
                 di++;
             }
             const long long orow = L.dst[di].idx ? (long long) __ldg(L.dst[di].idx + local) : (long long) local;
             int32_t *row = L.dst[di].out + orow * L.dst[di].stride;
-            uint32_t v0 = 0u - acc0[g], v1 = 0u - acc1[g];
-            if ((c0 == n || c1 == n) && blockIdx.y == 0) {
-                uint32_t b = (uint32_t) __ldg(L.u + (size_t) (g0 + g) * ustride + L.N) + (uint32_t) L.cst;
-                if (L.nsrc == 2) b += (uint32_t) __ldg(L.u + (size_t) (g0 + g + L.count) * ustride + L.N);
-                if (c0 == n) v0 += b;
-                else v1 += b;
-            }
-            if (kAtomic) {
-                if (c0 <= n) atomicAdd(reinterpret_cast<unsigned int *>(row + c0), v0);
-                if (c1 <= n) atomicAdd(reinterpret_cast<unsigned int *>(row + c1), v1);
-            } else {
-                if (c0 <= n) row[c0] = (int32_t) v0;
-                if (c1 <= n) row[c1] = (int32_t) v1;
+#pragma unroll
+            for (int c = 0; c < 4; c++) {
+                const int col = cq + c;
+                if (col > n) continue;
+                uint32_t v = 0u - acc[c][g];
+                if (col == n && blockIdx.y == 0) {
+                    v += (uint32_t) __ldg(L.u + (size_t) (g0 + gg) * ustride + L.N) + (uint32_t) L.cst;
+                    if (L.nsrc == 2) v += (uint32_t) __ldg(L.u + (size_t) (g0 + gg + L.count) * ustride + L.N);
+                }
+                if (kAtomic) atomicAdd(reinterpret_cast<unsigned int *>(row + col), v);
+                else row[col] = (int32_t) v;
             }
         }
     }
@@ -192,8 +195,14 @@ cudaError_t launch_keyswitch(const KsLaunch &L, int sm_count, cudaStream_t strea
     const int tiles = (L.count + kTile - 1) / kTile;
     int nsplit = 1;
     while (tiles * nsplit < 2 * sm_count && nsplit < 64 && (L.N / (nsplit * 2)) >= 8) nsplit *= 2;
-    const size_t smem = (size_t) (L.N / nsplit) * L.t * sizeof(uint32_t);
+    const size_t smem = (size_t) (L.N / nsplit) * L.t * 2 * sizeof(uint32_t);
     dim3 grid(tiles, nsplit);
+    if (smem > 48 * 1024) {  // up to 64 KiB of digits per CTA (attribute is per device: set on every launch)
+        cudaError_t e = nsplit > 1
+                            ? cudaFuncSetAttribute(keyswitch_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536)
+                            : cudaFuncSetAttribute(keyswitch_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536);
+        if (e != cudaSuccess) return e;
+    }
     if (nsplit > 1) {
         const long long total = (long long) L.count * (L.n + 1);
         ks_zero_kernel<<<(unsigned) ((total + 255) / 256), 256, 0, stream>>>(L, L.n + 1);
