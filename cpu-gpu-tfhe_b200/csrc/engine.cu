@@ -24,6 +24,7 @@ struct tfhe_b200_ctx {
     int sm_count;
     cpx *d_bk;        // [n][4][2][16][32] complex
     int32_t *d_ks;    // [N][t][base-1][512]
+    uint8_t *d_ks_mma;  // byte-limb tiles for the tensor-core key switch (large batches), or null
     size_t bk_bytes, ks_bytes;
     cudaStream_t stream;  // used by the host-buffer entry points
     std::atomic<unsigned long long> launches;
@@ -105,6 +106,23 @@ int check_ctx(const tfhe_b200_ctx *c, bool need_bk, bool need_ks) {
     return 0;
 }
 
+// large batches: the contraction runs on the tensor cores (128-gate tiles); small ones stay on
+// the SIMT kernel, which splits a single gate over the whole chip
+int run_keyswitch(tfhe_b200_ctx *c, const KsLaunch &K, cudaStream_t st) {
+    static const int mma_min = [] {
+        const char *v = getenv("TFHE_B200_KS_MMA_MIN");
+        return v ? atoi(v) : 2048;
+    }();
+    if (c->d_ks_mma && mma_min > 0 && K.count >= mma_min) {
+        CU(launch_keyswitch_mma(K, c->d_ks_mma, st));
+        c->launches += 1;
+    } else {
+        CU(launch_keyswitch(K, c->sm_count, st));
+        c->launches += (K.count > 0 && ((K.count + kKsTile - 1) / kKsTile) < 2 * c->sm_count) ? 2 : 1;
+    }
+    return 0;
+}
+
 // blind rotate (segments) -> u scratch -> key switch -> out
 int run_bootstrap_ks(tfhe_b200_ctx *c, BrLaunch &L, int nsrc, int32_t ks_cst, int32_t *d_out, int out_count,
                      cudaStream_t st, const KsLaunch::Out *dst = nullptr, int ndst = 0) {
@@ -144,8 +162,7 @@ int run_bootstrap_ks(tfhe_b200_ctx *c, BrLaunch &L, int nsrc, int32_t ks_cst, in
     K.N = c->p.N * c->p.k;
     K.t = c->p.ks_t;
     K.basebit = c->p.ks_basebit;
-    CU(launch_keyswitch(K, c->sm_count, st));
-    c->launches += (out_count > 0 && ((out_count + kKsTile - 1) / kKsTile) < 2 * c->sm_count) ? 2 : 1;
+    if (run_keyswitch(c, K, st)) return 1;
     if (c->timing) {
         CU(cudaEventRecord(e2, st));
         c->ev.push_back(e0);
@@ -217,6 +234,7 @@ int tfhe_b200_ctx_create(tfhe_b200_ctx **out, const tfhe_b200_params *p, int dev
     c->sm_count = prop.multiProcessorCount;
     c->d_bk = nullptr;
     c->d_ks = nullptr;
+    c->d_ks_mma = nullptr;
     c->bk_bytes = c->ks_bytes = 0;
     c->launches = 0;
     c->timing = false;
@@ -234,6 +252,7 @@ void tfhe_b200_ctx_destroy(tfhe_b200_ctx *c) {
     cudaStreamSynchronize(c->stream);
     if (c->d_bk) cudaFree(c->d_bk);
     if (c->d_ks) cudaFree(c->d_ks);
+    if (c->d_ks_mma) cudaFree(c->d_ks_mma);
     for (cudaEvent_t e : c->ev) cudaEventDestroy(e);
     cudaStreamDestroy(c->stream);
     delete c;
@@ -296,6 +315,11 @@ int tfhe_b200_load_keys_device(tfhe_b200_ctx *c, const int32_t *d_bk_coef, const
         }
         CU(launch_ks_relayout(d_ks, c->d_ks, N, t, base, n, st));
         c->launches += 1;
+        if (ks_mma_supported(N, t, c->p.ks_basebit, n)) {
+            if (!c->d_ks_mma) CU(cudaMalloc(&c->d_ks_mma, ks_mma_table_bytes()));
+            CU(launch_ks_mma_relayout(d_ks, c->d_ks_mma, base, n, st));
+            c->launches += 1;
+        }
     }
     return 0;
 }
@@ -576,9 +600,7 @@ int tfhe_b200_keyswitch(tfhe_b200_ctx *c, int32_t *d_out, const int32_t *d_u, in
     K.N = c->p.N * c->p.k;
     K.t = c->p.ks_t;
     K.basebit = c->p.ks_basebit;
-    CU(launch_keyswitch(K, c->sm_count, (cudaStream_t) stream));
-    c->launches += 1;
-    return 0;
+    return run_keyswitch(c, K, (cudaStream_t) stream);
 }
 
 int tfhe_b200_blind_rotate(tfhe_b200_ctx *c, int32_t *d_acc, const int32_t *d_bara, int n_iter, int count,

@@ -94,6 +94,12 @@ cudaError_t launch_lwe_linear(int32_t *out, long long out_stride, const int32_t 
                               const int32_t *in1, long long s1, int c1, int32_t cst, int count, int n,
                               cudaStream_t stream);
 
+// tensor-core key switch (keyswitch_mma.cu): same KsLaunch, table pre-tiled as unsigned byte limbs
+size_t ks_mma_table_bytes();
+bool ks_mma_supported(int N, int t, int basebit, int n);
+cudaError_t launch_ks_mma_relayout(const int32_t *src, uint8_t *dst, int base, int n, cudaStream_t stream);
+cudaError_t launch_keyswitch_mma(const KsLaunch &L, const uint8_t *tbl, cudaStream_t stream);
+
 cudaError_t launch_lwe_linear_idx(int32_t *out, const int32_t *in, long long stride, const int32_t *idx_out,
                                   const int32_t *idx_in, int c0, int32_t cst, int count, int n, cudaStream_t stream);
 

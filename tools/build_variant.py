@@ -16,7 +16,7 @@ os.makedirs(out, exist_ok=True)
 objs = []
 for s in B.SOURCES:
     obj = os.path.join(B.OBJ, s[:-3] + ".o")
-    if s in ("blind_rotate.cu", "keyswitch.cu"):
+    if s in ("blind_rotate.cu", "keyswitch.cu", "keyswitch_mma.cu", "engine.cu"):
         obj = os.path.join(out, s[:-3] + ".o")
         cmd = [B.NVCC] + B.FLAGS + flags + ["-Xptxas", "-v", "-c", os.path.join(B.CSRC, s), "-o", obj]
         r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
