@@ -114,6 +114,30 @@ def test_keyswitch_bit_exact(engine, ctx_ref, count):
         assert np.array_equal(got[i], ctx_ref.keyswitch(u[i])), i
 
 
+def test_tensor_core_keyswitch_equals_simt_kernel(engine):
+    """Batches of >= 2048 samples take the tcgen05 int8 path (keyswitch_mma.cu); smaller ones the
+    SIMT kernel.  Same integers, bit for bit, on a ragged batch (not a multiple of the 128-gate tile)."""
+    import torch
+
+    rng = np.random.default_rng(77)
+    count = 2309
+    u = engine.to_device(_rand_i32(rng, (count, 1025)))
+    got = engine.keyswitch(u)
+    parts = [engine.keyswitch(u[lo:lo + 1000].contiguous()) for lo in range(0, count, 1000)]
+    assert torch.equal(got, torch.cat(parts, 0))
+
+
+def test_large_mux_batch_through_tensor_core_keyswitch(engine, oracle, keys):
+    """bootsMUX on 2100 gates: the key switch adds the two extracted samples (nsrc = 2) on the tcgen05 path."""
+    rng = oracle.rng(31)
+    r = np.random.default_rng(5)
+    n = 2100
+    a, b, c = (r.integers(0, 2, n).astype(np.int32) for _ in range(3))
+    ea, eb, ec = (engine.to_device(oracle.encrypt_bits(keys, rng, x)) for x in (a, b, c))
+    out = engine.mux(ea, eb, ec).cpu().numpy()
+    assert np.array_equal(oracle.decrypt_bits(keys, out), np.where(a == 1, b, c))
+
+
 def _check_gate_outputs(oracle, keys, got, ref, expect_bits):
     assert np.array_equal(oracle.decrypt_bits(keys, got), expect_bits)
     assert np.array_equal(oracle.decrypt_bits(keys, ref), expect_bits)
