@@ -99,8 +99,11 @@ def lib():
         L.tfhe_b200_phases.argtypes = [_vp, _i, _vp, _i, _vp]
         L.tfhe_b200_set_timing.argtypes = [_vp, _i]
         for f in ("add", "mul", "matmul", "mul_ex", "matmul_ex", "sub", "neg", "compare", "minmax", "select", "abs",
-                  "shift", "div"):
+                  "shift", "div", "mul_full", "mul_karatsuba", "matmul_cannon"):
             getattr(L, "tfhe_b200_circuit_" + f).restype = _vp
+        L.tfhe_b200_circuit_mul_full.argtypes = [_vp, _i, _i, _i]
+        L.tfhe_b200_circuit_mul_karatsuba.argtypes = [_vp, _i, _i, _i]
+        L.tfhe_b200_circuit_matmul_cannon.argtypes = [_vp, _i, _i, _i]
         L.tfhe_b200_circuit_sub.argtypes = [_vp, _i, _i, _i]
         L.tfhe_b200_circuit_neg.argtypes = [_vp, _i, _i]
         L.tfhe_b200_circuit_compare.argtypes = [_vp, _i, _i, _i, _i]

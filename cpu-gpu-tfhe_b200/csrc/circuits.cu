@@ -615,6 +615,163 @@ tfhe_b200_circuit *tfhe_b200_circuit_matmul(tfhe_b200_ctx *ctx, int rows, int in
     return tfhe_b200_circuit_matmul_ex(ctx, rows, inner, cols, nbits, TFHE_B200_ADDER_RIPPLE);
 }
 
+// Full (double-precision) product of w-bit operands into 2w rows
+// (multiplyLweSamples / BOOTS_vectorMultiplication with isDoublePrecision, main.cu:1483, 1746):
+// addend i = (a & b_i) << i as a 2w-bit number whose other bits ARE the constant-zero row.
+static void build_mul_full(Builder &B, const std::vector<Bits> &a, const std::vector<Bits> &b,
+                           const std::vector<Bits> &out, int w, int adder, int zero_row) {
+    const int m = (int) a.size(), W = 2 * w;
+    std::vector<std::vector<Bits>> cur(w, std::vector<Bits>(m));
+    for (int i = 0; i < w; i++)
+        for (int p = 0; p < m; p++) {
+            cur[i][p].assign(W, zero_row);
+            for (int k = 0; k < w; k++) {
+                const int r = B.alloc(1);
+                B.gate(TFHE_B200_AND, a[p][k], b[p][i], r);
+                cur[i][p][i + k] = r;
+            }
+        }
+    B.end_level();
+    int live = w;
+    while (live > 1) {
+        const int half = live / 2;
+        std::vector<Bits> va, vb, vo;
+        std::vector<std::vector<Bits>> next;
+        for (int i = 0; i < half; i++) {
+            std::vector<Bits> dst(m);
+            for (int p = 0; p < m; p++) {
+                dst[p] = (live == 2) ? out[p] : B.alloc_bits(W);
+                va.push_back(cur[i][p]);
+                vb.push_back(cur[i + half][p]);
+                vo.push_back(dst[p]);
+            }
+            next.push_back(dst);
+        }
+        B.add(adder, va, vb, vo, W);
+        if (live & 1) next.push_back(cur[live - 1]);
+        cur = next;
+        live = (int) cur.size();
+    }
+    if (w == 1)
+        for (int p = 0; p < m; p++) {
+            B.copy(cur[0][p][0], out[p][0]);
+            B.constant(0, out[p][1]);
+        }
+    if (w == 1) B.end_level();
+}
+
+tfhe_b200_circuit *tfhe_b200_circuit_mul_full(tfhe_b200_ctx *ctx, int nbits, int count, int adder) {
+    if (nbits < 1 || count < 1 || adder < 0 || adder > 1) return nullptr;
+    tfhe_b200_circuit *c = new_plan(ctx);
+    Builder B(c);
+    const int a = B.operand(count * nbits), b = B.operand(count * nbits);
+    c->out_row0 = B.alloc(count * 2 * nbits);
+    c->out_rows = count * 2 * nbits;
+    c->row_zero = B.alloc(1);
+    build_mul_full(B, numbers_at(a, count, nbits), numbers_at(b, count, nbits), numbers_at(c->out_row0, count, 2 * nbits),
+                   nbits, adder, c->row_zero);
+    return finish(c);
+}
+
+// One level of Karatsuba (karatMasterSuba, main.cu:1866-2087): with h = nbits/2,
+//   X = Xl + 2^h Xr, Y = Yl + 2^h Yr,  P1 = Xl*Yl, P2 = Xr*Yr, P3 = (Xl+Xr)*(Yl+Yr),
+//   X*Y = P1 + 2^h (P3 - P1 - P2) + 2^2h P2
+// as: one vector addition (the two sums), ONE vector multiplication of the three half-size
+// products, and three additions.  Full 2*nbits-bit product.  (The reference truncates the
+// sums to h bits and concatenates the pieces without carries, so it is only right for small
+// operands; here the sums keep their carry bit and the recombination is a real addition.)
+tfhe_b200_circuit *tfhe_b200_circuit_mul_karatsuba(tfhe_b200_ctx *ctx, int nbits, int count, int adder) {
+    if (nbits < 2 || (nbits & 1) || count < 1 || adder < 0 || adder > 1) return nullptr;
+    tfhe_b200_circuit *c = new_plan(ctx);
+    Builder B(c);
+    const int a = B.operand(count * nbits), b = B.operand(count * nbits);
+    const int W = 2 * nbits, h = nbits / 2, e = h + 1;
+    c->out_row0 = B.alloc(count * W);
+    c->out_rows = count * W;
+    c->row_zero = B.alloc(1);
+    const int Z = c->row_zero;
+    std::vector<Bits> lo, hi, sums;  // [Xl.., Yl..], [Xr.., Yr..], [Sx.., Sy..], each e bits (zero extended)
+    for (int side = 0; side < 2; side++)
+        for (int i = 0; i < count; i++) {
+            const int base = (side == 0 ? a : b) + i * nbits;
+            Bits l = Builder::bits_at(base, h), r = Builder::bits_at(base + h, h);
+            l.push_back(Z);
+            r.push_back(Z);
+            lo.push_back(l);
+            hi.push_back(r);
+            sums.push_back(B.alloc_bits(e));
+        }
+    B.add(adder, lo, hi, sums, e);
+    // the three products of e-bit operands, 2e bits each: [P1.., P2.., P3..]
+    std::vector<Bits> ma, mb, mo;
+    for (int which = 0; which < 3; which++)
+        for (int i = 0; i < count; i++) {
+            const std::vector<Bits> &src = which == 0 ? lo : (which == 1 ? hi : sums);
+            ma.push_back(src[i]);
+            mb.push_back(src[count + i]);
+            mo.push_back(B.alloc_bits(2 * e));
+        }
+    build_mul_full(B, ma, mb, mo, e, adder, Z);
+    // E = P3 - (P1 + P2)
+    std::vector<Bits> p1(mo.begin(), mo.begin() + count), p2(mo.begin() + count, mo.begin() + 2 * count),
+        p3(mo.begin() + 2 * count, mo.end()), t(count), E(count);
+    for (int i = 0; i < count; i++) {
+        t[i] = B.alloc_bits(2 * e);
+        E[i] = B.alloc_bits(2 * e);
+    }
+    B.add(adder, p1, p2, t, 2 * e);
+    B.sub(adder, p3, t, E, 2 * e);
+    // result = (P1 | P2 << 2h) + (E << h): bits below h are P1's, the rest is one addition
+    std::vector<Bits> base_hi(count), e_hi(count), out_hi(count);
+    for (int i = 0; i < count; i++) {
+        for (int k = 0; k < h; k++) B.copy(p1[i][k], c->out_row0 + i * W + k);
+        for (int k = h; k < W; k++) {
+            base_hi[i].push_back(k < 2 * h ? p1[i][k] : p2[i][k - 2 * h]);
+            e_hi[i].push_back(k - h < 2 * e ? E[i][k - h] : Z);
+            out_hi[i].push_back(c->out_row0 + i * W + k);
+        }
+    }
+    B.add(adder, base_hi, e_hi, out_hi, W - h);
+    B.end_level();
+    return finish(c);
+}
+
+// Cannon's algorithm (BOOTS_CannonsAlgo, main.cu:2590-2644) for square n x n matrices: n steps of
+// one vector multiplication of the n*n aligned pairs (A[i][(i+j+s) % n], B[(i+j+s) % n][j]) and one
+// vector addition into C.  The reference rotates rows / columns between the steps; here a step is
+// just another index table.  Same result as tfhe_b200_circuit_matmul with a working set of n*n
+// instead of n*n*n products.
+tfhe_b200_circuit *tfhe_b200_circuit_matmul_cannon(tfhe_b200_ctx *ctx, int n, int nbits, int adder) {
+    if (n < 1 || nbits < 2 || adder < 0 || adder > 1) return nullptr;
+    tfhe_b200_circuit *c = new_plan(ctx);
+    Builder B(c);
+    const int A = B.operand(n * n * nbits), Bm = B.operand(n * n * nbits);
+    c->out_row0 = B.alloc(n * n * nbits);
+    c->out_rows = n * n * nbits;
+    c->row_zero = -2;
+    std::vector<Bits> acc;
+    for (int s = 0; s < n; s++) {
+        std::vector<Bits> va, vb, prod, sum;
+        for (int i = 0; i < n; i++)
+            for (int j = 0; j < n; j++) {
+                const int k = (i + j + s) % n;
+                va.push_back(Builder::bits_at(A + (i * n + k) * nbits, nbits));
+                vb.push_back(Builder::bits_at(Bm + (k * n + j) * nbits, nbits));
+                const Bits o = Builder::bits_at(c->out_row0 + (i * n + j) * nbits, nbits);
+                prod.push_back((n == 1) ? o : B.alloc_bits(nbits));
+                sum.push_back(s == n - 1 ? o : B.alloc_bits(nbits));
+            }
+        build_mul(B, va, vb, prod, nbits, adder);
+        if (s == 0) {
+            acc = prod;
+        } else {
+            B.add(adder, acc, prod, sum, nbits);
+            acc = sum;
+        }
+    }
+    return finish(c);
+}
+
 // ---- the rest of the Cipher arithmetic (Cipher.cu:237-630) as plans ------------------------
 
 // a - b mod 2^nbits (operator-, Cipher.cu:329-332)

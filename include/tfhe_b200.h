@@ -170,11 +170,17 @@ enum { TFHE_B200_ADDER_RIPPLE = 0, TFHE_B200_ADDER_PREFIX = 1 };
  * :1746, Cipher::operator* Cipher.cu:83) */
 tfhe_b200_circuit *tfhe_b200_circuit_mul(tfhe_b200_ctx *ctx, int nbits, int count);
 tfhe_b200_circuit *tfhe_b200_circuit_mul_ex(tfhe_b200_ctx *ctx, int nbits, int count, int adder);
+/* full 2*nbits-bit products (isDoublePrecision of BOOTS_vectorMultiplication, main.cu:1746): schoolbook,
+ * and one level of Karatsuba (karatMasterSuba, main.cu:1866; nbits even); output 2*nbits rows per pair */
+tfhe_b200_circuit *tfhe_b200_circuit_mul_full(tfhe_b200_ctx *ctx, int nbits, int count, int adder);
+tfhe_b200_circuit *tfhe_b200_circuit_mul_karatsuba(tfhe_b200_ctx *ctx, int nbits, int count, int adder);
 /* C[rows][cols] = A[rows][inner] * B[inner][cols], nbits-bit elements mod 2^nbits
  * (BOOTS_matrixMultiplication main.cu:2342; cpu/cloud.cpp:390-408) */
 tfhe_b200_circuit *tfhe_b200_circuit_matmul(tfhe_b200_ctx *ctx, int rows, int inner, int cols, int nbits);
 tfhe_b200_circuit *tfhe_b200_circuit_matmul_ex(tfhe_b200_ctx *ctx, int rows, int inner, int cols, int nbits,
                                                int adder);
+/* the same product of square n x n matrices by Cannon's schedule (BOOTS_CannonsAlgo, main.cu:2590) */
+tfhe_b200_circuit *tfhe_b200_circuit_matmul_cannon(tfhe_b200_ctx *ctx, int n, int nbits, int adder);
 /* ---- the rest of the Cipher arithmetic (Cipher.cu:237-630) ------------------
  * Same plan machinery; `adder` as above.  All operands have count numbers of nbits bits. */
 /* a - b (operator-, Cipher.cu:329) and -a (twosComplement, :286) */

@@ -210,3 +210,38 @@ def test_division_16_bit_random(pkg):
     circ = pkg.Circuit(None, "div", nbits, count, 0, 1)
     out = from_bits(circ.simulate(to_bits(a, nbits), to_bits(b, nbits)), nbits).reshape(-1, 2)
     assert np.array_equal(out[:, 0], a // b) and np.array_equal(out[:, 1], a % b)
+
+
+@pytest.mark.parametrize("adder", [0, 1])
+@pytest.mark.parametrize("kind", ["mul_full", "mul_karatsuba"])
+def test_full_precision_products_exhaustive(pkg, kind, adder):
+    """Double-precision product (BOOTS_vectorMultiplication isDoublePrecision) and one level of
+    Karatsuba (karatMasterSuba main.cu:1866): all pairs of 4-bit operands, and random 8/16-bit ones."""
+    a, b = all_pairs(4)
+    circ = pkg.Circuit(None, kind, 4, len(a), adder)
+    out = from_bits(circ.simulate(to_bits(a, 4), to_bits(b, 4)), 8)
+    assert np.array_equal(out, a * b)
+    rng = np.random.default_rng(4)
+    for nbits in (8, 16):
+        a, b = rng.integers(0, 2 ** nbits, 20), rng.integers(0, 2 ** nbits, 20)
+        a[0] = b[0] = 2 ** nbits - 1
+        circ = pkg.Circuit(None, kind, nbits, len(a), adder)
+        out = from_bits(circ.simulate(to_bits(a, nbits), to_bits(b, nbits)), 2 * nbits)
+        assert np.array_equal(out, a * b), nbits
+
+
+def test_karatsuba_uses_fewer_gates_at_32_bits(pkg):
+    full = pkg.Circuit(None, "mul_full", 32, 1, 1)
+    kar = pkg.Circuit(None, "mul_karatsuba", 32, 1, 1)
+    assert kar.gates < full.gates
+
+
+@pytest.mark.parametrize("adder", [0, 1])
+def test_cannon_matrix_multiply(pkg, adder):
+    nbits = 8
+    for n in (1, 2, 3, 4):
+        rng = np.random.default_rng(n)
+        A, B = rng.integers(-8, 8, (n, n)), rng.integers(-8, 8, (n, n))
+        circ = pkg.Circuit(None, "matmul_cannon", n, nbits, adder)
+        out = circ.simulate(to_bits(A.reshape(-1) & 0xFF, nbits), to_bits(B.reshape(-1) & 0xFF, nbits))
+        assert np.array_equal(from_bits(out, nbits).reshape(n, n), (A @ B) & 0xFF), n

@@ -171,3 +171,27 @@ def test_division(pkg, sk_engine, operands8, is_signed):
     else:
         q, r = a // b, a % b
     assert np.array_equal(out[:, 0], q & 0xFF) and np.array_equal(out[:, 1], r & 0xFF)
+
+
+def test_karatsuba_and_full_products(pkg, sk_engine):
+    """karatMasterSuba (main.cu:1866) and the double-precision product on ciphertexts: full 16-bit
+    products of 8-bit operands."""
+    sk, eng = sk_engine
+    a = np.array([255, 200, 17, 0, 128])
+    b = np.array([255, 3, 250, 99, 128])
+    ea, eb = enc_ints(pkg, eng, sk, a, 8, 41), enc_ints(pkg, eng, sk, b, 8, 42)
+    for kind in ("mul_karatsuba", "mul_full"):
+        out = pkg.Circuit(eng, kind, 8, len(a), 1).run(ea, eb)
+        assert np.array_equal(dec_ints(pkg, sk, out, 16), a * b), kind
+
+
+def test_cannon_matrix_multiply_3x3(pkg, sk_engine):
+    """BOOTS_CannonsAlgo (main.cu:2590) as a plan."""
+    sk, eng = sk_engine
+    nbits, n = 8, 3
+    rng = np.random.default_rng(11)
+    A, Bm = rng.integers(-8, 8, (n, n)), rng.integers(-8, 8, (n, n))
+    circ = pkg.Circuit(eng, "matmul_cannon", n, nbits, 1)
+    out = circ.run(enc_ints(pkg, eng, sk, A.reshape(-1) & 0xFF, nbits, 43),
+                   enc_ints(pkg, eng, sk, Bm.reshape(-1) & 0xFF, nbits, 44))
+    assert np.array_equal(dec_ints(pkg, sk, out, nbits).reshape(n, n), (A @ Bm) & 0xFF)
