@@ -469,6 +469,41 @@ LweSample_16 *convertBitToNumberZero_GPU(int bitSize, const TFheGateBootstrappin
     return s;
 }
 
+// convertBitToNumber (boot-gates.cu:513-532): `bitSize` LweSamples -> one HOST LweSample_16 (the
+// caller then moves `a` to the device itself, main.cu:911-915); convertNumberToBits (:534-548): back.
+LweSample_16 *convertBitToNumber(const LweSample *input, int bitSize, const TFheGateBootstrappingCloudKeySet *bk) {
+    const int n = bk->params->in_out_params->n;
+    LweSample_16 *s = (LweSample_16 *) malloc(sizeof(LweSample_16));
+    s->a = (int *) malloc(sizeof(int) * (size_t) bitSize * n);
+    s->b = (int *) malloc(sizeof(int) * (size_t) bitSize);
+    s->current_variance = (double *) malloc(sizeof(double) * (size_t) bitSize);
+    for (int i = 0; i < bitSize; i++) {
+        memcpy(s->a + (size_t) i * n, input[i].a, sizeof(int) * (size_t) n);
+        s->b[i] = input[i].b;
+        s->current_variance[i] = input[i].current_variance;
+    }
+    return s;
+}
+
+LweSample *convertNumberToBits(LweSample_16 *number, int bitSize, const TFheGateBootstrappingCloudKeySet *bk) {
+    const int n = bk->params->in_out_params->n;
+    LweSample *out = new_gate_bootstrapping_ciphertext_array(bitSize, bk->params);
+    for (int i = 0; i < bitSize; i++) {
+        memcpy(out[i].a, number->a + (size_t) i * n, sizeof(int) * (size_t) n);  // `a` must be a host pointer here
+        out[i].b = number->b[i];
+        out[i].current_variance = number->current_variance[i];
+    }
+    return out;
+}
+
+void freeLweSample_16(LweSample_16 *s) {  // boot-gates.cu:550-556 (host container)
+    if (!s) return;
+    free(s->a);
+    free(s->b);
+    free(s->current_variance);
+    free(s);
+}
+
 void freeLweSample_16_gpu(LweSample_16 *s) {  // main.cu:41
     if (!s) return;
     cudaFree(s->a);

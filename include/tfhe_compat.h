@@ -228,6 +228,10 @@ void bootsXORXOR_fullGPU_n_Bit_vector(LweSample_16 *result, const LweSample_16 *
 void bootsNOT_16(LweSample_16 *output, LweSample_16 *input, int bitSize, int params_n);
 /* boot-gates.cu:462-476 and main.cu:41 */
 LweSample_16 *convertBitToNumberZero_GPU(int bitSize, const TFheGateBootstrappingCloudKeySet *bk);
+/* host containers (boot-gates.cu:513-556): the caller moves `a` to the device itself, as main.cu:911-915 */
+LweSample_16 *convertBitToNumber(const LweSample *input, int bitSize, const TFheGateBootstrappingCloudKeySet *bk);
+LweSample *convertNumberToBits(LweSample_16 *number, int bitSize, const TFheGateBootstrappingCloudKeySet *bk);
+void freeLweSample_16(LweSample_16 *input);
 void freeLweSample_16_gpu(LweSample_16 *sample);
 
 #ifdef __cplusplus

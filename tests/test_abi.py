@@ -60,3 +60,58 @@ def test_client_side_keygen_encrypt_decrypt(pkg, oracle):
     ctx = oracle.ctx(keys, FFT_FOLDED)
     out = np.stack([ctx.gate("XOR", c[i], c[(i + 3) % 8]) for i in range(4)])
     assert np.array_equal(pkg.decrypt_bits(sk, out), bits[:4] ^ np.roll(bits, -3)[:4])
+
+
+def test_host_container_helpers_roundtrip(pkg):
+    """convertBitToNumber / convertNumberToBits / new_gate_bootstrapping_ciphertext_array
+    (boot-gates.cu:513-556, tfhe_gate_bootstrapping.cu:93-108): host-only helpers of the batched API."""
+    L = ctypes.CDLL(pkg.lib_path())
+    vp = ctypes.c_void_p
+
+    class LweParams(ctypes.Structure):
+        _fields_ = [("n", ctypes.c_int), ("alpha_min", ctypes.c_double), ("alpha_max", ctypes.c_double)]
+
+    class ParamSet(ctypes.Structure):
+        _fields_ = [("ks_t", ctypes.c_int), ("ks_basebit", ctypes.c_int), ("in_out_params", vp), ("tgsw_params", vp)]
+
+    class CloudKeySet(ctypes.Structure):
+        _fields_ = [("params", vp), ("bk", vp), ("bkFFT", vp)]
+
+    class LweSample(ctypes.Structure):
+        _fields_ = [("a", ctypes.POINTER(ctypes.c_int32)), ("b", ctypes.c_int32), ("current_variance", ctypes.c_double)]
+
+    class LweSample16(ctypes.Structure):
+        _fields_ = [("a", ctypes.POINTER(ctypes.c_int32)), ("b", ctypes.POINTER(ctypes.c_int32)),
+                    ("current_variance", ctypes.POINTER(ctypes.c_double))]
+
+    n, bits = 500, 5
+    lp = LweParams(n, 1e-5, 1e-2)
+    ps = ParamSet(8, 2, ctypes.addressof(lp), None)
+    ck = CloudKeySet(ctypes.addressof(ps), None, None)
+    L.new_gate_bootstrapping_ciphertext_array.restype = ctypes.POINTER(LweSample)
+    L.new_gate_bootstrapping_ciphertext_array.argtypes = [ctypes.c_int, vp]
+    L.convertBitToNumber.restype = ctypes.POINTER(LweSample16)
+    L.convertBitToNumber.argtypes = [ctypes.POINTER(LweSample), ctypes.c_int, vp]
+    L.convertNumberToBits.restype = ctypes.POINTER(LweSample)
+    L.convertNumberToBits.argtypes = [ctypes.POINTER(LweSample16), ctypes.c_int, vp]
+    arr = L.new_gate_bootstrapping_ciphertext_array(bits, ctypes.addressof(ps))
+    rng = np.random.default_rng(0)
+    ref = rng.integers(-2 ** 31, 2 ** 31, (bits, n + 1), dtype=np.int64).astype(np.int32)
+    for i in range(bits):
+        for j in range(n):
+            arr[i].a[j] = int(ref[i, j])
+        arr[i].b = int(ref[i, n])
+        arr[i].current_variance = 0.5 * i
+    num = L.convertBitToNumber(arr, bits, ctypes.addressof(ck))
+    flat = np.ctypeslib.as_array(num.contents.a, shape=(bits * n,)).reshape(bits, n)
+    assert np.array_equal(flat, ref[:, :n])
+    assert [num.contents.b[i] for i in range(bits)] == [int(x) for x in ref[:, n]]
+    back = L.convertNumberToBits(num, bits, ctypes.addressof(ck))
+    for i in range(bits):
+        assert back[i].b == int(ref[i, n]) and back[i].current_variance == 0.5 * i
+        assert [back[i].a[j] for j in (0, 1, n - 1)] == [int(ref[i, j]) for j in (0, 1, n - 1)]
+    L.freeLweSample_16.argtypes = [ctypes.POINTER(LweSample16)]
+    L.freeLweSample_16(num)
+    L.delete_gate_bootstrapping_ciphertext_array.argtypes = [ctypes.c_int, ctypes.POINTER(LweSample)]
+    L.delete_gate_bootstrapping_ciphertext_array(bits, arr)
+    L.delete_gate_bootstrapping_ciphertext_array(bits, back)
