@@ -192,6 +192,57 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+def circuit_latencies(pkg, eng, sk):
+    """BASELINE.json's latency metrics on one GPU (configs 1, 2, 4): single bootstrapped gate, 16-bit
+    addition and 32-bit multiplication, reference schedules and the parallel-prefix ones; results are
+    decrypted and checked.  Device time (CUDA events), plans built and warmed up outside the timing."""
+    import torch
+
+    def to_bits(v, nbits):
+        return ((np.asarray([v], dtype=np.int64)[:, None] >> np.arange(nbits)) & 1).astype(np.int32).reshape(-1)
+
+    def enc(v, nbits, seed):
+        return eng.to_device(pkg.encrypt_bits(sk, to_bits(v, nbits), seed))
+
+    def dec(t, nbits):
+        bits = pkg.decrypt_bits(sk, t.cpu().numpy()).reshape(-1, nbits).astype(np.int64)
+        return int((bits << np.arange(nbits)).sum(-1)[0])
+
+    def timed(fn, reps):
+        fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            out = fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / reps, out
+
+    res = {}
+    ca, cb = enc(1, 1, 1), enc(1, 1, 2)
+    ms, out = timed(lambda: eng.gate("NAND", ca, cb), 20)
+    res["single_gate_ms"] = ms
+    ok = dec(out, 1) == 0
+    a, b = 12345, (-6789) & 0xFFFF
+    da, db = enc(a, 16, 3), enc(b, 16, 4)
+    for mode, name in ((0, "add16_reference_bitwise"), (1, "add16_reference_numberwise"), (2, "add16_prefix")):
+        c = pkg.Circuit(eng, "add", 16, 1, mode)
+        ms, out = timed(lambda: c.run(da, db), 2)
+        ok = ok and dec(out, 16) == (a + b) & 0xFFFF
+        res[name] = {"ms": ms, "levels": c.levels, "gates": c.gates}
+        c.close()
+    da, db = enc(40000, 32, 5), enc(50000, 32, 6)
+    for adder, name in ((0, "mul32_reference"), (1, "mul32_prefix")):
+        c = pkg.Circuit(eng, "mul_ex", 32, 1, adder)
+        ms, out = timed(lambda: c.run(da, db), 1)
+        ok = ok and dec(out, 32) == (40000 * 50000) & 0xFFFFFFFF
+        res[name] = {"ms": ms, "levels": c.levels, "gates": c.gates}
+        c.close()
+    res["results_decrypt_ok"] = bool(ok)
+    return res
+
+
 def run_b200(args):
     import torch
     import torch.distributed as dist
@@ -316,6 +367,7 @@ def run_b200(args):
                 traffic = json.load(open(tpath)).get("blind_rotate_kernel_bytes_per_launch_65536")
             except Exception:
                 traffic = None
+        latency = circuit_latencies(pkg, eng, sk) if sk is not None and not args.no_latency else None
         cpu = None
         if not args.no_cpu_baseline and sk is not None:
             probe = cpu_reference_run(sk, pkg, 2)
@@ -349,6 +401,7 @@ def run_b200(args):
             },
             "clocks": sampler.result(),
             "cpu_baseline": cpu,
+            "latency": latency,
         }
         print(json.dumps(line), flush=True)
     eng.close()
@@ -362,6 +415,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-latency", action="store_true", help="skip the single-gate / circuit latency block")
     ap.add_argument("--batch", type=int, default=BATCH, help="gates per GPU per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

@@ -137,6 +137,8 @@ def lib():
         L.tfhe_b200_file_read_ciphertexts.argtypes = [ctypes.c_char_p, _i, _vp, _vp, _i]
         L.tfhe_b200_file_write_ciphertexts.argtypes = [ctypes.c_char_p, _i, _vp, _vp, _i, _i]
         L.tfhe_b200_file_last_error.restype = ctypes.c_char_p
+        L.tfhe_b200_keygen_device.argtypes = [_vp, _vp, ctypes.c_uint64, ctypes.c_double, ctypes.c_double, _vp, _vp,
+                                              _vp, _vp]
         L.tfhe_b200_get_timing.argtypes = [_vp, _vp, _vp, _vp]
         L.tfhe_b200_measure_fp64_peak.argtypes = [_i, _vp, _vp]
         _lib = L
@@ -335,6 +337,21 @@ class Engine:
     def load_bk_fourier(self, bkfft_ref):
         a = np.ascontiguousarray(bkfft_ref, dtype=np.complex128)
         self._ck(self.L.tfhe_b200_load_bk_fourier(self.h, a.ctypes.data))
+
+    def keygen(self, seed, want_flat=True):
+        """Fresh keys generated on this engine's GPU and loaded into it (tfhe_b200_keygen_device).
+        Returns SecretKeys (bk / ks are None unless want_flat)."""
+        p = self.p
+        a, b = ctypes.c_double(), ctypes.c_double()
+        self.L.tfhe_b200_default_noise(ctypes.byref(a), ctypes.byref(b))
+        kpl = (p.k + 1) * p.l
+        lwe, tlwe = np.zeros(p.n, np.int32), np.zeros(p.k * p.N, np.int32)
+        bk = np.zeros((p.n, kpl, p.k + 1, p.N), np.int32) if want_flat else None
+        ks = np.zeros((p.N * p.k, p.ks_t, 1 << p.ks_basebit, p.n + 1), np.int32) if want_flat else None
+        self._ck(self.L.tfhe_b200_keygen_device(self.h, ctypes.byref(p), seed, a.value, b.value, lwe.ctypes.data,
+                                                tlwe.ctypes.data, bk.ctypes.data if want_flat else None,
+                                                ks.ctypes.data if want_flat else None))
+        return SecretKeys(p, lwe, tlwe, bk, ks, a.value, b.value)
 
     @property
     def key_bytes(self):

@@ -14,7 +14,7 @@ CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "_obj")
 LIB = os.path.join(HERE, "libtfhe_b200.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-SOURCES = ["blind_rotate.cu", "keyswitch.cu", "keyswitch_mma.cu", "engine.cu", "client.cu", "microbench.cu", "compat.cu", "circuits.cu", "keyio.cu"]
+SOURCES = ["blind_rotate.cu", "keyswitch.cu", "keyswitch_mma.cu", "engine.cu", "client.cu", "microbench.cu", "compat.cu", "circuits.cu", "keyio.cu", "keygen.cu"]
 FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-std=c++17", "-O3", "-lineinfo",
     "-Xcompiler", "-fPIC,-O2,-Wall", "-I", os.path.join(HERE, "..", "include"),

@@ -291,6 +291,7 @@ int tfhe_b200_ctx_words(const tfhe_b200_ctx *c) { return c ? c->p.n + 1 : 0; }
 size_t tfhe_b200_key_bytes(const tfhe_b200_ctx *c) { return c ? c->bk_bytes + c->ks_bytes : 0; }
 unsigned long long tfhe_b200_launch_count(const tfhe_b200_ctx *c) { return c ? c->launches.load() : 0; }
 int tfhe_b200_sm_count(const tfhe_b200_ctx *c) { return c ? c->sm_count : 0; }
+int tfhe_b200_ctx_device(const tfhe_b200_ctx *c) { return c ? c->device : -1; }
 
 int tfhe_b200_load_keys_device(tfhe_b200_ctx *c, const int32_t *d_bk_coef, const int32_t *d_ks, void *stream) {
     if (!c) return fail("null context");

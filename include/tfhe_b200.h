@@ -216,6 +216,15 @@ int tfhe_b200_circuit_run(tfhe_b200_circuit *c, int32_t *d_out, const int32_t *c
  * plans built with ctx == NULL.  This is schedule verification, not a compute path. */
 int tfhe_b200_circuit_simulate(const tfhe_b200_circuit *c, int32_t *out_bits, const int32_t *const *operand_bits);
 int tfhe_b200_ctx_words(const tfhe_b200_ctx *ctx); /* n + 1 */
+int tfhe_b200_ctx_device(const tfhe_b200_ctx *ctx);
+
+/* Key generation ON THE GPU of ctx (new_random_gate_bootstrapping_secret_keyset,
+ * tfhe_gate_bootstrapping.cu:57-68): the secret bits are drawn on the host and returned, the 2000
+ * TLWE encryptions of the bootstrapping key and the 24576 key-switch samples are generated in
+ * device memory (Philox counter-based streams) and loaded into ctx without a host round trip.
+ * bk_out / ks_out (host, flat formats) may be NULL. */
+int tfhe_b200_keygen_device(tfhe_b200_ctx *ctx, const tfhe_b200_params *p, uint64_t seed, double alpha_lwe,
+                            double alpha_bk, int32_t *lwe_key, int32_t *tlwe_key, int32_t *bk_out, int32_t *ks_out);
 
 /* ---- key and ciphertext FILES of stock TFHE clients (host only) -------------
  * The serialisation of gpuParallel/tfhe_io.cu (text parameter sections + binary payloads):

@@ -292,3 +292,53 @@ def test_launch_counter_counts_native_kernels(engine, oracle, keys):
     before = engine.launch_count
     engine.gate("AND", engine.to_device(ca), engine.to_device(ca))
     assert engine.launch_count - before >= 2  # blind-rotate + key switch
+
+
+def test_gpu_key_generation(pkg, oracle):
+    """tfhe_b200_keygen_device: keys generated in device memory are valid TFHE keys.
+    (i) key-switch samples: phase = h * s'_i * 2^-(2(j+1)) + small noise, h = 0 rows are zero;
+    (ii) bootstrapping-key rows: b - a (*) s' = noise (+ s_i * h_q on the diagonal rows), checked with
+    an exact negacyclic product on the host; (iii) gates evaluated with these keys decrypt correctly,
+    also by the CPU oracle on the downloaded flat keys."""
+    from oracle.pyoracle import FFT_FOLDED, Keys
+
+    eng = pkg.Engine(device=0)
+    sk = eng.keygen(77)
+    p = sk.params
+    assert set(np.unique(sk.lwe_key)) <= {0, 1} and 200 < sk.lwe_key.sum() < 300
+    # (i) key switch
+    ks = sk.ks.reshape(-1, p.n + 1)
+    ph = pkg.phases(sk.lwe_key, ks).astype(np.int64).reshape(1024, 8, 4)
+    assert np.all(sk.ks[:, :, 0, :] == 0)
+    i, j, h = np.meshgrid(np.arange(1024), np.arange(8), np.arange(4), indexing="ij")
+    msg = (sk.tlwe_key[i] * h).astype(np.int64) << (32 - 2 * (j + 1))
+    err = ((ph - msg + 2 ** 31) % 2 ** 32 - 2 ** 31)[:, :, 1:] / 2.0 ** 32
+    assert np.abs(err).max() < 8 * sk.alpha_lwe and 0.8 * sk.alpha_lwe < err.std() < 1.2 * sk.alpha_lwe
+    assert abs(err.mean()) < 1e-6  # re-centred noise
+    # (ii) bootstrapping key, a few rows
+    s = sk.tlwe_key.astype(np.int64)
+    for (ii, r) in [(0, 0), (3, 1), (17, 2), (499, 3)]:
+        a, b = sk.bk[ii, r, 0].astype(np.int64), sk.bk[ii, r, 1].astype(np.int64)
+        bloc, q = divmod(r, 2)
+        mu = int(sk.lwe_key[ii]) << (32 - 10 * (q + 1))  # s_i * h_q sits on coefficient 0 of polynomial `bloc`
+        if bloc == 1:
+            b[0] -= mu
+        else:
+            a[0] -= mu
+        full = np.convolve(a, s)  # degree <= 2046; X^1024 = -1
+        prod = full[:1024].copy()
+        prod[:1023] -= full[1024:]
+        e = b - prod
+        e = ((e + 2 ** 31) % 2 ** 32 - 2 ** 31) / 2.0 ** 32
+        assert np.abs(e).max() < 8 * sk.alpha_bk, (ii, r, np.abs(e).max())
+    # (iii) gates with the device-generated keys (already loaded in eng)
+    bits_a = np.array([0, 0, 1, 1] * 8, np.int32)
+    bits_b = np.array([0, 1, 0, 1] * 8, np.int32)
+    ca, cb = pkg.encrypt_bits(sk, bits_a, 1), pkg.encrypt_bits(sk, bits_b, 2)
+    out = eng.gate("NAND", eng.to_device(ca), eng.to_device(cb)).cpu().numpy()
+    assert np.array_equal(pkg.decrypt_bits(sk, out), 1 - (bits_a & bits_b))
+    keys = Keys(oracle.params, sk.lwe_key, sk.tlwe_key, sk.bk, sk.ks)
+    ctx = oracle.ctx(keys, FFT_FOLDED)
+    ref = np.stack([ctx.gate("XOR", ca[k], cb[k]) for k in range(4)])
+    assert np.array_equal(pkg.decrypt_bits(sk, ref), bits_a[:4] ^ bits_b[:4])
+    eng.close()
