@@ -38,23 +38,49 @@ constexpr int kCtWarps = 4;                       // ciphertexts per CTA
 // shared-memory bytes per iteration but leaves every sub-partition with a single warp that
 // cannot hide its own latencies (profiles/README.md: 503 ms vs 455 ms per 65536 gates).
 constexpr int kThreads = 2 * kCtWarps * 32;
-// Key ring: 8 KiB chunks = one result-polynomial half of one TGSW row.  Each role has its
-// own ring so that every consumer of a ring takes every chunk in order (a warp skipping
-// chunks could get two mbarrier phases ahead on a stage: parity aliasing).  Role r
-// multiplies rows r and 2+r; chunk order per iteration:
+// Key ring.  Role r multiplies rows r and 2+r; per iteration it streams four 8 KiB
+// "halves" (one result polynomial of one TGSW row) in the order
 //   (row r, half r), (row r, half 1-r), (row 2+r, half r), (row 2+r, half 1-r)
-// i.e. always the half this role KEEPS first, then the half it GIVES to its partner.
-constexpr int kStages = 6;
-constexpr uint32_t kRingStages = 3;     // per role
-constexpr uint32_t kChunksPerIter = 4;  // per role
-constexpr uint32_t kStageBytes = kBkHalfCplx * sizeof(cpx);
+// i.e. always the half this role KEEPS first, then the half it GIVES to its partner.  A half is
+// streamed as 16/kChunkPos chunks of kChunkPos positions.  Each (stream, role) has its own ring so
+// that every consumer of a ring takes every chunk in order (a warp skipping chunks could get two
+// mbarrier phases ahead on a stage: parity aliasing).  kGroups = 1: one key stream for the four
+// ciphertexts of the CTA; kGroups = 2: ciphertexts {0,1} and {2,3} have their own streams (twice the
+// L2 -> shared-memory traffic) and can run out of phase with each other.
+#ifndef TFHE_B200_BR_GROUPS
+#define TFHE_B200_BR_GROUPS 1
+#endif
+#ifndef TFHE_B200_BR_CHUNK_POS
+#define TFHE_B200_BR_CHUNK_POS (16 / TFHE_B200_BR_GROUPS)
+#endif
+#ifndef TFHE_B200_BR_ANTIPHASE
+#define TFHE_B200_BR_ANTIPHASE 0
+#endif
+#ifndef TFHE_B200_BR_PAIR_SAME_SMSP
+#define TFHE_B200_BR_PAIR_SAME_SMSP 0
+#endif
+#ifndef TFHE_B200_BR_RING_ATOMIC
+#define TFHE_B200_BR_RING_ATOMIC 1
+#endif
+constexpr int kGroups = TFHE_B200_BR_GROUPS;
+constexpr int kGroupCts = kCtWarps / kGroups;          // consumer warps of one ring
+constexpr int kChunkPos = TFHE_B200_BR_CHUNK_POS;      // positions per chunk
+constexpr int kChunksPerHalf = 16 / kChunkPos;
+constexpr int kChunkCplx = kChunkPos * 32;
+constexpr uint32_t kStageBytes = kChunkCplx * sizeof(cpx);
+constexpr uint32_t kRingStages = (24u * 1024u / kGroups) / kStageBytes;   // per ring: 24 KiB per role in total
+constexpr uint32_t kChunksPerIter = 4 * kChunksPerHalf;                   // per role
+constexpr int kStages = kGroups * 2 * (int) kRingStages;
+static_assert(kGroups == 1 || kGroups == 2, "one or two key streams");
+static_assert(kRingStages >= 2, "ring too shallow");
 
 struct __align__(128) CtaSmem {
     WarpSmem w[kCtWarps];
     cpx e2[32 * kE2Row];
-    cpx ring[kStages][kBkHalfCplx];
+    cpx ring[kStages][kChunkCplx];
     unsigned long long full[kStages];   // mbarriers: TMA completion of a ring stage
-    unsigned int drained[kStages];      // warps that have finished with the stage's current row
+    unsigned long long empty[kStages];  // mbarriers: all consumer warps have read the stage
+    unsigned int drained[kStages];      // TFHE_B200_BR_RING_ATOMIC: warps that have finished with the stage
 };
 
 static_assert(sizeof(WarpSmem) % 16 == 0, "warp working set must keep 16 B alignment");
@@ -74,6 +100,10 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(unsigned long long *bar, u
                  : "memory");
 }
 
+__device__ __forceinline__ void mbar_arrive(unsigned long long *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
 __device__ __forceinline__ void mbar_wait(unsigned long long *bar, uint32_t parity) {
     asm volatile(
         "{\n"
@@ -86,6 +116,21 @@ __device__ __forceinline__ void mbar_wait(unsigned long long *bar, uint32_t pari
         "}\n" ::"r"(smem_u32(bar)),
         "r"(parity)
         : "memory");
+}
+
+// Non-blocking probe: has the phase with this parity completed?  (acquire, like the wait)
+__device__ __forceinline__ bool mbar_test(unsigned long long *bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
 }
 
 // 1-D bulk copy global -> shared, completion signalled on an mbarrier (TMA unit).
@@ -105,6 +150,11 @@ struct RingPos {
             stage = 0;
             phase ^= 1;
         }
+    }
+    __device__ __forceinline__ RingPos next(uint32_t nstages) const {
+        RingPos r = *this;
+        r.advance(nstages);
+        return r;
     }
 };
 
@@ -128,38 +178,143 @@ __device__ __forceinline__ void build_e2(cpx *e2) {
 // modSwitchFromTorus32(x, 2N), numeric-functions.cu:60-66  ==  ((uint32)x + 2^20) >> 21
 __device__ __forceinline__ int modswitch_2N(uint32_t x) { return (int) ((x + (1u << 20)) >> 21); }
 
-// Issue the TMA copy of chunk `chunk` of role `role`'s ring into absolute stage `stage`
-// (one elected lane).
-__device__ __forceinline__ void ring_fill(CtaSmem &S, const BrLaunch &L, int role, uint32_t chunk, uint32_t stage) {
-    const uint32_t it = (chunk >> 2) % (uint32_t) L.n_iter;
-    const uint32_t sub = chunk & 3u;
-    const uint32_t row = (uint32_t) role + 2u * (sub >> 1);
-    const uint32_t out = (sub & 1u) ? 1u - (uint32_t) role : (uint32_t) role;
-    const cpx *src = L.bk + ((size_t) (L.bk_first + it) * kKpl + row) * kBkRowCplx + out * kBkHalfCplx;
+#ifndef TFHE_B200_PHASE_TIMING
+#define TFHE_B200_PHASE_TIMING 0
+#endif
+#if TFHE_B200_PHASE_TIMING
+// Development aid: cycles spent per phase by warp 0 of CTA 0 (tools/phase_timing.py).
+__device__ long long g_phase_cycles[16];
+#define PHASE_T0() long long pt_ = clock64()
+#define PHASE_SUB0() long long ps_ = clock64()
+#define PHASE_SUB(i)                                               \
+    do {                                                           \
+        const long long now_ = clock64();                          \
+        if (blockIdx.x == 0 && threadIdx.x == TFHE_B200_PHASE_THREAD) atomicAdd((unsigned long long *) &g_phase_cycles[i], (unsigned long long) (now_ - ps_));   \
+        ps_ = now_;                                                \
+    } while (0)
+#define PHASE_MARK(i)                                              \
+    do {                                                           \
+        const long long now_ = clock64();                          \
+        if (blockIdx.x == 0 && threadIdx.x == TFHE_B200_PHASE_THREAD) atomicAdd((unsigned long long *) &g_phase_cycles[i], (unsigned long long) (now_ - pt_));   \
+        pt_ = now_;                                                \
+    } while (0)
+#ifndef TFHE_B200_PHASE_THREAD
+#define TFHE_B200_PHASE_THREAD 0
+#endif
+#else
+#define PHASE_T0() do {} while (0)
+#define PHASE_SUB0() do {} while (0)
+#define PHASE_SUB(i) do {} while (0)
+#define PHASE_MARK(i) do {} while (0)
+#endif
+
+// Issue the TMA copy of chunk `sub` (0..kChunksPerIter-1) of blind-rotation iteration `it` of role
+// `role`'s stream into absolute stage `stage` (one elected lane).
+__device__ __forceinline__ void ring_fill_at(CtaSmem &S, const BrLaunch &L, int role, uint32_t it, uint32_t sub,
+                                             uint32_t stage) {
+    const uint32_t hf = sub / kChunksPerHalf, part = sub % kChunksPerHalf;
+    const uint32_t row = (uint32_t) role + 2u * (hf >> 1);
+    const uint32_t out = (hf & 1u) ? 1u - (uint32_t) role : (uint32_t) role;
+    const cpx *src = L.bk + ((size_t) (L.bk_first + it) * kKpl + row) * kBkRowCplx + out * kBkHalfCplx +
+                     part * kChunkCplx;
     mbar_arrive_expect_tx(&S.full[stage], kStageBytes);
     tma_load_1d(S.ring[stage], src, kStageBytes, &S.full[stage]);
 }
 
-// Consumer side of one chunk: wait for it, use it, and let the last of the 4 warps that read
-// it issue the refill of its stage.
-template <typename Use>
-__device__ __forceinline__ void ring_consume(CtaSmem &S, const BrLaunch &L, int role, int lane, RingPos &rp,
-                                             uint32_t ring_base, uint32_t ring_chunks, Use use) {
-    const uint32_t st = ring_base + rp.stage;
-    mbar_wait(&S.full[st], rp.phase);
-    use(S.ring[st]);
-    __syncwarp();
-    if (lane == 0) {
-        const unsigned int seen = atomicAdd(&S.drained[st], 1u);
-        if ((seen & (kCtWarps - 1)) == kCtWarps - 1) {
-            const uint32_t next = rp.chunk + kRingStages;
-            if (next < ring_chunks) {
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                ring_fill(S, L, role, next, st);
-            }
+// The same by running chunk number (priming only: the modulo is a division by a run-time value).
+__device__ __forceinline__ void ring_fill(CtaSmem &S, const BrLaunch &L, int role, uint32_t chunk, uint32_t stage) {
+    ring_fill_at(S, L, role, (chunk / kChunksPerIter) % (uint32_t) L.n_iter, chunk % kChunksPerIter, stage);
+}
+
+// Where a consumer is in the key stream: ring position plus (iteration, chunk of the iteration),
+// kept incrementally so that a refill needs no division.
+struct StreamPos {
+    RingPos rp;
+    uint32_t it = 0, sub = 0;
+    __device__ __forceinline__ void advance(uint32_t n_iter) {
+        rp.advance(kRingStages);
+        if (++sub == kChunksPerIter) {
+            sub = 0;
+            if (++it == n_iter) it = 0;
         }
     }
-    rp.advance(kRingStages);
+};
+
+// Has the chunk `ahead` positions after the current one already landed?  Probed EARLY (before the
+// transform that precedes a multiply) so that the barrier round trip is off the critical path.
+__device__ __forceinline__ bool ring_probe(CtaSmem &S, const StreamPos &sp, uint32_t ring_base, int ahead) {
+    RingPos r = sp.rp;
+    for (int i = 0; i < ahead; i++) r.advance(kRingStages);
+    return mbar_test(&S.full[ring_base + r.stage], r.phase);
+}
+
+// Consumer side of one chunk.  Release is an mbarrier arrive (no round trip: the first version
+// counted drainers with an atomicAdd whose result every warp waited for, and the last drainer
+// issued the refill behind a proxy fence).  The refill of the stage a chunk leaves is issued
+// LAZILY by one designated consumer (round robin over the ring's warps) when it comes back for
+// its next chunk: by then the other warps have normally released the stage.
+template <typename Use>
+__device__ __forceinline__ void ring_consume(CtaSmem &S, const BrLaunch &L, int role, int lane, uint32_t my_idx,
+                                             StreamPos &sp, uint32_t ring_base, uint32_t ring_chunks, bool ready,
+                                             Use use) {
+    PHASE_SUB0();
+    const RingPos &rp = sp.rp;
+#ifdef TFHE_B200_EXP_NORING  // timing experiment only (results are garbage): a key stream that costs nothing
+    use(S.ring[ring_base + rp.stage]);
+    sp.advance((uint32_t) L.n_iter);
+    return;
+#endif
+#if TFHE_B200_BR_RING_ATOMIC
+    // first protocol: count drainers with an atomic, the last one refills the stage at once
+    {
+        const uint32_t st = ring_base + rp.stage;
+        if (!ready) mbar_wait(&S.full[st], rp.phase);
+        use(S.ring[st]);
+        __syncwarp();
+        if (lane == 0) {
+            const unsigned int seen = atomicAdd(&S.drained[st], 1u);
+            if ((seen % kGroupCts) == kGroupCts - 1 && rp.chunk + kRingStages < ring_chunks) {
+                uint32_t fsub = sp.sub + kRingStages, fit = sp.it;
+                if (fsub >= kChunksPerIter) {
+                    fsub -= kChunksPerIter;
+                    if (++fit >= (uint32_t) L.n_iter) fit = 0;
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                ring_fill_at(S, L, role, fit, fsub, st);
+            }
+        }
+        sp.advance((uint32_t) L.n_iter);
+        return;
+    }
+#endif
+    if (rp.chunk > 0) {
+        const uint32_t p = rp.chunk - 1;  // refill duty for the chunk released by the previous call
+        if ((p % (uint32_t) kGroupCts) == my_idx && p + kRingStages < ring_chunks && lane == 0) {
+            const uint32_t ps = rp.stage == 0 ? kRingStages - 1 : rp.stage - 1;
+            const uint32_t pphase = rp.stage == 0 ? rp.phase ^ 1u : rp.phase;
+            // chunk p + kRingStages = (kRingStages - 1) chunks after the current one
+            static_assert(kRingStages < kChunksPerIter, "refill target is at most one iteration ahead");
+            uint32_t fsub = sp.sub + kRingStages - 1, fit = sp.it;
+            if (fsub >= kChunksPerIter) {
+                fsub -= kChunksPerIter;
+                if (++fit >= (uint32_t) L.n_iter) fit = 0;
+            }
+            mbar_wait(&S.empty[ring_base + ps], pphase);
+            ring_fill_at(S, L, role, fit, fsub, ring_base + ps);
+        }
+    }
+    const uint32_t st = ring_base + rp.stage;
+    PHASE_SUB(12);
+#ifndef TFHE_B200_EXP_NOWAIT  // timing experiment only: results are garbage
+    if (!ready) mbar_wait(&S.full[st], rp.phase);
+#endif
+    PHASE_SUB(13);
+    use(S.ring[st]);
+    PHASE_SUB(14);
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&S.empty[st]);
+    sp.advance((uint32_t) L.n_iter);
+    PHASE_SUB(15);
 }
 
 // Operands of the gate prologue of bootstrap g (x = (0,cst) + sa*in0 + sb*in1 [+ sc*in2]).
@@ -205,6 +360,23 @@ __device__ __forceinline__ void named_sync(int id, int nthreads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
+__device__ __forceinline__ void named_arrive(int id, int nthreads) {
+    asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+// Fourier MAC of z against one 8 KiB half streamed as kChunksPerHalf ring chunks; `ready`: the first
+// chunk was seen complete by an earlier probe.
+template <int PART>
+__device__ __forceinline__ void mac_stream(CtaSmem &S, const BrLaunch &L, int role, int lane, uint32_t my_idx,
+                                           StreamPos &sp, uint32_t ring_base, uint32_t ring_chunks, bool ready,
+                                           const cpx (&z)[16], cpx (&acc)[16]) {
+    ring_consume(S, L, role, lane, my_idx, sp, ring_base, ring_chunks, PART == 0 && ready, [&](const cpx *part) {
+        phase_mac_part<PART * kChunkPos, kChunkPos>(lane, z, part, acc);
+    });
+    if constexpr (PART + 1 < kChunksPerHalf)
+        mac_stream<PART + 1>(S, L, role, lane, my_idx, sp, ring_base, ring_chunks, false, z, acc);
+}
+
 __global__ void __launch_bounds__(kThreads, 1) blind_rotate_kernel(const BrLaunch L) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     CtaSmem &S = *reinterpret_cast<CtaSmem *>(smem_raw);
@@ -223,27 +395,45 @@ __global__ void __launch_bounds__(kThreads, 1) blind_rotate_kernel(const BrLaunc
     if (threadIdx.x == 0) {
         for (int s = 0; s < kStages; s++) {
             mbar_init(&S.full[s], 1);
+            mbar_init(&S.empty[s], kGroupCts);
             S.drained[s] = 0;
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        // prime the ring; afterwards the last warp to drain a stage refills it (no producer warp:
-        // a ninth warp would cap the kernel at 168 registers per thread)
-        for (int r = 0; r < 2; r++)
+        // prime the rings; afterwards the consumers refill them (no producer warp: a ninth warp
+        // would cap the kernel at 168 registers per thread)
+        for (int r = 0; r < 2 * kGroups; r++)
             for (uint32_t c = 0; c < kRingStages && c < kChunksPerIter * iters_total; c++)
-                ring_fill(S, L, r, c, r * kRingStages + c);
+                ring_fill(S, L, r & 1, c, r * kRingStages + c);
     }
     __syncthreads();
     const bool rotate = (L.extern_only == 0);
 
     // -------------------- ciphertext warps ------------------------------------------
-    const int ct = warp >> 1, role = warp & 1;
+#if TFHE_B200_BR_PAIR_SAME_SMSP
+    const int ct = warp & 3, role = warp >> 2;   // both warps of a ciphertext on one sub-partition
+#else
+    const int ct = warp >> 1, role = warp & 1;   // sub-partition w%4 holds the same role of two ciphertexts
+#endif
     WarpSmem &W = S.w[ct];
     const int bar_id = 1 + ct;
     // barrier of the two warps of one ciphertext
+#ifdef TFHE_B200_EXP_NOSYNC  // timing experiment only: results are garbage
+    auto pair_sync = [bar_id]() { __syncwarp(); };
+#else
     auto pair_sync = [bar_id]() { named_sync(bar_id, 64); };
-    const uint32_t ring_base = role * kRingStages;
+#endif
+    const int grp_id = ct / kGroupCts;                    // key stream of this ciphertext
+    const uint32_t my_idx = (uint32_t) (ct % kGroupCts);  // consumer index inside the ring
+    const uint32_t ring_base = (uint32_t) (grp_id * 2 + role) * kRingStages;
     const uint32_t ring_chunks = kChunksPerIter * iters_total;
-    RingPos rp;
+#if TFHE_B200_BR_ANTIPHASE
+    // Stream B (ciphertexts 2,3) runs behind stream A (0,1): B starts iteration i only when A has
+    // reached its multiply phase, and A starts iteration i+1 only when B has reached its own, so
+    // the two warps that share an SM sub-partition are never both in the integer front phase.
+    static_assert(kGroups == 2, "anti-phase schedule needs two key streams");
+    uint32_t gi = 0;  // iterations done by this warp since kernel start
+#endif
+    StreamPos sp;
     for (int grp = blockIdx.x; grp < ngroups; grp += gridDim.x) {
         int g = grp * cpg + ct;
         const bool valid = ct < cpg && g < L.total;
@@ -273,6 +463,8 @@ __global__ void __launch_bounds__(kThreads, 1) blind_rotate_kernel(const BrLaunc
             }
         }
         pair_sync();
+        phase_ext_build(lane, W, role);
+        pair_sync();
 
         int a_blk = 0;  // lane l holds bara of iteration (it & ~31) + l
         for (int it = 0; it < n_iter; it++) {
@@ -281,10 +473,39 @@ __global__ void __launch_bounds__(kThreads, 1) blind_rotate_kernel(const BrLaunc
             // tfhe_blindRotate_FFT :705 skips barai == 0 (no-op); idle slots do no arithmetic either
             const bool active = valid && ((a != 0) || !rotate);
 
-            if (active) {
-                phase_f1q(lane, W, a, role, rotate);
+#if TFHE_B200_BR_ANTIPHASE
+            if (grp_id == 1) named_sync(5, 2 * kThreads / 2);          // B waits for A's multiply phase
+            else if (gi > 0) named_sync(6, 2 * kThreads / 2);          // A waits for B's previous one
+#endif
+            PHASE_T0();
+            if (!active) {
+                // nothing to compute (bara = 0, or an idle slot of a small batch): only keep this
+                // warp's place in the key stream
+#if TFHE_B200_BR_ANTIPHASE
+                if (grp_id == 0) named_arrive(5, 2 * kThreads / 2);
+                else if (gi + 1 < iters_total) named_arrive(6, 2 * kThreads / 2);
+                gi++;
+#endif
+#pragma unroll 1
+                for (uint32_t c = 0; c < kChunksPerIter; c++)
+                    ring_consume(S, L, role, lane, my_idx, sp, ring_base, ring_chunks, false, [](const cpx *) {});
+                continue;
+            }
+            // ---- one MuxRotate step: straight-line code, no per-phase conditionals -----------
+            {
+                cpx x[32];
+                phase_f1q_load(lane, W, a, role, rotate, x);
+                pair_sync();   // the stores overwrite the extended accumulator copy both warps read
+                if (!rotate) phase_acc_clear(lane, W, role);  // external product only: result replaces ACC
+                phase_f1q_store(lane, W, role, x);
                 __syncwarp();  // a warp multiplies exactly the rows it has just transformed
             }
+            PHASE_MARK(0);
+#if TFHE_B200_BR_ANTIPHASE
+            if (grp_id == 0) named_arrive(5, 2 * kThreads / 2);
+            else if (gi + 1 < iters_total) named_arrive(6, 2 * kThreads / 2);
+            gi++;
+#endif
             // keep / give: partial sums of the result polynomial this warp finishes / hands over
             cpx keep[16], give[16];
 #pragma unroll
@@ -295,25 +516,34 @@ __global__ void __launch_bounds__(kThreads, 1) blind_rotate_kernel(const BrLaunc
 #pragma unroll 1
             for (int row = role; row < kKpl; row += 2) {
                 cpx z[16];
-                if (active) phase_f2_fft(lane, W, S.e2, row, z);
-                ring_consume(S, L, role, lane, rp, ring_base, ring_chunks, [&](const cpx *half) {
-                    if (active) phase_mac_half(lane, z, half, keep);
-                });
-                ring_consume(S, L, role, lane, rp, ring_base, ring_chunks, [&](const cpx *half) {
-                    if (active) phase_mac_half(lane, z, half, give);
-                });
+                const bool rdy_keep = ring_probe(S, sp, ring_base, 0);
+                const bool rdy_give = ring_probe(S, sp, ring_base, kChunksPerHalf);
+                phase_f2_fft(lane, W, S.e2, row, z);
+                PHASE_MARK(1);
+                mac_stream<0>(S, L, role, lane, my_idx, sp, ring_base, ring_chunks, rdy_keep, z, keep);
+                PHASE_MARK(2);
+                mac_stream<0>(S, L, role, lane, my_idx, sp, ring_base, ring_chunks, rdy_give, z, give);
+                PHASE_MARK(3);
             }
-            if (active) {
-                phase_xchg_store(lane, W, role, give);
-                pair_sync();
-                phase_xchg_load_inv(lane, W, S.e2, role, keep);
-                pair_sync();
+            phase_xchg_store(lane, W, role, give);
+            PHASE_MARK(4);
+            pair_sync();
+            PHASE_MARK(5);
+            phase_xchg_load_inv(lane, W, S.e2, role, keep);
+            PHASE_MARK(6);
+            pair_sync();
+            PHASE_MARK(7);
+            {
                 cpx x[16];
                 phase_i2_half(lane, W, role, x);
+                PHASE_MARK(8);
                 pair_sync();
-                phase_i2_final(lane, W, role, x, rotate);
-                pair_sync();
+                PHASE_MARK(9);
+                phase_i2_final(lane, W, role, x);
             }
+            PHASE_MARK(10);
+            pair_sync();
+            PHASE_MARK(11);
         }
 
         if (valid && role == 0) {
@@ -341,6 +571,7 @@ __global__ void __launch_bounds__(kThreads, 1) blind_rotate_kernel(const BrLaunc
 #endif
 constexpr int kWarpCts = TFHE_B200_WARP_CTS;
 constexpr uint32_t kWRingStages = 3;
+constexpr uint32_t kWStageBytes = kBkHalfCplx * sizeof(cpx);
 constexpr uint32_t kWChunksPerIter = 2 * kKpl;
 
 struct __align__(128) CtaSmemW {
@@ -360,8 +591,8 @@ __device__ __forceinline__ void ring_fill_w(CtaSmemW &S, const BrLaunch &L, uint
     const uint32_t q = sub >> 2, o = (sub >> 1) & 1u, out = sub & 1u;
     const uint32_t row = o * kL + q;
     const cpx *src = L.bk + ((size_t) (L.bk_first + it) * kKpl + row) * kBkRowCplx + out * kBkHalfCplx;
-    mbar_arrive_expect_tx(&S.full[stage], kStageBytes);
-    tma_load_1d(S.ring[stage], src, kStageBytes, &S.full[stage]);
+    mbar_arrive_expect_tx(&S.full[stage], kWStageBytes);
+    tma_load_1d(S.ring[stage], src, kWStageBytes, &S.full[stage]);
 }
 
 template <typename Use>
@@ -519,6 +750,17 @@ forward_polys_kernel(const int32_t *__restrict__ coef, cpx *__restrict__ out, in
 }  // namespace
 
 size_t blind_rotate_smem_bytes() { return sizeof(CtaSmem); }
+
+#if TFHE_B200_PHASE_TIMING
+extern "C" int tfhe_b200_debug_phase_cycles(long long *out, int reset) {
+    if (cudaMemcpyFromSymbol(out, g_phase_cycles, sizeof(g_phase_cycles)) != cudaSuccess) return 1;
+    if (reset) {
+        long long z[16] = {0};
+        if (cudaMemcpyToSymbol(g_phase_cycles, z, sizeof(z)) != cudaSuccess) return 1;
+    }
+    return 0;
+}
+#endif
 
 cudaError_t blind_rotate_configure() {
     cudaError_t e = cudaFuncSetAttribute(blind_rotate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,

@@ -56,7 +56,8 @@ constexpr int kKpl = (kK + 1) * kL;
 constexpr uint32_t kDecompOffset = 0x80200000u;
 constexpr int kExchRow = 17;      // complex per exchange row (16 used)
 constexpr int kExchPoly = 32 * kExchRow;
-constexpr int kAccRow = 65;       // words per accumulator row (64 used)
+constexpr int kAccRow = 68;       // words per accumulator row (64 used): 16 B aligned rows whose 128-bit
+                                  // accesses by 8 lanes (rows j2..j2+7) cover the 32 banks exactly once
 constexpr int kAccPoly = 16 * kAccRow;
 constexpr int kE2Row = 5;         // complex per pass-2 constant row (4 used; 80 B stride is conflict free)
 constexpr int kBkHalfCplx = 16 * 32;                // one result polynomial of a TGSW row: [pos][m1]
@@ -67,11 +68,33 @@ struct cpx {
     double x, y;
 };
 
-// Per-warp shared-memory working set.
-struct WarpSmem {
-    cpx exch[kKpl][kExchPoly];     // 4 * 8704 B
-    int32_t acc[kK + 1][kAccPoly]; // 2 * 4160 B
+// Extended accumulator copy (see phase_f1q_load): row of 127 words per (o, j2),
+//   E[63 + k] = +row[k] (k = 0..63),  E[63 + k] = -row[64 + k] (k = -63..-1)
+// i.e. the negacyclic continuation of the 64-coefficient row to the left, so that a rotated read
+// is `base + e` with a per-lane base and NO per-element index or sign arithmetic.
+// Rows are 127 words (odd: the 16 rows of a polynomial start in 16 different banks, so the
+// single-word rotated reads are conflict free inside a polynomial; 16 B aligned rows, which
+// 128-bit stores would need, put 32 single-word readers on 8 banks: measured slower).
+constexpr int kExtRow = 127;
+constexpr int kExtOrg = 63;       // word of row[0]; -row[i] is at word i - 1 (row[0] has no left image)
+constexpr int kExtShift = 16;     // extra word offset of polynomial o = 1 (other half of the banks)
+
+struct alignas(16) word4 {
+    int32_t v[4];
 };
+
+// Per-ciphertext shared-memory working set.
+struct WarpSmem {
+    union {
+        cpx exch[kKpl][kExchPoly];          // 4 * 8704 B: transform exchange buffers
+        int32_t exw[kKpl][kExchPoly * 4];   // the same as words: buffers 2 and 3 hold the extended
+                                            // accumulator copy between iterations
+    };
+    int32_t acc[kK + 1][kAccPoly]; // 2 * 4160 B: the accumulator (master copy)
+};
+static_assert(16 * kExtRow + kExtShift <= kExchPoly * 4, "extended copy must fit an exchange buffer");
+
+TFHE_HD int32_t *ext_poly(WarpSmem &ws, int o) { return ws.exw[2 + o] + kExtShift * o; }
 
 TFHE_HD constexpr int bitrev5(int v) {
     return ((v & 1) << 4) | ((v & 2) << 2) | (v & 4) | ((v & 8) >> 2) | ((v & 16) >> 4);
@@ -111,9 +134,30 @@ TFHE_HD double digit_to_double(uint32_t dig) {
 #endif
 }
 
-// double -> Torus32 exactly as the reference does it: Torus32(int64_t(x)), i.e. truncation
-// toward zero, then wrap (fft_processor_fftw.cu:177).
-TFHE_HD uint32_t double_to_torus32(double x) { return (uint32_t) (int32_t) (long long) x; }
+// double -> Torus32.  The reference does Torus32(int64_t(x)) (fft_processor_fftw.cu:177): truncation
+// toward zero of a value that lies within fp64 rounding error (about 0.1) of the exact integer n
+// of the negacyclic product, i.e. n or n -+ 1 at random.  Default here: round to nearest through the
+// 2^52 + 2^51 magic constant (one DADD on the fp64 pipe; the low mantissa word is the two's
+// complement result for |x| < 2^51), which returns n itself; F2I.S64.F64 runs on the quarter-rate
+// XU pipe (8 cycles per warp instruction, measured) with a long latency in front of the
+// accumulator update.  -DTFHE_B200_TRUNCATE_LIKE_REFERENCE=1 restores the cast.
+#ifndef TFHE_B200_TRUNCATE_LIKE_REFERENCE
+#define TFHE_B200_TRUNCATE_LIKE_REFERENCE 0
+#endif
+TFHE_HD uint32_t double_to_torus32(double x) {
+#if TFHE_B200_TRUNCATE_LIKE_REFERENCE
+    return (uint32_t) (int32_t) (long long) x;
+#else
+    const double y = x + 6755399441055744.0;  // 2^52 + 2^51
+#ifdef __CUDA_ARCH__
+    return (uint32_t) __double2loint(y);
+#else
+    uint64_t bits;
+    __builtin_memcpy(&bits, &y, sizeof(bits));
+    return (uint32_t) bits;
+#endif
+#endif
+}
 
 // acc += z * w
 TFHE_HD void cmac(cpx &acc, const cpx &z, const cpx &w) {
@@ -288,45 +332,75 @@ TFHE_HD void phase_init(int lane, WarpSmem &ws, int barb, int32_t mu) {
 // Partial Fourier sums and the half-pass values are exchanged through exchange rows that
 // are free at that point.
 
+// Build the extended copy of both accumulator polynomials from the master copy (start of a
+// ciphertext; afterwards phase_i2_final keeps it up to date).  Role r copies coefficients
+// [32r, 32r + 32) of every row.
+TFHE_HD void phase_ext_build(int lane, WarpSmem &ws, int role) {
+    const int o = lane >> 4, j2 = lane & 15;
+    const int32_t *row = ws.acc[o] + j2 * kAccRow + 32 * role;
+    int32_t *ext = ext_poly(ws, o) + j2 * kExtRow + 32 * role;
+#pragma unroll 2
+    for (int b = 0; b < 32; b += 4) {
+        const word4 v = *reinterpret_cast<const word4 *>(row + b);
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            ext[kExtOrg + b + i] = v.v[i];
+            if (b + i > 0 || role != 0) ext[b + i - 1] = (int32_t) (0u - (uint32_t) v.v[i]);
+        }
+    }
+}
+
 // Pass 1 of the two forward transforms of digit level q (decomposed rows (o, q), o = 0..k),
 // fused with the rotation (torusPolynomialMulByXaiMinusOne, toruspolynomial-functions.cu:191-213)
 // and the gadget decomposition (tGswTorus32PolynomialDecompH, tgsw-functions.cu:301-352).
 // rotate == false: plain decomposition of ACC (stand-alone external product).
-TFHE_HD void phase_f1q(int lane, WarpSmem &ws, int a, int q, bool rotate = true) {
+//
+// Coefficient j = 16 e + j2 of X^a * ACC is (-1)^f * ACC[16 (e - sh) + j2p] continued negacyclically,
+// with a = 16 a_hi + a_lo, j2p = (j2 - a_lo) mod 16, sh = a_hi + [j2 < a_lo] = 64 f + h: in the
+// extended row of (o, j2p) that is word kExtOrg - h + e, so the 64 rotated values of a lane are read
+// at immediate offsets from ONE base.  Sign, the subtraction of ACC, the decomposition offset
+// and the digit shift are two integer multiply-adds (t * 2^(10 q) = v * (+-2^(10 q)) +
+// (ACC * -2^(10 q) + offset * 2^(10 q)); digit = top 10 bits), on the FMA pipe: the first version
+// spent 19 instructions per coefficient here, most of them on the half-rate ALU pipe.
+// The outputs are NOT stored: the extended copy lives in exchange buffers 2 and 3, which the
+// stores overwrite, so the pair synchronises between load and store.
+TFHE_HD void phase_f1q_load(int lane, WarpSmem &ws, int a, int q, bool rotate, cpx (&x)[32]) {
     const int o = lane >> 4, j2 = lane & 15;
     const int a_lo = a & 15, a_hi = a >> 4;
     const int j2p = (j2 - a_lo) & 15;
     const int sh = a_hi + (j2 < a_lo ? 1 : 0);
+    const int h = sh & 63;
+    const uint32_t m = 1u << (q * kBgbit);
+    const uint32_t sm = rotate ? (((sh >> 6) & 1) ? 0u - m : m) : 0u;  // multiplier of the rotated value
+    const uint32_t cm = rotate ? 0u - m : m;                            // multiplier of ACC itself
+    const uint32_t offm = kDecompOffset * m;
     const int32_t *own = ws.acc[o] + j2 * kAccRow;
-    const int32_t *rot = ws.acc[o] + j2p * kAccRow;
-    const int shift = 32 - (q + 1) * kBgbit;
-    const uint32_t rmask = rotate ? 0xffffffffu : 0u;  // rotate == false: T = ACC
-    cpx x[32];
-    // blocks of 16 coefficients: all shared-memory loads of a block are issued before its
-    // integer work so that their latencies overlap
+    const int32_t *rot = ext_poly(ws, o) + j2p * kExtRow + (kExtOrg - h);
 #pragma unroll
     for (int blk = 0; blk < 64; blk += 16) {
         uint32_t vr[16], vo[16];
 #pragma unroll
-        for (int i = 0; i < 16; i++) {
-            const int idx = (blk + i - sh) & 127;
-            vr[i] = (uint32_t) rot[idx & 63];
-            vo[i] = (uint32_t) own[blk + i];
+        for (int i = 0; i < 16; i++) vr[i] = (uint32_t) rot[blk + i];
+#pragma unroll
+        for (int i = 0; i < 16; i += 4) {
+            const word4 w = *reinterpret_cast<const word4 *>(own + blk + i);
+#pragma unroll
+            for (int k = 0; k < 4; k++) vo[i + k] = (uint32_t) w.v[k];
         }
 #pragma unroll
         for (int i = 0; i < 16; i++) {
             const int e = blk + i;
-            const int idx = (e - sh) & 127;
-            const uint32_t neg = 0u - (uint32_t) ((idx >> 6) & 1);  // branch-free negacyclic sign
-            const uint32_t v = ((vr[i] ^ neg) - neg) & rmask;
-            // rotate: X^a*ACC - ACC ; otherwise +ACC
-            const uint32_t t = (rotate ? v - vo[i] : vo[i]) + kDecompOffset;
-            const double d = digit_to_double((t >> shift) & 1023u);
+            const uint32_t t = vr[i] * sm + (vo[i] * cm + offm);
+            const double d = digit_to_double(t >> (32 - kBgbit));
             if (e < 32) x[e & 31].x = d;
             else x[e & 31].y = d;
         }
     }
     fwd32(x);
+}
+
+TFHE_HD void phase_f1q_store(int lane, WarpSmem &ws, int q, const cpx (&x)[32]) {
+    const int o = lane >> 4, j2 = lane & 15;
     cpx *dst = ws.exch[o * kL + q] + j2;
 #pragma unroll
     for (int pos = 0; pos < 32; pos++) dst[bitrev5(pos) * kExchRow] = x[pos];
@@ -346,6 +420,23 @@ TFHE_HD void phase_f2_fft(int lane, WarpSmem &ws, const cpx *e2, int row, cpx (&
 TFHE_HD void phase_mac_half(int lane, const cpx (&z)[16], const cpx *half, cpx (&acc)[16]) {
 #pragma unroll
     for (int pos = 0; pos < 16; pos++) cmac(acc[pos], z[pos], half[pos * 32 + lane]);
+}
+
+// The same over positions [POS0, POS0 + NPOS) only; `part` points at the ring chunk that holds
+// exactly those positions ([pos - POS0][m1]).
+template <int POS0, int NPOS>
+TFHE_HD void phase_mac_part(int lane, const cpx (&z)[16], const cpx *part, cpx (&acc)[16]) {
+#pragma unroll
+    for (int p = 0; p < NPOS; p++) {
+#ifdef TFHE_B200_EXP_NOKEYLDS  // timing experiment only: results are garbage
+        cpx w;
+        w.x = z[(POS0 + p + 1) & 15].x;
+        w.y = z[(POS0 + p + 1) & 15].y;
+        cmac(acc[POS0 + p], z[POS0 + p], w);
+#else
+        cmac(acc[POS0 + p], z[POS0 + p], part[p * 32 + lane]);
+#endif
+    }
 }
 
 // Hand the partial sum of the result polynomial the OTHER warp finishes to that warp:
@@ -396,54 +487,88 @@ TFHE_HD void phase_i2_half(int lane, WarpSmem &ws, int role, cpx (&x)[16]) {
             for (int i = 0; i < half; i++) bf_inv(x[b * 2 * half + i], x[b * 2 * half + i + half], er, ei);
         }
     }
+    // the last stage pairs position i of role 0 (u) with position i of role 1 (v): role 0 finishes
+    // pairs 0..7 and role 1 pairs 8..15, so each warp hands over only the 8 values the other needs
     cpx *dst = ws.exch[role] + lane;
+    if (role == 0) {
 #pragma unroll
-    for (int i = 0; i < 16; i++) dst[i * 32] = x[i];
+        for (int b = 0; b < 8; b++) dst[b * 32] = x[8 + b];
+    } else {
+#pragma unroll
+        for (int b = 0; b < 8; b++) dst[b * 32] = x[b];
+    }
 }
 
-// Inverse pass 1, last stage (pairs position i of role 0 with position i of role 1) for the
-// 16 outputs of this role, conversion to Torus32 (execute_direct_Torus32,
-// fft_processor_fftw.cu:168-181: double -> int64 truncation -> int32 wrap) and the tLweAddTo
-// of MuxRotate (tlwe-functions.cu:170).  Role 0 produces coefficients j1 = 0..15, role 1
-// j1 = 16..31 (and the matching upper-half coefficients from the imaginary parts).
-// accumulate == false: the result replaces ACC (stand-alone external product).
-TFHE_HD void phase_i2_final(int lane, WarpSmem &ws, int role, const cpx (&x)[16], bool accumulate = true) {
+// Inverse pass 1, last stage (pairs position i of role 0 with position i of role 1), conversion
+// to Torus32 (execute_direct_Torus32, fft_processor_fftw.cu:168-181; rounding: double_to_torus32)
+// and the tLweAddTo of MuxRotate (tlwe-functions.cu:170).  Role r finishes the 8 pairs
+// i = 8r .. 8r+7 completely: coefficients j1 = i and j1 = i + 16 of the row, and the matching
+// upper-half coefficients (+32) from the imaginary parts.
+template <int ROLE>
+TFHE_HD void i2_final_role(int lane, WarpSmem &ws, const cpx (&x)[16]) {
     const int o = lane >> 4, j2 = lane & 15;
-    const cpx *other = ws.exch[1 - role] + lane;
-    int32_t *row = ws.acc[o] + j2 * kAccRow + 16 * role;
+    const cpx *other = ws.exch[1 - ROLE] + lane;
+    int32_t *row = ws.acc[o] + j2 * kAccRow + 8 * ROLE;
+    int32_t *ext = ext_poly(ws, o) + j2 * kExtRow + 8 * ROLE;  // extended copy, same coefficients
     const double er = c1_re_rt(0), ei = c1_im_rt(0);
-    // blocks of 8 outputs: all loads, then all butterflies and conversions, then the updates
-    // (keeps the XU conversions and the shared-memory round trips overlapped)
+    // all loads first (128-bit accesses to the master copy: the 8 consecutive coefficients of a group
+    // are two aligned quads), then the butterflies and conversions, then the updates
+    cpx p[8];
+    word4 acc4[4][2];  // group g: coefficients 16 g + 8 ROLE + (0..7) of the row
 #pragma unroll
-    for (int blk = 0; blk < 16; blk += 8) {
-        cpx v[8];
-        uint32_t old_lo[8], old_hi[8];
+    for (int b = 0; b < 8; b++) p[b] = other[b * 32];
 #pragma unroll
-        for (int i = 0; i < 8; i++) {
-            v[i] = other[(blk + i) * 32];
-            old_lo[i] = accumulate ? (uint32_t) row[blk + i] : 0u;
-            old_hi[i] = accumulate ? (uint32_t) row[blk + i + 32] : 0u;
+    for (int g = 0; g < 4; g++)
+#pragma unroll
+        for (int h = 0; h < 2; h++) acc4[g][h] = *reinterpret_cast<const word4 *>(row + 16 * g + 4 * h);
+#pragma unroll
+    for (int b = 0; b < 8; b++) {
+        const cpx u = ROLE == 0 ? x[b] : p[b];
+        const cpx v = ROLE == 0 ? p[b] : x[8 + b];
+        const double sre = u.x + v.x, sim = u.y + v.y;      // u + v             -> coefficient j1 = i
+        const double tr = u.x - v.x, ti = u.y - v.y;        // conj(e) * (u - v) -> coefficient j1 = i + 16
+        const double dre = fma(er, tr, ei * ti), dim = fma(er, ti, -(ei * tr));
+        int32_t &c0 = acc4[0][b >> 2].v[b & 3], &c1 = acc4[1][b >> 2].v[b & 3];
+        int32_t &c2 = acc4[2][b >> 2].v[b & 3], &c3 = acc4[3][b >> 2].v[b & 3];
+        c0 = (int32_t) ((uint32_t) c0 + double_to_torus32(sre));
+        c1 = (int32_t) ((uint32_t) c1 + double_to_torus32(dre));
+        c2 = (int32_t) ((uint32_t) c2 + double_to_torus32(sim));   // imaginary parts: coefficients + 512
+        c3 = (int32_t) ((uint32_t) c3 + double_to_torus32(dim));
+    }
+#pragma unroll
+    for (int g = 0; g < 4; g++) {
+#pragma unroll
+        for (int h = 0; h < 2; h++) *reinterpret_cast<word4 *>(row + 16 * g + 4 * h) = acc4[g][h];
+        // extended copy: +value at kExtOrg + index, -value at index - 1 (index 0 has no left image)
+#pragma unroll
+        for (int b = 0; b < 8; b++) {
+            const uint32_t nv = (uint32_t) acc4[g][b >> 2].v[b & 3];
+            ext[kExtOrg + 16 * g + b] = (int32_t) nv;
+            if (16 * g + b > 0 || ROLE != 0) ext[16 * g + b - 1] = (int32_t) (0u - nv);
         }
-        uint32_t ure[8], uim[8];
+    }
+}
+
+// The role is a template argument of the body: with a run-time role inside the unrolled loop the
+// compiler kept one branch per output (15 BSSY/BRA pairs, no overlap between outputs: 1,440 cycles
+// for 500 cycles of work).
+TFHE_HD void phase_i2_final(int lane, WarpSmem &ws, int role, const cpx (&x)[16]) {
+    if (role == 0) i2_final_role<0>(lane, ws, x);
+    else i2_final_role<1>(lane, ws, x);
+}
+
+// Stand-alone external product: the result REPLACES the accumulator, so the master copy is
+// cleared once its decomposition has been read (role r clears the coefficients it will update).
+TFHE_HD void phase_acc_clear(int lane, WarpSmem &ws, int role) {
+    const int o = lane >> 4, j2 = lane & 15;
+    int32_t *row = ws.acc[o] + j2 * kAccRow + 8 * role;
+    word4 z;
 #pragma unroll
-        for (int i = 0; i < 8; i++) {
-            double re, im;
-            if (role == 0) {  // u + v
-                re = x[blk + i].x + v[i].x;
-                im = x[blk + i].y + v[i].y;
-            } else {          // conj(e) * (u - v), u = partner's value
-                const double tr = v[i].x - x[blk + i].x, ti = v[i].y - x[blk + i].y;
-                re = fma(er, tr, ei * ti);
-                im = fma(er, ti, -(ei * tr));
-            }
-            ure[i] = double_to_torus32(re);
-            uim[i] = double_to_torus32(im);
-        }
+    for (int k = 0; k < 4; k++) z.v[k] = 0;
 #pragma unroll
-        for (int i = 0; i < 8; i++) {
-            row[blk + i] = (int32_t) (old_lo[i] + ure[i]);
-            row[blk + i + 32] = (int32_t) (old_hi[i] + uim[i]);
-        }
+    for (int g = 0; g < 4; g++) {
+        *reinterpret_cast<word4 *>(row + 16 * g) = z;
+        *reinterpret_cast<word4 *>(row + 16 * g + 4) = z;
     }
 }
 

@@ -108,8 +108,14 @@ int main() {
         const int a = rots[it];
         for (int lane = 0; lane < 32; lane++) phase_load_acc(lane, *ws, acc.data());
         // warp pair: role q transforms digit level q (rotation + decomposition fused in)
+        if (it == 0)  // afterwards phase_i2_final keeps the extended copy up to date
+            for (int role = 0; role < 2; role++)
+                for (int lane = 0; lane < 32; lane++) phase_ext_build(lane, *ws, role);
+        static cpx x1[2][32][32];
         for (int role = 0; role < 2; role++)
-            for (int lane = 0; lane < 32; lane++) phase_f1q(lane, *ws, a, role);
+            for (int lane = 0; lane < 32; lane++) phase_f1q_load(lane, *ws, a, role, true, x1[role][lane]);
+        for (int role = 0; role < 2; role++)
+            for (int lane = 0; lane < 32; lane++) phase_f1q_store(lane, *ws, role, x1[role][lane]);
         cpx keep[2][32][16], give[2][32][16];
         memset(keep, 0, sizeof(keep));
         memset(give, 0, sizeof(give));
