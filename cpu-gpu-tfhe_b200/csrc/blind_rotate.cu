@@ -59,6 +59,12 @@ constexpr int kThreads = 2 * kCtWarps * 32;
 #ifndef TFHE_B200_BR_PAIR_SAME_SMSP
 #define TFHE_B200_BR_PAIR_SAME_SMSP 0
 #endif
+#ifndef TFHE_B200_BR_MAC_TAIL
+#define TFHE_B200_BR_MAC_TAIL 6   // positions multiplied after the stage release has been issued
+#endif
+#ifndef TFHE_B200_BR_LATE_RELEASE
+#define TFHE_B200_BR_LATE_RELEASE 0
+#endif
 #ifndef TFHE_B200_BR_RING_ATOMIC
 #define TFHE_B200_BR_RING_ATOMIC 1
 #endif
@@ -364,15 +370,62 @@ __device__ __forceinline__ void named_arrive(int id, int nthreads) {
     asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
+// Fourier MAC of z against one ring chunk (positions [POS0, POS0 + kChunkPos)), with the release of
+// the stage issued EARLY: the drained-counter atomic goes out right behind the last load of the
+// chunk (the shared-memory pipe serves one warp's requests in order, so every lane's reads precede
+// it, and the refill is at least three more atomics, a proxy fence and an L2 round trip away), and
+// its result is only looked at after the remaining multiply-adds.  With the release after the
+// arithmetic every chunk paid the atomic's round trip (4 per iteration).
+template <int POS0>
+__device__ __forceinline__ void mac_consume(CtaSmem &S, const BrLaunch &L, int role, int lane, StreamPos &sp,
+                                            uint32_t ring_base, uint32_t ring_chunks, bool ready,
+                                            const cpx (&z)[16], cpx (&acc)[16]) {
+    const RingPos &rp = sp.rp;
+    const uint32_t st = ring_base + rp.stage;
+    if (!ready) mbar_wait(&S.full[st], rp.phase);
+    const cpx *part = S.ring[st];
+    constexpr int kTail = TFHE_B200_BR_MAC_TAIL, kHead = kChunkPos - kTail;
+    phase_mac_part<POS0, kHead>(lane, z, part, acc);
+    cpx w[kTail];
+#pragma unroll
+    for (int p = 0; p < kTail; p++) w[p] = part[(kHead + p) * 32 + lane];
+    unsigned int seen = 0;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.eq.u32 p, %2, 0;\n"
+        "@p atom.shared.add.u32 %0, [%1], 1;\n"
+        "}\n"
+        : "+r"(seen)
+        : "r"(smem_u32(&S.drained[st])), "r"(lane)
+        : "memory");
+#pragma unroll
+    for (int p = 0; p < kTail; p++) cmac(acc[POS0 + kHead + p], z[POS0 + kHead + p], w[p]);
+    if (lane == 0 && (seen % kGroupCts) == kGroupCts - 1 && rp.chunk + kRingStages < ring_chunks) {
+        uint32_t fsub = sp.sub + kRingStages, fit = sp.it;
+        if (fsub >= kChunksPerIter) {
+            fsub -= kChunksPerIter;
+            if (++fit >= (uint32_t) L.n_iter) fit = 0;
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        ring_fill_at(S, L, role, fit, fsub, st);
+    }
+    sp.advance((uint32_t) L.n_iter);
+}
+
 // Fourier MAC of z against one 8 KiB half streamed as kChunksPerHalf ring chunks; `ready`: the first
 // chunk was seen complete by an earlier probe.
 template <int PART>
 __device__ __forceinline__ void mac_stream(CtaSmem &S, const BrLaunch &L, int role, int lane, uint32_t my_idx,
                                            StreamPos &sp, uint32_t ring_base, uint32_t ring_chunks, bool ready,
                                            const cpx (&z)[16], cpx (&acc)[16]) {
+#if TFHE_B200_BR_RING_ATOMIC && !defined(TFHE_B200_EXP_NORING) && !TFHE_B200_BR_LATE_RELEASE
+    mac_consume<PART * kChunkPos>(S, L, role, lane, sp, ring_base, ring_chunks, PART == 0 && ready, z, acc);
+#else
     ring_consume(S, L, role, lane, my_idx, sp, ring_base, ring_chunks, PART == 0 && ready, [&](const cpx *part) {
         phase_mac_part<PART * kChunkPos, kChunkPos>(lane, z, part, acc);
     });
+#endif
     if constexpr (PART + 1 < kChunksPerHalf)
         mac_stream<PART + 1>(S, L, role, lane, my_idx, sp, ring_base, ring_chunks, false, z, acc);
 }
@@ -398,6 +451,7 @@ __global__ void __launch_bounds__(kThreads, 1) blind_rotate_kernel(const BrLaunc
             mbar_init(&S.empty[s], kGroupCts);
             S.drained[s] = 0;
         }
+
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         // prime the rings; afterwards the consumers refill them (no producer warp: a ninth warp
         // would cap the kernel at 168 registers per thread)
@@ -494,7 +548,8 @@ __global__ void __launch_bounds__(kThreads, 1) blind_rotate_kernel(const BrLaunc
             // ---- one MuxRotate step: straight-line code, no per-phase conditionals -----------
             {
                 cpx x[32];
-                phase_f1q_load(lane, W, a, role, rotate, x);
+                phase_f1q_decomp(lane, W, a, role, rotate, x);
+                phase_f1q_fft(x);
                 pair_sync();   // the stores overwrite the extended accumulator copy both warps read
                 if (!rotate) phase_acc_clear(lane, W, role);  // external product only: result replaces ACC
                 phase_f1q_store(lane, W, role, x);
@@ -525,6 +580,10 @@ __global__ void __launch_bounds__(kThreads, 1) blind_rotate_kernel(const BrLaunc
                 mac_stream<0>(S, L, role, lane, my_idx, sp, ring_base, ring_chunks, rdy_give, z, give);
                 PHASE_MARK(3);
             }
+            // (Measured and dropped: multiplying the hand-over half first and overlapping the
+            // hand-over with the last multiply through an mbarrier, and a split arrive/wait barrier
+            // around the pass-1 transform: both 1 % slower; the pair barriers cost their round
+            // trips, not skew between the two warps.)
             phase_xchg_store(lane, W, role, give);
             PHASE_MARK(4);
             pair_sync();

@@ -68,7 +68,7 @@ struct cpx {
     double x, y;
 };
 
-// Extended accumulator copy (see phase_f1q_load): row of 127 words per (o, j2),
+// Extended accumulator copy (see phase_f1q_decomp): row of 127 words per (o, j2),
 //   E[63 + k] = +row[k] (k = 0..63),  E[63 + k] = -row[64 + k] (k = -63..-1)
 // i.e. the negacyclic continuation of the 64-coefficient row to the left, so that a rotated read
 // is `base + e` with a per-lane base and NO per-element index or sign arithmetic.
@@ -364,7 +364,7 @@ TFHE_HD void phase_ext_build(int lane, WarpSmem &ws, int role) {
 // spent 19 instructions per coefficient here, most of them on the half-rate ALU pipe.
 // The outputs are NOT stored: the extended copy lives in exchange buffers 2 and 3, which the
 // stores overwrite, so the pair synchronises between load and store.
-TFHE_HD void phase_f1q_load(int lane, WarpSmem &ws, int a, int q, bool rotate, cpx (&x)[32]) {
+TFHE_HD void phase_f1q_decomp(int lane, WarpSmem &ws, int a, int q, bool rotate, cpx (&x)[32]) {
     const int o = lane >> 4, j2 = lane & 15;
     const int a_lo = a & 15, a_hi = a >> 4;
     const int j2p = (j2 - a_lo) & 15;
@@ -396,8 +396,10 @@ TFHE_HD void phase_f1q_load(int lane, WarpSmem &ws, int a, int q, bool rotate, c
             else x[e & 31].y = d;
         }
     }
-    fwd32(x);
 }
+
+// Stages 0-4 of the two transforms on the decomposed digits (no shared-memory access).
+TFHE_HD void phase_f1q_fft(cpx (&x)[32]) { fwd32(x); }
 
 TFHE_HD void phase_f1q_store(int lane, WarpSmem &ws, int q, const cpx (&x)[32]) {
     const int o = lane >> 4, j2 = lane & 15;

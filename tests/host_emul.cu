@@ -113,7 +113,10 @@ int main() {
                 for (int lane = 0; lane < 32; lane++) phase_ext_build(lane, *ws, role);
         static cpx x1[2][32][32];
         for (int role = 0; role < 2; role++)
-            for (int lane = 0; lane < 32; lane++) phase_f1q_load(lane, *ws, a, role, true, x1[role][lane]);
+            for (int lane = 0; lane < 32; lane++) {
+                phase_f1q_decomp(lane, *ws, a, role, true, x1[role][lane]);
+                phase_f1q_fft(x1[role][lane]);
+            }
         for (int role = 0; role < 2; role++)
             for (int lane = 0; lane < 32; lane++) phase_f1q_store(lane, *ws, role, x1[role][lane]);
         cpx keep[2][32][16], give[2][32][16];
