@@ -38,55 +38,32 @@ constexpr int kCtWarps = 4;                       // ciphertexts per CTA
 // shared-memory bytes per iteration but leaves every sub-partition with a single warp that
 // cannot hide its own latencies (profiles/README.md: 503 ms vs 455 ms per 65536 gates).
 constexpr int kThreads = 2 * kCtWarps * 32;
-// Key ring.  Role r multiplies rows r and 2+r; per iteration it streams four 8 KiB
-// "halves" (one result polynomial of one TGSW row) in the order
+// Key ring.  Role r multiplies rows r and 2+r; per iteration it streams four 8 KiB chunks (one
+// result polynomial of one TGSW row each) in the order
 //   (row r, half r), (row r, half 1-r), (row 2+r, half r), (row 2+r, half 1-r)
-// i.e. always the half this role KEEPS first, then the half it GIVES to its partner.  A half is
-// streamed as 16/kChunkPos chunks of kChunkPos positions.  Each (stream, role) has its own ring so
-// that every consumer of a ring takes every chunk in order (a warp skipping chunks could get two
-// mbarrier phases ahead on a stage: parity aliasing).  kGroups = 1: one key stream for the four
-// ciphertexts of the CTA; kGroups = 2: ciphertexts {0,1} and {2,3} have their own streams (twice the
-// L2 -> shared-memory traffic) and can run out of phase with each other.
-#ifndef TFHE_B200_BR_GROUPS
-#define TFHE_B200_BR_GROUPS 1
-#endif
-#ifndef TFHE_B200_BR_CHUNK_POS
-#define TFHE_B200_BR_CHUNK_POS (16 / TFHE_B200_BR_GROUPS)
-#endif
-#ifndef TFHE_B200_BR_ANTIPHASE
-#define TFHE_B200_BR_ANTIPHASE 0
-#endif
-#ifndef TFHE_B200_BR_PAIR_SAME_SMSP
-#define TFHE_B200_BR_PAIR_SAME_SMSP 0
-#endif
-#ifndef TFHE_B200_BR_MAC_TAIL
-#define TFHE_B200_BR_MAC_TAIL 6   // positions multiplied after the stage release has been issued
-#endif
-#ifndef TFHE_B200_BR_LATE_RELEASE
-#define TFHE_B200_BR_LATE_RELEASE 0
-#endif
-#ifndef TFHE_B200_BR_RING_ATOMIC
-#define TFHE_B200_BR_RING_ATOMIC 1
-#endif
-constexpr int kGroups = TFHE_B200_BR_GROUPS;
-constexpr int kGroupCts = kCtWarps / kGroups;          // consumer warps of one ring
-constexpr int kChunkPos = TFHE_B200_BR_CHUNK_POS;      // positions per chunk
-constexpr int kChunksPerHalf = 16 / kChunkPos;
+// i.e. always the half this role KEEPS first, then the half it GIVES to its partner.  Each role has
+// its own 3-stage ring so that every consumer of a ring takes every chunk in order (a warp
+// skipping chunks could get two mbarrier phases ahead on a stage: parity aliasing).
+// Measured and dropped (profiles/README.md): 4 KiB / 2 KiB chunks (every extra wait + release per
+// iteration costs about 500 cycles), one key stream per ciphertext pair with the pairs forced half
+// an iteration out of phase, release by mbarrier arrive with a lazily refilling designated warp.
+constexpr int kChunkPos = 16;                          // positions per chunk
 constexpr int kChunkCplx = kChunkPos * 32;
 constexpr uint32_t kStageBytes = kChunkCplx * sizeof(cpx);
-constexpr uint32_t kRingStages = (24u * 1024u / kGroups) / kStageBytes;   // per ring: 24 KiB per role in total
-constexpr uint32_t kChunksPerIter = 4 * kChunksPerHalf;                   // per role
-constexpr int kStages = kGroups * 2 * (int) kRingStages;
-static_assert(kGroups == 1 || kGroups == 2, "one or two key streams");
-static_assert(kRingStages >= 2, "ring too shallow");
+constexpr uint32_t kRingStages = 3;                    // per role
+constexpr uint32_t kChunksPerIter = 4;                 // per role
+constexpr int kStages = 2 * (int) kRingStages;
+// positions of a chunk multiplied AFTER its stage release has been issued (mac_consume)
+#ifndef TFHE_B200_BR_MAC_TAIL
+#define TFHE_B200_BR_MAC_TAIL 6
+#endif
 
 struct __align__(128) CtaSmem {
     WarpSmem w[kCtWarps];
     cpx e2[32 * kE2Row];
     cpx ring[kStages][kChunkCplx];
     unsigned long long full[kStages];   // mbarriers: TMA completion of a ring stage
-    unsigned long long empty[kStages];  // mbarriers: all consumer warps have read the stage
-    unsigned int drained[kStages];      // TFHE_B200_BR_RING_ATOMIC: warps that have finished with the stage
+    unsigned int drained[kStages];      // warps that have finished with the stage's current chunk
 };
 
 static_assert(sizeof(WarpSmem) % 16 == 0, "warp working set must keep 16 B alignment");
@@ -104,10 +81,6 @@ __device__ __forceinline__ void mbar_init(unsigned long long *bar, uint32_t coun
 __device__ __forceinline__ void mbar_arrive_expect_tx(unsigned long long *bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
                  : "memory");
-}
-
-__device__ __forceinline__ void mbar_arrive(unsigned long long *bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
 __device__ __forceinline__ void mbar_wait(unsigned long long *bar, uint32_t parity) {
@@ -157,11 +130,6 @@ struct RingPos {
             phase ^= 1;
         }
     }
-    __device__ __forceinline__ RingPos next(uint32_t nstages) const {
-        RingPos r = *this;
-        r.advance(nstages);
-        return r;
-    }
 };
 
 __device__ __forceinline__ void build_e2(cpx *e2) {
@@ -191,13 +159,6 @@ __device__ __forceinline__ int modswitch_2N(uint32_t x) { return (int) ((x + (1u
 // Development aid: cycles spent per phase by warp 0 of CTA 0 (tools/phase_timing.py).
 __device__ long long g_phase_cycles[16];
 #define PHASE_T0() long long pt_ = clock64()
-#define PHASE_SUB0() long long ps_ = clock64()
-#define PHASE_SUB(i)                                               \
-    do {                                                           \
-        const long long now_ = clock64();                          \
-        if (blockIdx.x == 0 && threadIdx.x == TFHE_B200_PHASE_THREAD) atomicAdd((unsigned long long *) &g_phase_cycles[i], (unsigned long long) (now_ - ps_));   \
-        ps_ = now_;                                                \
-    } while (0)
 #define PHASE_MARK(i)                                              \
     do {                                                           \
         const long long now_ = clock64();                          \
@@ -209,8 +170,6 @@ __device__ long long g_phase_cycles[16];
 #endif
 #else
 #define PHASE_T0() do {} while (0)
-#define PHASE_SUB0() do {} while (0)
-#define PHASE_SUB(i) do {} while (0)
 #define PHASE_MARK(i) do {} while (0)
 #endif
 
@@ -218,11 +177,9 @@ __device__ long long g_phase_cycles[16];
 // `role`'s stream into absolute stage `stage` (one elected lane).
 __device__ __forceinline__ void ring_fill_at(CtaSmem &S, const BrLaunch &L, int role, uint32_t it, uint32_t sub,
                                              uint32_t stage) {
-    const uint32_t hf = sub / kChunksPerHalf, part = sub % kChunksPerHalf;
-    const uint32_t row = (uint32_t) role + 2u * (hf >> 1);
-    const uint32_t out = (hf & 1u) ? 1u - (uint32_t) role : (uint32_t) role;
-    const cpx *src = L.bk + ((size_t) (L.bk_first + it) * kKpl + row) * kBkRowCplx + out * kBkHalfCplx +
-                     part * kChunkCplx;
+    const uint32_t row = (uint32_t) role + 2u * (sub >> 1);
+    const uint32_t out = (sub & 1u) ? 1u - (uint32_t) role : (uint32_t) role;
+    const cpx *src = L.bk + ((size_t) (L.bk_first + it) * kKpl + row) * kBkRowCplx + out * kBkHalfCplx;
     mbar_arrive_expect_tx(&S.full[stage], kStageBytes);
     tma_load_1d(S.ring[stage], src, kStageBytes, &S.full[stage]);
 }
@@ -254,73 +211,35 @@ __device__ __forceinline__ bool ring_probe(CtaSmem &S, const StreamPos &sp, uint
     return mbar_test(&S.full[ring_base + r.stage], r.phase);
 }
 
-// Consumer side of one chunk.  Release is an mbarrier arrive (no round trip: the first version
-// counted drainers with an atomicAdd whose result every warp waited for, and the last drainer
-// issued the refill behind a proxy fence).  The refill of the stage a chunk leaves is issued
-// LAZILY by one designated consumer (round robin over the ring's warps) when it comes back for
-// its next chunk: by then the other warps have normally released the stage.
-template <typename Use>
-__device__ __forceinline__ void ring_consume(CtaSmem &S, const BrLaunch &L, int role, int lane, uint32_t my_idx,
-                                             StreamPos &sp, uint32_t ring_base, uint32_t ring_chunks, bool ready,
-                                             Use use) {
-    PHASE_SUB0();
-    const RingPos &rp = sp.rp;
-#ifdef TFHE_B200_EXP_NORING  // timing experiment only (results are garbage): a key stream that costs nothing
-    use(S.ring[ring_base + rp.stage]);
-    sp.advance((uint32_t) L.n_iter);
-    return;
-#endif
-#if TFHE_B200_BR_RING_ATOMIC
-    // first protocol: count drainers with an atomic, the last one refills the stage at once
-    {
-        const uint32_t st = ring_base + rp.stage;
-        if (!ready) mbar_wait(&S.full[st], rp.phase);
-        use(S.ring[st]);
-        __syncwarp();
-        if (lane == 0) {
-            const unsigned int seen = atomicAdd(&S.drained[st], 1u);
-            if ((seen % kGroupCts) == kGroupCts - 1 && rp.chunk + kRingStages < ring_chunks) {
-                uint32_t fsub = sp.sub + kRingStages, fit = sp.it;
-                if (fsub >= kChunksPerIter) {
-                    fsub -= kChunksPerIter;
-                    if (++fit >= (uint32_t) L.n_iter) fit = 0;
-                }
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                ring_fill_at(S, L, role, fit, fsub, st);
-            }
+// Release of the current stage by one warp (lane 0 only; `seen` = result of the drained-counter
+// atomic): the last of the four consumers refills the stage at once with the chunk kRingStages ahead.
+// (A release by mbarrier arrive with a designated, lazily refilling warp was 3.5 % slower: the
+// sooner the refill goes out, the better.)
+__device__ __forceinline__ void ring_refill_if_last(CtaSmem &S, const BrLaunch &L, int role, const StreamPos &sp,
+                                                    uint32_t st, unsigned int seen, uint32_t ring_chunks) {
+    if ((seen % kCtWarps) == kCtWarps - 1 && sp.rp.chunk + kRingStages < ring_chunks) {
+        static_assert(kRingStages < kChunksPerIter, "refill target is at most one iteration ahead");
+        uint32_t fsub = sp.sub + kRingStages, fit = sp.it;
+        if (fsub >= kChunksPerIter) {
+            fsub -= kChunksPerIter;
+            if (++fit >= (uint32_t) L.n_iter) fit = 0;
         }
-        sp.advance((uint32_t) L.n_iter);
-        return;
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        ring_fill_at(S, L, role, fit, fsub, st);
     }
-#endif
-    if (rp.chunk > 0) {
-        const uint32_t p = rp.chunk - 1;  // refill duty for the chunk released by the previous call
-        if ((p % (uint32_t) kGroupCts) == my_idx && p + kRingStages < ring_chunks && lane == 0) {
-            const uint32_t ps = rp.stage == 0 ? kRingStages - 1 : rp.stage - 1;
-            const uint32_t pphase = rp.stage == 0 ? rp.phase ^ 1u : rp.phase;
-            // chunk p + kRingStages = (kRingStages - 1) chunks after the current one
-            static_assert(kRingStages < kChunksPerIter, "refill target is at most one iteration ahead");
-            uint32_t fsub = sp.sub + kRingStages - 1, fit = sp.it;
-            if (fsub >= kChunksPerIter) {
-                fsub -= kChunksPerIter;
-                if (++fit >= (uint32_t) L.n_iter) fit = 0;
-            }
-            mbar_wait(&S.empty[ring_base + ps], pphase);
-            ring_fill_at(S, L, role, fit, fsub, ring_base + ps);
-        }
-    }
-    const uint32_t st = ring_base + rp.stage;
-    PHASE_SUB(12);
-#ifndef TFHE_B200_EXP_NOWAIT  // timing experiment only: results are garbage
-    if (!ready) mbar_wait(&S.full[st], rp.phase);
-#endif
-    PHASE_SUB(13);
-    use(S.ring[st]);
-    PHASE_SUB(14);
+}
+
+// A warp with nothing to compute keeps its place in the stream.
+__device__ __forceinline__ void ring_skip(CtaSmem &S, const BrLaunch &L, int role, int lane, StreamPos &sp,
+                                          uint32_t ring_base, uint32_t ring_chunks) {
+    const uint32_t st = ring_base + sp.rp.stage;
+    mbar_wait(&S.full[st], sp.rp.phase);
     __syncwarp();
-    if (lane == 0) mbar_arrive(&S.empty[st]);
+    if (lane == 0) {
+        const unsigned int seen = atomicAdd(&S.drained[st], 1u);
+        ring_refill_if_last(S, L, role, sp, st, seen, ring_chunks);
+    }
     sp.advance((uint32_t) L.n_iter);
-    PHASE_SUB(15);
 }
 
 // Operands of the gate prologue of bootstrap g (x = (0,cst) + sa*in0 + sb*in1 [+ sc*in2]).
@@ -370,22 +289,21 @@ __device__ __forceinline__ void named_arrive(int id, int nthreads) {
     asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
-// Fourier MAC of z against one ring chunk (positions [POS0, POS0 + kChunkPos)), with the release of
-// the stage issued EARLY: the drained-counter atomic goes out right behind the last load of the
-// chunk (the shared-memory pipe serves one warp's requests in order, so every lane's reads precede
-// it, and the refill is at least three more atomics, a proxy fence and an L2 round trip away), and
-// its result is only looked at after the remaining multiply-adds.  With the release after the
-// arithmetic every chunk paid the atomic's round trip (4 per iteration).
-template <int POS0>
+// Fourier MAC of z against the current ring chunk, with the release of the stage issued EARLY: the
+// drained-counter atomic goes out right behind the last load of the chunk (the shared-memory pipe
+// serves one warp's requests in order, so every lane's reads precede it, and the refill is at
+// least three more atomics, a proxy fence and an L2 round trip away), and its result is only
+// looked at after the remaining multiply-adds.  With the release after the arithmetic every chunk
+// paid the atomic's round trip and the refill left later (4.4 % of the kernel).
+// `ready`: the chunk was seen complete by an earlier probe.
 __device__ __forceinline__ void mac_consume(CtaSmem &S, const BrLaunch &L, int role, int lane, StreamPos &sp,
                                             uint32_t ring_base, uint32_t ring_chunks, bool ready,
                                             const cpx (&z)[16], cpx (&acc)[16]) {
-    const RingPos &rp = sp.rp;
-    const uint32_t st = ring_base + rp.stage;
-    if (!ready) mbar_wait(&S.full[st], rp.phase);
+    const uint32_t st = ring_base + sp.rp.stage;
+    if (!ready) mbar_wait(&S.full[st], sp.rp.phase);
     const cpx *part = S.ring[st];
     constexpr int kTail = TFHE_B200_BR_MAC_TAIL, kHead = kChunkPos - kTail;
-    phase_mac_part<POS0, kHead>(lane, z, part, acc);
+    phase_mac_part<0, kHead>(lane, z, part, acc);
     cpx w[kTail];
 #pragma unroll
     for (int p = 0; p < kTail; p++) w[p] = part[(kHead + p) * 32 + lane];
@@ -400,8 +318,10 @@ __device__ __forceinline__ void mac_consume(CtaSmem &S, const BrLaunch &L, int r
         : "r"(smem_u32(&S.drained[st])), "r"(lane)
         : "memory");
 #pragma unroll
-    for (int p = 0; p < kTail; p++) cmac(acc[POS0 + kHead + p], z[POS0 + kHead + p], w[p]);
-    if (lane == 0 && (seen % kGroupCts) == kGroupCts - 1 && rp.chunk + kRingStages < ring_chunks) {
+    for (int p = 0; p < kTail; p++) cmac(acc[kHead + p], z[kHead + p], w[p]);
+    // (one condition, written out here rather than through ring_refill_if_last: the compiler
+    // schedules the call form 1.7 % slower)
+    if (lane == 0 && (seen % kCtWarps) == kCtWarps - 1 && sp.rp.chunk + kRingStages < ring_chunks) {
         uint32_t fsub = sp.sub + kRingStages, fit = sp.it;
         if (fsub >= kChunksPerIter) {
             fsub -= kChunksPerIter;
@@ -411,23 +331,6 @@ __device__ __forceinline__ void mac_consume(CtaSmem &S, const BrLaunch &L, int r
         ring_fill_at(S, L, role, fit, fsub, st);
     }
     sp.advance((uint32_t) L.n_iter);
-}
-
-// Fourier MAC of z against one 8 KiB half streamed as kChunksPerHalf ring chunks; `ready`: the first
-// chunk was seen complete by an earlier probe.
-template <int PART>
-__device__ __forceinline__ void mac_stream(CtaSmem &S, const BrLaunch &L, int role, int lane, uint32_t my_idx,
-                                           StreamPos &sp, uint32_t ring_base, uint32_t ring_chunks, bool ready,
-                                           const cpx (&z)[16], cpx (&acc)[16]) {
-#if TFHE_B200_BR_RING_ATOMIC && !defined(TFHE_B200_EXP_NORING) && !TFHE_B200_BR_LATE_RELEASE
-    mac_consume<PART * kChunkPos>(S, L, role, lane, sp, ring_base, ring_chunks, PART == 0 && ready, z, acc);
-#else
-    ring_consume(S, L, role, lane, my_idx, sp, ring_base, ring_chunks, PART == 0 && ready, [&](const cpx *part) {
-        phase_mac_part<PART * kChunkPos, kChunkPos>(lane, z, part, acc);
-    });
-#endif
-    if constexpr (PART + 1 < kChunksPerHalf)
-        mac_stream<PART + 1>(S, L, role, lane, my_idx, sp, ring_base, ring_chunks, false, z, acc);
 }
 
 __global__ void __launch_bounds__(kThreads, 1) blind_rotate_kernel(const BrLaunch L) {
@@ -448,45 +351,27 @@ __global__ void __launch_bounds__(kThreads, 1) blind_rotate_kernel(const BrLaunc
     if (threadIdx.x == 0) {
         for (int s = 0; s < kStages; s++) {
             mbar_init(&S.full[s], 1);
-            mbar_init(&S.empty[s], kGroupCts);
             S.drained[s] = 0;
         }
 
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         // prime the rings; afterwards the consumers refill them (no producer warp: a ninth warp
         // would cap the kernel at 168 registers per thread)
-        for (int r = 0; r < 2 * kGroups; r++)
+        for (int r = 0; r < 2; r++)
             for (uint32_t c = 0; c < kRingStages && c < kChunksPerIter * iters_total; c++)
-                ring_fill(S, L, r & 1, c, r * kRingStages + c);
+                ring_fill(S, L, r, c, r * kRingStages + c);
     }
     __syncthreads();
     const bool rotate = (L.extern_only == 0);
 
     // -------------------- ciphertext warps ------------------------------------------
-#if TFHE_B200_BR_PAIR_SAME_SMSP
-    const int ct = warp & 3, role = warp >> 2;   // both warps of a ciphertext on one sub-partition
-#else
-    const int ct = warp >> 1, role = warp & 1;   // sub-partition w%4 holds the same role of two ciphertexts
-#endif
+    const int ct = warp >> 1, role = warp & 1;   // sub-partition w % 4 holds the same role of two ciphertexts
     WarpSmem &W = S.w[ct];
     const int bar_id = 1 + ct;
     // barrier of the two warps of one ciphertext
-#ifdef TFHE_B200_EXP_NOSYNC  // timing experiment only: results are garbage
-    auto pair_sync = [bar_id]() { __syncwarp(); };
-#else
     auto pair_sync = [bar_id]() { named_sync(bar_id, 64); };
-#endif
-    const int grp_id = ct / kGroupCts;                    // key stream of this ciphertext
-    const uint32_t my_idx = (uint32_t) (ct % kGroupCts);  // consumer index inside the ring
-    const uint32_t ring_base = (uint32_t) (grp_id * 2 + role) * kRingStages;
+    const uint32_t ring_base = (uint32_t) role * kRingStages;
     const uint32_t ring_chunks = kChunksPerIter * iters_total;
-#if TFHE_B200_BR_ANTIPHASE
-    // Stream B (ciphertexts 2,3) runs behind stream A (0,1): B starts iteration i only when A has
-    // reached its multiply phase, and A starts iteration i+1 only when B has reached its own, so
-    // the two warps that share an SM sub-partition are never both in the integer front phase.
-    static_assert(kGroups == 2, "anti-phase schedule needs two key streams");
-    uint32_t gi = 0;  // iterations done by this warp since kernel start
-#endif
     StreamPos sp;
     for (int grp = blockIdx.x; grp < ngroups; grp += gridDim.x) {
         int g = grp * cpg + ct;
@@ -527,22 +412,12 @@ __global__ void __launch_bounds__(kThreads, 1) blind_rotate_kernel(const BrLaunc
             // tfhe_blindRotate_FFT :705 skips barai == 0 (no-op); idle slots do no arithmetic either
             const bool active = valid && ((a != 0) || !rotate);
 
-#if TFHE_B200_BR_ANTIPHASE
-            if (grp_id == 1) named_sync(5, 2 * kThreads / 2);          // B waits for A's multiply phase
-            else if (gi > 0) named_sync(6, 2 * kThreads / 2);          // A waits for B's previous one
-#endif
             PHASE_T0();
             if (!active) {
                 // nothing to compute (bara = 0, or an idle slot of a small batch): only keep this
                 // warp's place in the key stream
-#if TFHE_B200_BR_ANTIPHASE
-                if (grp_id == 0) named_arrive(5, 2 * kThreads / 2);
-                else if (gi + 1 < iters_total) named_arrive(6, 2 * kThreads / 2);
-                gi++;
-#endif
 #pragma unroll 1
-                for (uint32_t c = 0; c < kChunksPerIter; c++)
-                    ring_consume(S, L, role, lane, my_idx, sp, ring_base, ring_chunks, false, [](const cpx *) {});
+                for (uint32_t c = 0; c < kChunksPerIter; c++) ring_skip(S, L, role, lane, sp, ring_base, ring_chunks);
                 continue;
             }
             // ---- one MuxRotate step: straight-line code, no per-phase conditionals -----------
@@ -556,11 +431,6 @@ __global__ void __launch_bounds__(kThreads, 1) blind_rotate_kernel(const BrLaunc
                 __syncwarp();  // a warp multiplies exactly the rows it has just transformed
             }
             PHASE_MARK(0);
-#if TFHE_B200_BR_ANTIPHASE
-            if (grp_id == 0) named_arrive(5, 2 * kThreads / 2);
-            else if (gi + 1 < iters_total) named_arrive(6, 2 * kThreads / 2);
-            gi++;
-#endif
             // keep / give: partial sums of the result polynomial this warp finishes / hands over
             cpx keep[16], give[16];
 #pragma unroll
@@ -572,12 +442,12 @@ __global__ void __launch_bounds__(kThreads, 1) blind_rotate_kernel(const BrLaunc
             for (int row = role; row < kKpl; row += 2) {
                 cpx z[16];
                 const bool rdy_keep = ring_probe(S, sp, ring_base, 0);
-                const bool rdy_give = ring_probe(S, sp, ring_base, kChunksPerHalf);
+                const bool rdy_give = ring_probe(S, sp, ring_base, 1);
                 phase_f2_fft(lane, W, S.e2, row, z);
                 PHASE_MARK(1);
-                mac_stream<0>(S, L, role, lane, my_idx, sp, ring_base, ring_chunks, rdy_keep, z, keep);
+                mac_consume(S, L, role, lane, sp, ring_base, ring_chunks, rdy_keep, z, keep);
                 PHASE_MARK(2);
-                mac_stream<0>(S, L, role, lane, my_idx, sp, ring_base, ring_chunks, rdy_give, z, give);
+                mac_consume(S, L, role, lane, sp, ring_base, ring_chunks, rdy_give, z, give);
                 PHASE_MARK(3);
             }
             // (Measured and dropped: multiplying the hand-over half first and overlapping the

@@ -429,16 +429,7 @@ TFHE_HD void phase_mac_half(int lane, const cpx (&z)[16], const cpx *half, cpx (
 template <int POS0, int NPOS>
 TFHE_HD void phase_mac_part(int lane, const cpx (&z)[16], const cpx *part, cpx (&acc)[16]) {
 #pragma unroll
-    for (int p = 0; p < NPOS; p++) {
-#ifdef TFHE_B200_EXP_NOKEYLDS  // timing experiment only: results are garbage
-        cpx w;
-        w.x = z[(POS0 + p + 1) & 15].x;
-        w.y = z[(POS0 + p + 1) & 15].y;
-        cmac(acc[POS0 + p], z[POS0 + p], w);
-#else
-        cmac(acc[POS0 + p], z[POS0 + p], part[p * 32 + lane]);
-#endif
-    }
+    for (int p = 0; p < NPOS; p++) cmac(acc[POS0 + p], z[POS0 + p], part[p * 32 + lane]);
 }
 
 // Hand the partial sum of the result polynomial the OTHER warp finishes to that warp:
