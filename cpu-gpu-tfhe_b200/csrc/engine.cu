@@ -27,6 +27,7 @@ struct tfhe_b200_ctx {
     uint8_t *d_ks_mma;  // byte-limb tiles for the tensor-core key switch (large batches), or null
     size_t bk_bytes, ks_bytes;
     cudaStream_t stream;  // used by the host-buffer entry points
+    cudaStream_t copy_in, copy_out;  // host-buffer entry points: copies of chunk i+1 / i-1 overlap chunk i
     std::atomic<unsigned long long> launches;
     // optional per-kernel timing (bench roofline): event triples around blind-rotate / key-switch
     bool timing;
@@ -238,7 +239,12 @@ int tfhe_b200_ctx_create(tfhe_b200_ctx **out, const tfhe_b200_params *p, int dev
     c->bk_bytes = c->ks_bytes = 0;
     c->launches = 0;
     c->timing = false;
-    if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) {
+    c->stream = c->copy_in = c->copy_out = nullptr;
+    if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&c->copy_in, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&c->copy_out, cudaStreamNonBlocking) != cudaSuccess) {
+        if (c->stream) cudaStreamDestroy(c->stream);
+        if (c->copy_in) cudaStreamDestroy(c->copy_in);
         delete c;
         return fail("cudaStreamCreate failed");
     }
@@ -255,6 +261,8 @@ void tfhe_b200_ctx_destroy(tfhe_b200_ctx *c) {
     if (c->d_ks_mma) cudaFree(c->d_ks_mma);
     for (cudaEvent_t e : c->ev) cudaEventDestroy(e);
     cudaStreamDestroy(c->stream);
+    cudaStreamDestroy(c->copy_in);
+    cudaStreamDestroy(c->copy_out);
     delete c;
 }
 
@@ -662,27 +670,69 @@ int tfhe_b200_extern_mul(tfhe_b200_ctx *c, int32_t *d_acc, int bk_index, int cou
 
 // ------------------------------------------------------ host-buffer variants --
 
+// Host-buffer gate batch (the reference-facing call: inputs and outputs are host arrays).
+// Large batches are cut into chunks of whole waves (16 x 4 ciphertexts per SM) and pipelined over
+// three streams: the H2D copy of chunk i+1 and the D2H copy of chunk i-1 run under the kernels of
+// chunk i, so the call costs the kernels plus one chunk's copies instead of all of them.
 static int host_gate_common(tfhe_b200_ctx *c, int gate, bool mux, int32_t *out, const int32_t *a, const int32_t *b,
                             const int32_t *cc, int count) {
     if (check_ctx(c, true, true)) return 1;
     if (count <= 0) return count < 0 ? fail("negative count") : 0;
     CU(cudaSetDevice(c->device));
-    const size_t bytes = (size_t) count * (c->p.n + 1) * sizeof(int32_t);
+    const size_t row = (size_t) (c->p.n + 1);
+    const size_t bytes = (size_t) count * row * sizeof(int32_t);
     int32_t *d_a = nullptr, *d_b = nullptr, *d_c = nullptr, *d_o = nullptr;
     cudaStream_t st = c->stream;
     CU(cudaMallocAsync(&d_a, bytes, st));
     CU(cudaMallocAsync(&d_b, bytes, st));
     CU(cudaMallocAsync(&d_o, bytes, st));
-    CU(cudaMemcpyAsync(d_a, a, bytes, cudaMemcpyHostToDevice, st));
-    CU(cudaMemcpyAsync(d_b, b, bytes, cudaMemcpyHostToDevice, st));
-    if (mux) {
-        CU(cudaMallocAsync(&d_c, bytes, st));
-        CU(cudaMemcpyAsync(d_c, cc, bytes, cudaMemcpyHostToDevice, st));
-    }
-    int rc = mux ? tfhe_b200_mux(c, d_o, d_a, d_b, d_c, count, st) : tfhe_b200_gate(c, gate, d_o, d_a, d_b, count, st);
-    if (!rc) {
-        cudaError_t e = cudaMemcpyAsync(out, d_o, bytes, cudaMemcpyDeviceToHost, st);
-        if (e != cudaSuccess) rc = fail("D2H copy failed: %s", cudaGetErrorString(e));
+    if (mux) CU(cudaMallocAsync(&d_c, bytes, st));
+    const int chunk = 16 * 4 * c->sm_count;  // 16 waves
+    const int nchunks = count >= 2 * chunk ? (count + chunk - 1) / chunk : 1;
+    int rc = 0;
+    if (nchunks == 1) {
+        CU(cudaMemcpyAsync(d_a, a, bytes, cudaMemcpyHostToDevice, st));
+        CU(cudaMemcpyAsync(d_b, b, bytes, cudaMemcpyHostToDevice, st));
+        if (mux) CU(cudaMemcpyAsync(d_c, cc, bytes, cudaMemcpyHostToDevice, st));
+        rc = mux ? tfhe_b200_mux(c, d_o, d_a, d_b, d_c, count, st) : tfhe_b200_gate(c, gate, d_o, d_a, d_b, count, st);
+        if (!rc) {
+            cudaError_t e = cudaMemcpyAsync(out, d_o, bytes, cudaMemcpyDeviceToHost, st);
+            if (e != cudaSuccess) rc = fail("D2H copy failed: %s", cudaGetErrorString(e));
+        }
+    } else {
+        std::vector<cudaEvent_t> ev(2 * (size_t) nchunks + 1, nullptr);
+        for (auto &e : ev)
+            if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) rc = fail("cudaEventCreate failed");
+        // the buffers were allocated on `st`: the copy streams may touch them only after that
+        if (!rc && (cudaEventRecord(ev[2 * nchunks], st) != cudaSuccess ||
+                    cudaStreamWaitEvent(c->copy_in, ev[2 * nchunks], 0) != cudaSuccess))
+            rc = fail("stream setup failed");
+        for (int i = 0; i < nchunks && !rc; i++) {
+            const int g0 = i * chunk, n = (count - g0 < chunk) ? count - g0 : chunk;
+            const size_t off = (size_t) g0 * row, nb = (size_t) n * row * sizeof(int32_t);
+            cudaError_t e = cudaMemcpyAsync(d_a + off, a + off, nb, cudaMemcpyHostToDevice, c->copy_in);
+            if (e == cudaSuccess) e = cudaMemcpyAsync(d_b + off, b + off, nb, cudaMemcpyHostToDevice, c->copy_in);
+            if (e == cudaSuccess && mux) e = cudaMemcpyAsync(d_c + off, cc + off, nb, cudaMemcpyHostToDevice, c->copy_in);
+            if (e == cudaSuccess) e = cudaEventRecord(ev[2 * i], c->copy_in);
+            if (e == cudaSuccess) e = cudaStreamWaitEvent(st, ev[2 * i], 0);
+            if (e != cudaSuccess) {
+                rc = fail("H2D copy failed: %s", cudaGetErrorString(e));
+                break;
+            }
+            rc = mux ? tfhe_b200_mux(c, d_o + off, d_a + off, d_b + off, d_c + off, n, st)
+                     : tfhe_b200_gate(c, gate, d_o + off, d_a + off, d_b + off, n, st);
+            if (rc) break;
+            e = cudaEventRecord(ev[2 * i + 1], st);
+            if (e == cudaSuccess) e = cudaStreamWaitEvent(c->copy_out, ev[2 * i + 1], 0);
+            if (e == cudaSuccess) e = cudaMemcpyAsync(out + off, d_o + off, nb, cudaMemcpyDeviceToHost, c->copy_out);
+            if (e != cudaSuccess) rc = fail("D2H copy failed: %s", cudaGetErrorString(e));
+        }
+        // everything the copy streams did must be over before the buffers go back to the pool
+        cudaError_t e1 = cudaStreamSynchronize(c->copy_in), e2 = cudaStreamSynchronize(c->copy_out);
+        if (!rc && (e1 != cudaSuccess || e2 != cudaSuccess))
+            rc = fail("gate batch failed: %s", cudaGetErrorString(e1 != cudaSuccess ? e1 : e2));
+        for (auto &e : ev)
+            if (e) cudaEventDestroy(e);
     }
     cudaFreeAsync(d_a, st);
     cudaFreeAsync(d_b, st);

@@ -97,6 +97,41 @@ int main() {
         CHECK(ok, "phase_init barb=%d", barb);
     }
 
+    // ---- B0. rotation + gadget decomposition, EVERY rotation amount, against the definition ----
+    // (toruspolynomial-functions.cu:191-213 torusPolynomialMulByXaiMinusOne, tgsw-functions.cu:301-352)
+    {
+        std::vector<int32_t> acc0(2 * kN);
+        for (auto &v : acc0) v = (int32_t) ((((uint32_t) rand()) << 16) ^ (uint32_t) rand() ^ (((uint32_t) rand()) << 31));
+        for (int lane = 0; lane < 32; lane++) phase_load_acc(lane, *ws, acc0.data());
+        for (int role = 0; role < 2; role++)
+            for (int lane = 0; lane < 32; lane++) phase_ext_build(lane, *ws, role);
+        long bad = 0;
+        for (int a = 0; a < 2 * kN; a++) {
+            for (int rot = 1; rot >= 0; rot--) {
+                if (!rot && a > 3) continue;  // rotate == false ignores a: a few values are enough
+                for (int q = 0; q < kL; q++)
+                    for (int lane = 0; lane < 32; lane++) {
+                        cpx x[32];
+                        phase_f1q_decomp(lane, *ws, a, q, rot != 0, x);
+                        const int o = lane >> 4, j2 = lane & 15;
+                        for (int e = 0; e < 64; e++) {
+                            const int j = 16 * e + j2;
+                            const uint32_t own = (uint32_t) acc0[o * kN + j];
+                            const int src = ((j - a) % (2 * kN) + 2 * kN) % (2 * kN);  // X^a * P: coefficient j comes from j - a
+                            uint32_t r = (uint32_t) acc0[o * kN + (src & (kN - 1))];
+                            if (src >= kN) r = 0u - r;
+                            const uint32_t t = (rot ? r - own : own) + kDecompOffset;
+                            const double want = (double) (int) ((t >> (32 - (q + 1) * kBgbit)) & 1023u) - 512.0;
+                            const double got = e < 32 ? x[e].x : x[e - 32].y;
+                            if (got != want) bad++;
+                        }
+                    }
+            }
+        }
+        printf("B0. rotation + decomposition, all 2048 rotations x 2 levels: %ld wrong digits\n", bad);
+        CHECK(bad == 0, "rotation/decomposition through the extended accumulator copy");
+    }
+
     // random accumulator, several rotations, teacher forcing against the exact path
     std::vector<int32_t> acc(2 * kN);
     for (auto &v : acc) v = (int32_t) ((((uint32_t) rand()) << 16) ^ (uint32_t) rand() ^ (((uint32_t) rand()) << 31));

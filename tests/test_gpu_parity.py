@@ -266,6 +266,21 @@ def test_host_buffer_entry_points(engine, oracle, keys):
     assert engine.gate_host("AND", ca[:0], cb[:0]).shape == (0, 501)  # empty batch is a no-op
 
 
+def test_host_buffer_entry_point_pipelined_chunks(engine, oracle, keys):
+    """Batches of two or more 16-wave chunks go through the three-stream pipeline of the host-buffer
+    entry point (copies of neighbouring chunks under the kernels): ragged last chunk, results in
+    place and identical to the device-resident call."""
+    n = 2 * 16 * 4 * engine.sm_count + 777
+    r = np.random.default_rng(77)
+    a, b = r.integers(0, 2, n).astype(np.int32), r.integers(0, 2, n).astype(np.int32)
+    rng = oracle.rng(701)
+    ca, cb = oracle.encrypt_bits(keys, rng, a), oracle.encrypt_bits(keys, rng, b)
+    out = engine.gate_host("NAND", ca, cb)
+    assert np.array_equal(oracle.decrypt_bits(keys, out), 1 - (a & b))
+    dev = engine.gate("NAND", engine.to_device(ca), engine.to_device(cb)).cpu().numpy()
+    assert np.array_equal(out, dev)  # same kernels on the same inputs: identical words
+
+
 def test_reference_fourier_key_import(pkg, oracle, keys, ctx_ref):
     """The key can also be supplied in the reference's own lagrangehalfc form."""
     eng = pkg.Engine(device=0)
