@@ -250,7 +250,10 @@ int tfhe_b200_file_write_ciphertexts(const char *path, int n, const int32_t *sam
                                      int count, int append);
 const char *tfhe_b200_file_last_error(void);
 
-/* ---- HOST-buffer convenience (synchronous; copies in and out) ------------- */
+/* ---- HOST-buffer convenience (synchronous; copies in and out) -------------
+ * Batches of two or more 16-wave chunks (16 * 4 * #SMs gates) are pipelined: the host-to-device
+ * copy of chunk i+1 and the device-to-host copy of chunk i-1 run under the kernels of chunk i.
+ * Page-locked host buffers make the copies asynchronous; pageable ones work, without overlap. */
 int tfhe_b200_gate_host(tfhe_b200_ctx *ctx, int gate, int32_t *out, const int32_t *ca, const int32_t *cb,
                         int count);
 int tfhe_b200_mux_host(tfhe_b200_ctx *ctx, int32_t *out, const int32_t *a, const int32_t *b, const int32_t *c,
