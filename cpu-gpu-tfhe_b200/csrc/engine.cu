@@ -683,20 +683,31 @@ static int host_gate_common(tfhe_b200_ctx *c, int gate, bool mux, int32_t *out, 
     const size_t bytes = (size_t) count * row * sizeof(int32_t);
     int32_t *d_a = nullptr, *d_b = nullptr, *d_c = nullptr, *d_o = nullptr;
     cudaStream_t st = c->stream;
-    CU(cudaMallocAsync(&d_a, bytes, st));
-    CU(cudaMallocAsync(&d_b, bytes, st));
-    CU(cudaMallocAsync(&d_o, bytes, st));
-    if (mux) CU(cudaMallocAsync(&d_c, bytes, st));
+    auto release = [&]() {  // stream-ordered: safe after any error below
+        if (d_a) cudaFreeAsync(d_a, st);
+        if (d_b) cudaFreeAsync(d_b, st);
+        if (d_o) cudaFreeAsync(d_o, st);
+        if (d_c) cudaFreeAsync(d_c, st);
+        return cudaStreamSynchronize(st);
+    };
+    if (cudaMallocAsync(&d_a, bytes, st) != cudaSuccess || cudaMallocAsync(&d_b, bytes, st) != cudaSuccess ||
+        cudaMallocAsync(&d_o, bytes, st) != cudaSuccess || (mux && cudaMallocAsync(&d_c, bytes, st) != cudaSuccess)) {
+        const cudaError_t e = cudaGetLastError();
+        release();
+        return fail("device allocation of %zu bytes per operand failed: %s", bytes, cudaGetErrorString(e));
+    }
     const int chunk = 16 * 4 * c->sm_count;  // 16 waves
     const int nchunks = count >= 2 * chunk ? (count + chunk - 1) / chunk : 1;
     int rc = 0;
     if (nchunks == 1) {
-        CU(cudaMemcpyAsync(d_a, a, bytes, cudaMemcpyHostToDevice, st));
-        CU(cudaMemcpyAsync(d_b, b, bytes, cudaMemcpyHostToDevice, st));
-        if (mux) CU(cudaMemcpyAsync(d_c, cc, bytes, cudaMemcpyHostToDevice, st));
-        rc = mux ? tfhe_b200_mux(c, d_o, d_a, d_b, d_c, count, st) : tfhe_b200_gate(c, gate, d_o, d_a, d_b, count, st);
+        cudaError_t e = cudaMemcpyAsync(d_a, a, bytes, cudaMemcpyHostToDevice, st);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(d_b, b, bytes, cudaMemcpyHostToDevice, st);
+        if (e == cudaSuccess && mux) e = cudaMemcpyAsync(d_c, cc, bytes, cudaMemcpyHostToDevice, st);
+        if (e != cudaSuccess) rc = fail("H2D copy failed: %s", cudaGetErrorString(e));
+        if (!rc)
+            rc = mux ? tfhe_b200_mux(c, d_o, d_a, d_b, d_c, count, st) : tfhe_b200_gate(c, gate, d_o, d_a, d_b, count, st);
         if (!rc) {
-            cudaError_t e = cudaMemcpyAsync(out, d_o, bytes, cudaMemcpyDeviceToHost, st);
+            e = cudaMemcpyAsync(out, d_o, bytes, cudaMemcpyDeviceToHost, st);
             if (e != cudaSuccess) rc = fail("D2H copy failed: %s", cudaGetErrorString(e));
         }
     } else {
@@ -734,11 +745,7 @@ static int host_gate_common(tfhe_b200_ctx *c, int gate, bool mux, int32_t *out, 
         for (auto &e : ev)
             if (e) cudaEventDestroy(e);
     }
-    cudaFreeAsync(d_a, st);
-    cudaFreeAsync(d_b, st);
-    cudaFreeAsync(d_o, st);
-    if (d_c) cudaFreeAsync(d_c, st);
-    cudaError_t e = cudaStreamSynchronize(st);
+    const cudaError_t e = release();
     if (!rc && e != cudaSuccess) rc = fail("gate batch failed: %s", cudaGetErrorString(e));
     return rc;
 }

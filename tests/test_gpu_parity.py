@@ -279,6 +279,10 @@ def test_host_buffer_entry_point_pipelined_chunks(engine, oracle, keys):
     assert np.array_equal(oracle.decrypt_bits(keys, out), 1 - (a & b))
     dev = engine.gate("NAND", engine.to_device(ca), engine.to_device(cb)).cpu().numpy()
     assert np.array_equal(out, dev)  # same kernels on the same inputs: identical words
+    c = r.integers(0, 2, n).astype(np.int32)
+    cc = oracle.encrypt_bits(keys, rng, c)
+    out = engine.mux_host(ca, cb, cc)
+    assert np.array_equal(oracle.decrypt_bits(keys, out), np.where(a == 1, b, c))
 
 
 def test_reference_fourier_key_import(pkg, oracle, keys, ctx_ref):
