@@ -441,8 +441,16 @@ TFHE_HD void phase_xchg_store(int lane, WarpSmem &ws, int role, const cpx (&give
     for (int i = 0; i < 16; i++) d[i] = give[i];
 }
 
-// keep += partner's partial; inverse pass 2 ("I1") of that result polynomial; the 16
-// outputs go to exchange buffer 2 (result a, role 0) or 3 (result b, role 1).
+// Inverse pass 2 ("I1") of the finished Fourier sum of result polynomial `role`; the 16 outputs go
+// to exchange buffer 2 (result a, role 0) or 3 (result b, role 1).
+TFHE_HD void phase_inv16_store(int lane, WarpSmem &ws, const cpx *e2, int role, cpx (&keep)[16]) {
+    inv16(keep, e2 + lane * kE2Row);
+    cpx *d = ws.exch[2 + role] + lane * kExchRow;
+#pragma unroll
+    for (int j2 = 0; j2 < 16; j2++) d[j2] = keep[j2];
+}
+
+// keep += partner's partial sum (parked by phase_xchg_store), then phase_inv16_store.
 TFHE_HD void phase_xchg_load_inv(int lane, WarpSmem &ws, const cpx *e2, int role, cpx (&keep)[16]) {
     const cpx *s = ws.exch[1 - role] + lane * kExchRow;
 #pragma unroll
@@ -451,16 +459,12 @@ TFHE_HD void phase_xchg_load_inv(int lane, WarpSmem &ws, const cpx *e2, int role
         keep[i].x += v.x;
         keep[i].y += v.y;
     }
-    inv16(keep, e2 + lane * kE2Row);
-    cpx *d = ws.exch[2 + role] + lane * kExchRow;
-#pragma unroll
-    for (int j2 = 0; j2 < 16; j2++) d[j2] = keep[j2];
+    phase_inv16_store(lane, ws, e2, role, keep);
 }
 
 // Inverse pass 1, first part: the four inner stages on positions [16*role, 16*role+16) of
-// both result polynomials (lane (o, j2)); the 16 values are parked in exchange buffer `role`
-// ([i][lane], conflict free) for the partner.
-TFHE_HD void phase_i2_half(int lane, WarpSmem &ws, int role, cpx (&x)[16]) {
+// both result polynomials (lane (o, j2)).
+TFHE_HD void phase_i2_half_compute(int lane, WarpSmem &ws, int role, cpx (&x)[16]) {
     const int o = lane >> 4, j2 = lane & 15;
     const cpx *src = ws.exch[2 + o] + j2;
 #pragma unroll
@@ -480,8 +484,13 @@ TFHE_HD void phase_i2_half(int lane, WarpSmem &ws, int role, cpx (&x)[16]) {
             for (int i = 0; i < half; i++) bf_inv(x[b * 2 * half + i], x[b * 2 * half + i + half], er, ei);
         }
     }
-    // the last stage pairs position i of role 0 (u) with position i of role 1 (v): role 0 finishes
-    // pairs 0..7 and role 1 pairs 8..15, so each warp hands over only the 8 values the other needs
+}
+
+// ... and the hand-over for the last stage, which pairs position i of role 0 (u) with position i
+// of role 1 (v): role 0 finishes pairs 0..7 and role 1 pairs 8..15, so each warp parks only the 8
+// values the other needs in exchange buffer `role` ([i][lane], conflict free).
+TFHE_HD void phase_i2_half(int lane, WarpSmem &ws, int role, cpx (&x)[16]) {
+    phase_i2_half_compute(lane, ws, role, x);
     cpx *dst = ws.exch[role] + lane;
     if (role == 0) {
 #pragma unroll
@@ -498,18 +507,14 @@ TFHE_HD void phase_i2_half(int lane, WarpSmem &ws, int role, cpx (&x)[16]) {
 // i = 8r .. 8r+7 completely: coefficients j1 = i and j1 = i + 16 of the row, and the matching
 // upper-half coefficients (+32) from the imaginary parts.
 template <int ROLE>
-TFHE_HD void i2_final_role(int lane, WarpSmem &ws, const cpx (&x)[16]) {
+TFHE_HD void i2_final_role(int lane, WarpSmem &ws, const cpx (&x)[16], const cpx (&p)[8]) {
     const int o = lane >> 4, j2 = lane & 15;
-    const cpx *other = ws.exch[1 - ROLE] + lane;
     int32_t *row = ws.acc[o] + j2 * kAccRow + 8 * ROLE;
     int32_t *ext = ext_poly(ws, o) + j2 * kExtRow + 8 * ROLE;  // extended copy, same coefficients
     const double er = c1_re_rt(0), ei = c1_im_rt(0);
     // all loads first (128-bit accesses to the master copy: the 8 consecutive coefficients of a group
     // are two aligned quads), then the butterflies and conversions, then the updates
-    cpx p[8];
     word4 acc4[4][2];  // group g: coefficients 16 g + 8 ROLE + (0..7) of the row
-#pragma unroll
-    for (int b = 0; b < 8; b++) p[b] = other[b * 32];
 #pragma unroll
     for (int g = 0; g < 4; g++)
 #pragma unroll
@@ -545,9 +550,18 @@ TFHE_HD void i2_final_role(int lane, WarpSmem &ws, const cpx (&x)[16]) {
 // The role is a template argument of the body: with a run-time role inside the unrolled loop the
 // compiler kept one branch per output (15 BSSY/BRA pairs, no overlap between outputs: 1,440 cycles
 // for 500 cycles of work).
+// p: the partner's 8 values for the pairs this role finishes.
+TFHE_HD void phase_i2_final_with(int lane, WarpSmem &ws, int role, const cpx (&x)[16], const cpx (&p)[8]) {
+    if (role == 0) i2_final_role<0>(lane, ws, x, p);
+    else i2_final_role<1>(lane, ws, x, p);
+}
+
 TFHE_HD void phase_i2_final(int lane, WarpSmem &ws, int role, const cpx (&x)[16]) {
-    if (role == 0) i2_final_role<0>(lane, ws, x);
-    else i2_final_role<1>(lane, ws, x);
+    const cpx *other = ws.exch[1 - role] + lane;  // parked by the partner's phase_i2_half
+    cpx p[8];
+#pragma unroll
+    for (int b = 0; b < 8; b++) p[b] = other[b * 32];
+    phase_i2_final_with(lane, ws, role, x, p);
 }
 
 // Stand-alone external product: the result REPLACES the accumulator, so the master copy is
