@@ -189,7 +189,7 @@ def run_reference(args):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=_RESULT_OUT, flush=True)
 
 
 def circuit_latencies(pkg, eng, sk):
@@ -403,10 +403,13 @@ def run_b200(args):
             "cpu_baseline": cpu,
             "latency": latency,
         }
-        print(json.dumps(line), flush=True)
+        print(json.dumps(line), file=_RESULT_OUT, flush=True)
     eng.close()
     if world > 1:
         dist.destroy_process_group()
+
+
+_RESULT_OUT = sys.stdout
 
 
 def main():
@@ -420,12 +423,21 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
+    # The contract is ONE JSON line on stdout.  Libraries write there too (NCCL prints its version
+    # banner on rank 0 when NCCL_DEBUG is set in the environment): everything that is not the
+    # result line goes to stderr; the line itself is written to the real stdout at the end.
+    sys.stdout.flush()
+    real_stdout = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    global _RESULT_OUT
+    _RESULT_OUT = real_stdout
     if args.impl == "reference":
         run_reference(args)
     else:
         if args.warmup < 3:
             args.warmup = 3  # timing rule: at least 3 warm-up steps
         run_b200(args)
+    real_stdout.flush()
 
 
 if __name__ == "__main__":
