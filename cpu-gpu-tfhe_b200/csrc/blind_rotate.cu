@@ -11,10 +11,14 @@
 //     barriers are needed between phases; both warps do identical work between
 //     barriers (two warps per SM sub-partition hide each other's latencies: ncu of
 //     the one-warp-per-ciphertext version showed 43 % fp64 pipe use);
+//   * the rotation X^a * ACC is read at immediate offsets from a negacyclically extended
+//     copy of the accumulator (br_core.cuh phase_f1q_decomp), sign / subtraction /
+//     decomposition offset / digit shift are two integer multiply-adds per coefficient;
 //   * 4 ciphertexts per CTA share each 16 KiB row of the bootstrapping key,
 //     streamed from L2/HBM with 1-D TMA bulk copies (cp.async.bulk + mbarrier
-//     expect_tx) into a 3-stage ring; the last warp to finish with a stage
-//     issues the refill, so there is no producer warp;
+//     expect_tx) into a 3-stage ring per role; a stage is released right behind the
+//     last load of its chunk and the last warp to release it issues the refill, so
+//     there is no producer warp (small batches: the idle last slot of the CTA refills);
 //   * the gate's linear prologue and the mod-switch are computed on the fly
 //     from the input samples (no temporaries in global memory);
 //   * grid = min(#groups, #SMs) CTAs, each looping over groups of 4 ciphertexts.
