@@ -74,6 +74,25 @@ def test_mux_rotate_step_teacher_forced(engine, oracle, keys):
         assert np.abs(d).max() <= 1, (i, a, np.abs(d).max())
 
 
+def test_blind_rotate_is_independent_of_batch_layout(engine):
+    """The same ciphertexts through the full-batch kernel (4 per SM, two passes over some SMs) and in
+    small batches (one per SM, the idle-slot refiller kernel) give identical words: the arithmetic
+    of a ciphertext does not depend on its slot, on idle iterations (bara = 0, 40 % here) of its
+    neighbours, or on which warp refills the key ring."""
+    rng = np.random.default_rng(21)
+    count, n_iter = 4 * engine.sm_count + 108, 8
+    acc = _rand_i32(rng, (count, 2, 1024))
+    bara = rng.integers(0, 2048, size=(count, n_iter)).astype(np.int32)
+    bara[rng.random((count, n_iter)) < 0.4] = 0
+    d_acc, d_bara = engine.to_device(acc), engine.to_device(bara)
+    big = engine.blind_rotate(d_acc.clone(), d_bara).cpu().numpy()
+    parts = []
+    for lo in range(0, count, 100):
+        parts.append(engine.blind_rotate(d_acc[lo:lo + 100].clone(), d_bara[lo:lo + 100].contiguous()).cpu().numpy())
+    assert np.array_equal(big, np.concatenate(parts, 0))
+    assert not np.array_equal(big, acc)
+
+
 def test_blind_rotate_short_run_tracks_oracle(engine, oracle, keys, ctx_ref):
     """A few consecutive iterations from the same accumulator.  Masks may differ entirely
     after the first decomposition-boundary flip (about 2 % of iterations), after which the
