@@ -13,12 +13,46 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "_obj")
 LIB = os.path.join(HERE, "libtfhe_b200.so")
+# The same library with the reference's truncating fp64 -> Torus32 conversion
+# (-DTFHE_B200_TRUNCATE_LIKE_REFERENCE=1, br_core.cuh double_to_torus32); only blind_rotate.cu differs.
+LIB_TRUNC = os.path.join(HERE, "libtfhe_b200_trunc.so")
+INCLUDE = os.path.join(HERE, "..", "include")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 SOURCES = ["blind_rotate.cu", "keyswitch.cu", "keyswitch_mma.cu", "engine.cu", "client.cu", "microbench.cu", "compat.cu", "circuits.cu", "keyio.cu", "keygen.cu"]
 FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-std=c++17", "-O3", "-lineinfo",
     "-Xcompiler", "-fPIC,-O2,-Wall", "-I", os.path.join(HERE, "..", "include"),
 ]
+
+
+def exported_symbols():
+    """The C ABI = every function declared in include/*.h (nothing else leaves the library)."""
+    import re
+
+    names = set()
+    for h in sorted(os.listdir(INCLUDE)):
+        if not h.endswith(".h"):
+            continue
+        text = open(os.path.join(INCLUDE, h)).read()
+        text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+        text = re.sub(r"//[^\n]*", "", text)
+        names |= set(re.findall(r"\b([A-Za-z_][A-Za-z0-9_]*)\s*\([^;{]*\)\s*;", text))
+    return sorted(n for n in names if not n.startswith("__"))
+
+
+def _version_script():
+    path = os.path.join(OBJ, "exports.map")
+    text = "{\n  global:\n" + "".join("    %s;\n" % n for n in exported_symbols()) + \
+           "    tfhe_b200_debug_*;\n  local: *;\n};\n"
+    if not os.path.exists(path) or open(path).read() != text:
+        with open(path, "w") as f:
+            f.write(text)
+    return path
+
+
+def _link(lib, objs):
+    _run([NVCC, "-shared", "-o", lib] + objs + ["-gencode", "arch=compute_100a,code=sm_100a",
+                                                 "-Xlinker", "--version-script=" + _version_script()])
 
 
 def _deps():
@@ -51,14 +85,25 @@ def build(force=False, verbose=True):
         objs.append(obj)
         if force or not os.path.exists(obj) or os.path.getmtime(obj) < max(os.path.getmtime(src), dep_time):
             jobs.append([NVCC] + FLAGS + ["-c", src, "-o", obj])
+    # truncating-conversion variant: one more object
+    br_src = os.path.join(CSRC, "blind_rotate.cu")
+    br_trunc = os.path.join(OBJ, "blind_rotate_trunc.o")
+    trunc_stale = force or not os.path.exists(br_trunc) or os.path.getmtime(br_trunc) < max(os.path.getmtime(br_src), dep_time)
+    if trunc_stale:
+        jobs.append([NVCC] + FLAGS + ["-DTFHE_B200_TRUNCATE_LIKE_REFERENCE=1", "-c", br_src, "-o", br_trunc])
     if verbose and jobs:
         print("[build] compiling %d CUDA translation units for sm_100a" % len(jobs), flush=True)
     with ThreadPoolExecutor(max_workers=4) as ex:
         list(ex.map(_run, jobs))
-    if force or jobs or not os.path.exists(LIB):
-        _run([NVCC, "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a"])
+    hdr_time = max(os.path.getmtime(os.path.join(INCLUDE, h)) for h in os.listdir(INCLUDE))
+    if force or jobs or not os.path.exists(LIB) or os.path.getmtime(LIB) < hdr_time:
+        _link(LIB, objs)
         if verbose:
             print("[build] linked", LIB, flush=True)
+    if force or jobs or not os.path.exists(LIB_TRUNC) or os.path.getmtime(LIB_TRUNC) < hdr_time:
+        _link(LIB_TRUNC, [br_trunc if o.endswith("blind_rotate.o") else o for o in objs])
+        if verbose:
+            print("[build] linked", LIB_TRUNC, flush=True)
     return LIB
 
 

@@ -26,10 +26,7 @@
 #include <stdint.h>
 #include <stdlib.h>
 
-#ifndef TFHE_B200_EXPERIMENTAL_WARP_KERNEL
-#define TFHE_B200_EXPERIMENTAL_WARP_KERNEL 0
-#endif
-#include "brw_core.cuh"
+#include "br_core.cuh"
 #include "kernels.h"
 
 namespace tfhe_b200 {
@@ -143,13 +140,6 @@ __device__ __forceinline__ void build_e2(cpx *e2) {
         sincospi(e2_shift(m1, idx), &s, &c);
         e2[m1 * kE2Row + idx].x = c;
         e2[m1 * kE2Row + idx].y = s;
-    }
-    // entry 4: stage-4 multiplier of the one-warp-per-ciphertext kernel (brw_core.cuh)
-    for (int m1 = threadIdx.x; m1 < 32; m1 += blockDim.x) {
-        double s, c;
-        sincospi(w_stage4_shift(m1), &s, &c);
-        e2[m1 * kE2Row + 4].x = m1 < 16 ? c : -c;
-        e2[m1 * kE2Row + 4].y = m1 < 16 ? s : -s;
     }
 }
 
@@ -505,174 +495,6 @@ __global__ void __launch_bounds__(kThreads, 1) blind_rotate_kernel(const BrLaunc
     }
 }
 
-// =================================================================================
-// EXPERIMENTAL (compiled only with -DTFHE_B200_EXPERIMENTAL_WARP_KERNEL=1, selected with
-// TFHE_B200_BR_VARIANT=2): ONE warp per ciphertext, 8 ciphertexts per SM (brw_core.cuh),
-// 24 KB of shared memory and one 255-register warp each, no cross-warp synchronisation.
-// Bit-identical results (all GPU tests pass), but measured 16 % SLOWER than the pair kernel
-// (20.4 vs 2 x 8.6 us per iteration of 8 ciphertexts per SM, profiles/README.md): the two
-// Fourier-domain sums (128 registers) stay live across pass 1 of the second digit level, and
-// ptxas spills around it.  Kept for round 2 (the sums could be parked in tensor memory).
-// One key ring for the whole CTA: every warp consumes all 8 chunks of an iteration in the
-// order (q, o, result polynomial); the last of the 8 warps to finish with a stage refills it.
-#if TFHE_B200_EXPERIMENTAL_WARP_KERNEL
-
-#ifndef TFHE_B200_WARP_CTS
-#define TFHE_B200_WARP_CTS 8
-#endif
-constexpr int kWarpCts = TFHE_B200_WARP_CTS;
-constexpr uint32_t kWRingStages = 3;
-constexpr uint32_t kWStageBytes = kBkHalfCplx * sizeof(cpx);
-constexpr uint32_t kWChunksPerIter = 2 * kKpl;
-
-struct __align__(128) CtaSmemW {
-    CtSmem w[kWarpCts];
-    cpx e2[32 * kE2Row];
-    cpx ring[kWRingStages][kBkHalfCplx];
-    unsigned long long full[kWRingStages];
-    unsigned int drained[kWRingStages];
-};
-static_assert(sizeof(CtSmem) % 128 == 0, "ciphertext working set must keep 128 B alignment");
-static_assert(offsetof(CtaSmemW, ring) % 128 == 0, "TMA destination alignment");
-static_assert(sizeof(CtaSmemW) <= 227 * 1024, "shared memory budget");
-
-__device__ __forceinline__ void ring_fill_w(CtaSmemW &S, const BrLaunch &L, uint32_t chunk, uint32_t stage) {
-    const uint32_t it = (chunk / kWChunksPerIter) % (uint32_t) L.n_iter;
-    const uint32_t sub = chunk % kWChunksPerIter;
-    const uint32_t q = sub >> 2, o = (sub >> 1) & 1u, out = sub & 1u;
-    const uint32_t row = o * kL + q;
-    const cpx *src = L.bk + ((size_t) (L.bk_first + it) * kKpl + row) * kBkRowCplx + out * kBkHalfCplx;
-    mbar_arrive_expect_tx(&S.full[stage], kWStageBytes);
-    tma_load_1d(S.ring[stage], src, kWStageBytes, &S.full[stage]);
-}
-
-template <typename Use>
-__device__ __forceinline__ void ring_consume_w(CtaSmemW &S, const BrLaunch &L, int lane, RingPos &rp,
-                                               uint32_t ring_chunks, Use use) {
-    const uint32_t st = rp.stage;
-    mbar_wait(&S.full[st], rp.phase);
-    use(S.ring[st]);
-    __syncwarp();
-    if (lane == 0) {
-        const unsigned int seen = atomicAdd(&S.drained[st], 1u);
-        if ((seen & (kWarpCts - 1)) == kWarpCts - 1) {
-            const uint32_t next = rp.chunk + kWRingStages;
-            if (next < ring_chunks) {
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                ring_fill_w(S, L, next, st);
-            }
-        }
-    }
-    rp.advance(kWRingStages);
-}
-
-// Pass 1 as a real call: inlined, ptxas schedules it as aggressively as if it had the whole
-// register file (178 registers stand-alone) and then spills the 128 live accumulator registers
-// around it; as a separate function it is allocated on its own (it needs fewer than 100).
-template <int O>
-__device__ __noinline__ void w_f1_call(int lane, CtSmem *W, int a, int q, bool rotate) {
-    w_phase_f1(lane, *W, a, O, q, rotate);
-}
-
-__global__ void __launch_bounds__(kWarpCts * 32, 1) blind_rotate_warp_kernel(const BrLaunch L) {
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    CtaSmemW &S = *reinterpret_cast<CtaSmemW *>(smem_raw);
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-
-    const int ngroups = (L.total + kWarpCts - 1) / kWarpCts;
-    const int n_iter = L.n_iter;
-    const int my_groups = (ngroups - (int) blockIdx.x + (int) gridDim.x - 1) / (int) gridDim.x;
-    const uint32_t ring_chunks = kWChunksPerIter * (uint32_t) my_groups * (uint32_t) n_iter;
-
-    build_e2(S.e2);
-    if (threadIdx.x == 0) {
-        for (uint32_t s = 0; s < kWRingStages; s++) {
-            mbar_init(&S.full[s], 1);
-            S.drained[s] = 0;
-        }
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        for (uint32_t c = 0; c < kWRingStages && c < ring_chunks; c++) ring_fill_w(S, L, c, c);
-    }
-    __syncthreads();
-    const bool rotate = (L.extern_only == 0);
-    CtSmem &W0 = S.w[warp];
-    RingPos rp;
-    for (int grp = blockIdx.x; grp < ngroups; grp += gridDim.x) {
-        int g = grp * kWarpCts + warp;
-        const bool valid = g < L.total;
-        if (!valid) g = L.total - 1;
-        const GateIn I = resolve_inputs(L, g);
-        {
-            int barb;
-            if (L.explicit_inputs != 0) barb = L.barb ? (L.barb[g] & (2 * kN - 1)) : 0;
-            else {
-                uint32_t xb = I.cst + I.sa * (uint32_t) __ldg(I.in0 + L.n) + I.sb * (uint32_t) __ldg(I.in1 + L.n);
-                if (I.in2 != nullptr) xb += I.sc * (uint32_t) __ldg(I.in2 + L.n);
-                barb = modswitch_2N(xb);
-            }
-            if (L.acc_in != nullptr) w_phase_load_acc(lane, W0, L.acc_in + (size_t) g * (kK + 1) * kN);
-            else if (L.testvect != nullptr) w_phase_init_testvect(lane, W0, barb, L.testvect);
-            else w_phase_init(lane, W0, barb, L.mu);
-        }
-        __syncwarp();
-
-        int a_blk = 0;  // lane l holds bara of iteration (it & ~31) + l
-        for (int it = 0; it < n_iter; it++) {
-            if ((it & 31) == 0) a_blk = load_bara(L, I, g, it + lane, n_iter, rotate);
-            const int a = __shfl_sync(0xffffffffu, a_blk, it & 31);
-            const bool active = (a != 0) || !rotate;  // tfhe_blindRotate_FFT :705 skips barai == 0 (no-op)
-            // The phases below derive all their shared-memory addresses from the lane index.
-            // Laundering it once per iteration keeps the compiler from hoisting ~100 loop-invariant
-            // addresses out of the iteration loop (they were spilled: 776 B of stack per thread).
-            int ln = lane;
-            asm volatile("" : "+r"(ln));
-            CtSmem &W = W0;
-
-            cpx acc0[16], acc1[16];  // Fourier-domain sums of the two result polynomials
-#pragma unroll
-            for (int i = 0; i < 16; i++) {
-                acc0[i].x = 0.0; acc0[i].y = 0.0;
-                acc1[i].x = 0.0; acc1[i].y = 0.0;
-            }
-#pragma unroll 1
-            for (int q = 0; q < kL; q++) {
-                if (active) {
-                    w_f1_call<0>(ln, &W, a, q, rotate);
-                    __syncwarp();
-                    w_f1_call<1>(ln, &W, a, q, rotate);
-                }
-                __syncwarp();
-#pragma unroll 1
-                for (int o = 0; o <= kK; o++) {
-                    cpx z[16];
-                    if (active) w_phase_f2(ln, W.x[o], S.e2, z);
-                    ring_consume_w(S, L, lane, rp, ring_chunks, [&](const cpx *half) {
-                        if (active) phase_mac_half(ln, z, half, acc0);
-                    });
-                    ring_consume_w(S, L, lane, rp, ring_chunks, [&](const cpx *half) {
-                        if (active) phase_mac_half(ln, z, half, acc1);
-                    });
-                }
-                __syncwarp();  // pass 1 of the next digit level overwrites the exchange buffers
-            }
-            if (active) {
-                w_phase_i1(ln, W.x[0], S.e2, acc0);
-                w_phase_i1(ln, W.x[1], S.e2, acc1);
-                __syncwarp();
-                w_phase_i2<0>(ln, W, rotate);
-                w_phase_i2<1>(ln, W, rotate);
-                __syncwarp();
-            }
-        }
-
-        if (valid) {
-            if (L.u_out != nullptr) w_phase_extract(lane, W0, L.u_out + (size_t) g * (kN + 1));
-            if (L.acc_out != nullptr) w_phase_dump_acc(lane, W0, L.acc_out + (size_t) g * (kK + 1) * kN);
-        }
-        __syncwarp();
-    }
-}
-#endif  // TFHE_B200_EXPERIMENTAL_WARP_KERNEL
 
 // ------------------------------------------------------------ key conversion
 
@@ -702,6 +524,11 @@ forward_polys_kernel(const int32_t *__restrict__ coef, cpx *__restrict__ out, in
 
 size_t blind_rotate_smem_bytes() { return sizeof(CtaSmem); }
 
+// 0: the fp64 products are rounded to the nearest integer (default: the accumulator equals the
+// exact negacyclic product); 1: built with -DTFHE_B200_TRUNCATE_LIKE_REFERENCE=1, the conversion
+// truncates like Torus32(int64_t(x)) of fft_processor_fftw.cu:177 (libtfhe_b200_trunc.so)
+extern "C" int tfhe_b200_conversion_mode(void) { return TFHE_B200_TRUNCATE_LIKE_REFERENCE ? 1 : 0; }
+
 #if TFHE_B200_PHASE_TIMING
 extern "C" int tfhe_b200_debug_phase_cycles(long long *out, int reset) {
     if (cudaMemcpyFromSymbol(out, g_phase_cycles, sizeof(g_phase_cycles)) != cudaSuccess) return 1;
@@ -720,11 +547,6 @@ cudaError_t blind_rotate_configure() {
     e = cudaFuncSetAttribute(blind_rotate_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              (int) sizeof(CtaSmem));
     if (e != cudaSuccess) return e;
-#if TFHE_B200_EXPERIMENTAL_WARP_KERNEL
-    e = cudaFuncSetAttribute(blind_rotate_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             (int) sizeof(CtaSmemW));
-    if (e != cudaSuccess) return e;
-#endif
     return cudaFuncSetAttribute(forward_polys_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 (int) sizeof(FwdSmem));
 }
@@ -736,17 +558,6 @@ cudaError_t launch_blind_rotate(const BrLaunch &L_in, int sm_count, cudaStream_t
     L.cts_per_group = cpg < 1 ? 1 : (cpg > kCtWarps ? kCtWarps : cpg);
     const int ngroups = (L.total + L.cts_per_group - 1) / L.cts_per_group;
     const int grid = ngroups < sm_count ? ngroups : sm_count;
-#if TFHE_B200_EXPERIMENTAL_WARP_KERNEL
-    static const int variant = [] {
-        const char *v = getenv("TFHE_B200_BR_VARIANT");
-        return v ? atoi(v) : 0;
-    }();
-    if (variant == 2) {
-        const int ng = (L.total + kWarpCts - 1) / kWarpCts;
-        blind_rotate_warp_kernel<<<ng < sm_count ? ng : sm_count, kWarpCts * 32, sizeof(CtaSmemW), stream>>>(L);
-        return cudaGetLastError();
-    }
-#endif
     // small batches: the always-idle last slot of every CTA refills the key rings (ring_skip<true>)
     if (L.cts_per_group < kCtWarps) blind_rotate_kernel<true><<<grid, kThreads, sizeof(CtaSmem), stream>>>(L);
     else blind_rotate_kernel<false><<<grid, kThreads, sizeof(CtaSmem), stream>>>(L);

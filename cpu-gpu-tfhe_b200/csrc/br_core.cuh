@@ -145,6 +145,9 @@ TFHE_HD double digit_to_double(uint32_t dig) {
 #define TFHE_B200_TRUNCATE_LIKE_REFERENCE 0
 #endif
 TFHE_HD uint32_t double_to_torus32(double x) {
+#if defined(TFHE_B200_CONV_PROBE) && !defined(__CUDA_ARCH__)
+    TFHE_B200_CONV_PROBE(x);  // host emulation only: tests record the distance of x from the integers
+#endif
 #if TFHE_B200_TRUNCATE_LIKE_REFERENCE
     return (uint32_t) (int32_t) (long long) x;
 #else

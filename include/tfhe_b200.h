@@ -282,6 +282,11 @@ int tfhe_b200_sm_count(const tfhe_b200_ctx *ctx);
  * timing is enabled: total blind-rotate ms, total key-switch ms, number of gate calls */
 int tfhe_b200_set_timing(tfhe_b200_ctx *ctx, int enable);
 int tfhe_b200_get_timing(tfhe_b200_ctx *ctx, double *blind_rotate_ms, double *keyswitch_ms, int *calls);
+/* How this build converts the fp64 products back to Torus32: 0 = round to nearest (default; every
+ * blind-rotation step equals the exact integer negacyclic product, tests/test_gpu_exact.py),
+ * 1 = truncation toward zero like the reference's Torus32(int64_t(x)), fft_processor_fftw.cu:177
+ * (the libtfhe_b200_trunc.so build, -DTFHE_B200_TRUNCATE_LIKE_REFERENCE=1) */
+int tfhe_b200_conversion_mode(void);
 /* fp64 FMA peak of `device` in TFLOP/s, measured live: best single launch and the mean over
  * ~0.4 s of back-to-back launches (roofline denominator of the blind-rotation kernel) */
 int tfhe_b200_measure_fp64_peak(int device, double *burst_tflops, double *sustained_tflops);

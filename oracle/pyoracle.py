@@ -172,6 +172,24 @@ class Oracle:
         return acc
 
 
+    def blind_rotate_exact(self, bk, accum, bara, n_iter=None, params=None):
+        """tfhe_blindRotate with exact products (no FFT): the integer answer."""
+        p = params or self.params
+        acc, bara, bk = _i32(accum).copy(), _i32(bara), _i32(bk)
+        self.L.oracle_blind_rotate_exact(ctypes.byref(p), _p(bk), _p(acc), _p(bara),
+                                         int(bara.size if n_iter is None else n_iter))
+        return acc
+
+    def bootstrap_woks_exact(self, bk, mu, x, threads=0, params=None):
+        """tfhe_bootstrap_woKS with exact products on a batch x[count][n+1] -> u[count][N+1]."""
+        p = params or self.params
+        x, bk = np.atleast_2d(_i32(x)), _i32(bk)
+        u = np.zeros((x.shape[0], p.N * p.k + 1), np.int32)
+        self.L.oracle_bootstrap_woks_exact_batch(ctypes.byref(p), _p(bk), ctypes.c_int32(int(mu)), _p(x), _p(u),
+                                                 int(x.shape[0]), int(threads))
+        return u
+
+
 class OracleCtx:
     def __init__(self, oracle, keys, fft_mode):
         self.o, self.L, self.keys, self.p = oracle, oracle.L, keys, keys.params
@@ -396,6 +414,13 @@ class Ref:
         acc = _i32(accum).copy()
         bara = _i32(bara)
         self.L.ref_blind_rotate(self.h, _p(acc), _p(bara), int(bara.size if n_iter is None else n_iter))
+        return acc
+
+    def blind_rotate_naive(self, accum, bara, n_iter=None):
+        """The reference's non-FFT blind rotation with torusPolynomialMultNaive products."""
+        acc = _i32(accum).copy()
+        bara = _i32(bara)
+        self.L.ref_blind_rotate_naive(self.h, _p(acc), _p(bara), int(bara.size if n_iter is None else n_iter))
         return acc
 
     def decomp(self, poly):

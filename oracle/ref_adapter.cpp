@@ -279,6 +279,38 @@ void ref_blind_rotate(const RefHandle *h, int32_t *accum, const int32_t *bara, i
     delete_TLweSample(acc);
 }
 
+/* The reference's NON-FFT blind rotation (tfhe_blindRotate / tfhe_MuxRotate,
+ * lwe-bootstrapping-functions.cu:34-79; tGswExternMulToTLwe, tgsw-functions.cu:156-170) with the
+ * polynomial products taken by the reference's own torusPolynomialMultNaive (multiplication.cu:72).
+ * As shipped, polynomials_arithmetic.h:112-114 routes torusPolynomialAddMulR to the FFT, so the
+ * sequence is spelled out here from the reference's functions; everything is integer arithmetic. */
+void ref_blind_rotate_naive(const RefHandle *h, int32_t *accum, const int32_t *bara, int n_iter) {
+    const TGswParams *gp = h->params->tgsw_params;
+    const TLweParams *tp = gp->tlwe_params;
+    const int N = tp->N, k = tp->k, kpl = gp->kpl;
+    TLweSample *acc = new_TLweSample(tp), *tmp = new_TLweSample(tp), *res = new_TLweSample(tp);
+    IntPolynomial *dec = new_IntPolynomial_array(kpl, N);
+    TorusPolynomial *prod = new_TorusPolynomial(N);
+    for (int j = 0; j <= k; j++) memcpy(acc->a[j].coefsT, accum + j * N, sizeof(int32_t) * N);
+    for (int i = 0; i < n_iter; i++) {
+        if (bara[i] == 0) continue;
+        tLweMulByXaiMinusOne(tmp, bara[i], acc, tp);
+        tGswTLweDecompH(dec, tmp, gp);
+        tLweClear(res, tp);
+        for (int r = 0; r < kpl; r++)
+            for (int j = 0; j <= k; j++) {
+                torusPolynomialMultNaive(prod, &dec[r], &h->bk->bk[i].all_sample[r].a[j]);
+                torusPolynomialAddTo(&res->a[j], prod);
+            }
+        tLweAddTo(res, acc, tp);
+        for (int j = 0; j <= k; j++) memcpy(acc->a[j].coefsT, res->a[j].coefsT, sizeof(int32_t) * N);
+    }
+    for (int j = 0; j <= k; j++) memcpy(accum + j * N, acc->a[j].coefsT, sizeof(int32_t) * N);
+    delete_TorusPolynomial(prod);
+    delete_IntPolynomial_array(kpl, dec);
+    delete_TLweSample(res); delete_TLweSample(tmp); delete_TLweSample(acc);
+}
+
 /* Gadget decomposition of one polynomial: tGswTorus32PolynomialDecompH */
 void ref_decomp(const RefHandle *h, const int32_t *poly, int32_t *out_l_by_N) {
     const TGswParams *gp = h->params->tgsw_params;

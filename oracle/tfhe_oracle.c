@@ -579,6 +579,60 @@ void oracle_bootstrap_woks(const OracleCtx *c, int32_t mu, const int32_t *x, int
     work_free(w);
 }
 
+/* ------------------------------------------------- exact (FFT-free) bootstrap
+ * The reference's non-FFT path (tfhe_MuxRotate / tfhe_blindRotate / tfhe_blindRotateAndExtract /
+ * tfhe_bootstrap_woKS, lwe-bootstrapping-functions.cu:34-179; tGswExternMulToTLwe
+ * tgsw-functions.cu:156-170) with every polynomial product taken by definition
+ * (torusPolynomialMultNaive, multiplication.cu:53-77): integer arithmetic mod 2^32 only, no
+ * rounding anywhere.  The CUDA path rounds its fp64 products to the nearest integer, so a complete
+ * blind rotation must reproduce these words exactly (tests/test_gpu_exact.py). */
+void oracle_blind_rotate_exact(const OracleParams *p, const int32_t *bk, int32_t *accum, const int32_t *bara,
+                               int n_iter) {
+    const int N = p->N, k = p->k, kpl = (k + 1) * p->l;
+    int32_t *tmp = (int32_t *) malloc(sizeof(int32_t) * (size_t) (k + 1) * N);
+    for (int i = 0; i < n_iter; i++) {
+        const int barai = bara[i];
+        if (barai == 0) continue;                                  /* lwe-bootstrapping-functions.cu:66 */
+        for (int j = 0; j <= k; j++)                               /* tLweMulByXaiMinusOne */
+            oracle_mul_by_xai_minus_one(barai, N, accum + (size_t) j * N, tmp + (size_t) j * N);
+        oracle_extern_mul_exact(p, bk + (size_t) i * kpl * (k + 1) * N, tmp);   /* tGswExternMulToTLwe */
+        for (int j = 0; j < (k + 1) * N; j++)                      /* tLweAddTo */
+            accum[j] = (int32_t) ((uint32_t) accum[j] + (uint32_t) tmp[j]);
+    }
+    free(tmp);
+}
+
+/* tfhe_blindRotateAndExtract (lwe-bootstrapping-functions.cu:95-126) + tfhe_bootstrap_woKS (:137-160) */
+void oracle_bootstrap_woks_exact(const OracleParams *p, const int32_t *bk, int32_t mu, const int32_t *x,
+                                 int32_t *u) {
+    const int N = p->N, n = p->n, k = p->k;
+    int32_t *testvect = (int32_t *) malloc(sizeof(int32_t) * (size_t) N);
+    int32_t *bara = (int32_t *) malloc(sizeof(int32_t) * (size_t) n);
+    int32_t *acc = (int32_t *) calloc((size_t) (k + 1) * N, sizeof(int32_t));
+    const int barb = oracle_modswitch_from(x[n], 2 * N);
+    for (int i = 0; i < n; i++) bara[i] = oracle_modswitch_from(x[i], 2 * N);
+    for (int i = 0; i < N; i++) testvect[i] = mu;
+    if (barb != 0) oracle_mul_by_xai(2 * N - barb, N, testvect, acc + (size_t) k * N);
+    else memcpy(acc + (size_t) k * N, testvect, sizeof(int32_t) * (size_t) N);
+    oracle_blind_rotate_exact(p, bk, acc, bara, n);
+    for (int i = 0; i < k; i++) {                                  /* tLweExtractLweSample, lwe.cu:41-56 */
+        u[i * N] = acc[(size_t) i * N];
+        for (int j = 1; j < N; j++) u[i * N + j] = (int32_t) (0u - (uint32_t) acc[(size_t) i * N + N - j]);
+    }
+    u[k * N] = acc[(size_t) k * N];
+    free(acc);
+    free(bara);
+    free(testvect);
+}
+
+void oracle_bootstrap_woks_exact_batch(const OracleParams *p, const int32_t *bk, int32_t mu, const int32_t *x,
+                                       int32_t *u, int count, int threads) {
+    if (threads <= 0) threads = omp_get_max_threads();
+#pragma omp parallel for schedule(dynamic, 1) num_threads(threads)
+    for (int g = 0; g < count; g++)
+        oracle_bootstrap_woks_exact(p, bk, mu, x + (size_t) g * (p->n + 1), u + (size_t) g * (p->N * p->k + 1));
+}
+
 /* --------------------------------------------------------------- key switch */
 
 /* lwe-keyswitch-functions.cu:955-987 and :101-127 */

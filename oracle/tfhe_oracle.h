@@ -132,6 +132,15 @@ void oracle_constant(const OracleParams *p, int value, int32_t *out);
  * lwe-bootstrapping-functions.cu:34-179 + multiplication.cu:53-77 */
 void oracle_extern_mul_exact(const OracleParams *p, const int32_t *bk_i, int32_t *accum);
 
+/* The whole non-FFT bootstrap with exact products (lwe-bootstrapping-functions.cu:34-179): bk is the
+ * flat coefficient-domain key; no floating point anywhere, so the result is THE integer answer. */
+void oracle_blind_rotate_exact(const OracleParams *p, const int32_t *bk, int32_t *accum, const int32_t *bara,
+                               int n_iter);
+void oracle_bootstrap_woks_exact(const OracleParams *p, const int32_t *bk, int32_t mu, const int32_t *x,
+                                 int32_t *u_out);
+void oracle_bootstrap_woks_exact_batch(const OracleParams *p, const int32_t *bk, int32_t mu, const int32_t *x,
+                                       int32_t *u_out, int count, int threads);
+
 /* Batch helpers (OpenMP over independent gates; used for the CPU baseline) */
 void oracle_gate_batch(const OracleCtx *c, int gate, const int32_t *ca, const int32_t *cb,
                        int32_t *out, int count, int threads);

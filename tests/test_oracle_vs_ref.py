@@ -68,3 +68,35 @@ def test_oracle_keys_run_through_the_reference(pair):
     out = r2.gate("NAND", c[0], c[1])
     assert o.decrypt_bits(keys, out[None])[0] == 1
     assert np.array_equal(out, o.ctx(keys, FFT_REF).gate("NAND", c[0], c[1]))
+
+
+def test_exact_blind_rotation_equals_reference_naive_path(pair):
+    """The oracle's FFT-free blind rotation (oracle_blind_rotate_exact) against the reference's own
+    non-FFT sequence — tLweMulByXaiMinusOne, tGswTLweDecompH, torusPolynomialMultNaive
+    (multiplication.cu:72), tLweAddTo, i.e. tfhe_MuxRotate / tfhe_blindRotate of
+    lwe-bootstrapping-functions.cu:34-79 with exact products — word for word; and the FFT path
+    stays within 1 LSB per step of it (truncation of a value next to the exact integer)."""
+    o, r, keys, ctx = pair
+    rng = np.random.default_rng(9)
+    acc = rng.integers(-2 ** 31, 2 ** 31, (2, 1024), dtype=np.int64).astype(np.int32)
+    bara = np.array([5, 0, 2047, 1024, 1, 1023, 777, 1500], np.int32)
+    exact = o.blind_rotate_exact(keys.bk, acc, bara)
+    assert np.array_equal(exact, r.blind_rotate_naive(acc, bara))
+    assert not np.array_equal(exact, acc)
+    one = np.array([0, 0, 333], np.int32)      # a single step: FFT path = exact or exact -+ 1
+    d = r.blind_rotate(acc, one).astype(np.int64) - o.blind_rotate_exact(keys.bk, acc, one).astype(np.int64)
+    assert np.abs((d + 2 ** 31) % 2 ** 32 - 2 ** 31).max() <= 1
+
+
+def test_exact_bootstrap_decrypts_and_matches_fft_bootstrap_bits(pair):
+    """tfhe_bootstrap_woKS with exact products: same decrypted bit as the reference's FFT bootstrap,
+    phase within bootstrap noise of it (the two differ in rounding only)."""
+    o, r, keys, ctx = pair
+    ca, cb = r.encrypt(1), r.encrypt(1)
+    x = o.gate_prologue("NAND", ca, cb)
+    u_exact = o.bootstrap_woks_exact(keys.bk, 1 << 29, x)[0]
+    u_fft = r.bootstrap_woks(1 << 29, x)
+    ke = np.concatenate([keys.tlwe_key.reshape(-1)])  # extracted key = TLWE key (lwe.cu:287-296)
+    ph = lambda u: int(o.phases(ke, u[None])[0])
+    assert ph(u_exact) < 0 and ph(u_fft) < 0          # NAND(1,1) = 0 -> -1/8
+    assert abs(ph(u_exact) - ph(u_fft)) / 2.0 ** 32 < 2.0 ** -5
