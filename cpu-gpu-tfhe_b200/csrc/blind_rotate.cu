@@ -39,9 +39,9 @@ constexpr int kCtWarps = 4;                       // ciphertexts per CTA
 // shared-memory bytes per iteration but leaves every sub-partition with a single warp that
 // cannot hide its own latencies (profiles/README.md: 503 ms vs 455 ms per 65536 gates).
 constexpr int kThreads = 2 * kCtWarps * 32;
-// Key ring.  Role r multiplies rows r and 2+r; per iteration it streams four 8 KiB chunks (one
-// result polynomial of one TGSW row each) in the order
-//   (row r, half r), (row r, half 1-r), (row 2+r, half r), (row 2+r, half 1-r)
+// Key ring.  Role r (= accumulator polynomial r) multiplies the decomposed rows 2r and 2r+1; per
+// iteration it streams four 8 KiB chunks (one result polynomial of one TGSW row each) in the order
+//   (row 2r, half r), (row 2r, half 1-r), (row 2r+1, half r), (row 2r+1, half 1-r)
 // i.e. always the half this role KEEPS first, then the half it GIVES to its partner.  Each role has
 // its own 3-stage ring so that every consumer of a ring takes every chunk in order (a warp
 // skipping chunks could get two mbarrier phases ahead on a stage: parity aliasing).
@@ -171,7 +171,7 @@ __device__ long long g_phase_cycles[16];
 // `role`'s stream into absolute stage `stage` (one elected lane).
 __device__ __forceinline__ void ring_fill_at(CtaSmem &S, const BrLaunch &L, int role, uint32_t it, uint32_t sub,
                                              uint32_t stage) {
-    const uint32_t row = (uint32_t) role + 2u * (sub >> 1);
+    const uint32_t row = 2u * (uint32_t) role + (sub >> 1);
     const uint32_t out = (sub & 1u) ? 1u - (uint32_t) role : (uint32_t) role;
     const cpx *src = L.bk + ((size_t) (L.bk_first + it) * kKpl + row) * kBkRowCplx + out * kBkHalfCplx;
     mbar_arrive_expect_tx(&S.full[stage], kStageBytes);
@@ -289,12 +289,16 @@ __device__ __forceinline__ int load_bara(const BrLaunch &L, const GateIn &I, int
     return modswitch_2N(xa);
 }
 
+// TFHE_B200_EXP_NOBAR: timing-only experiment (garbage results): the pair barriers cost nothing
+#ifndef TFHE_B200_EXP_NOBAR
+#define TFHE_B200_EXP_NOBAR 0
+#endif
 __device__ __forceinline__ void named_sync(int id, int nthreads) {
-    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+    if (!TFHE_B200_EXP_NOBAR) asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
 __device__ __forceinline__ void named_arrive(int id, int nthreads) {
-    asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+    if (!TFHE_B200_EXP_NOBAR) asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
 // Fourier MAC of z against the current ring chunk, with the release of the stage issued EARLY: the
@@ -378,9 +382,11 @@ __global__ void __launch_bounds__(kThreads, 1) blind_rotate_kernel(const BrLaunc
     // -------------------- ciphertext warps ------------------------------------------
     const int ct = warp >> 1, role = warp & 1;   // sub-partition w % 4 holds the same role of two ciphertexts
     WarpSmem &W = S.w[ct];
-    const int bar_id = 1 + ct;
-    // barrier of the two warps of one ciphertext
-    auto pair_sync = [bar_id]() { named_sync(bar_id, 64); };
+    // Named barriers of the pair: X = the hand-over of the partial sums (the one blocking barrier of an
+    // iteration); Y[r] = "the partner has read role r's buffer B" (arrive by the reader, sync by the
+    // owner before it overwrites B: a whole phase later, so the sync practically never waits).
+    const int bar_x = 1 + 3 * ct, bar_mine = 2 + 3 * ct + role, bar_partner = 2 + 3 * ct + (1 - role);
+    auto pair_sync = [bar_x]() { named_sync(bar_x, 64); };
     const uint32_t ring_base = (uint32_t) role * kRingStages;
     const uint32_t ring_chunks = kChunksPerIter * iters_total;
     StreamPos sp;
@@ -390,31 +396,36 @@ __global__ void __launch_bounds__(kThreads, 1) blind_rotate_kernel(const BrLaunc
         if (!valid) g = L.total - 1;
         const GateIn I = resolve_inputs(L, g);
 
-        if (role == 0) {
-            int barb;
-            if (L.explicit_inputs != 0) barb = L.barb ? (L.barb[g] & (2 * kN - 1)) : 0;
+        if (L.acc_in != nullptr || L.testvect != nullptr) {
+            if (role == 0) {
+                if (L.acc_in != nullptr) {
+                    phase_load_acc(lane, W, L.acc_in + (size_t) g * (kK + 1) * kN);
+                } else {
+                    // ACC = (0, X^{2N-barb} * testvect)
+                    const int barb = L.barb ? (__ldg(L.barb + g) & (2 * kN - 1)) : 0;
+                    for (int j = lane; j < kN; j += 32) {
+                        const int s = (j + barb) & (2 * kN - 1);
+                        const uint32_t v = (uint32_t) __ldg(L.testvect + (s & (kN - 1)));
+                        W.acc[0][(j & 15) * kAccRow + (j >> 4)] = 0;
+                        W.acc[kK][(j & 15) * kAccRow + (j >> 4)] = (int32_t) (s < kN ? v : 0u - v);
+                    }
+                }
+            }
+            pair_sync();
+        } else {
+            int barb;  // each role initialises its own polynomial
+            if (L.explicit_inputs != 0) barb = L.barb ? (__ldg(L.barb + g) & (2 * kN - 1)) : 0;
             else {
                 uint32_t xb = I.cst + I.sa * (uint32_t) __ldg(I.in0 + L.n) + I.sb * (uint32_t) __ldg(I.in1 + L.n);
                 if (I.in2 != nullptr) xb += I.sc * (uint32_t) __ldg(I.in2 + L.n);
                 barb = modswitch_2N(xb);
             }
-            if (L.acc_in != nullptr) {
-                phase_load_acc(lane, W, L.acc_in + (size_t) g * (kK + 1) * kN);
-            } else if (L.testvect != nullptr) {
-                // ACC = (0, X^{2N-barb} * testvect)
-                for (int j = lane; j < kN; j += 32) {
-                    const int s = (j + barb) & (2 * kN - 1);
-                    const uint32_t v = (uint32_t) __ldg(L.testvect + (s & (kN - 1)));
-                    W.acc[0][(j & 15) * kAccRow + (j >> 4)] = 0;
-                    W.acc[kK][(j & 15) * kAccRow + (j >> 4)] = (int32_t) (s < kN ? v : 0u - v);
-                }
-            } else {
-                phase_init(lane, W, barb, L.mu);
-            }
+            phase_init(lane, W, role, barb, L.mu);
         }
-        pair_sync();
+        __syncwarp();
         phase_ext_build(lane, W, role);
-        pair_sync();
+        __syncwarp();
+        named_arrive(bar_partner, 64);  // prime: nobody is reading the partner's buffer B
 
         int a_blk = 0;  // lane l holds bara of iteration (it & ~31) + l
         for (int it = 0; it < n_iter; it++) {
@@ -435,11 +446,12 @@ __global__ void __launch_bounds__(kThreads, 1) blind_rotate_kernel(const BrLaunc
             // ---- one MuxRotate step: straight-line code, no per-phase conditionals -----------
             {
                 cpx x[32];
-                phase_f1q_decomp(lane, W, a, role, rotate, x);
-                phase_f1q_fft(x);
-                pair_sync();   // the stores overwrite the extended accumulator copy both warps read
+                phase_f1_decomp(lane, W, role, a, rotate, x);
+                phase_f1_fft(x);
+                __syncwarp();  // the stores overwrite the extended copy the whole warp has just read
                 if (!rotate) phase_acc_clear(lane, W, role);  // external product only: result replaces ACC
-                phase_f1q_store(lane, W, role, x);
+                named_sync(bar_mine, 64);  // the partner has finished with last iteration's give in B
+                phase_f1_store(lane, W, role, x);
                 __syncwarp();  // a warp multiplies exactly the rows it has just transformed
             }
             PHASE_MARK(0);
@@ -451,7 +463,7 @@ __global__ void __launch_bounds__(kThreads, 1) blind_rotate_kernel(const BrLaunc
                 give[i].x = 0.0; give[i].y = 0.0;
             }
 #pragma unroll 1
-            for (int row = role; row < kKpl; row += 2) {
+            for (int row = 2 * role; row < 2 * role + 2; row++) {
                 cpx z[16];
                 const bool rdy_keep = ring_probe(S, sp, ring_base, 0);
                 const bool rdy_give = ring_probe(S, sp, ring_base, 1);
@@ -462,31 +474,35 @@ __global__ void __launch_bounds__(kThreads, 1) blind_rotate_kernel(const BrLaunc
                 mac_consume<HELPER>(S, L, role, lane, sp, ring_base, ring_chunks, rdy_give, z, give);
                 PHASE_MARK(3);
             }
-            // (Measured and dropped: multiplying the hand-over half first and overlapping the
-            // hand-over with the last multiply through an mbarrier, and a split arrive/wait barrier
-            // around the pass-1 transform: both 1 % slower; the pair barriers cost their round
-            // trips, not skew between the two warps.)
+            __syncwarp();  // every lane has read its pass-1 output in B
             phase_xchg_store(lane, W, role, give);
             PHASE_MARK(4);
             pair_sync();
             PHASE_MARK(5);
-            phase_xchg_load_inv(lane, W, S.e2, role, keep);
+            phase_xchg_load(lane, W, role, keep);
+            named_arrive(bar_partner, 64);  // done with the partner's B
+            phase_inv16_store(lane, W, S.e2, role, keep);
+            __syncwarp();
             PHASE_MARK(6);
-            pair_sync();
-            PHASE_MARK(7);
             {
-                cpx x[16];
-                phase_i2_half(lane, W, role, x);
+                cpx x[16], send[8], recv[8];
+                phase_i2_inner(lane, W, role, x);
+                PHASE_MARK(7);
+                phase_i2_send(lane, x, send);
+#pragma unroll
+                for (int b = 0; b < 8; b++) {
+                    recv[b].x = __shfl_xor_sync(0xffffffffu, send[b].x, 16);
+                    recv[b].y = __shfl_xor_sync(0xffffffffu, send[b].y, 16);
+                }
                 PHASE_MARK(8);
-                pair_sync();
-                PHASE_MARK(9);
-                phase_i2_final(lane, W, role, x);
+                __syncwarp();  // all reads of A (inverse pass-2 output) precede the extended-copy stores
+                phase_i2_final(lane, W, role, x, recv);
             }
-            PHASE_MARK(10);
-            pair_sync();
-            PHASE_MARK(11);
+            __syncwarp();
+            PHASE_MARK(9);
         }
-
+        named_sync(bar_mine, 64);  // drain the last arrive (keeps arrive / sync balanced)
+        pair_sync();               // the partner's polynomial is final
         if (valid && role == 0) {
             if (L.u_out != nullptr) phase_extract(lane, W, L.u_out + (size_t) g * (kN + 1));
             if (L.acc_out != nullptr) phase_dump_acc(lane, W, L.acc_out + (size_t) g * (kK + 1) * kN);
@@ -494,7 +510,6 @@ __global__ void __launch_bounds__(kThreads, 1) blind_rotate_kernel(const BrLaunc
         pair_sync();
     }
 }
-
 
 // ------------------------------------------------------------ key conversion
 

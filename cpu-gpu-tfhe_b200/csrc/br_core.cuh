@@ -68,7 +68,7 @@ struct cpx {
     double x, y;
 };
 
-// Extended accumulator copy (see phase_f1q_decomp): row of 127 words per (o, j2),
+// Extended accumulator copy (see phase_f1_decomp): row of 127 words per (o, j2),
 //   E[63 + k] = +row[k] (k = 0..63),  E[63 + k] = -row[64 + k] (k = -63..-1)
 // i.e. the negacyclic continuation of the 64-coefficient row to the left, so that a rotated read
 // is `base + e` with a per-lane base and NO per-element index or sign arithmetic.
@@ -77,7 +77,6 @@ struct cpx {
 // 128-bit stores would need, put 32 single-word readers on 8 banks: measured slower).
 constexpr int kExtRow = 127;
 constexpr int kExtOrg = 63;       // word of row[0]; -row[i] is at word i - 1 (row[0] has no left image)
-constexpr int kExtShift = 16;     // extra word offset of polynomial o = 1 (other half of the banks)
 
 struct alignas(16) word4 {
     int32_t v[4];
@@ -87,14 +86,14 @@ struct alignas(16) word4 {
 struct WarpSmem {
     union {
         cpx exch[kKpl][kExchPoly];          // 4 * 8704 B: transform exchange buffers
-        int32_t exw[kKpl][kExchPoly * 4];   // the same as words: buffers 2 and 3 hold the extended
-                                            // accumulator copy between iterations
+        int32_t exw[kKpl][kExchPoly * 4];   // the same as words: buffer 2o holds the extended copy of
+                                            // accumulator polynomial o between iterations
     };
     int32_t acc[kK + 1][kAccPoly]; // 2 * 4160 B: the accumulator (master copy)
 };
-static_assert(16 * kExtRow + kExtShift <= kExchPoly * 4, "extended copy must fit an exchange buffer");
+static_assert(16 * kExtRow <= kExchPoly * 4, "extended copy must fit an exchange buffer");
 
-TFHE_HD int32_t *ext_poly(WarpSmem &ws, int o) { return ws.exw[2 + o] + kExtShift * o; }
+TFHE_HD int32_t *ext_poly(WarpSmem &ws, int o) { return ws.exw[2 * o]; }
 
 TFHE_HD constexpr int bitrev5(int v) {
     return ((v & 1) << 4) | ((v & 2) << 2) | (v & 4) | ((v & 8) >> 2) | ((v & 16) >> 4);
@@ -306,69 +305,74 @@ TFHE_HD double e2_shift(int m1, int s) {
 }
 
 // ---------------------------------------------------------------- phases ---
+//
+// Two warps per ciphertext, split BY ACCUMULATOR POLYNOMIAL: warp `o` (o = 0: the mask polynomial a,
+// o = 1: the body b) owns polynomial o of the accumulator, its master copy acc[o], its extended copy
+// and the two exchange buffers exch[2o] ("A") and exch[2o+1] ("B").  One MuxRotate iteration of warp o:
+//   decompose (X^a - 1) * ACC_o into BOTH digit levels (lane (q, j2): digit level q, slice j2) and run
+//     pass 1 of the two forward transforms (decomposed rows 2o, 2o+1)          480 fp64 instr + 64 conversions
+//   pass 2 + MAC of those rows against BK rows 2o, 2o+1 -> partial sums of result polynomial o
+//     ("keep") and of result polynomial 1-o ("give")                            2 x 320
+//   park `give` in B | PAIR BARRIER | keep += partner's give                   the ONLY pair barrier
+//   inverse pass 2 of result polynomial o -> A; inverse pass 1 (lane (hh, j2): positions 16hh..16hh+15,
+//     last stage through lane ^ 16 by warp shuffles); to Torus32; ACC_o += ...; extended copy rewritten
+// Nothing else crosses the pair: a warp reads and writes only its own polynomial and buffers, so the
+// five pair barriers of the first version (split by digit level, both warps touching both polynomials
+// in the rotation and in the final stage) are one, plus a non-blocking arrive/sync pair that orders the
+// partner's read of B before B is overwritten by the next iteration's pass-1 output.
+// Buffer life times of warp o:  A: extended copy -> pass-1 output (q = 0) -> inverse pass-2 output ->
+// extended copy;  B: pass-1 output (q = 1) -> give (read by the partner).
 
 // ACC = (0, X^{2N-barb} * (mu, ..., mu))   tfhe_blindRotateAndExtract_FFT,
 // lwe-bootstrapping-functions-fft.cu:1425-1431 ; torusPolynomialMulByXai :492-519
-TFHE_HD void phase_init(int lane, WarpSmem &ws, int barb, int32_t mu) {
-    const int o = lane >> 4, j2 = lane & 15;
-    int32_t *row = ws.acc[o] + j2 * kAccRow;
+// Warp o initialises polynomial o: lane (h, j2) writes coefficients [32h, 32h+32) of row j2.
+TFHE_HD void phase_init(int lane, WarpSmem &ws, int o, int barb, int32_t mu) {
+    const int h = lane >> 4, j2 = lane & 15;
+    int32_t *row = ws.acc[o] + j2 * kAccRow + 32 * h;
 #pragma unroll 8
-    for (int e = 0; e < 64; e++) {
-        const int j = 16 * e + j2;
+    for (int e = 0; e < 32; e++) {
+        const int j = 16 * (e + 32 * h) + j2;
         int32_t v = 0;
         if (o == kK) v = (((j + barb) & (2 * kN - 1)) < kN) ? mu : (int32_t) (0u - (uint32_t) mu);
         row[e] = v;
     }
 }
 
-// ---- two warps per ciphertext -------------------------------------------------
-// The work of one MuxRotate iteration is split over a PAIR of warps so that every SM
-// sub-partition holds two warps (latency hiding) while a ciphertext still needs only one
-// shared-memory working set.  Both warps do the same amount of work between pair barriers:
-//   warp r (role r = 0, 1):
-//     pass 1 of digit level q = r (decomposed rows r and 2+r)          480 fp64 instr + 64 conversions
-//     pass 2 + MAC of those two rows against BK rows r, 2+r            2 x 320
-//     | barrier | partial sums exchanged; I1 of result polynomial r    288
-//     | barrier | half of the 32-point inverse pass (positions 16r..)  256
-//     | barrier | last butterfly stage for 16 of the outputs, to Torus32, += ACC
-//     | barrier |
-// Partial Fourier sums and the half-pass values are exchanged through exchange rows that
-// are free at that point.
-
-// Build the extended copy of both accumulator polynomials from the master copy (start of a
-// ciphertext; afterwards phase_i2_final keeps it up to date).  Role r copies coefficients
-// [32r, 32r + 32) of every row.
-TFHE_HD void phase_ext_build(int lane, WarpSmem &ws, int role) {
-    const int o = lane >> 4, j2 = lane & 15;
-    const int32_t *row = ws.acc[o] + j2 * kAccRow + 32 * role;
-    int32_t *ext = ext_poly(ws, o) + j2 * kExtRow + 32 * role;
+// Build the extended copy of accumulator polynomial o from its master copy (start of a ciphertext;
+// afterwards phase_i2_final keeps it up to date).  Lane (h, j2) copies coefficients [32h, 32h+32) of row j2.
+TFHE_HD void phase_ext_build(int lane, WarpSmem &ws, int o) {
+    const int h = lane >> 4, j2 = lane & 15;
+    const int32_t *row = ws.acc[o] + j2 * kAccRow + 32 * h;
+    int32_t *ext = ext_poly(ws, o) + j2 * kExtRow + 32 * h;
 #pragma unroll 2
     for (int b = 0; b < 32; b += 4) {
         const word4 v = *reinterpret_cast<const word4 *>(row + b);
 #pragma unroll
         for (int i = 0; i < 4; i++) {
             ext[kExtOrg + b + i] = v.v[i];
-            if (b + i > 0 || role != 0) ext[b + i - 1] = (int32_t) (0u - (uint32_t) v.v[i]);
+            if (b + i > 0 || h != 0) ext[b + i - 1] = (int32_t) (0u - (uint32_t) v.v[i]);
         }
     }
 }
 
-// Pass 1 of the two forward transforms of digit level q (decomposed rows (o, q), o = 0..k),
+// Pass 1 of the two forward transforms of accumulator polynomial o (decomposed rows (o, q), q = 0..l-1),
 // fused with the rotation (torusPolynomialMulByXaiMinusOne, toruspolynomial-functions.cu:191-213)
 // and the gadget decomposition (tGswTorus32PolynomialDecompH, tgsw-functions.cu:301-352).
+// Lane (q, j2): digit level q of slice j2; the two lanes of a slice read the same words (broadcast).
 // rotate == false: plain decomposition of ACC (stand-alone external product).
 //
 // Coefficient j = 16 e + j2 of X^a * ACC is (-1)^f * ACC[16 (e - sh) + j2p] continued negacyclically,
 // with a = 16 a_hi + a_lo, j2p = (j2 - a_lo) mod 16, sh = a_hi + [j2 < a_lo] = 64 f + h: in the
 // extended row of (o, j2p) that is word kExtOrg - h + e, so the 64 rotated values of a lane are read
-// at immediate offsets from ONE base.  Sign, the subtraction of ACC, the decomposition offset
-// and the digit shift are two integer multiply-adds (t * 2^(10 q) = v * (+-2^(10 q)) +
+// at immediate offsets from ONE base (conflict free: the 16 rows of a polynomial start in 16 different
+// banks and h differs by at most one between the lanes of a warp).  Sign, the subtraction of ACC, the
+// decomposition offset and the digit shift are two integer multiply-adds (t * 2^(10 q) = v * (+-2^(10 q)) +
 // (ACC * -2^(10 q) + offset * 2^(10 q)); digit = top 10 bits), on the FMA pipe: the first version
 // spent 19 instructions per coefficient here, most of them on the half-rate ALU pipe.
-// The outputs are NOT stored: the extended copy lives in exchange buffers 2 and 3, which the
-// stores overwrite, so the pair synchronises between load and store.
-TFHE_HD void phase_f1q_decomp(int lane, WarpSmem &ws, int a, int q, bool rotate, cpx (&x)[32]) {
-    const int o = lane >> 4, j2 = lane & 15;
+// The outputs are NOT stored here: the extended copy lives in buffer A, which the stores overwrite
+// (the caller separates the two with a __syncwarp).
+TFHE_HD void phase_f1_decomp(int lane, WarpSmem &ws, int o, int a, bool rotate, cpx (&x)[32]) {
+    const int q = lane >> 4, j2 = lane & 15;
     const int a_lo = a & 15, a_hi = a >> 4;
     const int j2p = (j2 - a_lo) & 15;
     const int sh = a_hi + (j2 < a_lo ? 1 : 0);
@@ -402,10 +406,10 @@ TFHE_HD void phase_f1q_decomp(int lane, WarpSmem &ws, int a, int q, bool rotate,
 }
 
 // Stages 0-4 of the two transforms on the decomposed digits (no shared-memory access).
-TFHE_HD void phase_f1q_fft(cpx (&x)[32]) { fwd32(x); }
+TFHE_HD void phase_f1_fft(cpx (&x)[32]) { fwd32(x); }
 
-TFHE_HD void phase_f1q_store(int lane, WarpSmem &ws, int q, const cpx (&x)[32]) {
-    const int o = lane >> 4, j2 = lane & 15;
+TFHE_HD void phase_f1_store(int lane, WarpSmem &ws, int o, const cpx (&x)[32]) {
+    const int q = lane >> 4, j2 = lane & 15;
     cpx *dst = ws.exch[o * kL + q] + j2;
 #pragma unroll
     for (int pos = 0; pos < 32; pos++) dst[bitrev5(pos) * kExchRow] = x[pos];
@@ -435,99 +439,94 @@ TFHE_HD void phase_mac_part(int lane, const cpx (&z)[16], const cpx *part, cpx (
     for (int p = 0; p < NPOS; p++) cmac(acc[POS0 + p], z[POS0 + p], part[p * 32 + lane]);
 }
 
-// Hand the partial sum of the result polynomial the OTHER warp finishes to that warp:
-// role 0 parks its partial b-sum in exchange buffer 0, role 1 its partial a-sum in buffer 1
-// (rows this lane owns; both buffers have been consumed by then).
-TFHE_HD void phase_xchg_store(int lane, WarpSmem &ws, int role, const cpx (&give)[16]) {
-    cpx *d = ws.exch[role] + lane * kExchRow;
+// Hand the partial sum of the result polynomial the OTHER warp finishes to that warp: warp o parks it
+// in its own buffer B (rows this lane owns; B's pass-1 output has been consumed by then).
+TFHE_HD void phase_xchg_store(int lane, WarpSmem &ws, int o, const cpx (&give)[16]) {
+    cpx *d = ws.exch[2 * o + 1] + lane * kExchRow;
 #pragma unroll
     for (int i = 0; i < 16; i++) d[i] = give[i];
 }
 
-// Inverse pass 2 ("I1") of the finished Fourier sum of result polynomial `role`; the 16 outputs go
-// to exchange buffer 2 (result a, role 0) or 3 (result b, role 1).
-TFHE_HD void phase_inv16_store(int lane, WarpSmem &ws, const cpx *e2, int role, cpx (&keep)[16]) {
-    inv16(keep, e2 + lane * kE2Row);
-    cpx *d = ws.exch[2 + role] + lane * kExchRow;
-#pragma unroll
-    for (int j2 = 0; j2 < 16; j2++) d[j2] = keep[j2];
-}
-
-// keep += partner's partial sum (parked by phase_xchg_store), then phase_inv16_store.
-TFHE_HD void phase_xchg_load_inv(int lane, WarpSmem &ws, const cpx *e2, int role, cpx (&keep)[16]) {
-    const cpx *s = ws.exch[1 - role] + lane * kExchRow;
+// keep += partner's partial sum (parked by its phase_xchg_store in ITS buffer B).
+TFHE_HD void phase_xchg_load(int lane, const WarpSmem &ws, int o, cpx (&keep)[16]) {
+    const cpx *s = ws.exch[2 * (1 - o) + 1] + lane * kExchRow;
 #pragma unroll
     for (int i = 0; i < 16; i++) {
         const cpx v = s[i];
         keep[i].x += v.x;
         keep[i].y += v.y;
     }
-    phase_inv16_store(lane, ws, e2, role, keep);
 }
 
-// Inverse pass 1, first part: the four inner stages on positions [16*role, 16*role+16) of
-// both result polynomials (lane (o, j2)).
-TFHE_HD void phase_i2_half_compute(int lane, WarpSmem &ws, int role, cpx (&x)[16]) {
-    const int o = lane >> 4, j2 = lane & 15;
-    const cpx *src = ws.exch[2 + o] + j2;
+// Inverse pass 2 of the finished Fourier sum of result polynomial o; the 16 outputs go to buffer A.
+TFHE_HD void phase_inv16_store(int lane, WarpSmem &ws, const cpx *e2, int o, cpx (&keep)[16]) {
+    inv16(keep, e2 + lane * kE2Row);
+    cpx *d = ws.exch[2 * o] + lane * kExchRow;
+#pragma unroll
+    for (int j2 = 0; j2 < 16; j2++) d[j2] = keep[j2];
+}
+
+// Inverse pass 1 of result polynomial o, first part: lane (hh, j2) runs the four inner stages on
+// positions [16 hh, 16 hh + 16) of slice j2 (the multipliers of block hh: lane dependent).
+TFHE_HD void phase_i2_inner(int lane, const WarpSmem &ws, int o, cpx (&x)[16]) {
+    const int hh = lane >> 4, j2 = lane & 15;
+    const cpx *src = ws.exch[2 * o] + j2 + hh * kExchRow;
 #pragma unroll
     for (int p = 0; p < 16; p++) {
-        // position 16*role + p holds frequency class m1 = bitrev5(16*role + p) = 2*bitrev4(p) + role
-        const int m1 = bitrev5(p) + role;  // bitrev5(p) for p < 16 is even
-        x[p] = src[m1 * kExchRow];
+        // position 16*hh + p holds frequency class m1 = bitrev5(16*hh + p) = 2*bitrev4(p) + hh
+        x[p] = src[bitrev5(p) * kExchRow];  // bitrev5(p) for p < 16 is even
     }
 #pragma unroll
     for (int s = 4; s >= 1; s--) {
         const int half = 16 >> s;
 #pragma unroll
         for (int b = 0; b < (1 << (s - 1)); b++) {
-            const int ci = (1 << s) - 1 + role * (1 << (s - 1)) + b;
-            const double er = c1_re_rt(ci), ei = c1_im_rt(ci);
+            const int c0 = (1 << s) - 1 + b, c1 = c0 + (1 << (s - 1));
+            const double er = hh ? c1_re_rt(c1) : c1_re_rt(c0), ei = hh ? c1_im_rt(c1) : c1_im_rt(c0);
 #pragma unroll
             for (int i = 0; i < half; i++) bf_inv(x[b * 2 * half + i], x[b * 2 * half + i + half], er, ei);
         }
     }
 }
 
-// ... and the hand-over for the last stage, which pairs position i of role 0 (u) with position i
-// of role 1 (v): role 0 finishes pairs 0..7 and role 1 pairs 8..15, so each warp parks only the 8
-// values the other needs in exchange buffer `role` ([i][lane], conflict free).
-TFHE_HD void phase_i2_half(int lane, WarpSmem &ws, int role, cpx (&x)[16]) {
-    phase_i2_half_compute(lane, ws, role, x);
-    cpx *dst = ws.exch[role] + lane;
-    if (role == 0) {
+// The last stage pairs position i of lane (0, j2) (u) with position i of lane (1, j2) (v).  Lane hh
+// finishes the 8 pairs i = 8 hh .. 8 hh + 7 completely, so it hands its partner lane (lane ^ 16) the 8
+// values of the OTHER pairs: warp shuffles on the device, an array in the host emulation.
+TFHE_HD void phase_i2_send(int lane, const cpx (&x)[16], cpx (&send)[8]) {
+    const int hh = lane >> 4;
 #pragma unroll
-        for (int b = 0; b < 8; b++) dst[b * 32] = x[8 + b];
-    } else {
-#pragma unroll
-        for (int b = 0; b < 8; b++) dst[b * 32] = x[b];
+    for (int b = 0; b < 8; b++) {
+        send[b].x = hh ? x[b].x : x[8 + b].x;
+        send[b].y = hh ? x[b].y : x[8 + b].y;
     }
 }
 
-// Inverse pass 1, last stage (pairs position i of role 0 with position i of role 1), conversion
-// to Torus32 (execute_direct_Torus32, fft_processor_fftw.cu:168-181; rounding: double_to_torus32)
-// and the tLweAddTo of MuxRotate (tlwe-functions.cu:170).  Role r finishes the 8 pairs
-// i = 8r .. 8r+7 completely: coefficients j1 = i and j1 = i + 16 of the row, and the matching
-// upper-half coefficients (+32) from the imaginary parts.
-template <int ROLE>
-TFHE_HD void i2_final_role(int lane, WarpSmem &ws, const cpx (&x)[16], const cpx (&p)[8]) {
-    const int o = lane >> 4, j2 = lane & 15;
-    int32_t *row = ws.acc[o] + j2 * kAccRow + 8 * ROLE;
-    int32_t *ext = ext_poly(ws, o) + j2 * kExtRow + 8 * ROLE;  // extended copy, same coefficients
-    const double er = c1_re_rt(0), ei = c1_im_rt(0);
+// Inverse pass 1, last stage, conversion to Torus32 (execute_direct_Torus32,
+// fft_processor_fftw.cu:168-181; rounding: double_to_torus32) and the tLweAddTo of MuxRotate
+// (tlwe-functions.cu:170).  p: the partner lane's 8 values (its phase_i2_send).  Lane hh updates
+// coefficients j1 = i and j1 = i + 16 (i = 8 hh + b) of row j2, and the matching upper-half
+// coefficients (+32) from the imaginary parts: four groups of 8 consecutive words.
+// With mine / theirs = the value of this lane / of the partner lane, u + v = mine + theirs and
+// conj(e) (u - v) = (+-conj(e)) (mine - theirs), sign by lane: identical arithmetic in both lanes.
+TFHE_HD void phase_i2_final(int lane, WarpSmem &ws, int o, const cpx (&x)[16], const cpx (&p)[8]) {
+    const int hh = lane >> 4, j2 = lane & 15;
+    int32_t *row = ws.acc[o] + j2 * kAccRow + 8 * hh;
+    int32_t *ext = ext_poly(ws, o) + j2 * kExtRow + 8 * hh;  // extended copy, same coefficients
+    const double er = hh ? -c1_re_rt(0) : c1_re_rt(0), ei = hh ? -c1_im_rt(0) : c1_im_rt(0);
     // all loads first (128-bit accesses to the master copy: the 8 consecutive coefficients of a group
     // are two aligned quads), then the butterflies and conversions, then the updates
-    word4 acc4[4][2];  // group g: coefficients 16 g + 8 ROLE + (0..7) of the row
+    word4 acc4[4][2];  // group g: coefficients 16 g + 8 hh + (0..7) of the row
 #pragma unroll
     for (int g = 0; g < 4; g++)
 #pragma unroll
         for (int h = 0; h < 2; h++) acc4[g][h] = *reinterpret_cast<const word4 *>(row + 16 * g + 4 * h);
 #pragma unroll
     for (int b = 0; b < 8; b++) {
-        const cpx u = ROLE == 0 ? x[b] : p[b];
-        const cpx v = ROLE == 0 ? p[b] : x[8 + b];
-        const double sre = u.x + v.x, sim = u.y + v.y;      // u + v             -> coefficient j1 = i
-        const double tr = u.x - v.x, ti = u.y - v.y;        // conj(e) * (u - v) -> coefficient j1 = i + 16
+        cpx mine;
+        mine.x = hh ? x[8 + b].x : x[b].x;
+        mine.y = hh ? x[8 + b].y : x[b].y;
+        const double sre = mine.x + p[b].x, sim = mine.y + p[b].y;  // u + v             -> coefficient j1 = i
+        const double tr = mine.x - p[b].x, ti = mine.y - p[b].y;    // conj(e) * (u - v) -> coefficient j1 = i + 16
         const double dre = fma(er, tr, ei * ti), dim = fma(er, ti, -(ei * tr));
         int32_t &c0 = acc4[0][b >> 2].v[b & 3], &c1 = acc4[1][b >> 2].v[b & 3];
         int32_t &c2 = acc4[2][b >> 2].v[b & 3], &c3 = acc4[3][b >> 2].v[b & 3];
@@ -545,33 +544,16 @@ TFHE_HD void i2_final_role(int lane, WarpSmem &ws, const cpx (&x)[16], const cpx
         for (int b = 0; b < 8; b++) {
             const uint32_t nv = (uint32_t) acc4[g][b >> 2].v[b & 3];
             ext[kExtOrg + 16 * g + b] = (int32_t) nv;
-            if (16 * g + b > 0 || ROLE != 0) ext[16 * g + b - 1] = (int32_t) (0u - nv);
+            if (16 * g + b > 0 || hh != 0) ext[16 * g + b - 1] = (int32_t) (0u - nv);
         }
     }
 }
 
-// The role is a template argument of the body: with a run-time role inside the unrolled loop the
-// compiler kept one branch per output (15 BSSY/BRA pairs, no overlap between outputs: 1,440 cycles
-// for 500 cycles of work).
-// p: the partner's 8 values for the pairs this role finishes.
-TFHE_HD void phase_i2_final_with(int lane, WarpSmem &ws, int role, const cpx (&x)[16], const cpx (&p)[8]) {
-    if (role == 0) i2_final_role<0>(lane, ws, x, p);
-    else i2_final_role<1>(lane, ws, x, p);
-}
-
-TFHE_HD void phase_i2_final(int lane, WarpSmem &ws, int role, const cpx (&x)[16]) {
-    const cpx *other = ws.exch[1 - role] + lane;  // parked by the partner's phase_i2_half
-    cpx p[8];
-#pragma unroll
-    for (int b = 0; b < 8; b++) p[b] = other[b * 32];
-    phase_i2_final_with(lane, ws, role, x, p);
-}
-
 // Stand-alone external product: the result REPLACES the accumulator, so the master copy is
-// cleared once its decomposition has been read (role r clears the coefficients it will update).
-TFHE_HD void phase_acc_clear(int lane, WarpSmem &ws, int role) {
-    const int o = lane >> 4, j2 = lane & 15;
-    int32_t *row = ws.acc[o] + j2 * kAccRow + 8 * role;
+// cleared once its decomposition has been read (lane (hh, j2) clears the coefficients it will update).
+TFHE_HD void phase_acc_clear(int lane, WarpSmem &ws, int o) {
+    const int hh = lane >> 4, j2 = lane & 15;
+    int32_t *row = ws.acc[o] + j2 * kAccRow + 8 * hh;
     word4 z;
 #pragma unroll
     for (int k = 0; k < 4; k++) z.v[k] = 0;

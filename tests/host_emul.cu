@@ -92,7 +92,8 @@ int main() {
     // init
     const int32_t mu = oracle_modswitch_to(1, 8);
     for (int barb : {0, 1, 17, 1023, 1024, 1500, 2047}) {
-        for (int lane = 0; lane < 32; lane++) phase_init(lane, *ws, barb, mu);
+        for (int o = 0; o < 2; o++)
+            for (int lane = 0; lane < 32; lane++) phase_init(lane, *ws, o, barb, mu);
         std::vector<int32_t> got(2 * kN), tv(kN, mu), exp_b(kN);
         for (int lane = 0; lane < 32; lane++) phase_dump_acc(lane, *ws, got.data());
         if (barb) oracle_mul_by_xai(2 * kN - barb, kN, tv.data(), exp_b.data());
@@ -108,17 +109,17 @@ int main() {
         std::vector<int32_t> acc0(2 * kN);
         for (auto &v : acc0) v = (int32_t) ((((uint32_t) rand()) << 16) ^ (uint32_t) rand() ^ (((uint32_t) rand()) << 31));
         for (int lane = 0; lane < 32; lane++) phase_load_acc(lane, *ws, acc0.data());
-        for (int role = 0; role < 2; role++)
-            for (int lane = 0; lane < 32; lane++) phase_ext_build(lane, *ws, role);
+        for (int o = 0; o < 2; o++)
+            for (int lane = 0; lane < 32; lane++) phase_ext_build(lane, *ws, o);
         long bad = 0;
         for (int a = 0; a < 2 * kN; a++) {
             for (int rot = 1; rot >= 0; rot--) {
                 if (!rot && a > 3) continue;  // rotate == false ignores a: a few values are enough
-                for (int q = 0; q < kL; q++)
+                for (int o = 0; o < 2; o++)
                     for (int lane = 0; lane < 32; lane++) {
                         cpx x[32];
-                        phase_f1q_decomp(lane, *ws, a, q, rot != 0, x);
-                        const int o = lane >> 4, j2 = lane & 15;
+                        phase_f1_decomp(lane, *ws, o, a, rot != 0, x);
+                        const int q = lane >> 4, j2 = lane & 15;
                         for (int e = 0; e < 64; e++) {
                             const int j = 16 * e + j2;
                             const uint32_t own = (uint32_t) acc0[o * kN + j];
@@ -147,40 +148,45 @@ int main() {
         const int i = it % P.n;
         const int a = rots[it];
         for (int lane = 0; lane < 32; lane++) phase_load_acc(lane, *ws, acc.data());
-        // warp pair: role q transforms digit level q (rotation + decomposition fused in)
+        // warp pair: warp o owns accumulator polynomial o (rotation + decomposition of both digit levels)
         if (it == 0)  // afterwards phase_i2_final keeps the extended copy up to date
-            for (int role = 0; role < 2; role++)
-                for (int lane = 0; lane < 32; lane++) phase_ext_build(lane, *ws, role);
+            for (int o = 0; o < 2; o++)
+                for (int lane = 0; lane < 32; lane++) phase_ext_build(lane, *ws, o);
         static cpx x1[2][32][32];
-        for (int role = 0; role < 2; role++)
+        for (int o = 0; o < 2; o++)
             for (int lane = 0; lane < 32; lane++) {
-                phase_f1q_decomp(lane, *ws, a, role, true, x1[role][lane]);
-                phase_f1q_fft(x1[role][lane]);
+                phase_f1_decomp(lane, *ws, o, a, true, x1[o][lane]);
+                phase_f1_fft(x1[o][lane]);
             }
-        for (int role = 0; role < 2; role++)
-            for (int lane = 0; lane < 32; lane++) phase_f1q_store(lane, *ws, role, x1[role][lane]);
+        for (int o = 0; o < 2; o++)
+            for (int lane = 0; lane < 32; lane++) phase_f1_store(lane, *ws, o, x1[o][lane]);
         cpx keep[2][32][16], give[2][32][16];
         memset(keep, 0, sizeof(keep));
         memset(give, 0, sizeof(give));
         for (int row = 0; row < kKpl; row++) {
-            const int role = row & 1;  // role r owns rows r and 2+r; keep = result polynomial r
+            const int o = row >> 1;  // warp o owns rows 2o, 2o+1; keep = result polynomial o
             const cpx *bkrow = bkdev.data() + ((size_t) i * kKpl + row) * kBkRowCplx;
             for (int lane = 0; lane < 32; lane++) {
                 cpx z[16];
                 phase_f2_fft(lane, *ws, e2.data(), row, z);
-                phase_mac_half(lane, z, bkrow + role * kBkHalfCplx, keep[role][lane]);
-                phase_mac_half(lane, z, bkrow + (1 - role) * kBkHalfCplx, give[role][lane]);
+                phase_mac_half(lane, z, bkrow + o * kBkHalfCplx, keep[o][lane]);
+                phase_mac_half(lane, z, bkrow + (1 - o) * kBkHalfCplx, give[o][lane]);
             }
         }
-        for (int role = 0; role < 2; role++)
-            for (int lane = 0; lane < 32; lane++) phase_xchg_store(lane, *ws, role, give[role][lane]);
-        for (int role = 0; role < 2; role++)
-            for (int lane = 0; lane < 32; lane++) phase_xchg_load_inv(lane, *ws, e2.data(), role, keep[role][lane]);
-        cpx xh[2][32][16];
-        for (int role = 0; role < 2; role++)
-            for (int lane = 0; lane < 32; lane++) phase_i2_half(lane, *ws, role, xh[role][lane]);
-        for (int role = 0; role < 2; role++)
-            for (int lane = 0; lane < 32; lane++) phase_i2_final(lane, *ws, role, xh[role][lane]);
+        for (int o = 0; o < 2; o++)
+            for (int lane = 0; lane < 32; lane++) phase_xchg_store(lane, *ws, o, give[o][lane]);
+        for (int o = 0; o < 2; o++)
+            for (int lane = 0; lane < 32; lane++) phase_xchg_load(lane, *ws, o, keep[o][lane]);
+        for (int o = 0; o < 2; o++)
+            for (int lane = 0; lane < 32; lane++) phase_inv16_store(lane, *ws, e2.data(), o, keep[o][lane]);
+        static cpx xh[2][32][16], snd[2][32][8];
+        for (int o = 0; o < 2; o++)
+            for (int lane = 0; lane < 32; lane++) {
+                phase_i2_inner(lane, *ws, o, xh[o][lane]);
+                phase_i2_send(lane, xh[o][lane], snd[o][lane]);
+            }
+        for (int o = 0; o < 2; o++)
+            for (int lane = 0; lane < 32; lane++) phase_i2_final(lane, *ws, o, xh[o][lane], snd[o][lane ^ 16]);
         std::vector<int32_t> got(2 * kN);
         for (int lane = 0; lane < 32; lane++) phase_dump_acc(lane, *ws, got.data());
         // expected: acc + BK_i (.) ((X^a - 1) acc), exact

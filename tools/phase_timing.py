@@ -13,9 +13,8 @@ lib = pkg.lib()
 sk = pkg.keygen(1)
 eng = pkg.Engine(device=0); eng.load_keys(sk.bk, sk.ks)
 rng = np.random.default_rng(12)
-names = ["f1q", "f2_fft", "mac keep (+wait)", "mac give (+wait)", "xchg_store", "sync1", "xchg_load_inv", "sync2",
-         "i2_half", "sync3", "i2_final", "sync4", " ring: refill duty", " ring: wait full", " ring: use (MAC)",
-         " ring: release"]
+names = ["f1 (decomp, pass 1, store)", "f2_fft (2 rows)", "mac keep (+wait)", "mac give (+wait)", "xchg_store",
+         "pair barrier", "xchg_load + inv16", "i2_inner", "i2 shuffles", "i2_final", "-", "-", "-", "-", "-", "-"]
 n_iter = 100
 buf = (ctypes.c_longlong * 16)()
 for count in [int(x) for x in sys.argv[1:]] or [148, 592]:
@@ -31,4 +30,5 @@ for count in [int(x) for x in sys.argv[1:]] or [148, 592]:
     print("count %d: %.3f ms, %.0f cycles per iteration (sum of phases), wall %.2f us/iter" % (
         count, e0.elapsed_time(e1), tot / n_iter, 1e3 * e0.elapsed_time(e1) / n_iter))
     for i, nm in enumerate(names):  # the ring rows are a breakdown of the two mac rows
-        print("   %-18s %8.0f  %5.1f%%" % (nm, buf[i] / n_iter, 100.0 * buf[i] / tot))
+        if nm != "-":
+            print("   %-28s %8.0f  %5.1f%%" % (nm, buf[i] / n_iter, 100.0 * buf[i] / tot))
