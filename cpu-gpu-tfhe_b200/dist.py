@@ -16,23 +16,27 @@ def shard_bounds(total, world, rank):
     return lo, lo + base + (1 if rank < rem else 0)
 
 
-def key_shapes(p):
+def key_shapes(p, with_secret_key=False):
     kpl = (p.k + 1) * p.l
-    return {
+    shapes = {
         "bk": (p.n, kpl, p.k + 1, p.N),
         "ks": (p.N * p.k, p.ks_t, 1 << p.ks_basebit, p.n + 1),
-        "lwe_key": (p.n,),
     }
+    if with_secret_key:
+        shapes["lwe_key"] = (p.n,)
+    return shapes
 
 
-def broadcast_cloud_keys(params, sk, device, src=0):
+def broadcast_cloud_keys(params, sk, device, src=0, with_secret_key=False):
     """Rank `src` passes its SecretKeys (others pass None); every rank gets int32 tensors
-    bk [n][kpl][k+1][N] and ks [N][t][base][n+1] on `device` (plus the LWE key, which the
-    benchmark uses to verify outputs — a real deployment would not ship it)."""
+    bk [n][kpl][k+1][N] and ks [N][t][base][n+1] on `device`: the CLOUD keys only.
+    with_secret_key=True additionally ships the LWE secret key ("lwe_key") — an explicit opt-in
+    for benchmarks and tests that verify every rank's outputs by decrypting them; a deployment
+    never does this."""
     import torch
     import torch.distributed as dist
 
-    shapes = key_shapes(params)
+    shapes = key_shapes(params, with_secret_key)
     out = {}
     multi = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
     rank = dist.get_rank() if multi else src

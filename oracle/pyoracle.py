@@ -288,6 +288,23 @@ class OracleCtx:
         return out
 
 
+    def cipher_mul(self, a, b, threads=1):
+        """Cipher operator* of the CPU reference (2*nbits-bit product, OpenMP reduction over `threads`)."""
+        a, b = _i32(a), _i32(b)
+        nbits = a.shape[0]
+        out = np.zeros((2 * nbits, a.shape[1]), np.int32)
+        self.L.oracle_cipher_mul(self.h, _p(a), _p(b), int(nbits), int(threads), _p(out))
+        return out
+
+    def matmul_units(self, a, b, cacc, threads=1):
+        """units x (temp = a*b; c += temp), the inner-loop body of cpuParallel/cloud.cpp:390-408."""
+        a, b = _i32(a), _i32(b)
+        cacc = _i32(cacc).copy()
+        units, nbits = a.shape[0], a.shape[1]
+        self.L.oracle_matmul_units(self.h, _p(a), _p(b), _p(cacc), int(nbits), int(units), int(threads))
+        return cacc
+
+
 class Ref:
     """The reference's own host path (default parameter set only)."""
 

@@ -825,3 +825,70 @@ void oracle_mul(const OracleCtx *c, const int32_t *a, const int32_t *b, int nbit
     free(row); free(acc); free(tmp);
     work_free(w);
 }
+
+/* ---- the CPU reference's Cipher schedules (cpuParallel/Cipher.cpp), for the CPU baseline ----------
+ * addNumberToSelf (cpuParallel/Cipher.cpp:198-226): ripple carry over all bits, 5 gates per bit. */
+static void add_to_self_w(Work *w, int32_t *self, const int32_t *a, int nbits) {
+    const int stride = w->c->p.n + 1;
+    int32_t *carry = (int32_t *) malloc(sizeof(int32_t) * (size_t) stride * 3);
+    int32_t *cnext = carry + stride, *sum = carry + 2 * stride;
+    oracle_constant(&w->c->p, 0, carry);
+    for (int i = 0; i < nbits; i++) {
+        add_bits_w(w, self + (size_t) i * stride, a + (size_t) i * stride, carry, sum, cnext);
+        memcpy(self + (size_t) i * stride, sum, sizeof(int32_t) * (size_t) stride);
+        memcpy(carry, cnext, sizeof(int32_t) * (size_t) stride);
+    }
+    free(carry);
+}
+
+/* Cipher operator* (cpuParallel/Cipher.cpp:83-112): 2*nbits-bit product; for every bit i of b:
+ * mulBinary (:244-249, nbits ANDs), innerLeftShift(i), out += sum (2*nbits-bit ripple add), under
+ * `#pragma omp parallel for schedule(static) reduction(OMP_CIPHER_SUM:out)` (:90-94): every thread
+ * accumulates its static chunk of i into a private zero-initialised sum, the private sums are then
+ * added into `out` one after the other (libgomp combines reductions under a lock).
+ * threads = 1 is the sequential form the file compiles to with PARALLEL undefined (:13). */
+void oracle_cipher_mul(const OracleCtx *c, const int32_t *a, const int32_t *b, int nbits, int threads,
+                       int32_t *out) {
+    const int stride = c->p.n + 1, nb = 2 * nbits;
+    if (threads < 1) threads = 1;
+    if (threads > nbits) threads = nbits;
+    for (int j = 0; j < nb; j++) oracle_constant(&c->p, 0, out + (size_t) j * stride);
+#pragma omp parallel num_threads(threads)
+    {
+        Work *w = work_new(c);
+        int32_t *priv = (int32_t *) malloc(sizeof(int32_t) * (size_t) stride * nb);
+        int32_t *sum = (int32_t *) malloc(sizeof(int32_t) * (size_t) stride * nb);
+        for (int j = 0; j < nb; j++) oracle_constant(&c->p, 0, priv + (size_t) j * stride);
+#pragma omp for schedule(static)
+        for (int i = 0; i < nbits; i++) {
+            for (int j = 0; j < nb; j++) oracle_constant(&c->p, 0, sum + (size_t) j * stride);
+            for (int j = 0; j < nbits; j++)  /* mulBinary + innerLeftShift(i) */
+                gate_w(w, ORACLE_AND, b + (size_t) i * stride, a + (size_t) j * stride, sum + (size_t) (i + j) * stride);
+            add_to_self_w(w, priv, sum, nb);
+        }
+#pragma omp critical
+        add_to_self_w(w, out, priv, nb);
+        free(sum);
+        free(priv);
+        work_free(w);
+    }
+}
+
+/* `units` independent inner-loop bodies of the CPU matrix multiply (cpuParallel/cloud.cpp:390-408):
+ * temp = A[i][k] * B[k][j] (operator*, sequential inside: nested inside `omp parallel for` over i, j)
+ * and C[i][j] = C[i][j] + temp (2*nbits-bit add), one unit per thread at a time.
+ * a, b: [units][nbits] samples; cacc: [units][2*nbits] samples, updated in place. */
+void oracle_matmul_units(const OracleCtx *c, const int32_t *a, const int32_t *b, int32_t *cacc, int nbits,
+                         int units, int threads) {
+    const int stride = c->p.n + 1, nb = 2 * nbits;
+    if (threads < 1) threads = 1;
+#pragma omp parallel for schedule(dynamic, 1) num_threads(threads)
+    for (int u = 0; u < units; u++) {
+        int32_t *temp = (int32_t *) malloc(sizeof(int32_t) * (size_t) stride * nb);
+        oracle_cipher_mul(c, a + (size_t) u * nbits * stride, b + (size_t) u * nbits * stride, nbits, 1, temp);
+        Work *w = work_new(c);
+        add_to_self_w(w, cacc + (size_t) u * nb * stride, temp, nb);
+        work_free(w);
+        free(temp);
+    }
+}

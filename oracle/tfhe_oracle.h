@@ -152,6 +152,14 @@ void oracle_gate_batch(const OracleCtx *c, int gate, const int32_t *ca, const in
 void oracle_add(const OracleCtx *c, const int32_t *a, const int32_t *b, int nbits, int32_t *out);
 void oracle_mul(const OracleCtx *c, const int32_t *a, const int32_t *b, int nbits, int32_t *out);
 
+/* The CPU reference's own schedules (cpuParallel/Cipher.cpp, cpuParallel/cloud.cpp), timed by
+ * bench.py beside the GPU circuits: operator* with its OpenMP reduction (2*nbits-bit product,
+ * :83-112) and the inner-loop body of the matrix multiply (cloud.cpp:390-408). */
+void oracle_cipher_mul(const OracleCtx *c, const int32_t *a, const int32_t *b, int nbits, int threads,
+                       int32_t *out_2nbits);
+void oracle_matmul_units(const OracleCtx *c, const int32_t *a, const int32_t *b, int32_t *cacc, int nbits,
+                         int units, int threads);
+
 #ifdef __cplusplus
 }
 #endif
