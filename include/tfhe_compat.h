@@ -210,6 +210,20 @@ void lweKeySwitch(LweSample *result, const LweKeySwitchKey *ks, const LweSample 
  * are replaced by ONE handle: pass tfhe_b200_keys_to_gpu(bk) as bkGPU; ksA / ksB are ignored. */
 void *tfhe_b200_keys_to_gpu(const TFheGateBootstrappingCloudKeySet *bk);
 void tfhe_b200_keys_free(const TFheGateBootstrappingCloudKeySet *bk);
+/* GPU contexts are cached per host key object (address + a fingerprint of the key MATERIAL, so a key
+ * rewritten in place or a new key at a recycled address is never served from a stale device copy;
+ * at most 8 bare TGSW / key-switch contexts are kept, least recently used first out).
+ * tfhe_b200_compat_invalidate drops the contexts of one key object (any of: cloud key set,
+ * LweBootstrappingKeyFFT, TGswSampleFFT array, LweKeySwitchKey); release_all drops everything. */
+void tfhe_b200_compat_invalidate(const void *key_object);
+void tfhe_b200_compat_release_all(void);
+int tfhe_b200_compat_cached_contexts(void);
+/* The classic single-sample gates (bootsNAND ... bootsMUX) are thread-safe and COALESCED: calls that
+ * arrive from different host threads while a batch is in flight (or within TFHE_B200_COALESCE_WINDOW_US,
+ * default 40 us, of a lone call) share one GPU launch (cpuParallel/Cipher.cpp:75-76, 94 call them from
+ * OpenMP workers).  Statistics: launches issued / gates served for this key set. */
+void tfhe_b200_compat_coalescer_stats(const TFheGateBootstrappingCloudKeySet *bk, unsigned long long *batches,
+                                      unsigned long long *gates);
 void bootsAND_fullGPU_n_Bit(LweSample_16 *result, const LweSample_16 *ca, const LweSample_16 *cb, int nBits,
                             void *bkGPU, Torus32 *ksA, Torus32 *ksB);
 void bootsXOR_fullGPU_n_Bit(LweSample_16 *result, const LweSample_16 *ca, const LweSample_16 *cb, int nBits,

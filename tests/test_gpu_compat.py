@@ -270,3 +270,170 @@ def test_cloud_program_flow_through_files(pkg, tmp_path):
     got = pkg.decrypt_bits(sk, ans)
     mux = np.where(bits_a == 1, bits_b, np.roll(bits_a, -1))
     assert np.array_equal(got, np.concatenate([bits_a & bits_b, bits_a ^ bits_b, 1 - (bits_a & bits_b), mux]))
+
+
+def test_classic_gates_coalesce_across_threads(world):
+    """SURVEY 8b "Threading": the classic entry points are called from OpenMP workers
+    (cpuParallel/Cipher.cpp:75-76, 94).  16 host threads x bootsAND / bootsXOR / bootsMUX on reference
+    objects: every result decrypts correctly, the calls shared launches (gate coalescer), and the
+    16 calls together take less than twice one lone call."""
+    import threading
+    import time
+
+    o, r, R, L, keys = world
+    cloud = vp(R.ref_cloud_keyset(r.h))
+    nthreads = 16
+    rng = np.random.default_rng(3)
+    bits = rng.integers(0, 2, (nthreads, 3))
+    samples = [[Sample(R, r.h, 500, r.encrypt(int(b))) for b in row] for row in bits]
+    results = [Sample(R, r.h, 500) for _ in range(nthreads)]
+    kinds = ["AND", "XOR", "MUX", "NAND"]
+
+    def call(i):
+        k = kinds[i % len(kinds)]
+        a, b, c = samples[i]
+        if k == "MUX":
+            L.bootsMUX(results[i].p, a.p, b.p, c.p, cloud)
+        else:
+            getattr(L, "boots" + k)(results[i].p, a.p, b.p, cloud)
+
+    def expected(i):
+        a, b, c = (int(x) for x in bits[i])
+        return {"AND": a & b, "XOR": a ^ b, "MUX": b if a else c, "NAND": 1 - (a & b)}[kinds[i % len(kinds)]]
+
+    call(0)  # context creation + key upload happen here
+    lone = []
+    for _ in range(3):
+        t0 = time.perf_counter()
+        call(0)
+        lone.append(time.perf_counter() - t0)
+    b0, g0 = ctypes.c_ulonglong(), ctypes.c_ulonglong()
+    L.tfhe_b200_compat_coalescer_stats(cloud, ctypes.byref(b0), ctypes.byref(g0))
+    best = None
+    for _ in range(3):
+        threads = [threading.Thread(target=call, args=(i,)) for i in range(nthreads)]
+        t0 = time.perf_counter()
+        for t in threads:
+            t.start()
+        for t in threads:
+            t.join()
+        dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+    b1, g1 = ctypes.c_ulonglong(), ctypes.c_ulonglong()
+    L.tfhe_b200_compat_coalescer_stats(cloud, ctypes.byref(b1), ctypes.byref(g1))
+    for i in range(nthreads):
+        assert int(r.phase(results[i].get()) > 0) == expected(i), i
+    assert g1.value - g0.value == 3 * nthreads
+    assert b1.value - b0.value < 3 * nthreads / 2, "calls from different threads did not share launches"
+    assert best < 2.0 * min(lone) + 2e-3, (best, lone)
+
+
+def test_xnor_not16_and_keys_free(world):
+    """The remaining exports of the batched family: bootsXNOR_fullGPU_n_Bit, bootsNOT_16
+    (boot-gates.cu:2953, :1274) and tfhe_b200_keys_free (contexts are rebuilt on the next use)."""
+    import torch
+
+    o, r, R, L, keys = world
+
+    class S16(ctypes.Structure):
+        _fields_ = [("a", vp), ("b", ctypes.POINTER(ctypes.c_int)), ("cv", ctypes.POINTER(ctypes.c_double))]
+
+    cloud = vp(R.ref_cloud_keyset(r.h))
+    handle = vp(L.tfhe_b200_keys_to_gpu(cloud))
+    nb = 5
+    rng = np.random.default_rng(6)
+    bits = [rng.integers(0, 2, nb) for _ in range(2)]
+    torch.zeros(1, device="cuda")
+    cudart = ctypes.CDLL("libcudart.so.12")
+    cudart.cudaMemcpy.argtypes = [vp, vp, ctypes.c_size_t, ctypes.c_int]
+
+    def make(bitvec):
+        s = ctypes.cast(L.convertBitToNumberZero_GPU(nb, cloud), ctypes.POINTER(S16))
+        flat = np.stack([r.encrypt(int(b)) for b in bitvec])
+        a = np.ascontiguousarray(flat[:, :-1])
+        assert cudart.cudaMemcpy(s.contents.a, a.ctypes.data_as(vp), a.nbytes, 1) == 0
+        for i in range(nb):
+            s.contents.b[i] = int(flat[i, -1])
+        return s, flat
+
+    def read(s, count):
+        a = np.zeros((count, 500), np.int32)
+        assert cudart.cudaMemcpy(a.ctypes.data_as(vp), s.contents.a, a.nbytes, 2) == 0
+        b = np.array([s.contents.b[i] for i in range(count)], np.int32)
+        return np.concatenate([a, b[:, None]], 1)
+
+    sa, fa = make(bits[0])
+    sb, fb = make(bits[1])
+    res = ctypes.cast(L.convertBitToNumberZero_GPU(nb, cloud), ctypes.POINTER(S16))
+    L.bootsXNOR_fullGPU_n_Bit(res, sa, sb, nb, handle, None, None)
+    assert np.array_equal((o.phases(keys.lwe_key, read(res, nb)) > 0).astype(int), 1 - (bits[0] ^ bits[1]))
+    L.bootsNOT_16(res, sa, nb, 500)
+    assert np.array_equal(read(res, nb), (-fa.astype(np.int64)).astype(np.int32))  # bit-exact negation
+    # keys_free drops the context; the next use rebuilds it and still computes correctly
+    L.tfhe_b200_compat_cached_contexts.restype = ctypes.c_int
+    before = L.tfhe_b200_compat_cached_contexts()
+    L.tfhe_b200_keys_free(cloud)
+    assert L.tfhe_b200_compat_cached_contexts() == before - 1
+    handle = vp(L.tfhe_b200_keys_to_gpu(cloud))
+    L.bootsAND_fullGPU_n_Bit(res, sa, sb, nb, handle, None, None)
+    assert np.array_equal((o.phases(keys.lwe_key, read(res, nb)) > 0).astype(int), bits[0] & bits[1])
+    for s in (sa, sb, res):
+        L.freeLweSample_16_gpu(s)
+
+
+def test_context_cache_follows_key_content(world):
+    """A GPU context is cached per host key object; the cache is validated by a fingerprint of the
+    key material, so a TGSW sample OVERWRITTEN IN PLACE (same address, new content) is re-uploaded,
+    and the number of bare-TGSW contexts stays bounded."""
+    o, r, R, L, keys = world
+    rng = np.random.default_rng(18)
+    acc = rng.integers(-2 ** 31, 2 ** 31, (2, 1024), dtype=np.int64).astype(np.int32)
+    params = vp(R.ref_tgsw_params(r.h))
+    base = R.ref_tgsw_fft_array(r.h)
+    t = vp(R.ref_tlwe_new(r.h))
+    got = np.zeros_like(acc)
+    L.tfhe_b200_compat_cached_contexts.restype = ctypes.c_int
+
+    def extern_mul(ptr):
+        R.ref_tlwe_set(t, acc.ctypes.data_as(vp), 1024, 1)
+        L.tGswFFTExternMulToTLwe(t, vp(ptr), params)
+        R.ref_tlwe_get(t, got.ctypes.data_as(vp), 1024, 1)
+        return got.copy()
+
+    # copy TGSW sample 3 into a scratch object at a fixed address, use it, then overwrite it with sample 9
+    # (struct TGswSampleFFT {all_samples, sample, k, l}: 24 bytes; data = 4 rows x 2 polys x 512 complex)
+    class LagrangeHalfC(ctypes.Structure):
+        _fields_ = [("data", vp), ("precomp", vp)]
+
+    class TLweSampleFFT(ctypes.Structure):
+        _fields_ = [("a", ctypes.POINTER(LagrangeHalfC)), ("b", vp), ("cv", ctypes.c_double), ("k", ctypes.c_int)]
+
+    class TGswSampleFFT(ctypes.Structure):
+        _fields_ = [("all_samples", ctypes.POINTER(TLweSampleFFT)), ("sample", vp), ("k", ctypes.c_int), ("l", ctypes.c_int)]
+
+    def poly_ptrs(idx):
+        s = ctypes.cast(vp(base + 24 * idx), ctypes.POINTER(TGswSampleFFT)).contents
+        return [s.all_samples[row].a[j].data for row in range(4) for j in range(2)]
+
+    scratch_idx, src_a, src_b = 20, 3, 9
+    saved = [ctypes.string_at(p, 8192) for p in poly_ptrs(scratch_idx)]
+    try:
+        for dst, src in zip(poly_ptrs(scratch_idx), poly_ptrs(src_a)):
+            ctypes.memmove(dst, src, 8192)
+        first = extern_mul(base + 24 * scratch_idx)
+        assert np.abs(wrap32(first.astype(np.int64) - o.extern_mul_exact(keys.bk[src_a], acc).astype(np.int64))).max() <= 1
+        for dst, src in zip(poly_ptrs(scratch_idx), poly_ptrs(src_b)):
+            ctypes.memmove(dst, src, 8192)   # same object, same address, new key material
+        second = extern_mul(base + 24 * scratch_idx)
+        assert np.abs(wrap32(second.astype(np.int64) - o.extern_mul_exact(keys.bk[src_b], acc).astype(np.int64))).max() <= 1
+    finally:
+        for dst, data in zip(poly_ptrs(scratch_idx), saved):
+            ctypes.memmove(dst, data, 8192)
+    # many distinct TGSW objects: the cache keeps at most 8 bare-TGSW contexts
+    L.tfhe_b200_compat_release_all()
+    for idx in range(40, 52):
+        extern_mul(base + 24 * idx)
+    assert L.tfhe_b200_compat_cached_contexts() <= 8
+    L.tfhe_b200_compat_invalidate(vp(base + 24 * 51))
+    assert L.tfhe_b200_compat_cached_contexts() <= 7
+    R.ref_tlwe_free(t)
