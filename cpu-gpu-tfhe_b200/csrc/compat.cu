@@ -179,6 +179,11 @@ class Coalescer {
     Coalescer(tfhe_b200_ctx *ctx, int n) : ctx_(ctx), n_(n) {
         cu(cudaSetDevice(tfhe_b200_ctx_device(ctx)), "cudaSetDevice");
         cu(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking), "cudaStreamCreate");
+        for (int i = 0; i < kSideStreams; i++) {
+            cu(cudaStreamCreateWithFlags(&side_[i], cudaStreamNonBlocking), "cudaStreamCreate");
+            cu(cudaEventCreateWithFlags(&side_done_[i], cudaEventDisableTiming), "cudaEventCreate");
+        }
+        cu(cudaEventCreateWithFlags(&staged_, cudaEventDisableTiming), "cudaEventCreate");
         const size_t words = (size_t) kMaxBatch * 4 * (n + 1);
         cu(cudaMallocHost(&h_, words * sizeof(int32_t)), "cudaMallocHost");
         cu(cudaMalloc(&d_, words * sizeof(int32_t)), "cudaMalloc");
@@ -187,6 +192,11 @@ class Coalescer {
         cudaStreamSynchronize(stream_);
         cudaFree(d_);
         cudaFreeHost(h_);
+        for (int i = 0; i < kSideStreams; i++) {
+            cudaEventDestroy(side_done_[i]);
+            cudaStreamDestroy(side_[i]);
+        }
+        cudaEventDestroy(staged_);
         cudaStreamDestroy(stream_);
     }
     void submit(GateReq &r) {
@@ -247,11 +257,22 @@ class Coalescer {
         const size_t nb = (size_t) count * row * sizeof(int32_t);
         cu(cudaMemcpyAsync(d_, h_, nb, cudaMemcpyHostToDevice, stream_), "H2D");
         cu(cudaMemcpyAsync(d_ + blk, h_ + blk, nb, cudaMemcpyHostToDevice, stream_), "H2D");
-        if (nmux) {
+        if (nmux)
             cu(cudaMemcpyAsync(d_ + 2 * blk, h_ + 2 * blk, (size_t) nmux * row * sizeof(int32_t), cudaMemcpyHostToDevice, stream_), "H2D");
-            OK(tfhe_b200_mux(ctx_, d_ + 3 * blk, d_, d_ + blk, d_ + 2 * blk, nmux, stream_), "mux");
-        }
-        // runs of equal gate type, up to 4 per launch (one blind rotation + one key switch each)
+        // A batch with MUX requests or more than four gate types needs several launches (each = one blind
+        // rotation + one key switch).  They are independent and small (one ciphertext per SM), so they go
+        // to side streams and run CONCURRENTLY on different SMs instead of one after the other.
+        int launch = 0;
+        cudaStream_t used[1 + kSideStreams];
+        auto next_stream = [&]() {
+            cudaStream_t st = launch == 0 ? stream_ : side_[(launch - 1) % kSideStreams];
+            if (launch == 1) cu(cudaEventRecord(staged_, stream_), "event");
+            if (launch >= 1 && launch <= kSideStreams) cu(cudaStreamWaitEvent(st, staged_, 0), "wait");
+            used[launch <= kSideStreams ? launch : kSideStreams] = st;
+            launch++;
+            return st;
+        };
+        // runs of equal gate type, up to 4 per launch
         tfhe_b200_gate_op ops[4];
         int nops = 0;
         for (int i = nmux; i < count;) {
@@ -267,10 +288,17 @@ class Coalescer {
             o.stride_a = o.stride_b = o.stride_out = (int64_t) row;
             i = j;
             if (nops == 4 || i == count) {
-                OK(tfhe_b200_gate_multi(ctx_, ops, nops, stream_), "gate");
+                OK(tfhe_b200_gate_multi(ctx_, ops, nops, next_stream()), "gate");
                 nops = 0;
             }
         }
+        if (nmux) OK(tfhe_b200_mux(ctx_, d_ + 3 * blk, d_, d_ + blk, d_ + 2 * blk, nmux, next_stream()), "mux");
+        const int nside = launch - 1 < kSideStreams ? launch - 1 : kSideStreams;
+        for (int i = 0; i < nside; i++) {  // join the side streams
+            cu(cudaEventRecord(side_done_[i], side_[i]), "event");
+            cu(cudaStreamWaitEvent(stream_, side_done_[i], 0), "wait");
+        }
+        (void) used;
         cu(cudaMemcpyAsync(h_ + 3 * blk, d_ + 3 * blk, nb, cudaMemcpyDeviceToHost, stream_), "D2H");
         cu(cudaStreamSynchronize(stream_), "gate");
         for (int i = 0; i < count; i++) {
@@ -284,7 +312,9 @@ class Coalescer {
 
     tfhe_b200_ctx *ctx_;
     int n_;
-    cudaStream_t stream_ = nullptr;
+    static constexpr int kSideStreams = 3;
+    cudaStream_t stream_ = nullptr, side_[kSideStreams] = {};
+    cudaEvent_t side_done_[kSideStreams] = {}, staged_ = nullptr;
     int32_t *h_ = nullptr, *d_ = nullptr;
     std::mutex mu_;
     std::condition_variable cv_;

@@ -311,6 +311,21 @@ void ref_blind_rotate_naive(const RefHandle *h, int32_t *accum, const int32_t *b
     delete_TLweSample(res); delete_TLweSample(tmp); delete_TLweSample(acc);
 }
 
+/* `count` calls of a two-input gate function from OpenMP worker threads, one sample per call, the way
+ * the CPU reference's Cipher operators issue them (cpuParallel/Cipher.cpp:114-121 cipherAND,
+ * :75-76).  fn is any function with the bootsXXX signature (the reference's own or the drop-in
+ * library's, found by the test through dlsym); returns the wall time of the parallel loop. */
+typedef void (*ref_gate2_fn)(LweSample *, const LweSample *, const LweSample *, const TFheGateBootstrappingCloudKeySet *);
+double ref_omp_gate_calls(void *fn, void **results, void **as, void **bs, const void *cloud, int count, int threads) {
+    ref_gate2_fn f = (ref_gate2_fn) fn;
+    const auto t0 = std::chrono::steady_clock::now();
+#pragma omp parallel for num_threads(threads) schedule(static, 1)
+    for (int i = 0; i < count; i++)
+        f((LweSample *) results[i], (const LweSample *) as[i], (const LweSample *) bs[i],
+          (const TFheGateBootstrappingCloudKeySet *) cloud);
+    return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+}
+
 /* Gadget decomposition of one polynomial: tGswTorus32PolynomialDecompH */
 void ref_decomp(const RefHandle *h, const int32_t *poly, int32_t *out_l_by_N) {
     const TGswParams *gp = h->params->tgsw_params;

@@ -325,7 +325,23 @@ def test_classic_gates_coalesce_across_threads(world):
         assert int(r.phase(results[i].get()) > 0) == expected(i), i
     assert g1.value - g0.value == 3 * nthreads
     assert b1.value - b0.value < 3 * nthreads / 2, "calls from different threads did not share launches"
-    assert best < 2.0 * min(lone) + 2e-3, (best, lone)
+    assert best < 3.0 * min(lone) + 2e-3, (best, lone)   # Python threads start ~0.1 ms apart: two rounds
+
+    # the same from real OpenMP workers (cpuParallel/Cipher.cpp:114-121 cipherAND): 16 threads x bootsAND
+    # arrive together, share ONE launch and finish in less than twice a lone call
+    R.ref_omp_gate_calls.restype = ctypes.c_double
+    R.ref_omp_gate_calls.argtypes = [vp, vp, vp, vp, vp, ctypes.c_int, ctypes.c_int]
+    fn = ctypes.cast(L.bootsAND, vp)
+    arr = lambda objs: (vp * nthreads)(*[x.p for x in objs])
+    res_p, a_p, b_p = arr(results), arr([s[0] for s in samples]), arr([s[1] for s in samples])
+    R.ref_omp_gate_calls(fn, res_p, a_p, b_p, cloud, nthreads, nthreads)  # thread pool start-up
+    L.tfhe_b200_compat_coalescer_stats(cloud, ctypes.byref(b0), ctypes.byref(g0))
+    omp = min(R.ref_omp_gate_calls(fn, res_p, a_p, b_p, cloud, nthreads, nthreads) for _ in range(5))
+    L.tfhe_b200_compat_coalescer_stats(cloud, ctypes.byref(b1), ctypes.byref(g1))
+    for i in range(nthreads):
+        assert int(r.phase(results[i].get()) > 0) == int(bits[i][0] & bits[i][1]), i
+    assert g1.value - g0.value == 5 * nthreads and b1.value - b0.value <= 10
+    assert omp < 2.0 * min(lone), (omp, lone)
 
 
 def test_xnor_not16_and_keys_free(world):
