@@ -16,6 +16,7 @@ from .binding import (  # noqa: F401
     GATE_ID,
     Circuit,
     Engine,
+    MultiEngine,
     EngineError,
     Params,
     SecretKeys,

@@ -141,6 +141,18 @@ def lib():
                                               _vp, _vp]
         L.tfhe_b200_get_timing.argtypes = [_vp, _vp, _vp, _vp]
         L.tfhe_b200_measure_fp64_peak.argtypes = [_i, _vp, _vp]
+        L.tfhe_b200_multi_create.argtypes = [ctypes.POINTER(_vp), ctypes.POINTER(Params), _vp, _i]
+        L.tfhe_b200_multi_destroy.argtypes = [_vp]
+        L.tfhe_b200_multi_devices.argtypes = [_vp]
+        L.tfhe_b200_multi_ctx.argtypes = [_vp, _i]
+        L.tfhe_b200_multi_ctx.restype = _vp
+        L.tfhe_b200_multi_load_keys.argtypes = [_vp, _vp, _vp]
+        L.tfhe_b200_multi_gate_host.argtypes = [_vp, _i, _vp, _vp, _vp, ctypes.c_longlong]
+        L.tfhe_b200_multi_mux_host.argtypes = [_vp, _vp, _vp, _vp, _vp, ctypes.c_longlong]
+        L.tfhe_b200_multi_launch_count.argtypes = [_vp]
+        L.tfhe_b200_multi_launch_count.restype = ctypes.c_ulonglong
+        L.tfhe_b200_multi_last_error.restype = ctypes.c_char_p
+        L.tfhe_b200_conversion_mode.restype = _i
         _lib = L
     return _lib
 
@@ -559,6 +571,58 @@ class Circuit:
     def close(self):
         if getattr(self, "h", None):
             self.L.tfhe_b200_circuit_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class MultiEngine:
+    """Several GPUs in one process (tfhe_b200_multi_*, include/tfhe_b200.h): one context per device,
+    host batches sharded contiguously, keys uploaded once and copied device to device."""
+
+    def __init__(self, devices=None, params=None):
+        self.L = lib()
+        self.p = params or default_params()
+        h = _vp()
+        arr = (ctypes.c_int * len(devices))(*devices) if devices else None
+        if self.L.tfhe_b200_multi_create(ctypes.byref(h), ctypes.byref(self.p), arr, len(devices) if devices else 0):
+            raise EngineError(self.L.tfhe_b200_multi_last_error().decode())
+        self.h = h
+        self.ndevices = int(self.L.tfhe_b200_multi_devices(self.h))
+
+    def _ck(self, rc):
+        if rc:
+            raise EngineError(self.L.tfhe_b200_multi_last_error().decode())
+
+    def load_keys(self, bk_coef, ks):
+        bk, k = _np_i32(bk_coef), _np_i32(ks)
+        self._ck(self.L.tfhe_b200_multi_load_keys(self.h, bk.ctypes.data, k.ctypes.data))
+
+    def gate_host(self, name, ca, cb, out=None):
+        ca, cb = _np_i32(ca), _np_i32(cb)
+        out = np.empty_like(ca) if out is None else out
+        self._ck(self.L.tfhe_b200_multi_gate_host(self.h, GATE_ID[name], out.ctypes.data, ca.ctypes.data,
+                                                  cb.ctypes.data, ca.shape[0]))
+        return out
+
+    def mux_host(self, a, b, c):
+        a, b, c = _np_i32(a), _np_i32(b), _np_i32(c)
+        out = np.empty_like(a)
+        self._ck(self.L.tfhe_b200_multi_mux_host(self.h, out.ctypes.data, a.ctypes.data, b.ctypes.data,
+                                                 c.ctypes.data, a.shape[0]))
+        return out
+
+    @property
+    def launch_count(self):
+        return int(self.L.tfhe_b200_multi_launch_count(self.h))
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.tfhe_b200_multi_destroy(self.h)
             self.h = None
 
     def __del__(self):

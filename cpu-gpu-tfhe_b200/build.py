@@ -18,7 +18,7 @@ LIB = os.path.join(HERE, "libtfhe_b200.so")
 LIB_TRUNC = os.path.join(HERE, "libtfhe_b200_trunc.so")
 INCLUDE = os.path.join(HERE, "..", "include")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-SOURCES = ["blind_rotate.cu", "keyswitch.cu", "keyswitch_mma.cu", "engine.cu", "client.cu", "microbench.cu", "compat.cu", "circuits.cu", "keyio.cu", "keygen.cu"]
+SOURCES = ["blind_rotate.cu", "keyswitch.cu", "keyswitch_mma.cu", "engine.cu", "client.cu", "microbench.cu", "compat.cu", "circuits.cu", "keyio.cu", "keygen.cu", "multi.cu"]
 FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-std=c++17", "-O3", "-lineinfo",
     "-Xcompiler", "-fPIC,-O2,-Wall,-Wno-unknown-pragmas", "-I", os.path.join(HERE, "..", "include"),

@@ -680,6 +680,32 @@ static int host_gate_common(tfhe_b200_ctx *c, int gate, bool mux, int32_t *out, 
     if (count <= 0) return count < 0 ? fail("negative count") : 0;
     CU(cudaSetDevice(c->device));
     const size_t row = (size_t) (c->p.n + 1);
+    {
+        // Memory-capped sub-batching (the reference: cudaMemGetInfo -> bootsLimit -> loop over
+        // sub-batches, boot-gates.cu:2869-2907): operands, result and the extracted samples of a
+        // sub-batch must fit in 80 % of the free device memory.  TFHE_B200_HOST_BATCH_LIMIT (gates)
+        // lowers the cap (tests).
+        size_t free_b = 0, total_b = 0;
+        CU(cudaMemGetInfo(&free_b, &total_b));
+        const size_t per_gate = ((mux ? 4 : 3) * row + (mux ? 2 : 1) * (size_t) (kN + 1)) * sizeof(int32_t);
+        size_t cap = (size_t) ((double) free_b * 0.8 / (double) per_gate);
+        static const long long env_cap = [] {
+            const char *v = getenv("TFHE_B200_HOST_BATCH_LIMIT");
+            return v ? atoll(v) : 0ll;
+        }();
+        if (env_cap > 0 && (size_t) env_cap < cap) cap = (size_t) env_cap;
+        const size_t wave = 4 * (size_t) c->sm_count;
+        if (cap > wave) cap -= cap % wave;  // whole waves
+        if (cap == 0) return fail("not enough free device memory for a single gate (%zu bytes free)", free_b);
+        if ((size_t) count > cap) {
+            for (size_t g0 = 0; g0 < (size_t) count; g0 += cap) {
+                const int nsub = (int) ((size_t) count - g0 < cap ? (size_t) count - g0 : cap);
+                const size_t off = g0 * row;
+                if (host_gate_common(c, gate, mux, out + off, a + off, b + off, mux ? cc + off : nullptr, nsub)) return 1;
+            }
+            return 0;
+        }
+    }
     const size_t bytes = (size_t) count * row * sizeof(int32_t);
     int32_t *d_a = nullptr, *d_b = nullptr, *d_c = nullptr, *d_o = nullptr;
     cudaStream_t st = c->stream;

@@ -259,6 +259,27 @@ int tfhe_b200_gate_host(tfhe_b200_ctx *ctx, int gate, int32_t *out, const int32_
 int tfhe_b200_mux_host(tfhe_b200_ctx *ctx, int32_t *out, const int32_t *a, const int32_t *b, const int32_t *c,
                        int count);
 
+/* ---- several GPUs in ONE process (C / C++ hosts) ------------------------------
+ * The reference uses device 0 only (boot-gates.cu:3344).  A multi-GPU handle owns one context per
+ * device; gates are independent, so a host batch is cut into contiguous shards (sizes differ by at
+ * most one), one per device, driven by one host thread each; nothing is exchanged on the data path.
+ * tfhe_b200_multi_load_keys uploads the keys to the first device once and copies them device to
+ * device to the others (cudaMemcpyPeerAsync, NVLink where peer access exists).
+ * devices == NULL or ndevices <= 0: all visible devices.  The same device may be listed twice
+ * (two contexts on one GPU).  Errors: non-zero return, tfhe_b200_multi_last_error(). */
+typedef struct tfhe_b200_multi tfhe_b200_multi;
+int tfhe_b200_multi_create(tfhe_b200_multi **m, const tfhe_b200_params *p, const int *devices, int ndevices);
+void tfhe_b200_multi_destroy(tfhe_b200_multi *m);
+int tfhe_b200_multi_devices(const tfhe_b200_multi *m);
+tfhe_b200_ctx *tfhe_b200_multi_ctx(tfhe_b200_multi *m, int index); /* per-device context (borrowed) */
+int tfhe_b200_multi_load_keys(tfhe_b200_multi *m, const int32_t *bk_coef, const int32_t *ks);
+int tfhe_b200_multi_gate_host(tfhe_b200_multi *m, int gate, int32_t *out, const int32_t *ca, const int32_t *cb,
+                              long long count);
+int tfhe_b200_multi_mux_host(tfhe_b200_multi *m, int32_t *out, const int32_t *a, const int32_t *b, const int32_t *c,
+                             long long count);
+unsigned long long tfhe_b200_multi_launch_count(const tfhe_b200_multi *m);
+const char *tfhe_b200_multi_last_error(void);
+
 /* ---- client side: key generation, encryption, decryption (HOST, CPU) -------
  * These belong to the key owner, not to the evaluation path; the reference runs them on
  * the host as well (new_random_gate_bootstrapping_secret_keyset tfhe_gate_bootstrapping.cu:57-68,
