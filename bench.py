@@ -300,18 +300,21 @@ def circuit_latencies(pkg, eng, sk):
         bits = pkg.decrypt_bits(sk, t.cpu().numpy()).reshape(-1, nbits).astype(np.int64)
         return int((bits << np.arange(nbits)).sum(-1)[0])
 
-    def timed(fn, reps):
-        fn()
-        torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(reps):
-            out = fn()
-        e1.record()
+    def timed(fn, reps, stream=None):
+        with torch.cuda.stream(stream if stream is not None else torch.cuda.current_stream()):
+            fn()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(reps):
+                out = fn()
+            e1.record()
         torch.cuda.synchronize()
         return e0.elapsed_time(e1) / reps, out
 
     res = {}
+    side = torch.cuda.Stream()  # plans replay a captured CUDA graph on a non-default stream
+    torch.cuda.synchronize()
     ca, cb = enc(1, 1, 1), enc(1, 1, 2)
     for _ in range(5):
         eng.gate("NAND", ca, cb)
@@ -324,16 +327,24 @@ def circuit_latencies(pkg, eng, sk):
     da, db = enc(a, 16, 3), enc(b, 16, 4)
     for mode, name in ((0, "add16_reference_bitwise"), (1, "add16_reference_numberwise"), (2, "add16_prefix")):
         c = pkg.Circuit(eng, "add", 16, 1, mode)
-        ms, out = timed(lambda: c.run(da, db), 2)
+        ms, out = timed(lambda: c.run(da, db), 2, side)
         ok = ok and dec(out, 16) == (a + b) & 0xFFFF
-        res[name] = {"ms": ms, "levels": c.levels, "gates": c.gates}
+        res[name] = {"ms": ms, "levels": c.levels, "gates": c.gates, "cuda_graph": c.used_graph}
+        c.close()
+    # eight independent 16-bit additions merged level by level (tfhe_b200_circuit_run_many)
+    plans = [pkg.Circuit(eng, "add", 16, 1, 2) for _ in range(8)]
+    ops = [[enc(1000 * i + 7, 16, 40 + i), enc(555 * i + 1, 16, 60 + i)] for i in range(8)]
+    ms, outs = timed(lambda: pkg.Circuit.run_many(plans, ops), 2, side)
+    ok = ok and all(dec(o, 16) == (1000 * i + 7 + 555 * i + 1) & 0xFFFF for i, o in enumerate(outs))
+    res["add16_prefix_x8_merged"] = {"ms": ms, "ms_per_addition": ms / 8, "plans": 8}
+    for c in plans:
         c.close()
     da, db = enc(40000, 32, 5), enc(50000, 32, 6)
     for adder, name in ((0, "mul32_reference"), (1, "mul32_prefix")):
         c = pkg.Circuit(eng, "mul_ex", 32, 1, adder)
-        ms, out = timed(lambda: c.run(da, db), 1)
+        ms, out = timed(lambda: c.run(da, db), 1, side)
         ok = ok and dec(out, 32) == (40000 * 50000) & 0xFFFFFFFF
-        res[name] = {"ms": ms, "levels": c.levels, "gates": c.gates}
+        res[name] = {"ms": ms, "levels": c.levels, "gates": c.gates, "cuda_graph": c.used_graph}
         c.close()
     res["results_decrypt_ok"] = bool(ok)
     return res

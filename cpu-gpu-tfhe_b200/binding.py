@@ -128,6 +128,10 @@ def lib():
         L.tfhe_b200_circuit_operand_rows.argtypes = [_vp, _i]
         L.tfhe_b200_circuit_output_rows.argtypes = [_vp]
         L.tfhe_b200_circuit_run.argtypes = [_vp, _vp, _vp, _vp]
+        L.tfhe_b200_circuit_run_many.argtypes = [_vp, _i, _vp, _vp, _vp]
+        L.tfhe_b200_circuit_set_graph.argtypes = [_vp, _i]
+        L.tfhe_b200_circuit_used_graph.argtypes = [_vp]
+        L.tfhe_b200_count_launches.argtypes = [_vp, ctypes.c_ulonglong]
         L.tfhe_b200_file_read_cloud_key.argtypes = [ctypes.c_char_p, _vp, _vp, _vp, _vp, _vp]
         L.tfhe_b200_file_write_cloud_key.argtypes = [ctypes.c_char_p, _vp, _vp, _vp, _vp, _vp]
         L.tfhe_b200_file_read_secret_key.argtypes = [ctypes.c_char_p, _vp, _vp, _vp, _vp, _vp, _vp, _vp]
@@ -555,6 +559,37 @@ class Circuit:
         if self.L.tfhe_b200_circuit_run(self.h, out.data_ptr(), ptrs, self.eng._stream(stream)):
             raise EngineError(self.L.tfhe_b200_last_error().decode())
         return out
+
+    def set_graph(self, enable):
+        """CUDA-graph replay of the plan's launch sequence (default on; needs a non-default stream)."""
+        return bool(self.L.tfhe_b200_circuit_set_graph(self.h, int(bool(enable))))
+
+    @property
+    def used_graph(self):
+        return bool(self.L.tfhe_b200_circuit_used_graph(self.h))
+
+    @staticmethod
+    def run_many(plans, operand_lists, stream=None):
+        """K independent plans of one engine, merged level by level into shared launches
+        (tfhe_b200_circuit_run_many).  Returns the list of result tensors."""
+        eng = plans[0].eng
+        outs = [eng.empty(p.out_rows) for p in plans]
+        k = len(plans)
+        keep = []
+        op_arrays = (_vp * k)()
+        for i, (p, ops) in enumerate(zip(plans, operand_lists)):
+            assert len(ops) == len(p.operand_rows)
+            for t, rows in zip(ops, p.operand_rows):
+                eng._chk(t, eng.words)
+                assert t.numel() == rows * eng.words, "operand has the wrong number of samples"
+            arr = (_vp * len(ops))(*[t.data_ptr() for t in ops])
+            keep.append(arr)
+            op_arrays[i] = ctypes.cast(arr, _vp)
+        plan_arr = (_vp * k)(*[p.h for p in plans])
+        out_arr = (_vp * k)(*[o.data_ptr() for o in outs])
+        if eng.L.tfhe_b200_circuit_run_many(plan_arr, k, out_arr, op_arrays, eng._stream(stream)):
+            raise EngineError(eng.L.tfhe_b200_last_error().decode())
+        return outs
 
     def simulate(self, *operand_bits):
         """Plaintext evaluation of the schedule on the host (schedule check; not a compute path)."""

@@ -19,6 +19,7 @@
 #include <vector>
 
 #include "../../include/tfhe_b200.h"
+#include "kernels.h"
 
 namespace {
 
@@ -53,7 +54,14 @@ struct tfhe_b200_circuit {
     std::vector<int32_t> h_idx;
     int32_t *d_idx = nullptr;
     int32_t *d_ws = nullptr;
+    int32_t *d_u = nullptr;             // extracted samples of the widest level (plan-owned scratch)
+    size_t u_bytes = 0;
     long long n_gates = 0;
+    // CUDA graph of the launch sequence (all levels; operand / result copies stay outside, so the graph
+    // does not depend on the caller's buffers)
+    bool graph_enabled = true, graph_failed = false, used_graph = false;
+    cudaGraphExec_t graph_exec = nullptr;
+    unsigned long long graph_launches = 0;  // kernel launches one replay stands for
 };
 
 namespace {
@@ -418,13 +426,25 @@ tfhe_b200_circuit *finish(tfhe_b200_circuit *c) { return c; }
 int ensure_device(tfhe_b200_circuit *c) {
     if (c->d_idx != nullptr) return 0;
     const size_t ib = c->h_idx.size() * sizeof(int32_t);
-    if (cudaMalloc(&c->d_idx, ib ? ib : 4) != cudaSuccess ||
+    // widest bootstrap batch of the plan: its extracted samples (N+1 words each) need scratch
+    long long widest = 1;
+    for (const Level &lv : c->levels) {
+        long long w = 0;
+        for (int i = 0; i < lv.nops; i++) w += lv.ops[i].count;
+        if (lv.type == LV_MUX) w *= 2;
+        if (lv.type != LV_LINEAR && w > widest) widest = w;
+    }
+    c->u_bytes = (size_t) widest * (tfhe_b200::kKsRowWords * 2 + 1) * sizeof(int32_t);  // N + 1 = 1025 words
+    if (cudaSetDevice(tfhe_b200_ctx_device(c->ctx)) != cudaSuccess || cudaMalloc(&c->d_idx, ib ? ib : 4) != cudaSuccess ||
         cudaMalloc(&c->d_ws, (size_t) c->nrows * c->words * sizeof(int32_t)) != cudaSuccess ||
+        cudaMalloc(&c->d_u, c->u_bytes) != cudaSuccess ||
         cudaMemcpy(c->d_idx, c->h_idx.data(), ib, cudaMemcpyHostToDevice) != cudaSuccess) {
         if (c->d_idx) cudaFree(c->d_idx);
         if (c->d_ws) cudaFree(c->d_ws);
+        if (c->d_u) cudaFree(c->d_u);
         c->d_idx = nullptr;
         c->d_ws = nullptr;
+        c->d_u = nullptr;
         return fail_msg("device allocation failed");
     }
     return 0;
@@ -993,8 +1013,10 @@ tfhe_b200_circuit *tfhe_b200_circuit_div(tfhe_b200_ctx *ctx, int nbits, int coun
 
 void tfhe_b200_circuit_destroy(tfhe_b200_circuit *c) {
     if (!c) return;
+    if (c->graph_exec) cudaGraphExecDestroy(c->graph_exec);
     if (c->d_idx) cudaFree(c->d_idx);
     if (c->d_ws) cudaFree(c->d_ws);
+    if (c->d_u) cudaFree(c->d_u);
     delete c;
 }
 
@@ -1006,11 +1028,55 @@ int tfhe_b200_circuit_operand_rows(const tfhe_b200_circuit *c, int o) {
 }
 int tfhe_b200_circuit_output_rows(const tfhe_b200_circuit *c) { return c ? c->out_rows : 0; }
 
-// Runs the plan: operands[o] and d_out are DEVICE arrays of samples (rows of n+1 words).
-int tfhe_b200_circuit_run(tfhe_b200_circuit *c, int32_t *d_out, const int32_t *const *operands, void *stream) {
-    if (!c || !d_out || !operands) return fail_msg("null argument");
-    if (!c->ctx) return fail_msg("plan was built without an engine context (simulation only)");
-    if (ensure_device(c)) return 1;
+}  // extern "C"
+
+namespace {
+
+// one run of a GATES group as the engine's gate_op (rows of the plan's workspace, index tables)
+void fill_gate_op(const tfhe_b200_circuit *c, const Op &op, tfhe_b200_gate_op &o) {
+    o.gate = op.gate;
+    o.count = op.count;
+    o.a = o.b = c->d_ws;
+    o.out = c->d_ws;
+    o.stride_a = o.stride_b = o.stride_out = c->words;
+    o.idx_a = c->d_idx + op.off_a;
+    o.idx_b = c->d_idx + op.off_b;
+    o.idx_out = c->d_idx + op.off_out;
+    o.c = op.off_c >= 0 ? c->d_ws : nullptr;
+    o.stride_c = c->words;
+    o.idx_c = op.off_c >= 0 ? c->d_idx + op.off_c : nullptr;
+}
+
+int issue_mux_or_linear(tfhe_b200_circuit *c, const Level &lv, void *stream) {
+    const Op &op = lv.ops[0];
+    if (lv.type == LV_MUX)
+        return tfhe_b200_mux_gather(c->ctx, c->d_ws, c->words, c->d_idx + op.off_a, c->d_idx + op.off_b,
+                                    c->d_idx + op.off_c, c->d_idx + op.off_out, op.count, stream);
+    const int coef = op.gate == LIN_COPY ? 1 : (op.gate == LIN_NOT ? -1 : 0);
+    const int32_t cst = op.gate == LIN_ONE ? 0x20000000 : (op.gate == LIN_ZERO ? (int32_t) 0xE0000000 : 0);
+    return tfhe_b200_linear_gather(c->ctx, c->d_ws, c->words, c->d_idx + op.off_a, c->d_idx + op.off_out, coef, cst,
+                                   op.count, stream);
+}
+
+// every launch group of the plan, in order, on `stream` (scratch: the plan's own)
+int issue_levels(tfhe_b200_circuit *c, void *stream) {
+    tfhe_b200::engine_set_thread_scratch(c->d_u, c->u_bytes);
+    int rc = 0;
+    for (const Level &lv : c->levels) {
+        if (lv.type == LV_GATES) {
+            tfhe_b200_gate_op ops[4];
+            for (int i = 0; i < lv.nops; i++) fill_gate_op(c, lv.ops[i], ops[i]);
+            rc = tfhe_b200_gate_multi(c->ctx, ops, lv.nops, stream);
+        } else {
+            rc = issue_mux_or_linear(c, lv, stream);
+        }
+        if (rc) break;
+    }
+    tfhe_b200::engine_set_thread_scratch(nullptr, 0);
+    return rc;
+}
+
+int copy_operands_in(tfhe_b200_circuit *c, const int32_t *const *operands, void *stream) {
     cudaStream_t st = (cudaStream_t) stream;
     const size_t rb = (size_t) c->words * sizeof(int32_t);
     if (c->row_zero == -2) {
@@ -1022,42 +1088,126 @@ int tfhe_b200_circuit_run(tfhe_b200_circuit *c, int32_t *d_out, const int32_t *c
         if (cudaMemcpyAsync(c->d_ws + (size_t) c->in_row0[o] * c->words, operands[o], rb * c->in_rows[o],
                             cudaMemcpyDeviceToDevice, st) != cudaSuccess)
             return fail_msg("operand copy failed");
-    for (const Level &lv : c->levels) {
-        if (lv.type == LV_GATES) {
-            tfhe_b200_gate_op ops[4];
-            for (int i = 0; i < lv.nops; i++) {
-                const Op &op = lv.ops[i];
-                ops[i].gate = op.gate;
-                ops[i].count = op.count;
-                ops[i].a = ops[i].b = c->d_ws;
-                ops[i].out = c->d_ws;
-                ops[i].stride_a = ops[i].stride_b = ops[i].stride_out = c->words;
-                ops[i].idx_a = c->d_idx + op.off_a;
-                ops[i].idx_b = c->d_idx + op.off_b;
-                ops[i].idx_out = c->d_idx + op.off_out;
-                ops[i].c = op.off_c >= 0 ? c->d_ws : nullptr;
-                ops[i].stride_c = c->words;
-                ops[i].idx_c = op.off_c >= 0 ? c->d_idx + op.off_c : nullptr;
-            }
-            if (tfhe_b200_gate_multi(c->ctx, ops, lv.nops, stream)) return 1;
-        } else if (lv.type == LV_MUX) {
-            const Op &op = lv.ops[0];
-            if (tfhe_b200_mux_gather(c->ctx, c->d_ws, c->words, c->d_idx + op.off_a, c->d_idx + op.off_b,
-                                     c->d_idx + op.off_c, c->d_idx + op.off_out, op.count, stream))
-                return 1;
-        } else {
-            const Op &op = lv.ops[0];
-            const int coef = op.gate == LIN_COPY ? 1 : (op.gate == LIN_NOT ? -1 : 0);
-            const int32_t cst = op.gate == LIN_ONE ? 0x20000000 : (op.gate == LIN_ZERO ? (int32_t) 0xE0000000 : 0);
-            if (tfhe_b200_linear_gather(c->ctx, c->d_ws, c->words, c->d_idx + op.off_a, c->d_idx + op.off_out, coef,
-                                        cst, op.count, stream))
-                return 1;
-        }
-    }
-    if (cudaMemcpyAsync(d_out, c->d_ws + (size_t) c->out_row0 * c->words, rb * c->out_rows,
-                        cudaMemcpyDeviceToDevice, st) != cudaSuccess)
+    return 0;
+}
+
+int copy_result_out(tfhe_b200_circuit *c, int32_t *d_out, void *stream) {
+    const size_t rb = (size_t) c->words * sizeof(int32_t);
+    if (cudaMemcpyAsync(d_out, c->d_ws + (size_t) c->out_row0 * c->words, rb * c->out_rows, cudaMemcpyDeviceToDevice,
+                        (cudaStream_t) stream) != cudaSuccess)
         return fail_msg("result copy failed");
     return 0;
+}
+
+// Capture the launch sequence once (thread-local capture mode: other threads keep using the device).
+// A failed capture is not an error: the plan then launches its kernels directly, as before.
+void try_capture(tfhe_b200_circuit *c, cudaStream_t st) {
+    const unsigned long long l0 = tfhe_b200_launch_count(c->ctx);
+    if (cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
+        cudaGetLastError();
+        c->graph_failed = true;
+        return;
+    }
+    const int rc = issue_levels(c, st);
+    cudaGraph_t graph = nullptr;
+    const cudaError_t e = cudaStreamEndCapture(st, &graph);
+    const unsigned long long l1 = tfhe_b200_launch_count(c->ctx);
+    if (rc == 0 && e == cudaSuccess && graph != nullptr &&
+        cudaGraphInstantiate(&c->graph_exec, graph, nullptr, nullptr, 0) == cudaSuccess) {
+        c->graph_launches = l1 - l0;
+    } else {
+        cudaGetLastError();
+        c->graph_exec = nullptr;
+        c->graph_failed = true;
+    }
+    if (graph) cudaGraphDestroy(graph);
+    // the capture itself launched nothing: take its count back
+    tfhe_b200_count_launches(c->ctx, (unsigned long long) 0 - (l1 - l0));
+}
+
+}  // namespace
+
+extern "C" {
+
+int tfhe_b200_circuit_set_graph(tfhe_b200_circuit *c, int enable) {
+    if (!c) return 0;
+    const int prev = c->graph_enabled ? 1 : 0;
+    c->graph_enabled = enable != 0;
+    return prev;
+}
+
+int tfhe_b200_circuit_used_graph(const tfhe_b200_circuit *c) { return (c && c->used_graph) ? 1 : 0; }
+
+// Runs the plan: operands[o] and d_out are DEVICE arrays of samples (rows of n+1 words).
+int tfhe_b200_circuit_run(tfhe_b200_circuit *c, int32_t *d_out, const int32_t *const *operands, void *stream) {
+    if (!c || !d_out || !operands) return fail_msg("null argument");
+    if (!c->ctx) return fail_msg("plan was built without an engine context (simulation only)");
+    if (ensure_device(c)) return 1;
+    cudaStream_t st = (cudaStream_t) stream;
+    if (cudaSetDevice(tfhe_b200_ctx_device(c->ctx)) != cudaSuccess) return fail_msg("cudaSetDevice failed");
+    if (copy_operands_in(c, operands, stream)) return 1;
+    c->used_graph = false;
+    // the legacy default stream cannot be captured; plans of fewer than three groups gain nothing
+    if (c->graph_enabled && !c->graph_failed && st != nullptr && c->graph_exec == nullptr && c->levels.size() >= 3)
+        try_capture(c, st);
+    if (c->graph_enabled && c->graph_exec != nullptr && st != nullptr) {
+        if (cudaGraphLaunch(c->graph_exec, st) != cudaSuccess) return fail_msg("graph launch failed");
+        tfhe_b200_count_launches(c->ctx, c->graph_launches);
+        c->used_graph = true;
+    } else if (issue_levels(c, stream)) {
+        return 1;
+    }
+    return copy_result_out(c, d_out, stream);
+}
+
+// K independent plans, zipped group by group: the GATES groups at the same position of all plans share
+// launches (up to TFHE_B200_MAX_RUNS runs each); MUX and LINEAR groups are issued per plan.
+int tfhe_b200_circuit_run_many(tfhe_b200_circuit *const *plans, int nplans, int32_t *const *d_outs,
+                               const int32_t *const *const *operands, void *stream) {
+    if (!plans || !d_outs || !operands || nplans < 1) return fail_msg("null argument");
+    tfhe_b200_ctx *ctx = plans[0] ? plans[0]->ctx : nullptr;
+    if (!ctx) return fail_msg("plan was built without an engine context (simulation only)");
+    size_t longest = 0, u_need = 0;
+    for (int p = 0; p < nplans; p++) {
+        tfhe_b200_circuit *c = plans[p];
+        if (!c || c->ctx != ctx) return fail_msg("all plans of a merged run must belong to one context");
+        for (int q = 0; q < p; q++)
+            if (plans[q] == c) return fail_msg("a plan may appear only once in a merged run (it has one workspace)");
+        if (ensure_device(c)) return 1;
+        if (c->levels.size() > longest) longest = c->levels.size();
+    }
+    if (cudaSetDevice(tfhe_b200_ctx_device(ctx)) != cudaSuccess) return fail_msg("cudaSetDevice failed");
+    // scratch of a merged launch: the sum of the plans' widest levels bounds every merged level
+    for (int p = 0; p < nplans; p++) u_need += plans[p]->u_bytes;
+    int32_t *d_u = nullptr;
+    if (cudaMallocAsync(&d_u, u_need, (cudaStream_t) stream) != cudaSuccess) return fail_msg("scratch allocation failed");
+    int rc = 0;
+    for (int p = 0; p < nplans && !rc; p++) rc = copy_operands_in(plans[p], operands[p], stream);
+    tfhe_b200::engine_set_thread_scratch(d_u, u_need);
+    for (size_t pos = 0; pos < longest && !rc; pos++) {
+        tfhe_b200_gate_op ops[TFHE_B200_MAX_RUNS];
+        int nops = 0;
+        for (int p = 0; p < nplans && !rc; p++) {
+            tfhe_b200_circuit *c = plans[p];
+            if (pos >= c->levels.size()) continue;
+            const Level &lv = c->levels[pos];
+            if (lv.type != LV_GATES) continue;
+            if (nops + lv.nops > TFHE_B200_MAX_RUNS) {
+                rc = tfhe_b200_gate_multi(ctx, ops, nops, stream);
+                nops = 0;
+            }
+            for (int i = 0; i < lv.nops; i++) fill_gate_op(c, lv.ops[i], ops[nops++]);
+        }
+        if (!rc && nops) rc = tfhe_b200_gate_multi(ctx, ops, nops, stream);
+        for (int p = 0; p < nplans && !rc; p++) {
+            tfhe_b200_circuit *c = plans[p];
+            if (pos < c->levels.size() && c->levels[pos].type != LV_GATES) rc = issue_mux_or_linear(c, c->levels[pos], stream);
+        }
+    }
+    tfhe_b200::engine_set_thread_scratch(nullptr, 0);
+    for (int p = 0; p < nplans && !rc; p++) rc = copy_result_out(plans[p], d_outs[p], stream);
+    cudaFreeAsync(d_u, (cudaStream_t) stream);
+    return rc;
 }
 
 // Evaluates the plan on PLAINTEXT bits on the host (one int per sample row), group by group

@@ -37,6 +37,8 @@ struct tfhe_b200_ctx {
 namespace {
 
 thread_local char g_err[512] = "";
+thread_local int32_t *tl_scratch_u = nullptr;   // engine_set_thread_scratch
+thread_local size_t tl_scratch_bytes = 0;
 
 int fail(const char *fmt, ...) {
     va_list ap;
@@ -130,10 +132,15 @@ int run_bootstrap_ks(tfhe_b200_ctx *c, BrLaunch &L, int nsrc, int32_t ks_cst, in
     CU(cudaSetDevice(c->device));
     int32_t *d_u = nullptr;
     const size_t ubytes = (size_t) L.total * (kN + 1) * sizeof(int32_t);
-    CU(cudaMallocAsync(&d_u, ubytes, st));
+    const bool own_scratch = !(tl_scratch_u != nullptr && tl_scratch_bytes >= ubytes);
+    if (own_scratch) CU(cudaMallocAsync(&d_u, ubytes, st));
+    else d_u = tl_scratch_u;
     L.u_out = d_u;
     cudaEvent_t e0 = nullptr, e1 = nullptr, e2 = nullptr;
-    if (c->timing) {
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    if (st != nullptr) CU(cudaStreamIsCapturing(st, &cap));
+    const bool timing = c->timing && cap == cudaStreamCaptureStatusNone;  // no timing events inside a graph
+    if (timing) {
         CU(cudaEventCreate(&e0));
         CU(cudaEventCreate(&e1));
         CU(cudaEventCreate(&e2));
@@ -141,7 +148,7 @@ int run_bootstrap_ks(tfhe_b200_ctx *c, BrLaunch &L, int nsrc, int32_t ks_cst, in
     }
     CU(launch_blind_rotate(L, c->sm_count, st));
     c->launches += 1;
-    if (c->timing) CU(cudaEventRecord(e1, st));
+    if (timing) CU(cudaEventRecord(e1, st));
     KsLaunch K;
     memset(&K, 0, sizeof(K));
     K.ks = c->d_ks;
@@ -164,17 +171,24 @@ int run_bootstrap_ks(tfhe_b200_ctx *c, BrLaunch &L, int nsrc, int32_t ks_cst, in
     K.t = c->p.ks_t;
     K.basebit = c->p.ks_basebit;
     if (run_keyswitch(c, K, st)) return 1;
-    if (c->timing) {
+    if (timing) {
         CU(cudaEventRecord(e2, st));
         c->ev.push_back(e0);
         c->ev.push_back(e1);
         c->ev.push_back(e2);
     }
-    CU(cudaFreeAsync(d_u, st));
+    if (own_scratch) CU(cudaFreeAsync(d_u, st));
     return 0;
 }
 
 }  // namespace
+
+namespace tfhe_b200 {
+void engine_set_thread_scratch(int32_t *d_u, size_t bytes) {
+    tl_scratch_u = d_u;
+    tl_scratch_bytes = d_u ? bytes : 0;
+}
+}  // namespace tfhe_b200
 
 extern "C" {
 
@@ -299,6 +313,9 @@ int tfhe_b200_ctx_words(const tfhe_b200_ctx *c) { return c ? c->p.n + 1 : 0; }
 size_t tfhe_b200_key_bytes(const tfhe_b200_ctx *c) { return c ? c->bk_bytes + c->ks_bytes : 0; }
 unsigned long long tfhe_b200_launch_count(const tfhe_b200_ctx *c) { return c ? c->launches.load() : 0; }
 int tfhe_b200_sm_count(const tfhe_b200_ctx *c) { return c ? c->sm_count : 0; }
+void tfhe_b200_count_launches(tfhe_b200_ctx *c, unsigned long long n) {
+    if (c) c->launches += n;
+}
 int tfhe_b200_ctx_device(const tfhe_b200_ctx *c) { return c ? c->device : -1; }
 
 int tfhe_b200_load_keys_device(tfhe_b200_ctx *c, const int32_t *d_bk_coef, const int32_t *d_ks, void *stream) {

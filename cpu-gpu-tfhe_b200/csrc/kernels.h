@@ -29,7 +29,7 @@ struct BrSegment {
     int count;
 };
 
-constexpr int kMaxSegments = 4;
+constexpr int kMaxSegments = 16;  // runs of one bootstrap batch (tfhe_b200_gate_multi, merged circuit levels)
 
 struct BrLaunch {
     BrSegment seg[kMaxSegments];
@@ -99,6 +99,11 @@ size_t ks_mma_table_bytes();
 bool ks_mma_supported(int N, int t, int basebit, int n);
 cudaError_t launch_ks_mma_relayout(const int32_t *src, uint8_t *dst, int base, int n, cudaStream_t stream);
 cudaError_t launch_keyswitch_mma(const KsLaunch &L, const uint8_t *tbl, cudaStream_t stream);
+
+// Scratch for the extracted samples of the calling thread's NEXT bootstrap launches (engine.cu
+// run_bootstrap_ks): circuit plans own their scratch so that a captured CUDA graph holds no
+// allocation nodes.  nullptr restores the stream-ordered allocator.
+void engine_set_thread_scratch(int32_t *d_u, size_t bytes);
 
 cudaError_t launch_lwe_linear_idx(int32_t *out, const int32_t *in, long long stride, const int32_t *idx_out,
                                   const int32_t *idx_in, int c0, int32_t cst, int count, int n, cudaStream_t stream);

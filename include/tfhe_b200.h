@@ -115,7 +115,8 @@ typedef struct {
     int64_t stride_c;
     const int32_t *idx_c;
 } tfhe_b200_gate_op;
-/* Up to 4 runs in ONE bootstrap batch (one blind-rotate launch + one key-switch launch). */
+/* Up to TFHE_B200_MAX_RUNS runs in ONE bootstrap batch (one blind-rotate launch + one key-switch launch). */
+#define TFHE_B200_MAX_RUNS 16
 int tfhe_b200_gate_multi(tfhe_b200_ctx *ctx, const tfhe_b200_gate_op *ops, int nops, void *stream);
 /* MUX(a,b,c) = a ? b : c  (bootsMUX, boot-gates.cu:407-448; bootsMUX_fullGPU_n_Bit :2987) */
 int tfhe_b200_mux(tfhe_b200_ctx *ctx, int32_t *d_out, const int32_t *d_a, const int32_t *d_b,
@@ -212,6 +213,20 @@ int tfhe_b200_circuit_operand_rows(const tfhe_b200_circuit *c, int operand);
 int tfhe_b200_circuit_output_rows(const tfhe_b200_circuit *c);
 /* operands[o]: device array of tfhe_b200_circuit_operand_rows(c, o) samples */
 int tfhe_b200_circuit_run(tfhe_b200_circuit *c, int32_t *d_out, const int32_t *const *operands, void *stream);
+/* The launch sequence of a plan (all its levels) is captured into a CUDA graph at the first run on a
+ * non-default stream and replayed afterwards (one graph launch instead of two kernel launches per
+ * level).  enable = 0 switches the plan back to direct launches.  Returns the previous setting. */
+int tfhe_b200_circuit_set_graph(tfhe_b200_circuit *c, int enable);
+/* 1 if the last run of the plan replayed a captured graph */
+int tfhe_b200_circuit_used_graph(const tfhe_b200_circuit *c);
+/* K INDEPENDENT plans of one context run together, level by level: the gate runs of level j of all
+ * plans share ONE blind-rotate + ONE key-switch launch (up to TFHE_B200_MAX_RUNS runs per launch), so
+ * K narrow circuits cost about as much as one (a level of a lone 16-bit adder occupies a dozen SMs for
+ * a full bootstrap latency).  The reference's counterpart is the vLength dimension of its vector
+ * circuits (taskLevelParallelAdd_bitwise_vector_coalInput, main.cu:1138-1302), which only batches
+ * copies of the SAME circuit.  operands[p][o]: operand o of plan p; d_outs[p]: its result rows. */
+int tfhe_b200_circuit_run_many(tfhe_b200_circuit *const *plans, int nplans, int32_t *const *d_outs,
+                               const int32_t *const *const *operands, void *stream);
 /* Host-only check of a plan on PLAINTEXT bits (one int per sample row); needs no GPU and accepts
  * plans built with ctx == NULL.  This is schedule verification, not a compute path. */
 int tfhe_b200_circuit_simulate(const tfhe_b200_circuit *c, int32_t *out_bits, const int32_t *const *operand_bits);
@@ -298,6 +313,8 @@ int tfhe_b200_phases(const int32_t *key, int n, const int32_t *samples, int coun
 /* ---- introspection (tests, bench) ---------------------------------------- */
 /* kernels launched by this context so far (each = one launch of one of this library's kernels) */
 unsigned long long tfhe_b200_launch_count(const tfhe_b200_ctx *ctx);
+/* adds n to the counter (circuit plans replaying a captured CUDA graph account their launches here) */
+void tfhe_b200_count_launches(tfhe_b200_ctx *ctx, unsigned long long n);
 int tfhe_b200_sm_count(const tfhe_b200_ctx *ctx);
 /* per-kernel device time (CUDA events on the launching stream) of the gate calls issued while
  * timing is enabled: total blind-rotate ms, total key-switch ms, number of gate calls */

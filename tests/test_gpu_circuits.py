@@ -195,3 +195,67 @@ def test_cannon_matrix_multiply_3x3(pkg, sk_engine):
     out = circ.run(enc_ints(pkg, eng, sk, A.reshape(-1) & 0xFF, nbits, 43),
                    enc_ints(pkg, eng, sk, Bm.reshape(-1) & 0xFF, nbits, 44))
     assert np.array_equal(dec_ints(pkg, sk, out, nbits).reshape(n, n), (A @ Bm) & 0xFF)
+
+
+def test_plan_replays_a_cuda_graph_with_identical_results(pkg, sk_engine):
+    """The launch sequence of a plan is captured into a CUDA graph at the first run on a non-default
+    stream and replayed afterwards: same ciphertext words as direct launches (the kernels are
+    deterministic), launch accounting intact."""
+    import torch
+
+    sk, eng = sk_engine
+    nbits = 16
+    a, b = np.array([12345, 7]), np.array([(-6789) & 0xFFFF, 65530])
+    ea, eb = enc_ints(pkg, eng, sk, a, nbits, 51), enc_ints(pkg, eng, sk, b, nbits, 52)
+    circ = pkg.Circuit(eng, "add", nbits, len(a), 2)
+    st = torch.cuda.Stream()
+    with torch.cuda.stream(st):
+        circ.set_graph(False)
+        l0 = eng.launch_count
+        direct = circ.run(ea, eb).clone()
+        per_run = eng.launch_count - l0
+        assert not circ.used_graph
+        circ.set_graph(True)
+        first = circ.run(ea, eb).clone()     # captures, then replays
+        assert circ.used_graph
+        l1 = eng.launch_count
+        again = circ.run(ea, eb).clone()
+        assert circ.used_graph and eng.launch_count - l1 == per_run
+    st.synchronize()
+    assert torch.equal(direct, first) and torch.equal(direct, again)
+    assert np.array_equal(dec_ints(pkg, sk, again, nbits), (a + b) & 0xFFFF)
+    # on the legacy default stream (not capturable) the plan launches directly
+    out = circ.run(ea, eb)
+    assert not circ.used_graph and torch.equal(out, direct)
+
+
+def test_independent_plans_merged_level_by_level(pkg, sk_engine):
+    """tfhe_b200_circuit_run_many: a 16-bit prefix adder, an 8-bit ripple adder, a comparison and a
+    multiplier run TOGETHER, their levels sharing launches; same words as running them one by one,
+    with far fewer launches."""
+    import torch
+
+    sk, eng = sk_engine
+    specs = [("add", (16, 2, 2), [np.array([1234, 65535]), np.array([4321, 1])], 16, lambda x, y: (x + y) & 0xFFFF),
+             ("add", (8, 3, 0), [np.array([200, 17, 0]), np.array([100, 3, 255])], 8, lambda x, y: (x + y) & 0xFF),
+             ("sub", (12, 1, 1), [np.array([100]), np.array([3000])], 12, lambda x, y: (x - y) & 0xFFF),
+             ("mul_ex", (6, 2, 1), [np.array([13, 63]), np.array([5, 63])], 6, lambda x, y: (x * y) & 0x3F)]
+    plans, operands = [], []
+    for i, (kind, args, vals, nbits, _) in enumerate(specs):
+        plans.append(pkg.Circuit(eng, kind, *args))
+        operands.append([enc_ints(pkg, eng, sk, v, nbits, 60 + 2 * i + j) for j, v in enumerate(vals)])
+    for p in plans:
+        p.set_graph(False)
+    l0 = eng.launch_count
+    single = [p.run(*ops).clone() for p, ops in zip(plans, operands)]
+    l1 = eng.launch_count
+    merged = pkg.Circuit.run_many(plans, operands)
+    l2 = eng.launch_count
+    torch.cuda.synchronize()
+    for (kind, args, vals, nbits, f), s, m in zip(specs, single, merged):
+        assert torch.equal(s, m), kind
+        assert np.array_equal(dec_ints(pkg, sk, m, nbits), f(*vals)), kind
+    assert (l2 - l1) < 0.6 * (l1 - l0), (l1 - l0, l2 - l1)
+    # the same plan twice in one merged run is refused (one workspace per plan)
+    with pytest.raises(pkg.EngineError):
+        pkg.Circuit.run_many([plans[0], plans[0]], [operands[0], operands[0]])
