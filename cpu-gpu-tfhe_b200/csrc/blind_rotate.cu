@@ -58,6 +58,11 @@ constexpr int kStages = 2 * (int) kRingStages;
 #ifndef TFHE_B200_BR_MAC_TAIL
 #define TFHE_B200_BR_MAC_TAIL 6
 #endif
+// Stage release ordered by the PTX memory model (data-dependent release atomic + acquire fence at the
+// refill) instead of by the in-order shared-memory pipe alone; see mac_consume.
+#ifndef TFHE_B200_RING_STRICT
+#define TFHE_B200_RING_STRICT 1
+#endif
 
 struct __align__(128) CtaSmem {
     WarpSmem w[kCtWarps];
@@ -218,6 +223,9 @@ __device__ __forceinline__ void ring_refill_if_last(CtaSmem &S, const BrLaunch &
             fsub -= kChunksPerIter;
             if (++fit >= (uint32_t) L.n_iter) fit = 0;
         }
+#if TFHE_B200_RING_STRICT
+        asm volatile("fence.acq_rel.cta;" ::: "memory");  // acquire: the other consumers' releases
+#endif
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         ring_fill_at(S, L, role, fit, fsub, st);
     }
@@ -237,13 +245,22 @@ __device__ __forceinline__ void ring_skip(CtaSmem &S, const BrLaunch &L, int rol
     mbar_wait(&S.full[st], sp.rp.phase);
     __syncwarp();
     if (lane == 0) {
+#if TFHE_B200_RING_STRICT
+        unsigned int seen;
+        asm volatile("atom.release.cta.shared.add.u32 %0, [%1], 1;" : "=r"(seen) : "r"(smem_u32(&S.drained[st])) : "memory");
+#else
         const unsigned int seen = atomicAdd(&S.drained[st], 1u);
+#endif
         if (!HELPER) {
             ring_refill_if_last(S, L, role, sp, st, seen, ring_chunks);
         } else if (designated) {
             const unsigned int target = seen - (seen % kCtWarps) + kCtWarps;  // all four releases of this chunk
-            volatile unsigned int *cnt = &S.drained[st];
-            while ((int) (*cnt - target) < 0) __nanosleep(40);
+            auto poll = [&]() {
+                unsigned int v;
+                asm volatile("ld.acquire.cta.shared.u32 %0, [%1];" : "=r"(v) : "r"(smem_u32(&S.drained[st])) : "memory");
+                return v;
+            };
+            while ((int) (poll() - target) < 0) __nanosleep(40);
             ring_refill_if_last(S, L, role, sp, st, (unsigned int) (kCtWarps - 1), ring_chunks);
         }
     }
@@ -321,6 +338,23 @@ __device__ __forceinline__ void mac_consume(CtaSmem &S, const BrLaunch &L, int r
 #pragma unroll
     for (int p = 0; p < kTail; p++) w[p] = part[(kHead + p) * 32 + lane];
     unsigned int seen = 0;
+#if TFHE_B200_RING_STRICT
+    // Release with a true dependency on the LAST value loaded from the stage (`dep` is always 0, but
+    // the hardware cannot issue the atomic before that load has returned; the loads of one warp return
+    // in order) and with release semantics, paired with the acquire fence in front of the refill: the
+    // write-after-read order "all reads of the stage, then the TMA refill" holds in the PTX memory
+    // model, not only through the in-order shared-memory pipe.
+    const unsigned int dep = (unsigned int) (__double2hiint(w[kTail - 1].y) & 0);
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.eq.u32 p, %2, 0;\n"
+        "@p atom.release.cta.shared.add.u32 %0, [%1], %3;\n"
+        "}\n"
+        : "+r"(seen)
+        : "r"(smem_u32(&S.drained[st])), "r"(lane), "r"(1u + dep)
+        : "memory");
+#else
     asm volatile(
         "{\n"
         ".reg .pred p;\n"
@@ -330,6 +364,7 @@ __device__ __forceinline__ void mac_consume(CtaSmem &S, const BrLaunch &L, int r
         : "+r"(seen)
         : "r"(smem_u32(&S.drained[st])), "r"(lane)
         : "memory");
+#endif
 #pragma unroll
     for (int p = 0; p < kTail; p++) cmac(acc[kHead + p], z[kHead + p], w[p]);
     // (one condition, written out here rather than through ring_refill_if_last: the compiler
@@ -340,6 +375,9 @@ __device__ __forceinline__ void mac_consume(CtaSmem &S, const BrLaunch &L, int r
             fsub -= kChunksPerIter;
             if (++fit >= (uint32_t) L.n_iter) fit = 0;
         }
+#if TFHE_B200_RING_STRICT
+        asm volatile("fence.acq_rel.cta;" ::: "memory");  // acquire: the other consumers' releases
+#endif
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         ring_fill_at(S, L, role, fit, fsub, st);
     }

@@ -6,24 +6,17 @@
 // 2000 TLWE encryptions of the bootstrapping key.
 #include <cmath>
 #include <cstring>
-#include <random>
 #include <thread>
 #include <vector>
 
 #include "../../include/tfhe_b200.h"
+#include "csprng.h"
 
 namespace {
 
-struct Rng {
-    std::mt19937_64 gen;
-    explicit Rng(uint64_t seed) : gen(seed) {}
-    int32_t torus() { return (int32_t) (gen() >> 32); }
-    int bit() { return (int) (gen() >> 63); }
-    double gauss(double sigma) {
-        std::normal_distribution<double> d(0., sigma);
-        return d(gen);
-    }
-};
+// All randomness is ChaCha20 keystream (csprng.h): the key comes from the operating system unless the
+// caller passes a non-zero seed (reproducible TEST material, not secure).
+using Rng = tfhe_b200::ChaChaRng;
 
 // dtot32, numeric-functions.cu:33-35
 int32_t dtot32(double d) { return (int32_t) (int64_t) ((d - (double) (int64_t) d) * 4294967296.); }
@@ -61,7 +54,9 @@ int tfhe_b200_keygen(const tfhe_b200_params *p, uint64_t seed, double alpha_lwe,
     if (!p || !lwe_key || !tlwe_key || !bk || !ks) return 1;
     const int n = p->n, N = p->N, k = p->k, l = p->l, kpl = (k + 1) * l;
     const int t = p->ks_t, basebit = p->ks_basebit, base = 1 << basebit;
-    Rng rng(seed);
+    tfhe_b200::ChaChaKey ckey;
+    if (!tfhe_b200::chacha_key_from_seed(seed, &ckey)) return 1;  // seed 0: getrandom(); else test key
+    Rng rng(ckey, 0);
     // lweKeyGen lwe-functions.cu:21-27 ; tLweKeyGen tlwe-functions.cu:15-23
     for (int i = 0; i < n; i++) lwe_key[i] = rng.bit();
     for (int i = 0; i < k * N; i++) tlwe_key[i] = rng.bit();
@@ -101,11 +96,9 @@ int tfhe_b200_keygen(const tfhe_b200_params *p, uint64_t seed, double alpha_lwe,
     {
         const unsigned hw = std::thread::hardware_concurrency();
         const int nthreads = (int) (hw ? (hw > 16 ? 16 : hw) : 4);
-        std::vector<uint64_t> seeds(n);
-        for (auto &s : seeds) s = rng.gen();
         auto work = [&](int tid) {
             for (int i = tid; i < n; i += nthreads) {
-                Rng r(seeds[i]);
+                Rng r(ckey, 1 + (uint64_t) i);  // one keystream per TGSW sample
                 for (int row_i = 0; row_i < kpl; row_i++) {
                     uint32_t *row = (uint32_t *) bk + ((size_t) i * kpl + row_i) * (k + 1) * N;
                     uint32_t *b = row + (size_t) k * N;
@@ -135,7 +128,9 @@ int tfhe_b200_encrypt_bits(const tfhe_b200_params *p, const int32_t *lwe_key, ui
                            const int32_t *bits, int count, int32_t *out) {
     if (!p || !lwe_key || !out || count < 0) return 1;
     const int n = p->n;
-    Rng rng(seed);
+    tfhe_b200::ChaChaKey ckey;
+    if (!tfhe_b200::chacha_key_from_seed(seed, &ckey)) return 1;  // seed 0: getrandom(); else test key
+    Rng rng(ckey, 0x656e63ull);
     for (int g = 0; g < count; g++) {
         int32_t *s = out + (size_t) g * (n + 1);
         uint32_t b = (uint32_t) ((bits && bits[g]) ? 0x20000000 : -0x20000000) + (uint32_t) dtot32(rng.gauss(alpha));

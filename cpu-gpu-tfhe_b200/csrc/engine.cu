@@ -219,8 +219,11 @@ int tfhe_b200_ctx_create(tfhe_b200_ctx **out, const tfhe_b200_params *p, int dev
     if (p->N != kN || p->k != kK || p->l != kL || p->Bgbit != kBgbit)
         return fail("unsupported TGSW parameters (N=%d k=%d l=%d Bgbit=%d): this build instantiates "
                     "N=1024 k=1 l=2 Bgbit=10", p->N, p->k, p->l, p->Bgbit);
-    if (p->ks_basebit != 2 || p->ks_t < 1 || p->ks_t > 15 || p->n < 1 || p->n > 511)
-        return fail("unsupported LWE / key-switch parameters (n=%d t=%d basebit=%d)", p->n, p->ks_t, p->ks_basebit);
+    // ks_t <= 8: the SIMT key switch holds N * t digit words per tile in shared memory (64 KiB opt-in at
+    // t = 8) and the tensor-core key switch is built for t = 8
+    if (p->ks_basebit != 2 || p->ks_t < 1 || p->ks_t > 8 || p->n < 1 || p->n > 511)
+        return fail("unsupported LWE / key-switch parameters (n=%d t=%d basebit=%d): this build supports "
+                    "basebit=2, 1<=t<=8, 1<=n<=511", p->n, p->ks_t, p->ks_basebit);
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
     if (e != cudaSuccess || ndev == 0)
@@ -229,7 +232,8 @@ int tfhe_b200_ctx_create(tfhe_b200_ctx **out, const tfhe_b200_params *p, int dev
     CU(cudaSetDevice(device));
     cudaDeviceProp prop;
     CU(cudaGetDeviceProperties(&prop, device));
-    if (prop.major < 9) return fail("device %d is sm_%d%d; sm_100a required", device, prop.major, prop.minor);
+    // the library contains sm_100a code only (tcgen05 / TMA paths are not forward compatible)
+    if (prop.major != 10) return fail("device %d is sm_%d%d; this library is built for sm_100a (B200) only", device, prop.major, prop.minor);
     if ((size_t) prop.sharedMemPerBlockOptin < blind_rotate_smem_bytes())
         return fail("device offers %zu B of shared memory per block, kernel needs %zu",
                     (size_t) prop.sharedMemPerBlockOptin, blind_rotate_smem_bytes());

@@ -6,22 +6,24 @@
 // mask polynomial, a negacyclic product with the binary key, Gaussian noise) and the 24576
 // samples of the key-switch key (lweCreateKeySwitchKey, lwe-keyswitch-functions.cu:890-942).
 // Both are embarrassingly parallel: one CTA per TLWE row / per key-switch sample, counter-based
-// random numbers (Philox4x32-10 from the CUDA toolkit's header-only device API, one stream per
-// row).  The tiny parts stay on the host: the secret bits and the re-centred key-switch noise
+// random numbers: ChaCha20 keystream blocks (csprng.h), one stream per thread, the 256-bit key from
+// the operating system (or from the caller's non-zero TEST seed).  The tiny parts stay on the host: the secret bits and the re-centred key-switch noise
 // (the reference subtracts the mean of all its noise terms, :905-912).
 // The flat keys are produced directly in device memory and handed to
 // tfhe_b200_load_keys_device (Fourier conversion + table re-layouts), so a context can be keyed
 // without the 82 MB host round trip; they can also be downloaded (to be saved with keyio.cu).
 #include <cuda_runtime.h>
-#include <curand_kernel.h>
 
 #include <cmath>
 #include <cstdio>
 #include <cstring>
-#include <random>
 #include <vector>
 
 #include "../../include/tfhe_b200.h"
+#include "csprng.h"
+
+using tfhe_b200::ChaChaKey;
+using tfhe_b200::ChaChaStream;
 
 namespace {
 
@@ -34,22 +36,29 @@ __device__ __forceinline__ int32_t dtot32_dev(double d) {
 // bk[(i*kpl + r)][k+1][N]:  a_m uniform, b = sum_m a_m (*) key_m + e, then + s_i * H on the diagonal rows.
 __global__ void __launch_bounds__(256) bk_gen_kernel(int32_t *__restrict__ bk, const int32_t *__restrict__ lwe_key,
                                                      const int32_t *__restrict__ tlwe_key, int N, int k, int l,
-                                                     int Bgbit, double alpha, unsigned long long seed) {
+                                                     int Bgbit, double alpha, const ChaChaKey ckey) {
     extern __shared__ uint32_t sh[];  // a[N] then key bits[N]
     uint32_t *a = sh, *key = sh + N;
     const int kpl = (k + 1) * l;
     const int row = blockIdx.x, i = row / kpl, r = row % kpl;
     uint32_t *dst = reinterpret_cast<uint32_t *>(bk) + (size_t) row * (k + 1) * N;
-    curandStatePhilox4_32_10_t st;
-    curand_init(seed, (unsigned long long) row * blockDim.x + threadIdx.x, 0, &st);
+    ChaChaStream st(ckey, 0x100000000ull + (unsigned long long) row * blockDim.x + threadIdx.x);
     const int per = N / blockDim.x;  // coefficients per thread (4 for N = 1024)
     uint32_t b[8];
-    for (int c = 0; c < per; c++) b[c] = (uint32_t) dtot32_dev(curand_normal_double(&st) * alpha);
+    for (int c = 0; c < per; c += 2) {  // Box-Muller: two normals from two 53-bit uniforms
+        const uint32_t w0 = st.word(), w1 = st.word(), w2 = st.word(), w3 = st.word();
+        const double u1 = tfhe_b200::chacha_unit(w0, w1), u2 = tfhe_b200::chacha_unit(w2, w3);
+        const double r = sqrt(-2.0 * log(u1));
+        double sn, cs;
+        sincospi(2.0 * u2, &sn, &cs);
+        b[c] = (uint32_t) dtot32_dev(r * cs * alpha);
+        if (c + 1 < per) b[c + 1] = (uint32_t) dtot32_dev(r * sn * alpha);
+    }
     for (int m = 0; m < k; m++) {
         __syncthreads();
         for (int c = 0; c < per; c++) {
             const int j = threadIdx.x + c * blockDim.x;
-            const uint32_t v = curand(&st);
+            const uint32_t v = st.word();
             a[j] = v;
             key[j] = (uint32_t) tlwe_key[(size_t) m * N + j];
             dst[(size_t) m * N + j] = v;
@@ -77,7 +86,7 @@ __global__ void __launch_bounds__(256) bk_gen_kernel(int32_t *__restrict__ bk, c
 __global__ void __launch_bounds__(128) ks_gen_kernel(int32_t *__restrict__ ks, const int32_t *__restrict__ lwe_key,
                                                      const int32_t *__restrict__ tlwe_key,
                                                      const int32_t *__restrict__ noise, int n, int t, int basebit,
-                                                     unsigned long long seed) {
+                                                     const ChaChaKey ckey) {
     __shared__ uint32_t red[128];
     const int base = 1 << basebit;
     const int sample = blockIdx.x, h = sample % base, ij = sample / base, j = ij % t, i = ij / t;
@@ -86,11 +95,10 @@ __global__ void __launch_bounds__(128) ks_gen_kernel(int32_t *__restrict__ ks, c
         for (int c = threadIdx.x; c <= n; c += blockDim.x) row[c] = 0;
         return;
     }
-    curandStatePhilox4_32_10_t st;
-    curand_init(seed, (unsigned long long) sample * blockDim.x + threadIdx.x, 0, &st);
+    ChaChaStream st(ckey, 0x200000000ull + (unsigned long long) sample * blockDim.x + threadIdx.x);
     uint32_t dot = 0;
     for (int c = threadIdx.x; c < n; c += blockDim.x) {
-        const uint32_t v = curand(&st);
+        const uint32_t v = st.word();
         row[c] = (int32_t) v;
         dot += v * (uint32_t) lwe_key[c];
     }
@@ -133,16 +141,17 @@ int tfhe_b200_keygen_device(tfhe_b200_ctx *ctx, const tfhe_b200_params *p, uint6
     const int n = p->n, N = p->N, k = p->k, l = p->l, kpl = (k + 1) * l, t = p->ks_t, base = 1 << p->ks_basebit;
     if (N % 256 != 0 || N / 256 > 8) return kg_fail("unsupported ring degree");
     if (cudaSetDevice(tfhe_b200_ctx_device(ctx)) != cudaSuccess) return kg_fail("no CUDA device");
-    std::mt19937_64 gen(seed);
-    for (int i = 0; i < n; i++) lwe_key[i] = (int32_t) (gen() >> 63);
-    for (int i = 0; i < k * N; i++) tlwe_key[i] = (int32_t) (gen() >> 63);
+    ChaChaKey ckey;
+    if (!tfhe_b200::chacha_key_from_seed(seed, &ckey)) return kg_fail("getrandom failed");  // seed 0: OS entropy
+    tfhe_b200::ChaChaRng gen(ckey, 0);
+    for (int i = 0; i < n; i++) lwe_key[i] = (int32_t) gen.bit();
+    for (int i = 0; i < k * N; i++) tlwe_key[i] = (int32_t) gen.bit();
     // key-switch noise, re-centred on its mean (lwe-keyswitch-functions.cu:905-912)
     const size_t nnoise = (size_t) N * k * t * (base - 1);
     std::vector<double> noise(nnoise);
-    std::normal_distribution<double> dist(0., alpha_lwe);
     double mean = 0;
     for (auto &v : noise) {
-        v = dist(gen);
+        v = gen.gauss(alpha_lwe);
         mean += v;
     }
     mean /= (double) nnoise;
@@ -151,7 +160,6 @@ int tfhe_b200_keygen_device(tfhe_b200_ctx *ctx, const tfhe_b200_params *p, uint6
         const double d = noise[i] - mean;
         noise32[i] = (int32_t) (int64_t) ((d - (double) (int64_t) d) * 4294967296.);
     }
-    const unsigned long long seed_bk = gen(), seed_ks = gen();
 
     int32_t *d_bk = nullptr, *d_ks = nullptr, *d_lwe = nullptr, *d_tlwe = nullptr, *d_noise = nullptr;
     const size_t bkb = tfhe_b200_bk_words(p) * sizeof(int32_t), ksb = tfhe_b200_ks_words(p) * sizeof(int32_t);
@@ -163,9 +171,9 @@ int tfhe_b200_keygen_device(tfhe_b200_ctx *ctx, const tfhe_b200_params *p, uint6
     KG(cudaMemcpy(d_lwe, lwe_key, sizeof(int32_t) * n, cudaMemcpyHostToDevice));
     KG(cudaMemcpy(d_tlwe, tlwe_key, sizeof(int32_t) * k * N, cudaMemcpyHostToDevice));
     KG(cudaMemcpy(d_noise, noise32.data(), sizeof(int32_t) * nnoise, cudaMemcpyHostToDevice));
-    bk_gen_kernel<<<n * kpl, 256, 2 * N * sizeof(uint32_t)>>>(d_bk, d_lwe, d_tlwe, N, k, l, p->Bgbit, alpha_bk, seed_bk);
+    bk_gen_kernel<<<n * kpl, 256, 2 * N * sizeof(uint32_t)>>>(d_bk, d_lwe, d_tlwe, N, k, l, p->Bgbit, alpha_bk, ckey);
     KG(cudaGetLastError());
-    ks_gen_kernel<<<N * k * t * base, 128>>>(d_ks, d_lwe, d_tlwe, d_noise, n, t, p->ks_basebit, seed_ks);
+    ks_gen_kernel<<<N * k * t * base, 128>>>(d_ks, d_lwe, d_tlwe, d_noise, n, t, p->ks_basebit, ckey);
     KG(cudaGetLastError());
     if (tfhe_b200_load_keys_device(ctx, d_bk, d_ks, nullptr)) {
         cudaFree(d_bk); cudaFree(d_ks); cudaFree(d_lwe); cudaFree(d_tlwe); cudaFree(d_noise);

@@ -299,6 +299,10 @@ const char *tfhe_b200_multi_last_error(void);
  * These belong to the key owner, not to the evaluation path; the reference runs them on
  * the host as well (new_random_gate_bootstrapping_secret_keyset tfhe_gate_bootstrapping.cu:57-68,
  * bootsSymEncrypt :114, bootsSymDecrypt :122, lwePhase lwe-functions.cu:72). */
+/* RANDOMNESS: every secret bit, mask word and noise term is ChaCha20 keystream (csrc/csprng.h).
+ * seed == 0: the 256-bit key comes from the operating system (getrandom) — use this for real keys and
+ * ciphertexts.  seed != 0: the key is derived from the seed: REPRODUCIBLE material for tests and
+ * benchmarks, NOT secure (64 bits, known to the caller). */
 size_t tfhe_b200_bk_words(const tfhe_b200_params *p);
 size_t tfhe_b200_ks_words(const tfhe_b200_params *p);
 void tfhe_b200_default_noise(double *alpha_lwe, double *alpha_bk);
