@@ -58,10 +58,16 @@ constexpr int kStages = 2 * (int) kRingStages;
 #ifndef TFHE_B200_BR_MAC_TAIL
 #define TFHE_B200_BR_MAC_TAIL 6
 #endif
-// Stage release ordered by the PTX memory model (data-dependent release atomic + acquire fence at the
-// refill) instead of by the in-order shared-memory pipe alone; see mac_consume.
+// TFHE_B200_RING_STRICT=1: the stage release carries a true data dependency on the last loads of the
+// chunk (+ an acquire fence in front of the refill), so the write-after-read order "all reads of a
+// stage, then its TMA refill" no longer rests on the shared-memory pipe serving the loads and the
+// atomic of a warp in issue order.  Measured: +3.2 % kernel time (395.9 vs 383.7 ms per 65536 gates;
+// an atom.release instead: +2.0 %), because the release then leaves a load latency later, four times
+// per iteration.  The default (0) keeps the early release: it is HARDWARE DEPENDENT (in-order LDS /
+// ATOMS per warp, true on sm_100a), and guarded by tests/test_gpu_parity.py::test_key_ring_stress_*
+// (exact results under maximal skip ratios and mixed idle slots); build with =1 for the strict form.
 #ifndef TFHE_B200_RING_STRICT
-#define TFHE_B200_RING_STRICT 1
+#define TFHE_B200_RING_STRICT 0
 #endif
 
 struct __align__(128) CtaSmem {
@@ -245,12 +251,7 @@ __device__ __forceinline__ void ring_skip(CtaSmem &S, const BrLaunch &L, int rol
     mbar_wait(&S.full[st], sp.rp.phase);
     __syncwarp();
     if (lane == 0) {
-#if TFHE_B200_RING_STRICT
-        unsigned int seen;
-        asm volatile("atom.release.cta.shared.add.u32 %0, [%1], 1;" : "=r"(seen) : "r"(smem_u32(&S.drained[st])) : "memory");
-#else
-        const unsigned int seen = atomicAdd(&S.drained[st], 1u);
-#endif
+        const unsigned int seen = atomicAdd(&S.drained[st], 1u);  // an idle warp reads nothing from the stage
         if (!HELPER) {
             ring_refill_if_last(S, L, role, sp, st, seen, ring_chunks);
         } else if (designated) {
@@ -339,20 +340,26 @@ __device__ __forceinline__ void mac_consume(CtaSmem &S, const BrLaunch &L, int r
     for (int p = 0; p < kTail; p++) w[p] = part[(kHead + p) * 32 + lane];
     unsigned int seen = 0;
 #if TFHE_B200_RING_STRICT
-    // Release with a true dependency on the LAST value loaded from the stage (`dep` is always 0, but
-    // the hardware cannot issue the atomic before that load has returned; the loads of one warp return
-    // in order) and with release semantics, paired with the acquire fence in front of the refill: the
-    // write-after-read order "all reads of the stage, then the TMA refill" holds in the PTX memory
-    // model, not only through the in-order shared-memory pipe.
-    const unsigned int dep = (unsigned int) (__double2hiint(w[kTail - 1].y) & 0);
+    // The release must not overtake the reads of the stage.  The atomic is predicated on a value
+    // computed from the LAST loads of the chunk (their high words, never all-ones for finite doubles:
+    // the predicate is always true for lane 0, but the hardware cannot issue the atomic before those
+    // loads have returned, and a warp's shared-memory loads return in order), and the refilling warp
+    // executes an acquire fence before the proxy fence and the TMA copy.  The write-after-read order
+    // "every consumer's reads, then the refill" therefore rests on a true data dependency, not on the
+    // shared-memory pipe serving loads and atomics of a warp in issue order (which the first version
+    // relied on).  An atom.release here (a membar in front of every release) cost 2 % of the kernel.
+    unsigned int live = 0xffffffffu;
+#pragma unroll
+    for (int p = 0; p < kTail; p++) live &= (unsigned int) __double2hiint(w[p].y);
     asm volatile(
         "{\n"
         ".reg .pred p;\n"
         "setp.eq.u32 p, %2, 0;\n"
-        "@p atom.release.cta.shared.add.u32 %0, [%1], %3;\n"
+        "setp.ne.and.u32 p, %3, 0xffffffff, p;\n"
+        "@p atom.shared.add.u32 %0, [%1], 1;\n"
         "}\n"
         : "+r"(seen)
-        : "r"(smem_u32(&S.drained[st])), "r"(lane), "r"(1u + dep)
+        : "r"(smem_u32(&S.drained[st])), "r"(lane), "r"(live)
         : "memory");
 #else
     asm volatile(

@@ -380,3 +380,24 @@ def test_gpu_key_generation(pkg, oracle):
     ref = np.stack([ctx.gate("XOR", ca[k], cb[k]) for k in range(4)])
     assert np.array_equal(pkg.decrypt_bits(sk, ref), bits_a[:4] ^ bits_b[:4])
     eng.close()
+
+
+@pytest.mark.parametrize("skip", [0.0, 0.5, 0.93])
+def test_key_ring_stress_exact_results(engine, oracle, keys, skip):
+    """The key ring of the blind-rotation kernel releases a stage right behind the last load of a
+    chunk (mac_consume; hardware-ordered, see TFHE_B200_RING_STRICT).  Stress it: several waves of full
+    4-ciphertext groups plus a ragged tail, iterations skipped at random per ciphertext (bara = 0:
+    that warp only keeps its place in the stream, so neighbours run ahead of each other by up to the
+    ring depth), and compare sampled ciphertexts with the exact integer path word for word."""
+    rng = np.random.default_rng(300 + int(skip * 100))
+    count, n_iter = 3 * 4 * engine.sm_count + 5, 24
+    acc = _rand_i32(rng, (count, 2, 1024))
+    bara = rng.integers(1, 2048, size=(count, n_iter)).astype(np.int32)
+    bara[rng.random((count, n_iter)) < skip] = 0
+    bara[::7] = 0                               # whole ciphertexts idle next to busy ones
+    got = engine.blind_rotate(engine.to_device(acc).clone(), engine.to_device(bara)).cpu().numpy()
+    exact_bar = 0 if engine.L.tfhe_b200_conversion_mode() == 0 else n_iter
+    for r in list(range(0, count, 211)) + [1, 2, 3, count - 1]:
+        want = oracle.blind_rotate_exact(keys.bk, acc[r], bara[r])
+        assert np.abs(wrap32(got[r].astype(np.int64) - want.astype(np.int64))).max() <= exact_bar, (r, skip)
+    assert np.array_equal(got[::7], acc[::7])    # untouched accumulators come back unchanged
