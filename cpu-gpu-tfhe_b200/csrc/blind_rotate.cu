@@ -244,9 +244,13 @@ __device__ __forceinline__ void ring_refill_if_last(CtaSmem &S, const BrLaunch &
 // the proxy fence and the TMA issue (a lone ciphertext is always the last to release: 4 refills
 // per iteration on its critical path otherwise; single gate 2.36 -> 2.16 ms).  Lending that slot's
 // working set to the ring as two more stages per role was measured on top: no further gain.
+// In the HELPER instantiation the slots between the last used one and the helper slot leave the kernel
+// at once (they would only spin next to the computing warps of their sub-partition), so a stage has
+// `ncons` = cts_per_group + 1 consumers there.
 template <bool HELPER>
 __device__ __forceinline__ void ring_skip(CtaSmem &S, const BrLaunch &L, int role, int lane, bool designated,
-                                          StreamPos &sp, uint32_t ring_base, uint32_t ring_chunks) {
+                                          StreamPos &sp, uint32_t ring_base, uint32_t ring_chunks,
+                                          unsigned int ncons) {
     const uint32_t st = ring_base + sp.rp.stage;
     mbar_wait(&S.full[st], sp.rp.phase);
     __syncwarp();
@@ -255,7 +259,7 @@ __device__ __forceinline__ void ring_skip(CtaSmem &S, const BrLaunch &L, int rol
         if (!HELPER) {
             ring_refill_if_last(S, L, role, sp, st, seen, ring_chunks);
         } else if (designated) {
-            const unsigned int target = seen - (seen % kCtWarps) + kCtWarps;  // all four releases of this chunk
+            const unsigned int target = seen - (seen % ncons) + ncons;  // all releases of this chunk
             auto poll = [&]() {
                 unsigned int v;
                 asm volatile("ld.acquire.cta.shared.u32 %0, [%1];" : "=r"(v) : "r"(smem_u32(&S.drained[st])) : "memory");
@@ -426,6 +430,9 @@ __global__ void __launch_bounds__(kThreads, 1) blind_rotate_kernel(const BrLaunc
 
     // -------------------- ciphertext warps ------------------------------------------
     const int ct = warp >> 1, role = warp & 1;   // sub-partition w % 4 holds the same role of two ciphertexts
+    // small batches: slots that never hold a ciphertext and are not the helper slot have nothing to do
+    if (HELPER && ct >= cpg && ct != kCtWarps - 1) return;
+    const unsigned int ncons = HELPER ? (unsigned int) cpg + 1u : (unsigned int) kCtWarps;
     WarpSmem &W = S.w[ct];
     // Named barriers of the pair: X = the hand-over of the partial sums (the one blocking barrier of an
     // iteration); Y[r] = "the partner has read role r's buffer B" (arrive by the reader, sync by the
@@ -485,7 +492,7 @@ __global__ void __launch_bounds__(kThreads, 1) blind_rotate_kernel(const BrLaunc
                 // warp's place in the key stream
 #pragma unroll 1
                 for (uint32_t c = 0; c < kChunksPerIter; c++)
-                    ring_skip<HELPER>(S, L, role, lane, ct == kCtWarps - 1, sp, ring_base, ring_chunks);
+                    ring_skip<HELPER>(S, L, role, lane, ct == kCtWarps - 1, sp, ring_base, ring_chunks, ncons);
                 continue;
             }
             // ---- one MuxRotate step: straight-line code, no per-phase conditionals -----------
