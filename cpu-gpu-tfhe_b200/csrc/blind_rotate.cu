@@ -563,6 +563,255 @@ __global__ void __launch_bounds__(kThreads, 1) blind_rotate_kernel(const BrLaunc
     }
 }
 
+// =================================================================================
+// LATENCY kernel: FOUR warps per ciphertext, one ciphertext per CTA (batches of at most one
+// ciphertext per SM: a single gate, the narrow levels of an adder or multiplier).
+//
+// The throughput kernel gives a ciphertext two warps because eight 255-register warps fill an SM with
+// four ciphertexts.  A lone ciphertext on an SM leaves six warps idle, and its iteration is a chain of
+// dependent phases.  Here warp (o, q) decomposes accumulator polynomial o at digit level q only and
+// runs pass 1 (split over lane pairs: a lone warp issues one fp64 instruction per ~3.4 cycles, so the
+// length of the per-lane instruction stream is what counts), pass 2 and the Fourier multiply of ITS ONE
+// decomposed row (o, q) against BK row 2o+q (two key chunks instead of four: one ring of three stages per row); the partial sums meet in shared
+// memory, warp (o, 0) reduces the four contributions to result polynomial o and runs the inverse
+// transform and the accumulator update as in the throughput kernel.  The second half of the CTA
+// (warps 4..7) keeps the four key rings filled (one helper warp per ring) so that no computing warp
+// ever pays a proxy fence or a TMA issue.  Two CTA-half barriers (128 threads) per iteration.
+// Results are the same Torus32 words as the throughput kernel's: both return the exact integer
+// product (the fp64 sums are taken in a different order, far inside the rounding margin;
+// tests/test_gpu_parity.py compares the two kernels word for word).
+constexpr uint32_t kQStages = 3;          // per ring
+constexpr uint32_t kQChunksPerIter = 2;   // per ring: (row, half o) then (row, half 1-o)
+constexpr int kQRings = kKpl;
+
+struct __align__(128) QuadCtaSmem {
+    QuadSmem w;
+    cpx e2[32 * kE2Row];
+    cpx ring[kQRings * kQStages][kChunkCplx];
+    unsigned long long full[kQRings * kQStages];
+    unsigned int drained[kQRings * kQStages];
+};
+static_assert(offsetof(QuadCtaSmem, ring) % 128 == 0, "TMA destination alignment");
+static_assert(sizeof(QuadCtaSmem) <= 227 * 1024, "shared memory budget");
+
+// chunk `c` (ring-local running number) of ring r = 2o + q
+__device__ __forceinline__ void quad_fill(QuadCtaSmem &S, const BrLaunch &L, uint32_t r, uint32_t c, uint32_t stage) {
+    const uint32_t it = (c / kQChunksPerIter) % (uint32_t) L.n_iter, sub = c % kQChunksPerIter;
+    const uint32_t o = r >> 1, half = sub ? 1u - o : o;
+    const cpx *src = L.bk + ((size_t) (L.bk_first + it) * kKpl + r) * kBkRowCplx + half * kBkHalfCplx;
+    const uint32_t st = r * kQStages + stage;
+    mbar_arrive_expect_tx(&S.full[st], kStageBytes);
+    tma_load_1d(S.ring[st], src, kStageBytes, &S.full[st]);
+}
+
+struct QuadPos {
+    uint32_t stage = 0, phase = 0, chunk = 0;
+    __device__ __forceinline__ void advance() {
+        chunk++;
+        if (++stage == kQStages) {
+            stage = 0;
+            phase ^= 1;
+        }
+    }
+};
+
+// a computing warp gives its current stage back (lane 0); the ring's helper warp refills it
+__device__ __forceinline__ void quad_release(QuadCtaSmem &S, uint32_t st, int lane) {
+    if (lane == 0) atomicAdd(&S.drained[st], 1u);
+}
+
+// Fourier multiply of z against the current chunk of ring r, stage released right behind the last load
+// (see mac_consume above; same hardware-ordered early release)
+__device__ __forceinline__ void quad_mac(QuadCtaSmem &S, uint32_t r, int lane, QuadPos &qp, const cpx (&z)[16],
+                                         cpx (&acc)[16]) {
+    const uint32_t st = r * kQStages + qp.stage;
+    mbar_wait(&S.full[st], qp.phase);
+    const cpx *part = S.ring[st];
+    constexpr int kTail = TFHE_B200_BR_MAC_TAIL, kHead = kChunkPos - kTail;
+    phase_mac_part<0, kHead>(lane, z, part, acc);
+    cpx w[kTail];
+#pragma unroll
+    for (int p = 0; p < kTail; p++) w[p] = part[(kHead + p) * 32 + lane];
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        ".reg .u32 t;\n"
+        "setp.eq.u32 p, %1, 0;\n"
+        "@p atom.shared.add.u32 t, [%0], 1;\n"
+        "}\n" ::"r"(smem_u32(&S.drained[st])),
+        "r"(lane)
+        : "memory");
+#pragma unroll
+    for (int p = 0; p < kTail; p++) cmac(acc[kHead + p], z[kHead + p], w[p]);
+    qp.advance();
+}
+
+__global__ void __launch_bounds__(kThreads, 1) blind_rotate_quad_kernel(const BrLaunch L) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    QuadCtaSmem &S = *reinterpret_cast<QuadCtaSmem *>(smem_raw);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n_iter = L.n_iter;
+    const int my_groups = (L.total - (int) blockIdx.x + (int) gridDim.x - 1) / (int) gridDim.x;  // one ciphertext per group
+    const uint32_t ring_chunks = kQChunksPerIter * (uint32_t) my_groups * (uint32_t) n_iter;
+
+    build_e2(S.e2);
+    if (threadIdx.x == 0) {
+        for (uint32_t s = 0; s < kQRings * kQStages; s++) {
+            mbar_init(&S.full[s], 1);
+            S.drained[s] = 0;
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        for (uint32_t r = 0; r < (uint32_t) kQRings; r++)
+            for (uint32_t c = 0; c < kQStages && c < ring_chunks; c++) quad_fill(S, L, r, c, c);
+    }
+    __syncthreads();
+    const bool rotate = (L.extern_only == 0);
+
+    if (warp >= 4) {
+        // ---- helper warp of ring r: every chunk is released twice (by the computing warp and here);
+        //      when both have happened the stage is refilled with the chunk kQStages ahead
+        const uint32_t r = (uint32_t) warp - 4u;
+        QuadPos qp;
+        if (lane == 0) {
+            for (uint32_t c = 0; c < ring_chunks; c++) {
+                const uint32_t st = r * kQStages + qp.stage;
+                mbar_wait(&S.full[st], qp.phase);
+                const unsigned int seen = atomicAdd(&S.drained[st], 1u);
+                const unsigned int target = seen - (seen % 2u) + 2u;
+                unsigned int v;
+                do {
+                    asm volatile("ld.acquire.cta.shared.u32 %0, [%1];" : "=r"(v) : "r"(smem_u32(&S.drained[st])) : "memory");
+                    if ((int) (v - target) < 0) __nanosleep(32);
+                } while ((int) (v - target) < 0);
+                if (c + kQStages < ring_chunks) {
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    quad_fill(S, L, r, c + kQStages, qp.stage);
+                }
+                qp.advance();
+            }
+        }
+        return;
+    }
+
+    // ---- computing warps (o, q) --------------------------------------------------------------
+    const int o = warp >> 1, q = warp & 1;
+    const uint32_t r = (uint32_t) warp;  // ring = decomposed row = 2o + q
+    QuadSmem &W = S.w;
+    const int tid4 = threadIdx.x;        // 0..127 over the four computing warps
+    auto quad_sync = [](int id) { named_sync(id, 128); };
+    QuadPos qp;
+    for (int g = blockIdx.x; g < L.total; g += gridDim.x) {
+        const GateIn I = resolve_inputs(L, g);
+        // ---- accumulator initialisation (all four warps share the copies)
+        if (L.acc_in != nullptr) {
+            phase_load_acc_p(tid4, 128, W.acc, L.acc_in + (size_t) g * (kK + 1) * kN);
+        } else if (L.testvect != nullptr) {
+            const int barb = L.barb ? (__ldg(L.barb + g) & (2 * kN - 1)) : 0;
+            for (int j = tid4; j < kN; j += 128) {
+                const int s = (j + barb) & (2 * kN - 1);
+                const uint32_t v = (uint32_t) __ldg(L.testvect + (s & (kN - 1)));
+                W.acc[0][(j & 15) * kAccRow + (j >> 4)] = 0;
+                W.acc[kK][(j & 15) * kAccRow + (j >> 4)] = (int32_t) (s < kN ? v : 0u - v);
+            }
+        } else if (q == 0) {
+            int barb;
+            if (L.explicit_inputs != 0) barb = L.barb ? (__ldg(L.barb + g) & (2 * kN - 1)) : 0;
+            else {
+                uint32_t xb = I.cst + I.sa * (uint32_t) __ldg(I.in0 + L.n) + I.sb * (uint32_t) __ldg(I.in1 + L.n);
+                if (I.in2 != nullptr) xb += I.sc * (uint32_t) __ldg(I.in2 + L.n);
+                barb = modswitch_2N(xb);
+            }
+            phase_init_p(lane, W.acc[o], o, barb, L.mu);
+        }
+        quad_sync(1);
+        if (q == 0) phase_ext_build_p(lane, W.acc[o], W.ext[o]);
+        quad_sync(2);
+
+        int a_blk = 0;  // lane l holds bara of iteration (it & ~31) + l
+        for (int it = 0; it < n_iter; it++) {
+            if ((it & 31) == 0) a_blk = load_bara(L, I, g, it + lane, n_iter, rotate);
+            const int a = __shfl_sync(0xffffffffu, a_blk, it & 31);
+            if (a == 0 && rotate) {  // tfhe_blindRotate_FFT :705: nothing to do; keep the place in the key stream
+#pragma unroll 1
+                for (uint32_t c = 0; c < kQChunksPerIter; c++) {
+                    const uint32_t st = r * kQStages + qp.stage;
+                    mbar_wait(&S.full[st], qp.phase);
+                    __syncwarp();
+                    quad_release(S, st, lane);
+                    qp.advance();
+                }
+                continue;
+            }
+            cpx keep[16], give[16];
+            PHASE_T0();
+            {
+                // pass 1 of row (o, q) split over lane pairs: lane (hh, j2) transforms points
+                // 16 hh .. 16 hh + 15 of slice j2, stage 0 through lane ^ 16 (br_core.cuh phase_f1h_*)
+                const int hh = lane >> 4, j2 = lane & 15;
+                cpx x[16], w[16], recv[16];
+                phase_f1h_decomp_p(hh, j2, q, W.acc[o], W.ext[o], a, rotate, x);
+                phase_f1h_cross_send(hh, x, w);
+#pragma unroll
+                for (int i = 0; i < 16; i++) {
+                    recv[i].x = __shfl_xor_sync(0xffffffffu, w[i].x, 16);
+                    recv[i].y = __shfl_xor_sync(0xffffffffu, w[i].y, 16);
+                }
+                phase_f1h_finish(hh, w, recv, x);
+                phase_f1h_store_p(hh, j2, W.exch[r], x);  // own buffer: free since the barrier that ended the last iteration
+                __syncwarp();
+            }
+            PHASE_MARK(0);
+#pragma unroll
+            for (int i = 0; i < 16; i++) {
+                keep[i].x = 0.0; keep[i].y = 0.0;
+                give[i].x = 0.0; give[i].y = 0.0;
+            }
+            {
+                cpx z[16];
+                phase_f2_fft_p(lane, W.exch[r], S.e2, z);
+                PHASE_MARK(1);
+                quad_mac(S, r, lane, qp, z, keep);
+                PHASE_MARK(2);
+                quad_mac(S, r, lane, qp, z, give);
+                PHASE_MARK(3);
+            }
+            __syncwarp();  // every lane has read its pass-1 output
+            phase_part_store(lane, W.exch[r], give);
+            if (q == 1) phase_part_store(lane, W.red[o], keep);
+            PHASE_MARK(4);
+            quad_sync(1);
+            PHASE_MARK(5);
+            if (q == 0) {
+                phase_part_add(lane, W.red[o], keep);                     // warp (o, 1): rows of polynomial o
+                phase_part_add(lane, W.exch[2 * (1 - o)], keep);          // the two warps of polynomial 1-o
+                phase_part_add(lane, W.exch[2 * (1 - o) + 1], keep);
+                if (!rotate) phase_acc_clear_p(lane, W.acc[o]);          // external product only: result replaces ACC
+                __syncwarp();
+                PHASE_MARK(6);
+                phase_inv16_store_p(lane, W.red[o], S.e2, keep);
+                __syncwarp();
+                PHASE_MARK(7);
+                cpx x[16], send[8], recv[8];
+                phase_i2_inner_p(lane, W.red[o], x);
+                PHASE_MARK(8);
+                phase_i2_send(lane, x, send);
+#pragma unroll
+                for (int b = 0; b < 8; b++) {
+                    recv[b].x = __shfl_xor_sync(0xffffffffu, send[b].x, 16);
+                    recv[b].y = __shfl_xor_sync(0xffffffffu, send[b].y, 16);
+                }
+                phase_i2_final_p(lane, W.acc[o], W.ext[o], x, recv);
+                PHASE_MARK(9);
+            }
+            quad_sync(2);  // ACC and its extended copy are final; every partial-sum buffer is free again
+            PHASE_MARK(10);
+        }
+        if (L.u_out != nullptr) phase_extract_p(tid4, 128, W.acc, L.u_out + (size_t) g * (kN + 1));
+        if (L.acc_out != nullptr) phase_dump_acc_p(tid4, 128, W.acc, L.acc_out + (size_t) g * (kK + 1) * kN);
+        quad_sync(1);
+    }
+}
+
 // ------------------------------------------------------------ key conversion
 
 struct __align__(128) FwdSmem {
@@ -614,6 +863,9 @@ cudaError_t blind_rotate_configure() {
     e = cudaFuncSetAttribute(blind_rotate_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              (int) sizeof(CtaSmem));
     if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(blind_rotate_quad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int) sizeof(QuadCtaSmem));
+    if (e != cudaSuccess) return e;
     return cudaFuncSetAttribute(forward_polys_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 (int) sizeof(FwdSmem));
 }
@@ -625,6 +877,16 @@ cudaError_t launch_blind_rotate(const BrLaunch &L_in, int sm_count, cudaStream_t
     L.cts_per_group = cpg < 1 ? 1 : (cpg > kCtWarps ? kCtWarps : cpg);
     const int ngroups = (L.total + L.cts_per_group - 1) / L.cts_per_group;
     const int grid = ngroups < sm_count ? ngroups : sm_count;
+    // at most one ciphertext per SM: the latency kernel (four warps per ciphertext).
+    // TFHE_B200_BR_QUAD=0 keeps such batches on the two-warp kernel (A/B measurements).
+    static const bool use_quad = [] {
+        const char *v = getenv("TFHE_B200_BR_QUAD");
+        return v == nullptr || atoi(v) != 0;
+    }();
+    if (use_quad && L.total <= sm_count) {
+        blind_rotate_quad_kernel<<<L.total, kThreads, sizeof(QuadCtaSmem), stream>>>(L);
+        return cudaGetLastError();
+    }
     // small batches: the always-idle last slot of every CTA refills the key rings (ring_skip<true>)
     if (L.cts_per_group < kCtWarps) blind_rotate_kernel<true><<<grid, kThreads, sizeof(CtaSmem), stream>>>(L);
     else blind_rotate_kernel<false><<<grid, kThreads, sizeof(CtaSmem), stream>>>(L);

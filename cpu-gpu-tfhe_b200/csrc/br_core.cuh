@@ -93,6 +93,19 @@ struct WarpSmem {
 };
 static_assert(16 * kExtRow <= kExchPoly * 4, "extended copy must fit an exchange buffer");
 
+// Working set of the LATENCY kernel (four warps per ciphertext, one ciphertext per CTA: blind_rotate.cu
+// blind_rotate_quad_kernel): the extended accumulator copies have buffers of their own (both warps of
+// a polynomial read them while the exchange buffers are being rewritten), and two more buffers take
+// the partial sums of the q = 1 warps / the inverse pass-2 output.
+constexpr int kExtPolyWords = 2048;   // 16 rows of 127 words, padded
+struct QuadSmem {
+    cpx exch[kKpl][kExchPoly];          // row (o, q): pass-1 output, then that warp's `give` partial sums
+    cpx red[kK + 1][kExchPoly];         // polynomial o: `keep` partial sums of warp (o, 1), then inverse pass-2 output
+    int32_t acc[kK + 1][kAccPoly];
+    int32_t ext[kK + 1][kExtPolyWords];
+};
+static_assert(16 * kExtRow <= kExtPolyWords, "extended copy must fit its buffer");
+
 TFHE_HD int32_t *ext_poly(WarpSmem &ws, int o) { return ws.exw[2 * o]; }
 
 TFHE_HD constexpr int bitrev5(int v) {
@@ -326,9 +339,9 @@ TFHE_HD double e2_shift(int m1, int s) {
 // ACC = (0, X^{2N-barb} * (mu, ..., mu))   tfhe_blindRotateAndExtract_FFT,
 // lwe-bootstrapping-functions-fft.cu:1425-1431 ; torusPolynomialMulByXai :492-519
 // Warp o initialises polynomial o: lane (h, j2) writes coefficients [32h, 32h+32) of row j2.
-TFHE_HD void phase_init(int lane, WarpSmem &ws, int o, int barb, int32_t mu) {
+TFHE_HD void phase_init_p(int lane, int32_t *acc_o, int o, int barb, int32_t mu) {
     const int h = lane >> 4, j2 = lane & 15;
-    int32_t *row = ws.acc[o] + j2 * kAccRow + 32 * h;
+    int32_t *row = acc_o + j2 * kAccRow + 32 * h;
 #pragma unroll 8
     for (int e = 0; e < 32; e++) {
         const int j = 16 * (e + 32 * h) + j2;
@@ -338,12 +351,14 @@ TFHE_HD void phase_init(int lane, WarpSmem &ws, int o, int barb, int32_t mu) {
     }
 }
 
+TFHE_HD void phase_init(int lane, WarpSmem &ws, int o, int barb, int32_t mu) { phase_init_p(lane, ws.acc[o], o, barb, mu); }
+
 // Build the extended copy of accumulator polynomial o from its master copy (start of a ciphertext;
 // afterwards phase_i2_final keeps it up to date).  Lane (h, j2) copies coefficients [32h, 32h+32) of row j2.
-TFHE_HD void phase_ext_build(int lane, WarpSmem &ws, int o) {
+TFHE_HD void phase_ext_build_p(int lane, const int32_t *acc_o, int32_t *ext_o) {
     const int h = lane >> 4, j2 = lane & 15;
-    const int32_t *row = ws.acc[o] + j2 * kAccRow + 32 * h;
-    int32_t *ext = ext_poly(ws, o) + j2 * kExtRow + 32 * h;
+    const int32_t *row = acc_o + j2 * kAccRow + 32 * h;
+    int32_t *ext = ext_o + j2 * kExtRow + 32 * h;
 #pragma unroll 2
     for (int b = 0; b < 32; b += 4) {
         const word4 v = *reinterpret_cast<const word4 *>(row + b);
@@ -354,6 +369,8 @@ TFHE_HD void phase_ext_build(int lane, WarpSmem &ws, int o) {
         }
     }
 }
+
+TFHE_HD void phase_ext_build(int lane, WarpSmem &ws, int o) { phase_ext_build_p(lane, ws.acc[o], ext_poly(ws, o)); }
 
 // Pass 1 of the two forward transforms of accumulator polynomial o (decomposed rows (o, q), q = 0..l-1),
 // fused with the rotation (torusPolynomialMulByXaiMinusOne, toruspolynomial-functions.cu:191-213)
@@ -371,8 +388,9 @@ TFHE_HD void phase_ext_build(int lane, WarpSmem &ws, int o) {
 // spent 19 instructions per coefficient here, most of them on the half-rate ALU pipe.
 // The outputs are NOT stored here: the extended copy lives in buffer A, which the stores overwrite
 // (the caller separates the two with a __syncwarp).
-TFHE_HD void phase_f1_decomp(int lane, WarpSmem &ws, int o, int a, bool rotate, cpx (&x)[32]) {
-    const int q = lane >> 4, j2 = lane & 15;
+// (pointer form: digit level q of slice j2 of the polynomial whose master / extended copy are given)
+TFHE_HD void phase_f1_decomp_p(int j2, int q, const int32_t *acc_o, const int32_t *ext_o, int a, bool rotate,
+                               cpx (&x)[32]) {
     const int a_lo = a & 15, a_hi = a >> 4;
     const int j2p = (j2 - a_lo) & 15;
     const int sh = a_hi + (j2 < a_lo ? 1 : 0);
@@ -381,8 +399,8 @@ TFHE_HD void phase_f1_decomp(int lane, WarpSmem &ws, int o, int a, bool rotate, 
     const uint32_t sm = rotate ? (((sh >> 6) & 1) ? 0u - m : m) : 0u;  // multiplier of the rotated value
     const uint32_t cm = rotate ? 0u - m : m;                            // multiplier of ACC itself
     const uint32_t offm = kDecompOffset * m;
-    const int32_t *own = ws.acc[o] + j2 * kAccRow;
-    const int32_t *rot = ext_poly(ws, o) + j2p * kExtRow + (kExtOrg - h);
+    const int32_t *own = acc_o + j2 * kAccRow;
+    const int32_t *rot = ext_o + j2p * kExtRow + (kExtOrg - h);
 #pragma unroll
     for (int blk = 0; blk < 64; blk += 16) {
         uint32_t vr[16], vo[16];
@@ -405,22 +423,114 @@ TFHE_HD void phase_f1_decomp(int lane, WarpSmem &ws, int o, int a, bool rotate, 
     }
 }
 
+TFHE_HD void phase_f1_decomp(int lane, WarpSmem &ws, int o, int a, bool rotate, cpx (&x)[32]) {
+    phase_f1_decomp_p(lane & 15, lane >> 4, ws.acc[o], ext_poly(ws, o), a, rotate, x);
+}
+
 // Stages 0-4 of the two transforms on the decomposed digits (no shared-memory access).
 TFHE_HD void phase_f1_fft(cpx (&x)[32]) { fwd32(x); }
 
-TFHE_HD void phase_f1_store(int lane, WarpSmem &ws, int o, const cpx (&x)[32]) {
-    const int q = lane >> 4, j2 = lane & 15;
-    cpx *dst = ws.exch[o * kL + q] + j2;
+TFHE_HD void phase_f1_store_p(int j2, cpx *buf, const cpx (&x)[32]) {
+    cpx *dst = buf + j2;
 #pragma unroll
     for (int pos = 0; pos < 32; pos++) dst[bitrev5(pos) * kExchRow] = x[pos];
 }
 
-// Pass 2 of the forward transform of decomposed polynomial `row` (lane m1: 16 values).
-TFHE_HD void phase_f2_fft(int lane, WarpSmem &ws, const cpx *e2, int row, cpx (&z)[16]) {
-    const cpx *src = ws.exch[row] + lane * kExchRow;
+TFHE_HD void phase_f1_store(int lane, WarpSmem &ws, int o, const cpx (&x)[32]) {
+    phase_f1_store_p(lane & 15, ws.exch[o * kL + (lane >> 4)], x);
+}
+
+// ---- pass 1 split over lane PAIRS (latency kernel) --------------------------------------------
+// A decomposed row has 16 slices of 32 points, so a warp that transforms ONE row keeps half its lanes
+// idle if a lane takes a whole slice.  Here lane (hh, j2) takes the points j1 = 16 hh .. 16 hh + 15 of
+// slice j2: stage 0 pairs point j1 of lane (0, j2) with point j1 + 16 of lane (1, j2) — one exchange
+// through lane ^ 16 — and stages 1-4 are local (the multipliers of block hh: lane dependent).
+// 288 instead of 480 fp64 instructions per lane, 32 instead of 64 digit conversions.
+// The sums are taken in a different order than in fwd32, so the Fourier values differ in the last
+// bits from the throughput kernel's; the accumulator words do not (both are the exact product).
+
+// decomposition of the 32 coefficients lane (hh, j2) needs: e = 16 hh + i (real) and 32 + 16 hh + i (imag)
+TFHE_HD void phase_f1h_decomp_p(int hh, int j2, int q, const int32_t *acc_o, const int32_t *ext_o, int a, bool rotate,
+                                cpx (&x)[16]) {
+    const int a_lo = a & 15, a_hi = a >> 4;
+    const int j2p = (j2 - a_lo) & 15;
+    const int sh = a_hi + (j2 < a_lo ? 1 : 0);
+    const int h = sh & 63;
+    const uint32_t m = 1u << (q * kBgbit);
+    const uint32_t sm = rotate ? (((sh >> 6) & 1) ? 0u - m : m) : 0u;
+    const uint32_t cm = rotate ? 0u - m : m;
+    const uint32_t offm = kDecompOffset * m;
+    const int32_t *own = acc_o + j2 * kAccRow + 16 * hh;
+    const int32_t *rot = ext_o + j2p * kExtRow + (kExtOrg - h) + 16 * hh;
+#pragma unroll
+    for (int part = 0; part < 2; part++) {  // real parts (e < 32), imaginary parts (e >= 32)
+        uint32_t vr[16], vo[16];
+#pragma unroll
+        for (int i = 0; i < 16; i++) vr[i] = (uint32_t) rot[32 * part + i];
+#pragma unroll
+        for (int i = 0; i < 16; i += 4) {
+            const word4 w = *reinterpret_cast<const word4 *>(own + 32 * part + i);
+#pragma unroll
+            for (int k = 0; k < 4; k++) vo[i + k] = (uint32_t) w.v[k];
+        }
+#pragma unroll
+        for (int i = 0; i < 16; i++) {
+            const uint32_t t = vr[i] * sm + (vo[i] * cm + offm);
+            const double d = digit_to_double(t >> (32 - kBgbit));
+            if (part == 0) x[i].x = d;
+            else x[i].y = d;
+        }
+    }
+}
+
+// stage 0, first half: w = kappa * x with kappa = 1 (hh = 0: the lane holds the a's) or e0 (hh = 1: the b's)
+TFHE_HD void phase_f1h_cross_send(int hh, const cpx (&x)[16], cpx (&w)[16]) {
+    const double kr = hh ? c1_re_rt(0) : 1.0, ki = hh ? c1_im_rt(0) : 0.0;
+#pragma unroll
+    for (int i = 0; i < 16; i++) {
+        w[i].x = fma(kr, x[i].x, -(ki * x[i].y));
+        w[i].y = fma(kr, x[i].y, ki * x[i].x);
+    }
+}
+
+// stage 0, second half (recv = the partner lane's w): hh = 0: a + e0 b, hh = 1: a - e0 b; then stages 1-4
+TFHE_HD void phase_f1h_finish(int hh, const cpx (&w)[16], const cpx (&recv)[16], cpx (&x)[16]) {
+    const double sg = hh ? -1.0 : 1.0;
+#pragma unroll
+    for (int i = 0; i < 16; i++) {
+        x[i].x = fma(sg, w[i].x, recv[i].x);
+        x[i].y = fma(sg, w[i].y, recv[i].y);
+    }
+#pragma unroll
+    for (int s = 1; s < 5; s++) {
+        const int half = 16 >> s;
+#pragma unroll
+        for (int b = 0; b < (1 << (s - 1)); b++) {
+            const int c0 = (1 << s) - 1 + b, c1 = c0 + (1 << (s - 1));
+            const double er = hh ? c1_re_rt(c1) : c1_re_rt(c0), ei = hh ? c1_im_rt(c1) : c1_im_rt(c0);
+#pragma unroll
+            for (int i = 0; i < half; i++) bf_fwd(x[b * 2 * half + i], x[b * 2 * half + i + half], er, ei);
+        }
+    }
+}
+
+// x[i] is output position 16 hh + i of slice j2 (bit-reversed frequency class, as in phase_f1_store_p)
+TFHE_HD void phase_f1h_store_p(int hh, int j2, cpx *buf, const cpx (&x)[16]) {
+    cpx *dst = buf + j2 + hh * kExchRow;
+#pragma unroll
+    for (int i = 0; i < 16; i++) dst[bitrev5(i) * kExchRow] = x[i];  // bitrev5(16 hh + i) = bitrev5(i) + hh
+}
+
+// Pass 2 of the forward transform of a decomposed polynomial from its exchange buffer (lane m1: 16 values).
+TFHE_HD void phase_f2_fft_p(int lane, const cpx *buf, const cpx *e2, cpx (&z)[16]) {
+    const cpx *src = buf + lane * kExchRow;
 #pragma unroll
     for (int j2 = 0; j2 < 16; j2++) z[j2] = src[j2];
     fwd16(z, e2 + lane * kE2Row);
+}
+
+TFHE_HD void phase_f2_fft(int lane, WarpSmem &ws, const cpx *e2, int row, cpx (&z)[16]) {
+    phase_f2_fft_p(lane, ws.exch[row], e2, z);
 }
 
 // Fourier MAC against one result-polynomial half of a TGSW row (tLweFFTAddMulRTo,
@@ -441,36 +551,50 @@ TFHE_HD void phase_mac_part(int lane, const cpx (&z)[16], const cpx *part, cpx (
 
 // Hand the partial sum of the result polynomial the OTHER warp finishes to that warp: warp o parks it
 // in its own buffer B (rows this lane owns; B's pass-1 output has been consumed by then).
-TFHE_HD void phase_xchg_store(int lane, WarpSmem &ws, int o, const cpx (&give)[16]) {
-    cpx *d = ws.exch[2 * o + 1] + lane * kExchRow;
+// (pointer forms: a lane's 16 partial sums parked in / added from rows it owns of an exchange buffer)
+TFHE_HD void phase_part_store(int lane, cpx *buf, const cpx (&v)[16]) {
+    cpx *d = buf + lane * kExchRow;
 #pragma unroll
-    for (int i = 0; i < 16; i++) d[i] = give[i];
+    for (int i = 0; i < 16; i++) d[i] = v[i];
+}
+
+TFHE_HD void phase_part_add(int lane, const cpx *buf, cpx (&acc)[16]) {
+    const cpx *s = buf + lane * kExchRow;
+#pragma unroll
+    for (int i = 0; i < 16; i++) {
+        const cpx v = s[i];
+        acc[i].x += v.x;
+        acc[i].y += v.y;
+    }
+}
+
+TFHE_HD void phase_xchg_store(int lane, WarpSmem &ws, int o, const cpx (&give)[16]) {
+    phase_part_store(lane, ws.exch[2 * o + 1], give);
 }
 
 // keep += partner's partial sum (parked by its phase_xchg_store in ITS buffer B).
 TFHE_HD void phase_xchg_load(int lane, const WarpSmem &ws, int o, cpx (&keep)[16]) {
-    const cpx *s = ws.exch[2 * (1 - o) + 1] + lane * kExchRow;
-#pragma unroll
-    for (int i = 0; i < 16; i++) {
-        const cpx v = s[i];
-        keep[i].x += v.x;
-        keep[i].y += v.y;
-    }
+    phase_part_add(lane, ws.exch[2 * (1 - o) + 1], keep);
 }
 
-// Inverse pass 2 of the finished Fourier sum of result polynomial o; the 16 outputs go to buffer A.
-TFHE_HD void phase_inv16_store(int lane, WarpSmem &ws, const cpx *e2, int o, cpx (&keep)[16]) {
+// Inverse pass 2 of the finished Fourier sum of a result polynomial; the 16 outputs go to `buf`.
+TFHE_HD void phase_inv16_store_p(int lane, cpx *buf, const cpx *e2, cpx (&keep)[16]) {
     inv16(keep, e2 + lane * kE2Row);
-    cpx *d = ws.exch[2 * o] + lane * kExchRow;
+    cpx *d = buf + lane * kExchRow;
 #pragma unroll
     for (int j2 = 0; j2 < 16; j2++) d[j2] = keep[j2];
 }
 
+// ... of result polynomial o: to buffer A.
+TFHE_HD void phase_inv16_store(int lane, WarpSmem &ws, const cpx *e2, int o, cpx (&keep)[16]) {
+    phase_inv16_store_p(lane, ws.exch[2 * o], e2, keep);
+}
+
 // Inverse pass 1 of result polynomial o, first part: lane (hh, j2) runs the four inner stages on
 // positions [16 hh, 16 hh + 16) of slice j2 (the multipliers of block hh: lane dependent).
-TFHE_HD void phase_i2_inner(int lane, const WarpSmem &ws, int o, cpx (&x)[16]) {
+TFHE_HD void phase_i2_inner_p(int lane, const cpx *buf, cpx (&x)[16]) {
     const int hh = lane >> 4, j2 = lane & 15;
-    const cpx *src = ws.exch[2 * o] + j2 + hh * kExchRow;
+    const cpx *src = buf + j2 + hh * kExchRow;
 #pragma unroll
     for (int p = 0; p < 16; p++) {
         // position 16*hh + p holds frequency class m1 = bitrev5(16*hh + p) = 2*bitrev4(p) + hh
@@ -487,6 +611,10 @@ TFHE_HD void phase_i2_inner(int lane, const WarpSmem &ws, int o, cpx (&x)[16]) {
             for (int i = 0; i < half; i++) bf_inv(x[b * 2 * half + i], x[b * 2 * half + i + half], er, ei);
         }
     }
+}
+
+TFHE_HD void phase_i2_inner(int lane, const WarpSmem &ws, int o, cpx (&x)[16]) {
+    phase_i2_inner_p(lane, ws.exch[2 * o], x);
 }
 
 // The last stage pairs position i of lane (0, j2) (u) with position i of lane (1, j2) (v).  Lane hh
@@ -508,10 +636,10 @@ TFHE_HD void phase_i2_send(int lane, const cpx (&x)[16], cpx (&send)[8]) {
 // coefficients (+32) from the imaginary parts: four groups of 8 consecutive words.
 // With mine / theirs = the value of this lane / of the partner lane, u + v = mine + theirs and
 // conj(e) (u - v) = (+-conj(e)) (mine - theirs), sign by lane: identical arithmetic in both lanes.
-TFHE_HD void phase_i2_final(int lane, WarpSmem &ws, int o, const cpx (&x)[16], const cpx (&p)[8]) {
+TFHE_HD void phase_i2_final_p(int lane, int32_t *acc_o, int32_t *ext_o, const cpx (&x)[16], const cpx (&p)[8]) {
     const int hh = lane >> 4, j2 = lane & 15;
-    int32_t *row = ws.acc[o] + j2 * kAccRow + 8 * hh;
-    int32_t *ext = ext_poly(ws, o) + j2 * kExtRow + 8 * hh;  // extended copy, same coefficients
+    int32_t *row = acc_o + j2 * kAccRow + 8 * hh;
+    int32_t *ext = ext_o + j2 * kExtRow + 8 * hh;  // extended copy, same coefficients
     const double er = hh ? -c1_re_rt(0) : c1_re_rt(0), ei = hh ? -c1_im_rt(0) : c1_im_rt(0);
     // all loads first (128-bit accesses to the master copy: the 8 consecutive coefficients of a group
     // are two aligned quads), then the butterflies and conversions, then the updates
@@ -549,11 +677,15 @@ TFHE_HD void phase_i2_final(int lane, WarpSmem &ws, int o, const cpx (&x)[16], c
     }
 }
 
+TFHE_HD void phase_i2_final(int lane, WarpSmem &ws, int o, const cpx (&x)[16], const cpx (&p)[8]) {
+    phase_i2_final_p(lane, ws.acc[o], ext_poly(ws, o), x, p);
+}
+
 // Stand-alone external product: the result REPLACES the accumulator, so the master copy is
 // cleared once its decomposition has been read (lane (hh, j2) clears the coefficients it will update).
-TFHE_HD void phase_acc_clear(int lane, WarpSmem &ws, int o) {
+TFHE_HD void phase_acc_clear_p(int lane, int32_t *acc_o) {
     const int hh = lane >> 4, j2 = lane & 15;
-    int32_t *row = ws.acc[o] + j2 * kAccRow + 8 * hh;
+    int32_t *row = acc_o + j2 * kAccRow + 8 * hh;
     word4 z;
 #pragma unroll
     for (int k = 0; k < 4; k++) z.v[k] = 0;
@@ -564,31 +696,40 @@ TFHE_HD void phase_acc_clear(int lane, WarpSmem &ws, int o) {
     }
 }
 
-TFHE_HD int32_t acc_coef(const WarpSmem &ws, int o, int j) {
-    return ws.acc[o][(j & 15) * kAccRow + (j >> 4)];
+TFHE_HD void phase_acc_clear(int lane, WarpSmem &ws, int o) { phase_acc_clear_p(lane, ws.acc[o]); }
+
+// coefficient j of polynomial o of a master copy int32[k+1][kAccPoly]
+TFHE_HD int32_t acc_coef_p(const int32_t (*acc)[kAccPoly], int o, int j) {
+    return acc[o][(j & 15) * kAccRow + (j >> 4)];
 }
 
 // Sample extraction at index 0 (tLweExtractLweSampleIndex, lwe.cu:41-56):
 // u.a[0] = ACC.a[0], u.a[j] = -ACC.a[N-j], u.b = ACC.b[0].  u: int32[N+1].
-TFHE_HD void phase_extract(int lane, const WarpSmem &ws, int32_t *u) {
-    for (int j = lane; j < kN; j += 32) {
-        const int32_t v = (j == 0) ? acc_coef(ws, 0, 0) : (int32_t) (0u - (uint32_t) acc_coef(ws, 0, kN - j));
+// `step` lanes share the work (32: one warp; 128: the four warps of the latency kernel).
+TFHE_HD void phase_extract_p(int lane, int step, const int32_t (*acc)[kAccPoly], int32_t *u) {
+    for (int j = lane; j < kN; j += step) {
+        const int32_t v = (j == 0) ? acc_coef_p(acc, 0, 0) : (int32_t) (0u - (uint32_t) acc_coef_p(acc, 0, kN - j));
         u[j] = v;
     }
-    if (lane == 0) u[kN] = acc_coef(ws, kK, 0);
+    if (lane == 0) u[kN] = acc_coef_p(acc, kK, 0);
 }
 
 // Raw accumulator dump, natural coefficient order: int32[2][N].
-TFHE_HD void phase_dump_acc(int lane, const WarpSmem &ws, int32_t *out) {
-    for (int j = lane; j < (kK + 1) * kN; j += 32) out[j] = acc_coef(ws, j >> 10, j & (kN - 1));
+TFHE_HD void phase_dump_acc_p(int lane, int step, const int32_t (*acc)[kAccPoly], int32_t *out) {
+    for (int j = lane; j < (kK + 1) * kN; j += step) out[j] = acc_coef_p(acc, j >> 10, j & (kN - 1));
 }
 
-TFHE_HD void phase_load_acc(int lane, WarpSmem &ws, const int32_t *in) {
-    for (int j = lane; j < (kK + 1) * kN; j += 32) {
+TFHE_HD void phase_load_acc_p(int lane, int step, int32_t (*acc)[kAccPoly], const int32_t *in) {
+    for (int j = lane; j < (kK + 1) * kN; j += step) {
         const int o = j >> 10, c = j & (kN - 1);
-        ws.acc[o][(c & 15) * kAccRow + (c >> 4)] = in[j];
+        acc[o][(c & 15) * kAccRow + (c >> 4)] = in[j];
     }
 }
+
+TFHE_HD int32_t acc_coef(const WarpSmem &ws, int o, int j) { return acc_coef_p(ws.acc, o, j); }
+TFHE_HD void phase_extract(int lane, const WarpSmem &ws, int32_t *u) { phase_extract_p(lane, 32, ws.acc, u); }
+TFHE_HD void phase_dump_acc(int lane, const WarpSmem &ws, int32_t *out) { phase_dump_acc_p(lane, 32, ws.acc, out); }
+TFHE_HD void phase_load_acc(int lane, WarpSmem &ws, const int32_t *in) { phase_load_acc_p(lane, 32, ws.acc, in); }
 
 // ------------------------------------------------ generic forward transform -
 // Forward transform of 4 polynomials given as doubles via `fetch(p, j)`; used

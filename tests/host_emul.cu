@@ -212,6 +212,92 @@ int main() {
     CHECK(g_max_frac < 0.25, "fp64 rounding error too close to 1/2");
 #endif
 
+    // ---- B3. the same steps through the LATENCY kernel's split (four warps per ciphertext) ----------
+    // warp (o, q): decomposition + pass 1 + pass 2 + MAC of row (o, q); partial sums reduced by warp (o, 0)
+    // (own keep + keep of (o, 1) + the two gives of polynomial 1-o), which also runs the inverse.
+    {
+        QuadSmem *qs = new QuadSmem();
+        std::vector<int32_t> accq = acc0;
+        int maxdiffq = 0;
+        for (int it = 0; it < 12; it++) {
+            const int i = it % P.n;
+            const int a = rots[it];
+            for (int lane = 0; lane < 32; lane++) phase_load_acc_p(lane, 32, qs->acc, accq.data());
+            if (it == 0)
+                for (int o = 0; o < 2; o++)
+                    for (int lane = 0; lane < 32; lane++) phase_ext_build_p(lane, qs->acc[o], qs->ext[o]);
+            // pass 1 split over lane pairs: lane (hh, j2) transforms half a slice, stage 0 through lane ^ 16
+            static cpx xq[4][32][16], wq[4][32][16];
+            for (int w = 0; w < 4; w++)
+                for (int lane = 0; lane < 32; lane++) {
+                    phase_f1h_decomp_p(lane >> 4, lane & 15, w & 1, qs->acc[w >> 1], qs->ext[w >> 1], a, true, xq[w][lane]);
+                    phase_f1h_cross_send(lane >> 4, xq[w][lane], wq[w][lane]);
+                }
+            for (int w = 0; w < 4; w++)
+                for (int lane = 0; lane < 32; lane++) {
+                    phase_f1h_finish(lane >> 4, wq[w][lane], wq[w][lane ^ 16], xq[w][lane]);
+                    phase_f1h_store_p(lane >> 4, lane & 15, qs->exch[w], xq[w][lane]);
+                }
+            static cpx keepq[4][32][16], giveq[4][32][16];
+            memset(keepq, 0, sizeof(keepq));
+            memset(giveq, 0, sizeof(giveq));
+            for (int w = 0; w < 4; w++) {
+                const int o = w >> 1;
+                const cpx *bkrow = bkdev.data() + ((size_t) i * kKpl + w) * kBkRowCplx;
+                for (int lane = 0; lane < 32; lane++) {
+                    cpx z[16];
+                    phase_f2_fft_p(lane, qs->exch[w], e2.data(), z);
+                    phase_mac_half(lane, z, bkrow + o * kBkHalfCplx, keepq[w][lane]);
+                    phase_mac_half(lane, z, bkrow + (1 - o) * kBkHalfCplx, giveq[w][lane]);
+                }
+            }
+            for (int w = 0; w < 4; w++)
+                for (int lane = 0; lane < 32; lane++) {
+                    phase_part_store(lane, qs->exch[w], giveq[w][lane]);
+                    if (w & 1) phase_part_store(lane, qs->red[w >> 1], keepq[w][lane]);
+                }
+            static cpx xhq[2][32][16], sndq[2][32][8];
+            for (int o = 0; o < 2; o++) {
+                for (int lane = 0; lane < 32; lane++) {
+                    cpx(&k)[16] = keepq[2 * o][lane];
+                    phase_part_add(lane, qs->red[o], k);
+                    phase_part_add(lane, qs->exch[2 * (1 - o)], k);
+                    phase_part_add(lane, qs->exch[2 * (1 - o) + 1], k);
+                }
+                for (int lane = 0; lane < 32; lane++) phase_inv16_store_p(lane, qs->red[o], e2.data(), keepq[2 * o][lane]);
+                for (int lane = 0; lane < 32; lane++) {
+                    phase_i2_inner_p(lane, qs->red[o], xhq[o][lane]);
+                    phase_i2_send(lane, xhq[o][lane], sndq[o][lane]);
+                }
+                for (int lane = 0; lane < 32; lane++)
+                    phase_i2_final_p(lane, qs->acc[o], qs->ext[o], xhq[o][lane], sndq[o][lane ^ 16]);
+            }
+            std::vector<int32_t> got(2 * kN);
+            for (int lane = 0; lane < 32; lane++) phase_dump_acc_p(lane, 32, qs->acc, got.data());
+            std::vector<int32_t> tmp(2 * kN);
+            for (int o = 0; o < 2; o++) oracle_mul_by_xai_minus_one(a, kN, accq.data() + o * kN, tmp.data() + o * kN);
+            oracle_extern_mul_exact(&P, bk.data() + (size_t) i * kKpl * 2 * kN, tmp.data());
+            for (int j = 0; j < 2 * kN; j++) {
+                const int32_t e = (int32_t) ((uint32_t) accq[j] + (uint32_t) tmp[j]);
+                const int d = abs((int) ((uint32_t) got[j] - (uint32_t) e));
+                if (d > maxdiffq) maxdiffq = d;
+            }
+            accq = got;
+        }
+        printf("B3. latency-kernel split (4 warps per ciphertext) vs exact: max |diff| = %d LSB\n", maxdiffq);
+#if TFHE_B200_TRUNCATE_LIKE_REFERENCE
+        CHECK(maxdiffq <= 1, "latency-kernel split differs from exact result by more than truncation");
+#else
+        CHECK(maxdiffq == 0, "latency-kernel split differs from the exact integer product");
+#endif
+        std::vector<int32_t> u(kN + 1), u2(kN + 1);
+        for (int lane = 0; lane < 128; lane++) phase_extract_p(lane, 128, qs->acc, u.data());
+        for (int lane = 0; lane < 32; lane++) phase_load_acc(lane, *ws, accq.data());
+        for (int lane = 0; lane < 32; lane++) phase_extract(lane, *ws, u2.data());
+        CHECK(u == u2, "extraction by 128 lanes");
+        delete qs;
+    }
+
     // ---- C. extraction ----------------------------------------------------
     {
         for (int lane = 0; lane < 32; lane++) phase_load_acc(lane, *ws, acc.data());

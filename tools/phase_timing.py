@@ -15,6 +15,9 @@ eng = pkg.Engine(device=0); eng.load_keys(sk.bk, sk.ks)
 rng = np.random.default_rng(12)
 names = ["f1 (decomp, pass 1, store)", "f2_fft (2 rows)", "mac keep (+wait)", "mac give (+wait)", "xchg_store",
          "pair barrier", "xchg_load + inv16", "i2_inner", "i2 shuffles", "i2_final", "-", "-", "-", "-", "-", "-"]
+if os.environ.get("QUAD_NAMES"):
+    names = ["f1 (decomp, pass 1, store)", "f2_fft (1 row)", "mac keep (+wait)", "mac give (+wait)", "partial store",
+             "barrier 1", "reduce (3 adds)", "inv16 + store", "i2_inner", "shuffles + final", "barrier 2", "-", "-", "-", "-", "-"]
 n_iter = 100
 buf = (ctypes.c_longlong * 16)()
 for count in [int(x) for x in sys.argv[1:]] or [148, 592]:
