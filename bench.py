@@ -340,7 +340,7 @@ def circuit_latencies(pkg, eng, sk):
     for c in plans:
         c.close()
     da, db = enc(40000, 32, 5), enc(50000, 32, 6)
-    for adder, name in ((0, "mul32_reference"), (1, "mul32_prefix")):
+    for adder, name in ((0, "mul32_reference"), (1, "mul32_prefix"), (2, "mul32_carry_save")):
         c = pkg.Circuit(eng, "mul_ex", 32, 1, adder)
         ms, out = timed(lambda: c.run(da, db), 1, side)
         ok = ok and dec(out, 32) == (40000 * 50000) & 0xFFFFFFFF
@@ -373,7 +373,7 @@ def matmul_config5(pkg, eng, tdist, sk, p, dev, world, rank, barrier):
         dist.broadcast(enc, 0)
     eA, eB = enc[:rows].contiguous(), enc[rows:].contiguous()
     res = {}
-    for adder, name, warm in ((1, "matmul16x16_8bit", True), (0, "matmul16x16_8bit_reference_schedule", False)):
+    for adder, name, warm in ((2, "matmul16x16_8bit", True), (0, "matmul16x16_8bit_reference_schedule", False)):
         sm = tdist.ShardedMatmul(pkg, eng, nmat, nmat, nmat, nbits, adder)
         if warm:
             sm.run(eA, eB, gather=False)
@@ -386,8 +386,12 @@ def matmul_config5(pkg, eng, tdist, sk, p, dev, world, rank, barrier):
         t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        gates = torch.tensor([float(sm.circ.gates) if sm.circ else 0.0], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(gates, op=dist.ReduceOp.SUM)
         entry = {"ms": float(t.item()), "n_gpus": world, "levels": sm.circ.levels if sm.circ else 0,
-                 "adder": "prefix" if adder else "ripple (reference schedule)"}
+                 "gates": int(gates.item()),
+                 "adder": "carry-save tree + prefix addition" if adder == 2 else "ripple (reference schedule)"}
         if rank == 0:
             got = pkg.decrypt_bits(sk, out.cpu().numpy()).reshape(-1, nbits).astype(np.int64)
             C = (got << np.arange(nbits)).sum(-1).reshape(nmat, nmat)

@@ -9,6 +9,7 @@ is missing the calls raise.
 The directory name contains a hyphen, so import it through
 ``__graft_entry__.load_package()`` (registers it as ``cpu_gpu_tfhe_b200``).
 """
+from . import binding  # noqa: F401
 from .binding import (  # noqa: F401
     CMP,
     GATES,

@@ -23,6 +23,8 @@ _i = ctypes.c_int
 CMP = {"GT": 0, "LE": 1, "LT": 2, "GE": 3, "EQ": 4, "NE": 5}   # TFHE_B200_CMP_*
 SHIFT = {"LEFT": 0, "RIGHT_LOGICAL": 1, "RIGHT_ARITH": 2}         # TFHE_B200_SHIFT_*
 GPC = 10      # TFHE_B200_GPC: carry operator g | (p & c) for mutually exclusive g, p (extension)
+XOR3, MAJ = 11, 12   # full-adder outputs a ^ b ^ c and majority(a, b, c), one bootstrap each (extensions)
+ADDER = {"RIPPLE": 0, "PREFIX": 1, "CARRY_SAVE": 2}   # TFHE_B200_ADDER_*
 
 
 class EngineError(RuntimeError):
@@ -427,6 +429,17 @@ class Engine:
         out = self.empty(count) if out is None else out
         self._ck(self.L.tfhe_b200_gate(self.h, GATE_ID[name], out.data_ptr(), ca.data_ptr(), cb.data_ptr(), count,
                                        self._stream(stream)))
+        return out
+
+    def gate3(self, gate_id, a, b, c, out=None, stream=None):
+        """A three-input threshold gate (GPC, XOR3, MAJ) on batches of samples, one bootstrap each."""
+        for t in (a, b, c):
+            self._chk(t, self.words)
+        count = a.shape[0]
+        out = self.empty(count) if out is None else out
+        op = GateOp(gate_id, count, a.data_ptr(), b.data_ptr(), out.data_ptr(), self.words, self.words, self.words,
+                    None, None, None, c.data_ptr(), self.words, None)
+        self._ck(self.L.tfhe_b200_gate_multi(self.h, ctypes.byref(op), 1, self._stream(stream)))
         return out
 
     def carry_gate(self, g, p, c, out=None, stream=None):

@@ -14,6 +14,7 @@
 // just different indices).  Running a plan issues no host synchronisation.
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cstdio>
 #include <cstring>
 #include <vector>
@@ -391,6 +392,85 @@ struct Builder {
         return reduce_tree(TFHE_B200_AND, e);
     }
 
+    // Carry-save reduction.  cols[i][k] = rows of the bits of weight 2^k that add up to number i
+    // (k < nbits; carries out of the top column are dropped: arithmetic mod 2^nbits).  Every level
+    // compresses each column's bits in triples with full adders — sum bit stays, carry bit moves one
+    // column up; both are ONE bootstrap each (TFHE_B200_XOR3 / TFHE_B200_MAJ) and all full adders of
+    // a level form one batch — until no column holds more than two bits; the two remaining rows go
+    // through one addition (`adder`).  zero_row: an encryption of 0 that is never written.
+    void carry_save_sum(std::vector<std::vector<std::vector<int>>> cols, const std::vector<Bits> &out, int nbits,
+                        int adder, int zero_row) {
+        const int m = (int) cols.size();
+        // Dadda's height sequence 2, 3, 4, 6, 9, 13, 19, 28, ... (d' = floor(3d/2)): every stage brings all
+        // columns down to the next target with as few adders as possible, so the number of stages is
+        // logarithmic in the tallest column even for ragged (triangular) bit matrices, where compressing
+        // greedily lets a carry ripple one column per level.
+        size_t tallest = 0;
+        for (int i = 0; i < m; i++)
+            for (int k = 0; k < nbits; k++) tallest = std::max(tallest, cols[i][k].size());
+        std::vector<size_t> targets;
+        for (size_t d = 2; d < tallest; d = d * 3 / 2) targets.push_back(d);
+        for (size_t st = targets.size(); st-- > 0;) {
+            const size_t d = targets[st];
+            std::vector<std::vector<std::vector<int>>> next(m, std::vector<std::vector<int>>(nbits));
+            for (int i = 0; i < m; i++) {
+                size_t carries_in = 0;  // carries produced by column k-1 in this stage
+                for (int k = 0; k < nbits; k++) {
+                    const std::vector<int> &col = cols[i][k];
+                    size_t used = 0, height = col.size() + carries_in, carries_out = 0;
+                    while (height > d) {
+                        if (height == d + 1 && used + 2 <= col.size()) {  // half adder: XOR + AND
+                            const int sum = alloc(1);
+                            gate(TFHE_B200_XOR, col[used], col[used + 1], sum);
+                            next[i][k].push_back(sum);
+                            if (k + 1 < nbits) {
+                                const int carry = alloc(1);
+                                gate(TFHE_B200_AND, col[used], col[used + 1], carry);
+                                next[i][k + 1].push_back(carry);
+                            }
+                            used += 2;
+                            height -= 1;
+                        } else {  // full adder: XOR3 + MAJ
+                            const int sum = alloc(1);
+                            gate(TFHE_B200_XOR3, col[used], col[used + 1], sum, col[used + 2]);
+                            next[i][k].push_back(sum);
+                            if (k + 1 < nbits) {
+                                const int carry = alloc(1);
+                                gate(TFHE_B200_MAJ, col[used], col[used + 1], carry, col[used + 2]);
+                                next[i][k + 1].push_back(carry);
+                            }
+                            used += 3;
+                            height -= 2;
+                        }
+                        carries_out++;
+                    }
+                    for (; used < col.size(); used++) next[i][k].push_back(col[used]);
+                    carries_in = carries_out;
+                }
+            }
+            end_level();
+            cols.swap(next);
+        }
+        // two rows left: x + y (columns with one or no bit are padded with the constant 0)
+        std::vector<Bits> x(m, Bits(nbits, zero_row)), y(m, Bits(nbits, zero_row));
+        bool need_add = false;
+        for (int i = 0; i < m; i++)
+            for (int k = 0; k < nbits; k++) {
+                if (cols[i][k].size() >= 1) x[i][k] = cols[i][k][0];
+                if (cols[i][k].size() >= 2) {
+                    y[i][k] = cols[i][k][1];
+                    need_add = true;
+                }
+            }
+        if (need_add) {
+            add(adder == TFHE_B200_ADDER_RIPPLE ? TFHE_B200_ADDER_RIPPLE : TFHE_B200_ADDER_PREFIX, x, y, out, nbits);
+        } else {
+            for (int i = 0; i < m; i++)
+                for (int k = 0; k < nbits; k++) copy(x[i][k], out[i][k]);
+            end_level();
+        }
+    }
+
     // out = -a (twosComplement, Cipher.cu:286-298: out_i = a_i ^ (a_0 | ... | a_{i-1})), with the
     // running OR computed as a Kogge-Stone scan instead of a serial chain.
     void negate(const std::vector<Bits> &a, const std::vector<Bits> &out, int nbits) {
@@ -464,6 +544,8 @@ int gate_truth(int g, int a, int b, int c3) {
         case TFHE_B200_ORNY: return !a || b;
         case TFHE_B200_ORYN: return a || !b;
         case TFHE_B200_GPC: return a || (b && c3);
+        case TFHE_B200_XOR3: return a ^ b ^ c3;
+        case TFHE_B200_MAJ: return (a + b + c3) >= 2;
         default: return 0;
     }
 }
@@ -531,9 +613,28 @@ tfhe_b200_circuit *tfhe_b200_circuit_add(tfhe_b200_ctx *ctx, int nbits, int coun
 // a * b mod 2^nbits for `count` pairs (multiplyLweSamples main.cu:1483-1579, single precision;
 // BOOTS_vectorMultiplication :1746): one AND level over the partial-product matrix, then a
 // binary tree of lock-step adders (ripple carry as in the reference, or parallel prefix).
+// partial-product bits of a * b mod 2^nbits appended to the columns of one number: ONE AND gate each
+static void partial_products(Builder &B, const Bits &a, const Bits &b, int nbits,
+                             std::vector<std::vector<int>> &cols) {
+    for (int i = 0; i < nbits; i++)
+        for (int k = i; k < nbits; k++) {
+            const int r = B.alloc(1);
+            B.gate(TFHE_B200_AND, a[k - i], b[i], r);
+            cols[k].push_back(r);
+        }
+}
+
 static void build_mul(Builder &B, const std::vector<Bits> &a, const std::vector<Bits> &b,
                       const std::vector<Bits> &out, int nbits, int adder) {
     const int m = (int) a.size();
+    if (adder == TFHE_B200_ADDER_CARRY_SAVE) {
+        const int zero_row = B.alloc(1);  // never written: the workspace is initialised to the constant 0
+        std::vector<std::vector<std::vector<int>>> cols(m, std::vector<std::vector<int>>(nbits));
+        for (int p = 0; p < m; p++) partial_products(B, a[p], b[p], nbits, cols[p]);
+        B.end_level();
+        B.carry_save_sum(cols, out, nbits, TFHE_B200_ADDER_PREFIX, zero_row);
+        return;
+    }
     // addend rows R[i][p]: (a << i) & b_i ; bits below i are the constant 0 (the whole workspace
     // is initialised to the constant at run time, those rows are never written)
     std::vector<std::vector<Bits>> R(nbits, std::vector<Bits>(m));
@@ -567,7 +668,7 @@ static void build_mul(Builder &B, const std::vector<Bits> &a, const std::vector<
 }
 
 tfhe_b200_circuit *tfhe_b200_circuit_mul_ex(tfhe_b200_ctx *ctx, int nbits, int count, int adder) {
-    if (nbits < 2 || count < 1 || adder < 0 || adder > 1) return nullptr;
+    if (nbits < 2 || count < 1 || adder < 0 || adder > 2) return nullptr;
     tfhe_b200_circuit *c = new_plan(ctx);
     Builder B(c);
     const int a = B.operand(count * nbits), b = B.operand(count * nbits);
@@ -588,13 +689,26 @@ tfhe_b200_circuit *tfhe_b200_circuit_mul(tfhe_b200_ctx *ctx, int nbits, int coun
 // multiplication, then a tree of vector additions over the inner index).
 tfhe_b200_circuit *tfhe_b200_circuit_matmul_ex(tfhe_b200_ctx *ctx, int rows, int inner, int cols, int nbits,
                                                int adder) {
-    if (rows < 1 || inner < 1 || cols < 1 || nbits < 2 || adder < 0 || adder > 1) return nullptr;
+    if (rows < 1 || inner < 1 || cols < 1 || nbits < 2 || adder < 0 || adder > 2) return nullptr;
     tfhe_b200_circuit *c = new_plan(ctx);
     Builder B(c);
     const int A = B.operand(rows * inner * nbits), Bm = B.operand(inner * cols * nbits);
     c->out_row0 = B.alloc(rows * cols * nbits);
     c->out_rows = rows * cols * nbits;
     c->row_zero = -2;
+    if (adder == TFHE_B200_ADDER_CARRY_SAVE) {
+        // every element of C is ONE carry-save sum over the partial-product bits of all its `inner` products
+        const int zero_row = B.alloc(1);
+        std::vector<std::vector<std::vector<int>>> colsv(rows * cols, std::vector<std::vector<int>>(nbits));
+        for (int r = 0; r < rows; r++)
+            for (int q = 0; q < cols; q++)
+                for (int k = 0; k < inner; k++)
+                    partial_products(B, Builder::bits_at(A + (r * inner + k) * nbits, nbits),
+                                     Builder::bits_at(Bm + (k * cols + q) * nbits, nbits), nbits, colsv[r * cols + q]);
+        B.end_level();
+        B.carry_save_sum(colsv, numbers_at(c->out_row0, rows * cols, nbits), nbits, TFHE_B200_ADDER_PREFIX, zero_row);
+        return finish(c);
+    }
     std::vector<Bits> va, vb, vo;
     std::vector<std::vector<Bits>> prod(inner);
     for (int k = 0; k < inner; k++)

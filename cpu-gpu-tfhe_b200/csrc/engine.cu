@@ -79,6 +79,10 @@ const GateDef kGates[TFHE_B200_NUM_GATES_EXT] = {
     // One bootstrap instead of AND followed by OR; not in the reference (extension used by the
     // parallel-prefix adder).  Noise weight 6 sigma^2 < XOR's 8 sigma^2.
     /* GPC   */ {kMu, 2, 1, 1},
+    // Full-adder outputs (carry-save arithmetic): a + b + c in {+-1/8, +-3/8} has the sign of the
+    // majority; -2 (a + b + c) = +-1/4 mod 1, positive for an odd number of ones.
+    /* XOR3  */ {0, -2, -2, -2},
+    /* MAJ   */ {0, 1, 1, 1},
 };
 
 BrLaunch base_launch(const tfhe_b200_ctx *c) {

@@ -63,7 +63,13 @@ enum {
     /* extension (not in the reference): carry operator g | (p & c) for mutually exclusive g, p,
      * one bootstrap of (1/8) + 2g + p + c; operands a = g, b = p, c = c (tfhe_b200_gate_op.c) */
     TFHE_B200_GPC = 10,
-    TFHE_B200_NUM_GATES_EXT = 11
+    /* extensions for carry-save (3:2 compressor) arithmetic: the two outputs of a FULL ADDER, one
+     * bootstrap each, both in the same level.  With bits encoded as +-1/8: a + b + c is +-1/8 or +-3/8,
+     * its sign is the majority (the carry); -2(a + b + c) mod 1 is +1/4 for an odd number of ones and
+     * -1/4 for an even one (the sum bit).  Margins 1/8 and 1/4, input noise 3 and 12 sigma^2. */
+    TFHE_B200_XOR3 = 11, /* a ^ b ^ c */
+    TFHE_B200_MAJ = 12,  /* majority(a, b, c) */
+    TFHE_B200_NUM_GATES_EXT = 13
 };
 
 const char *tfhe_b200_last_error(void);
@@ -166,7 +172,13 @@ tfhe_b200_circuit *tfhe_b200_circuit_add(tfhe_b200_ctx *ctx, int nbits, int coun
  * (3*nbits-3 levels per addition); PREFIX is a Kogge-Stone adder whose carry operator is one
  * three-input bootstrap (TFHE_B200_GPC): 2 + ceil(log2(nbits-1)) levels per addition (SURVEY
  * 8f rank 4, not in the reference).  tfhe_b200_circuit_add mode 2 is the PREFIX adder. */
-enum { TFHE_B200_ADDER_RIPPLE = 0, TFHE_B200_ADDER_PREFIX = 1 };
+enum { TFHE_B200_ADDER_RIPPLE = 0, TFHE_B200_ADDER_PREFIX = 1,
+       /* multipliers / matrix products only: all partial-product bits of a result go through a
+        * carry-save (Wallace) tree of full adders — one level per 3:2 compression, two bootstraps per
+        * full adder (TFHE_B200_XOR3 / TFHE_B200_MAJ) — down to two rows, then ONE parallel-prefix
+        * addition.  32 bits: 16 levels and 2.5 k gates instead of 36 levels and 10.2 k (prefix adders)
+        * or 466 levels (the reference's schedule, multiplyLweSamples main.cu:1483-1579). */
+       TFHE_B200_ADDER_CARRY_SAVE = 2 };
 /* a * b mod 2^nbits for count pairs (multiplyLweSamples main.cu:1483, BOOTS_vectorMultiplication
  * :1746, Cipher::operator* Cipher.cu:83) */
 tfhe_b200_circuit *tfhe_b200_circuit_mul(tfhe_b200_ctx *ctx, int nbits, int count);

@@ -245,3 +245,47 @@ def test_cannon_matrix_multiply(pkg, adder):
         circ = pkg.Circuit(None, "matmul_cannon", n, nbits, adder)
         out = circ.simulate(to_bits(A.reshape(-1) & 0xFF, nbits), to_bits(B.reshape(-1) & 0xFF, nbits))
         assert np.array_equal(from_bits(out, nbits).reshape(n, n), (A @ B) & 0xFF), n
+
+
+@pytest.mark.parametrize("nbits", [2, 3, 4, 5, 8, 16, 32])
+def test_carry_save_multiplication_schedule(pkg, nbits):
+    """TFHE_B200_ADDER_CARRY_SAVE: partial products -> Wallace tree of full adders (XOR3 / MAJ, one level
+    per 3:2 compression) -> one prefix addition.  Exhaustive for small widths, random + corner cases else."""
+    if nbits <= 4:
+        a, b = np.meshgrid(np.arange(2 ** nbits), np.arange(2 ** nbits))
+        a, b = a.reshape(-1), b.reshape(-1)
+    else:
+        rng = np.random.default_rng(nbits)
+        a = rng.integers(0, 2 ** nbits, 40)
+        b = rng.integers(0, 2 ** nbits, 40)
+        a[0] = b[0] = 2 ** nbits - 1
+        a[1], b[1] = 2 ** nbits - 1, 1
+        a[2], b[2] = 0, 2 ** nbits - 1
+    circ = pkg.Circuit(None, "mul_ex", nbits, len(a), 2)
+    out = circ.simulate(to_bits(a, nbits), to_bits(b, nbits))
+    assert np.array_equal(from_bits(out, nbits), (a.astype(object) * b.astype(object)) % 2 ** nbits)
+    circ.close()
+
+
+def test_carry_save_depth_and_size(pkg):
+    """32 bits: 1 AND level + 8 compression levels + 7 levels of the final prefix addition = 16, with a
+    quarter of the gates of the prefix-adder tree (BASELINE config 4)."""
+    cs, prefix = pkg.Circuit(None, "mul_ex", 32, 1, 2), pkg.Circuit(None, "mul_ex", 32, 1, 1)
+    assert cs.levels == 16 and prefix.levels == 36
+    assert cs.gates < prefix.gates / 3
+    a, b = np.array([40000]), np.array([50000])
+    assert from_bits(cs.simulate(to_bits(a, 32), to_bits(b, 32)), 32)[0] == (40000 * 50000) % 2 ** 32
+
+
+def test_carry_save_matrix_multiply_schedule(pkg):
+    nbits, n = 8, 5
+    rng = np.random.default_rng(13)
+    A = rng.integers(-8, 8, (n, n + 1))
+    B = rng.integers(-8, 8, (n + 1, n - 1))
+    circ = pkg.Circuit(None, "matmul_ex", n, n + 1, n - 1, nbits, 2)
+    out = circ.simulate(to_bits(A.reshape(-1) & 0xFF, nbits), to_bits(B.reshape(-1) & 0xFF, nbits))
+    assert np.array_equal(from_bits(out, nbits).reshape(n, n - 1), (A @ B) & 0xFF)
+    ripple = pkg.Circuit(None, "matmul_ex", n, n + 1, n - 1, nbits, 0)
+    assert circ.gates < ripple.gates / 2 and circ.levels < ripple.levels / 4
+    big = pkg.Circuit(None, "matmul_ex", 16, 16, 16, 8, 2)   # BASELINE config 5
+    print("16x16x16 8-bit matmul, carry-save: %d levels, %d gates" % (big.levels, big.gates))

@@ -72,20 +72,49 @@ def test_8_bit_multiplication_vector(pkg, sk_engine):
     circ.close()
 
 
-@pytest.mark.parametrize("adder", [0, 1])
+def test_full_adder_gates(pkg, sk_engine):
+    """TFHE_B200_XOR3 / TFHE_B200_MAJ: sum and carry of a full adder, one bootstrap each, all 8 inputs,
+    on fresh encryptions AND on bootstrapped outputs (the noise a carry-save tree really feeds them)."""
+    sk, eng = sk_engine
+    reps = 60
+    combos = [(a, b, c) for a in (0, 1) for b in (0, 1) for c in (0, 1)]
+    a, b, c = [np.repeat(np.array([x[i] for x in combos], np.int32), reps) for i in range(3)]
+    ea, eb, ec = (eng.to_device(pkg.encrypt_bits(sk, v, 70 + i)) for i, v in enumerate((a, b, c)))
+    assert np.array_equal(pkg.decrypt_bits(sk, eng.gate3(pkg.binding.XOR3, ea, eb, ec).cpu().numpy()), a ^ b ^ c)
+    assert np.array_equal(pkg.decrypt_bits(sk, eng.gate3(pkg.binding.MAJ, ea, eb, ec).cpu().numpy()), (a + b + c) >= 2)
+    ba, bb, bc = (eng.gate("AND", t, t) for t in (ea, eb, ec))   # bootstrapped copies: output noise level
+    assert np.array_equal(pkg.decrypt_bits(sk, eng.gate3(pkg.binding.XOR3, ba, bb, bc).cpu().numpy()), a ^ b ^ c)
+    assert np.array_equal(pkg.decrypt_bits(sk, eng.gate3(pkg.binding.MAJ, ba, bb, bc).cpu().numpy()), (a + b + c) >= 2)
+
+
+@pytest.mark.parametrize("adder", [0, 1, 2])
 def test_32_bit_multiplication(pkg, sk_engine, adder):
-    """BASELINE config 4 (multiplyLweSamples schedule, single precision); adder 1 = prefix tree."""
+    """BASELINE config 4 (multiplyLweSamples schedule, single precision); adder 1 = prefix tree,
+    2 = carry-save tree + one prefix addition."""
     sk, eng = sk_engine
     nbits = 32
     a, b = np.array([40000]), np.array([50000])
     circ = pkg.Circuit(eng, "mul_ex", nbits, 1, adder)
-    assert circ.levels == (466 if adder == 0 else 36)
+    assert circ.levels == {0: 466, 1: 36, 2: 16}[adder]
     out = circ.run(enc_ints(pkg, eng, sk, a, nbits, 7), enc_ints(pkg, eng, sk, b, nbits, 8))
     assert np.array_equal(dec_ints(pkg, sk, out, nbits), (a * b) & 0xFFFFFFFF)
     circ.close()
 
 
-@pytest.mark.parametrize("adder", [0, 1])
+def test_carry_save_multiplier_many_operands(pkg, sk_engine):
+    """16-bit carry-save products of 24 random pairs incl. the all-ones corner (deep carry chains)."""
+    sk, eng = sk_engine
+    nbits = 16
+    rng = np.random.default_rng(44)
+    a, b = rng.integers(0, 2 ** nbits, 24), rng.integers(0, 2 ** nbits, 24)
+    a[0] = b[0] = 2 ** nbits - 1
+    circ = pkg.Circuit(eng, "mul_ex", nbits, len(a), 2)
+    out = circ.run(enc_ints(pkg, eng, sk, a, nbits, 45), enc_ints(pkg, eng, sk, b, nbits, 46))
+    assert np.array_equal(dec_ints(pkg, sk, out, nbits), (a * b) & 0xFFFF)
+    circ.close()
+
+
+@pytest.mark.parametrize("adder", [0, 1, 2])
 def test_matrix_multiply_4x4_of_8_bit(pkg, sk_engine, adder):
     """Reduced BASELINE config 5 (the reference's own test driver uses 4x4, main.cu:2471)."""
     sk, eng = sk_engine
