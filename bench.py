@@ -353,7 +353,7 @@ def circuit_latencies(pkg, eng, sk):
 def matmul_config5(pkg, eng, tdist, sk, p, dev, world, rank, barrier):
     """BASELINE configs[4]: 16x16 matrix multiply of 8-bit integers on the launched GPUs
     (cpu-gpu-tfhe_b200/dist.py ShardedMatmul: rows of C sharded, every rank holds the encrypted A and
-    B, the only exchange is the final gather).  Two schedules: the parallel-prefix adders (the product's
+    B, the only exchange is the final gather).  Two schedules: a carry-save tree per element of C (the product's
     own) and the reference's ripple adders (BOOTS_matrixMultiplication, main.cu:2342).  Device time,
     max over ranks; rank 0 decrypts and checks."""
     import torch
@@ -606,7 +606,10 @@ def run_b200(args):
             "roofline": {
                 "bound": "fp64", "kernel": "blind_rotate_kernel", "achieved": achieved, "peak": peak_sust,
                 "unit": "TFLOP/s", "frac": achieved / peak_sust, "traffic": traffic,
-                "peak_burst": peak_burst, "peak_source": "measured live (DFMA micro-benchmark, sustained 0.4 s)",
+                "peak_burst": peak_burst, "peak_source": "measured live (DFMA micro-benchmark, sustained 0.4 s); "
+                "MEASURED_PEAKS.json has no fp64 entry",
+                "peak_theoretical": eng.sm_count * 128 * (sampler.result()["sm_max_mhz"] or 1965) * 1e6 / 1e12,
+                "frac_of_theoretical": achieved / (eng.sm_count * 128 * (sampler.result()["sm_max_mhz"] or 1965) * 1e6 / 1e12),
                 "kernel_ms_per_launch": br_ms_per_launch,
                 "flop_per_launch": batch * FLOP_PER_BOOTSTRAP,
                 "share_of_step": br_ms / ms, "keyswitch_ms_per_launch": ks_ms / max(1, calls),
