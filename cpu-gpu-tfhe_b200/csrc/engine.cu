@@ -418,6 +418,44 @@ int tfhe_b200_load_bk_fourier(tfhe_b200_ctx *c, const double *ref) {
     return 0;
 }
 
+// ---- device buffers through the library's own runtime (hosts without CUDA headers) ----------
+int tfhe_b200_device_alloc(tfhe_b200_ctx *c, void **d_ptr, size_t bytes) {
+    if (!c || !d_ptr) return fail("null argument");
+    CU(cudaSetDevice(c->device));
+    CU(cudaMalloc(d_ptr, bytes ? bytes : 1));
+    return 0;
+}
+
+int tfhe_b200_device_free(tfhe_b200_ctx *c, void *d_ptr) {
+    if (!c) return fail("null context");
+    CU(cudaSetDevice(c->device));
+    CU(cudaFree(d_ptr));
+    return 0;
+}
+
+int tfhe_b200_copy_to_device(tfhe_b200_ctx *c, void *d_dst, const void *h_src, size_t bytes, void *stream) {
+    if (!c || (!d_dst && bytes) || (!h_src && bytes)) return fail("null argument");
+    CU(cudaSetDevice(c->device));
+    CU(cudaMemcpyAsync(d_dst, h_src, bytes, cudaMemcpyHostToDevice, (cudaStream_t) stream));
+    CU(cudaStreamSynchronize((cudaStream_t) stream));
+    return 0;
+}
+
+int tfhe_b200_copy_to_host(tfhe_b200_ctx *c, void *h_dst, const void *d_src, size_t bytes, void *stream) {
+    if (!c || (!h_dst && bytes) || (!d_src && bytes)) return fail("null argument");
+    CU(cudaSetDevice(c->device));
+    CU(cudaMemcpyAsync(h_dst, d_src, bytes, cudaMemcpyDeviceToHost, (cudaStream_t) stream));
+    CU(cudaStreamSynchronize((cudaStream_t) stream));
+    return 0;
+}
+
+int tfhe_b200_synchronize(tfhe_b200_ctx *c, void *stream) {
+    if (!c) return fail("null context");
+    CU(cudaSetDevice(c->device));
+    CU(cudaStreamSynchronize((cudaStream_t) stream));
+    return 0;
+}
+
 // ------------------------------------------------------------------- gates --
 
 int tfhe_b200_gate(tfhe_b200_ctx *c, int gate, int32_t *d_out, const int32_t *d_ca, const int32_t *d_cb,

@@ -94,6 +94,17 @@ int tfhe_b200_load_ks(tfhe_b200_ctx *ctx, const int32_t *ks);
 /* bytes of device memory held by the keys */
 size_t tfhe_b200_key_bytes(const tfhe_b200_ctx *ctx);
 
+/* ---- device buffers for hosts without the CUDA headers (cgo / JNI / plain C) ----------------
+ * Sample batches for the device-buffer entry points below can be allocated and moved with any CUDA
+ * runtime in the process; these five calls are the same thing through this library's own runtime,
+ * so that a host needs nothing but this header.  bytes = rows * (n + 1) * 4 for samples.  stream = NULL:
+ * the default stream; the copies are synchronous with respect to the host. */
+int tfhe_b200_device_alloc(tfhe_b200_ctx *ctx, void **d_ptr, size_t bytes);
+int tfhe_b200_device_free(tfhe_b200_ctx *ctx, void *d_ptr);
+int tfhe_b200_copy_to_device(tfhe_b200_ctx *ctx, void *d_dst, const void *h_src, size_t bytes, void *stream);
+int tfhe_b200_copy_to_host(tfhe_b200_ctx *ctx, void *h_dst, const void *d_src, size_t bytes, void *stream);
+int tfhe_b200_synchronize(tfhe_b200_ctx *ctx, void *stream);
+
 /* ---- batched gates on DEVICE buffers (asynchronous on `stream`) ----------
  * out may alias an input (the reference's callers do this, Cipher.cu:373). */
 int tfhe_b200_gate(tfhe_b200_ctx *ctx, int gate, int32_t *d_out, const int32_t *d_ca, const int32_t *d_cb,
