@@ -116,9 +116,12 @@ int check_ctx(const tfhe_b200_ctx *c, bool need_bk, bool need_ks) {
 // large batches: the contraction runs on the tensor cores (128-gate tiles); small ones stay on
 // the SIMT kernel, which splits a single gate over the whole chip
 int run_keyswitch(tfhe_b200_ctx *c, const KsLaunch &K, cudaStream_t st) {
+    // crossover measured in round 2 (tools/ks_bench.py): the tensor-core kernel costs a flat 0.285 ms up
+    // to 1024 gates (one pass over its quarter of the table per CTA), the SIMT kernel 0.09 ms (1 gate),
+    // 0.27 ms (256), 0.38 ms (296), 0.72 ms (592), 0.96 ms (1024)
     static const int mma_min = [] {
         const char *v = getenv("TFHE_B200_KS_MMA_MIN");
-        return v ? atoi(v) : 2048;
+        return v ? atoi(v) : 272;
     }();
     if (c->d_ks_mma && mma_min > 0 && K.count >= mma_min) {
         CU(launch_keyswitch_mma(K, c->d_ks_mma, st));

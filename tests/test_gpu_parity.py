@@ -123,7 +123,7 @@ def test_init_and_extract_exact(engine, oracle, ctx_ref):
         assert np.array_equal(u[r], expect), barb
 
 
-@pytest.mark.parametrize("count", [1, 3, 16, 17, 5000])
+@pytest.mark.parametrize("count", [1, 3, 16, 17, 271, 272, 300, 5000])
 def test_keyswitch_bit_exact(engine, ctx_ref, count):
     rng = np.random.default_rng(15 + count)
     u = _rand_i32(rng, (count, 1025))
@@ -134,7 +134,7 @@ def test_keyswitch_bit_exact(engine, ctx_ref, count):
 
 
 def test_tensor_core_keyswitch_equals_simt_kernel(engine):
-    """Batches of >= 2048 samples take the tcgen05 int8 path (keyswitch_mma.cu); smaller ones the
+    """Batches of >= 272 samples take the tcgen05 int8 path (keyswitch_mma.cu); smaller ones the
     SIMT kernel.  Same integers, bit for bit, on a ragged batch (not a multiple of the 128-gate tile)."""
     import torch
 
@@ -142,7 +142,7 @@ def test_tensor_core_keyswitch_equals_simt_kernel(engine):
     count = 2309
     u = engine.to_device(_rand_i32(rng, (count, 1025)))
     got = engine.keyswitch(u)
-    parts = [engine.keyswitch(u[lo:lo + 1000].contiguous()) for lo in range(0, count, 1000)]
+    parts = [engine.keyswitch(u[lo:lo + 250].contiguous()) for lo in range(0, count, 250)]   # SIMT kernel
     assert torch.equal(got, torch.cat(parts, 0))
 
 
