@@ -77,6 +77,21 @@ struct cpx {
 // 128-bit stores would need, put 32 single-word readers on 8 banks: measured slower).
 constexpr int kExtRow = 127;
 constexpr int kExtOrg = 63;       // word of row[0]; -row[i] is at word i - 1 (row[0] has no left image)
+// Bank placement of the 16 rows of a polynomial.  With consecutive rows (GAP = 0) row j2 starts in bank
+// -j2: the rotated single-word reads of 16 rows are conflict free, but the final stage stores, in ONE
+// instruction, words w (lanes (0, j2)) and w + 8 (lanes (1, j2)) of all 16 rows: the two 16-bank windows
+// overlap by 8 banks (2-way conflict on every one of the 127 stores: 19 % of all store wavefronts of the
+// round-2 kernel, ncu l1tex__data_bank_conflicts_pipe_lsu_mem_shared_op_st).  GAP = 24 words in front of
+// row 8 puts rows 0..7 in banks {0, 31 .. 25} and rows 8..15 in banks {16 .. 9}: that set and the same
+// set + 8 are disjoint, and the rotated reads stay conflict free (the lanes whose rotation wraps read one
+// word lower: still distinct banks).  The latency kernel reads words w and w + 16 of a row in one
+// instruction (lane-pair split of pass 1) and keeps GAP = 0.
+#ifndef TFHE_B200_EXT_GAP
+#define TFHE_B200_EXT_GAP 24
+#endif
+constexpr int kExtGapThroughput = TFHE_B200_EXT_GAP;
+template <int GAP>
+TFHE_HD int ext_row_off(int j2) { return j2 * kExtRow + GAP * (j2 >> 3); }
 
 struct alignas(16) word4 {
     int32_t v[4];
@@ -91,7 +106,7 @@ struct WarpSmem {
     };
     int32_t acc[kK + 1][kAccPoly]; // 2 * 4160 B: the accumulator (master copy)
 };
-static_assert(16 * kExtRow <= kExchPoly * 4, "extended copy must fit an exchange buffer");
+static_assert(16 * kExtRow + kExtGapThroughput <= kExchPoly * 4, "extended copy must fit an exchange buffer");
 
 // Working set of the LATENCY kernel (four warps per ciphertext, one ciphertext per CTA: blind_rotate.cu
 // blind_rotate_quad_kernel): the extended accumulator copies have buffers of their own (both warps of
@@ -355,10 +370,11 @@ TFHE_HD void phase_init(int lane, WarpSmem &ws, int o, int barb, int32_t mu) { p
 
 // Build the extended copy of accumulator polynomial o from its master copy (start of a ciphertext;
 // afterwards phase_i2_final keeps it up to date).  Lane (h, j2) copies coefficients [32h, 32h+32) of row j2.
+template <int GAP = 0>
 TFHE_HD void phase_ext_build_p(int lane, const int32_t *acc_o, int32_t *ext_o) {
     const int h = lane >> 4, j2 = lane & 15;
     const int32_t *row = acc_o + j2 * kAccRow + 32 * h;
-    int32_t *ext = ext_o + j2 * kExtRow + 32 * h;
+    int32_t *ext = ext_o + ext_row_off<GAP>(j2) + 32 * h;
 #pragma unroll 2
     for (int b = 0; b < 32; b += 4) {
         const word4 v = *reinterpret_cast<const word4 *>(row + b);
@@ -370,7 +386,9 @@ TFHE_HD void phase_ext_build_p(int lane, const int32_t *acc_o, int32_t *ext_o) {
     }
 }
 
-TFHE_HD void phase_ext_build(int lane, WarpSmem &ws, int o) { phase_ext_build_p(lane, ws.acc[o], ext_poly(ws, o)); }
+TFHE_HD void phase_ext_build(int lane, WarpSmem &ws, int o) {
+    phase_ext_build_p<kExtGapThroughput>(lane, ws.acc[o], ext_poly(ws, o));
+}
 
 // Pass 1 of the two forward transforms of accumulator polynomial o (decomposed rows (o, q), q = 0..l-1),
 // fused with the rotation (torusPolynomialMulByXaiMinusOne, toruspolynomial-functions.cu:191-213)
@@ -389,6 +407,7 @@ TFHE_HD void phase_ext_build(int lane, WarpSmem &ws, int o) { phase_ext_build_p(
 // The outputs are NOT stored here: the extended copy lives in buffer A, which the stores overwrite
 // (the caller separates the two with a __syncwarp).
 // (pointer form: digit level q of slice j2 of the polynomial whose master / extended copy are given)
+template <int GAP = 0>
 TFHE_HD void phase_f1_decomp_p(int j2, int q, const int32_t *acc_o, const int32_t *ext_o, int a, bool rotate,
                                cpx (&x)[32]) {
     const int a_lo = a & 15, a_hi = a >> 4;
@@ -400,7 +419,7 @@ TFHE_HD void phase_f1_decomp_p(int j2, int q, const int32_t *acc_o, const int32_
     const uint32_t cm = rotate ? 0u - m : m;                            // multiplier of ACC itself
     const uint32_t offm = kDecompOffset * m;
     const int32_t *own = acc_o + j2 * kAccRow;
-    const int32_t *rot = ext_o + j2p * kExtRow + (kExtOrg - h);
+    const int32_t *rot = ext_o + ext_row_off<GAP>(j2p) + (kExtOrg - h);
 #pragma unroll
     for (int blk = 0; blk < 64; blk += 16) {
         uint32_t vr[16], vo[16];
@@ -424,7 +443,7 @@ TFHE_HD void phase_f1_decomp_p(int j2, int q, const int32_t *acc_o, const int32_
 }
 
 TFHE_HD void phase_f1_decomp(int lane, WarpSmem &ws, int o, int a, bool rotate, cpx (&x)[32]) {
-    phase_f1_decomp_p(lane & 15, lane >> 4, ws.acc[o], ext_poly(ws, o), a, rotate, x);
+    phase_f1_decomp_p<kExtGapThroughput>(lane & 15, lane >> 4, ws.acc[o], ext_poly(ws, o), a, rotate, x);
 }
 
 // Stages 0-4 of the two transforms on the decomposed digits (no shared-memory access).
@@ -636,10 +655,11 @@ TFHE_HD void phase_i2_send(int lane, const cpx (&x)[16], cpx (&send)[8]) {
 // coefficients (+32) from the imaginary parts: four groups of 8 consecutive words.
 // With mine / theirs = the value of this lane / of the partner lane, u + v = mine + theirs and
 // conj(e) (u - v) = (+-conj(e)) (mine - theirs), sign by lane: identical arithmetic in both lanes.
+template <int GAP = 0>
 TFHE_HD void phase_i2_final_p(int lane, int32_t *acc_o, int32_t *ext_o, const cpx (&x)[16], const cpx (&p)[8]) {
     const int hh = lane >> 4, j2 = lane & 15;
     int32_t *row = acc_o + j2 * kAccRow + 8 * hh;
-    int32_t *ext = ext_o + j2 * kExtRow + 8 * hh;  // extended copy, same coefficients
+    int32_t *ext = ext_o + ext_row_off<GAP>(j2) + 8 * hh;  // extended copy, same coefficients
     const double er = hh ? -c1_re_rt(0) : c1_re_rt(0), ei = hh ? -c1_im_rt(0) : c1_im_rt(0);
     // all loads first (128-bit accesses to the master copy: the 8 consecutive coefficients of a group
     // are two aligned quads), then the butterflies and conversions, then the updates
@@ -678,7 +698,7 @@ TFHE_HD void phase_i2_final_p(int lane, int32_t *acc_o, int32_t *ext_o, const cp
 }
 
 TFHE_HD void phase_i2_final(int lane, WarpSmem &ws, int o, const cpx (&x)[16], const cpx (&p)[8]) {
-    phase_i2_final_p(lane, ws.acc[o], ext_poly(ws, o), x, p);
+    phase_i2_final_p<kExtGapThroughput>(lane, ws.acc[o], ext_poly(ws, o), x, p);
 }
 
 // Stand-alone external product: the result REPLACES the accumulator, so the master copy is
