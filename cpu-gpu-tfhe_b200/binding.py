@@ -24,6 +24,7 @@ CMP = {"GT": 0, "LE": 1, "LT": 2, "GE": 3, "EQ": 4, "NE": 5}   # TFHE_B200_CMP_*
 SHIFT = {"LEFT": 0, "RIGHT_LOGICAL": 1, "RIGHT_ARITH": 2}         # TFHE_B200_SHIFT_*
 GPC = 10      # TFHE_B200_GPC: carry operator g | (p & c) for mutually exclusive g, p (extension)
 XOR3, MAJ = 11, 12   # full-adder outputs a ^ b ^ c and majority(a, b, c), one bootstrap each (extensions)
+SUMC = 13            # a ^ (b | (c & d)), b and c exclusive: fused sum bit of the prefix adder (extension)
 ADDER = {"RIPPLE": 0, "PREFIX": 1, "CARRY_SAVE": 2}   # TFHE_B200_ADDER_*
 
 
@@ -37,7 +38,8 @@ class GateOp(ctypes.Structure):
                 ("out", ctypes.c_void_p), ("stride_a", ctypes.c_int64), ("stride_b", ctypes.c_int64),
                 ("stride_out", ctypes.c_int64), ("idx_a", ctypes.c_void_p), ("idx_b", ctypes.c_void_p),
                 ("idx_out", ctypes.c_void_p), ("c", ctypes.c_void_p), ("stride_c", ctypes.c_int64),
-                ("idx_c", ctypes.c_void_p)]
+                ("idx_c", ctypes.c_void_p), ("d", ctypes.c_void_p), ("stride_d", ctypes.c_int64),
+                ("idx_d", ctypes.c_void_p)]
 
 
 class Params(ctypes.Structure):
@@ -431,14 +433,15 @@ class Engine:
                                        self._stream(stream)))
         return out
 
-    def gate3(self, gate_id, a, b, c, out=None, stream=None):
-        """A three-input threshold gate (GPC, XOR3, MAJ) on batches of samples, one bootstrap each."""
-        for t in (a, b, c):
+    def gate3(self, gate_id, a, b, c, out=None, stream=None, d=None):
+        """A three- (GPC, XOR3, MAJ) or four-input (SUMC, with d) threshold gate on batches of samples."""
+        for t in (a, b, c) + ((d,) if d is not None else ()):
             self._chk(t, self.words)
         count = a.shape[0]
         out = self.empty(count) if out is None else out
         op = GateOp(gate_id, count, a.data_ptr(), b.data_ptr(), out.data_ptr(), self.words, self.words, self.words,
-                    None, None, None, c.data_ptr(), self.words, None)
+                    None, None, None, c.data_ptr(), self.words, None,
+                    d.data_ptr() if d is not None else None, self.words, None)
         self._ck(self.L.tfhe_b200_gate_multi(self.h, ctypes.byref(op), 1, self._stream(stream)))
         return out
 

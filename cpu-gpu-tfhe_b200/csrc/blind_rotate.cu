@@ -272,11 +272,19 @@ __device__ __forceinline__ void ring_skip(CtaSmem &S, const BrLaunch &L, int rol
     sp.advance((uint32_t) L.n_iter);
 }
 
-// Operands of the gate prologue of bootstrap g (x = (0,cst) + sa*in0 + sb*in1 [+ sc*in2]).
+// Operands of the gate prologue of bootstrap g (x = (0,cst) + sa*in0 + sb*in1 [+ sc*in2 [+ sd*in3]]).
 struct GateIn {
-    const int32_t *in0 = nullptr, *in1 = nullptr, *in2 = nullptr;
-    uint32_t sa = 0, sb = 0, sc = 0, cst = 0;
+    const int32_t *in0 = nullptr, *in1 = nullptr, *in2 = nullptr, *in3 = nullptr;
+    uint32_t sa = 0, sb = 0, sc = 0, sd = 0, cst = 0;
 };
+
+// word `idx` of the linear combination (idx = n: the body, incl. the gate's constant)
+__device__ __forceinline__ uint32_t prologue_word(const GateIn &I, int idx, uint32_t cst) {
+    uint32_t x = cst + I.sa * (uint32_t) __ldg(I.in0 + idx) + I.sb * (uint32_t) __ldg(I.in1 + idx);
+    if (I.in2 != nullptr) x += I.sc * (uint32_t) __ldg(I.in2 + idx);
+    if (I.in3 != nullptr) x += I.sd * (uint32_t) __ldg(I.in3 + idx);
+    return x;
+}
 
 __device__ __forceinline__ GateIn resolve_inputs(const BrLaunch &L, int g) {
     GateIn I;
@@ -298,6 +306,11 @@ __device__ __forceinline__ GateIn resolve_inputs(const BrLaunch &L, int g) {
         I.in2 = L.seg[si].in2 + r2 * L.seg[si].stride2;
         I.sc = (uint32_t) L.seg[si].sc;
     }
+    if (L.seg[si].in3 != nullptr) {
+        const long long r3 = L.seg[si].idx3 ? (long long) __ldg(L.seg[si].idx3 + local) : (long long) local;
+        I.in3 = L.seg[si].in3 + r3 * L.seg[si].stride3;
+        I.sd = (uint32_t) L.seg[si].sd;
+    }
     I.cst = (uint32_t) L.seg[si].cst;
     return I;
 }
@@ -306,9 +319,7 @@ __device__ __forceinline__ GateIn resolve_inputs(const BrLaunch &L, int g) {
 __device__ __forceinline__ int load_bara(const BrLaunch &L, const GateIn &I, int g, int idx, int n_iter, bool rotate) {
     if (idx >= n_iter || !rotate) return 0;
     if (L.explicit_inputs != 0) return __ldg(L.bara + (size_t) g * n_iter + idx) & (2 * kN - 1);
-    uint32_t xa = I.sa * (uint32_t) __ldg(I.in0 + idx) + I.sb * (uint32_t) __ldg(I.in1 + idx);
-    if (I.in2 != nullptr) xa += I.sc * (uint32_t) __ldg(I.in2 + idx);
-    return modswitch_2N(xa);
+    return modswitch_2N(prologue_word(I, idx, 0u));
 }
 
 // TFHE_B200_EXP_NOBAR: timing-only experiment (garbage results): the pair barriers cost nothing
@@ -429,7 +440,11 @@ __global__ void __launch_bounds__(kThreads, 1) blind_rotate_kernel(const BrLaunc
     const bool rotate = (L.extern_only == 0);
 
     // -------------------- ciphertext warps ------------------------------------------
-    const int ct = warp >> 1, role = warp & 1;   // sub-partition w % 4 holds the same role of two ciphertexts
+#ifndef TFHE_B200_ROLE_SWIZZLE
+#define TFHE_B200_ROLE_SWIZZLE 0
+#endif
+    // sub-partition w % 4 holds the same role of two ciphertexts (SWIZZLE: the two roles, experiment)
+    const int ct = warp >> 1, role = TFHE_B200_ROLE_SWIZZLE ? ((warp & 1) ^ ((warp >> 2) & 1)) : (warp & 1);
     // small batches: slots that never hold a ciphertext and are not the helper slot have nothing to do
     if (HELPER && ct >= cpg && ct != kCtWarps - 1) return;
     const unsigned int ncons = HELPER ? (unsigned int) cpg + 1u : (unsigned int) kCtWarps;
@@ -468,9 +483,7 @@ __global__ void __launch_bounds__(kThreads, 1) blind_rotate_kernel(const BrLaunc
             int barb;  // each role initialises its own polynomial
             if (L.explicit_inputs != 0) barb = L.barb ? (__ldg(L.barb + g) & (2 * kN - 1)) : 0;
             else {
-                uint32_t xb = I.cst + I.sa * (uint32_t) __ldg(I.in0 + L.n) + I.sb * (uint32_t) __ldg(I.in1 + L.n);
-                if (I.in2 != nullptr) xb += I.sc * (uint32_t) __ldg(I.in2 + L.n);
-                barb = modswitch_2N(xb);
+                barb = modswitch_2N(prologue_word(I, L.n, I.cst));
             }
             phase_init(lane, W, role, barb, L.mu);
         }
@@ -717,9 +730,7 @@ __global__ void __launch_bounds__(kThreads, 1) blind_rotate_quad_kernel(const Br
             int barb;
             if (L.explicit_inputs != 0) barb = L.barb ? (__ldg(L.barb + g) & (2 * kN - 1)) : 0;
             else {
-                uint32_t xb = I.cst + I.sa * (uint32_t) __ldg(I.in0 + L.n) + I.sb * (uint32_t) __ldg(I.in1 + L.n);
-                if (I.in2 != nullptr) xb += I.sc * (uint32_t) __ldg(I.in2 + L.n);
-                barb = modswitch_2N(xb);
+                barb = modswitch_2N(prologue_word(I, L.n, I.cst));
             }
             phase_init_p(lane, W.acc[o], o, barb, L.mu);
         }

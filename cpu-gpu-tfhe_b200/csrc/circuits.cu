@@ -33,6 +33,7 @@ enum { LIN_COPY = 0, LIN_NOT = 1, LIN_ZERO = 2, LIN_ONE = 3, LIN_KINDS = 4 };
 
 struct Op {
     int gate, count, off_a, off_b, off_out, off_c;
+    int off_d = -1;  // fourth operand (TFHE_B200_SUMC)
 };
 
 struct Level {
@@ -78,7 +79,7 @@ struct Builder {
     tfhe_b200_circuit *c;
     // gates of the level under construction, grouped by gate type
     std::vector<int> ga[TFHE_B200_NUM_GATES_EXT], gb[TFHE_B200_NUM_GATES_EXT], go[TFHE_B200_NUM_GATES_EXT],
-        gc[TFHE_B200_NUM_GATES_EXT];
+        gc[TFHE_B200_NUM_GATES_EXT], gd[TFHE_B200_NUM_GATES_EXT];
     std::vector<int> ms, mb, mc, mo;                  // MUX: selector, then-value, else-value, out
     std::vector<int> li[LIN_KINDS], lo[LIN_KINDS];    // LINEAR
 
@@ -111,11 +112,12 @@ struct Builder {
     }
 
     // schedule out = gate(a, b [, c3]) in the current level
-    void gate(int g, int a, int b, int out, int c3 = -1) {
+    void gate(int g, int a, int b, int out, int c3 = -1, int c4 = -1) {
         ga[g].push_back(a);
         gb[g].push_back(b);
         go[g].push_back(out);
         if (c3 >= 0) gc[g].push_back(c3);
+        if (c4 >= 0) gd[g].push_back(c4);
     }
     void mux(int sel, int b, int cc, int out) {  // out = sel ? b : cc
         ms.push_back(sel);
@@ -154,11 +156,13 @@ struct Builder {
             op.off_b = push_idx(gb[g]);
             op.off_out = push_idx(go[g]);
             op.off_c = gc[g].empty() ? -1 : push_idx(gc[g]);
+            op.off_d = gd[g].empty() ? -1 : push_idx(gd[g]);
             c->n_gates += op.count;
             ga[g].clear();
             gb[g].clear();
             go[g].clear();
             gc[g].clear();
+            gd[g].clear();
         }
         if (lv.nops) {
             c->levels.push_back(lv);
@@ -238,9 +242,24 @@ struct Builder {
     // generate signal of bits [0, k] (the carry into bit k+1).  The generate / propagate signals
     // of a bit group are mutually exclusive, so the carry operator G' = G | (P & G_prev) is ONE
     // three-input threshold bootstrap (TFHE_B200_GPC).  np positions per number.
-    void prefix_scan(std::vector<Bits> &G, std::vector<Bits> &P, int np) {
+    // fuse_prop / fuse_out (optional): the LAST level does not produce the carries but, fused with the
+    // carry operator, the sum bits themselves: out[k+1] = prop[k+1] ^ carry_k in ONE bootstrap
+    // (TFHE_B200_SUMC: prop ^ (G | (P & G_prev))), or prop[k+1] ^ G[k] for the carries that are final
+    // already — so an addition ends with its last scan level instead of one level after it.
+    void prefix_scan(std::vector<Bits> &G, std::vector<Bits> &P, int np, const std::vector<Bits> *fuse_prop = nullptr,
+                     const std::vector<Bits> *fuse_out = nullptr) {
         const int m = (int) G.size();
         for (int d = 1; d < np; d *= 2) {
+            if (fuse_prop != nullptr && 2 * d >= np) {  // last level
+                for (int i = 0; i < m; i++)
+                    for (int k = 0; k < np; k++) {
+                        const int prow = (*fuse_prop)[i][k + 1], orow = (*fuse_out)[i][k + 1];
+                        if (k >= d) gate(TFHE_B200_SUMC, prow, G[i][k], orow, P[i][k], G[i][k - d]);
+                        else gate(TFHE_B200_XOR, prow, G[i][k], orow);
+                    }
+                end_level();
+                return;
+            }
             // position k holds the signals of bits [max(0, k-d+1), k]; after this level 2d bits
             std::vector<Bits> G2 = G, P2 = P;
             const bool more = 2 * d < np;
@@ -259,7 +278,8 @@ struct Builder {
         }
     }
 
-    // Parallel-prefix addition: 2 + ceil(log2(nbits-1)) levels instead of 3*nbits - 3
+    // Parallel-prefix addition: 1 + ceil(log2(nbits-1)) levels instead of 3*nbits - 3 (the last scan level
+    // produces the sum bits directly, TFHE_B200_SUMC)
     // (the ripple schedules are bound by sequential depth).
     void prefix_add(const std::vector<Bits> &a, const std::vector<Bits> &b, const std::vector<Bits> &out, int nbits,
                     bool cin1 = false) {
@@ -282,8 +302,9 @@ struct Builder {
             }
         }
         end_level();
-        if (np > 0) prefix_scan(G, P, np);
-        if (nbits > 1) {
+        if (np > 1) {  // at least one scan level: the last one produces the sum bits directly
+            prefix_scan(G, P, np, &prop, &out);
+        } else if (nbits > 1) {
             for (int i = 0; i < m; i++)
                 for (int bit = 1; bit < nbits; bit++) gate(TFHE_B200_XOR, prop[i][bit], G[i][bit - 1], out[i][bit]);
             end_level();
@@ -531,7 +552,7 @@ int ensure_device(tfhe_b200_circuit *c) {
 }
 
 // plaintext truth tables of the gate ids (boot-gates.cu:98-397 and the GPC extension)
-int gate_truth(int g, int a, int b, int c3) {
+int gate_truth(int g, int a, int b, int c3, int c4 = 0) {
     switch (g) {
         case TFHE_B200_NAND: return !(a && b);
         case TFHE_B200_OR: return a || b;
@@ -546,6 +567,7 @@ int gate_truth(int g, int a, int b, int c3) {
         case TFHE_B200_GPC: return a || (b && c3);
         case TFHE_B200_XOR3: return a ^ b ^ c3;
         case TFHE_B200_MAJ: return (a + b + c3) >= 2;
+        case TFHE_B200_SUMC: return a ^ (b || (c3 && c4));
         default: return 0;
     }
 }
@@ -571,7 +593,7 @@ extern "C" {
 // a + b for `count` pairs of nbits-bit integers (LSB first).  mode 0: bit-wise ripple carry,
 // 3*nbits - 3 levels; mode 1: number-wise carry-save iteration (taskLevelParallelAdd,
 // main.cu:619-652): nbits levels of 2*nbits gates per number; mode 2: parallel-prefix adder,
-// 2 + ceil(log2(nbits-1)) levels (not in the reference).
+// 1 + ceil(log2(nbits-1)) levels (not in the reference).
 tfhe_b200_circuit *tfhe_b200_circuit_add(tfhe_b200_ctx *ctx, int nbits, int count, int mode) {
     if (nbits < 1 || count < 1 || mode < 0 || mode > 2) return nullptr;
     tfhe_b200_circuit *c = new_plan(ctx);
@@ -1159,6 +1181,9 @@ void fill_gate_op(const tfhe_b200_circuit *c, const Op &op, tfhe_b200_gate_op &o
     o.c = op.off_c >= 0 ? c->d_ws : nullptr;
     o.stride_c = c->words;
     o.idx_c = op.off_c >= 0 ? c->d_idx + op.off_c : nullptr;
+    o.d = op.off_d >= 0 ? c->d_ws : nullptr;
+    o.stride_d = c->words;
+    o.idx_d = op.off_d >= 0 ? c->d_idx + op.off_d : nullptr;
 }
 
 int issue_mux_or_linear(tfhe_b200_circuit *c, const Level &lv, void *stream) {
@@ -1342,7 +1367,8 @@ int tfhe_b200_circuit_simulate(const tfhe_b200_circuit *c, int32_t *out_bits, co
                 if (lv.type == LV_GATES) {
                     const int a = ws[c->h_idx[op.off_a + g]], b = ws[c->h_idx[op.off_b + g]];
                     const int c3 = op.off_c >= 0 ? ws[c->h_idx[op.off_c + g]] : 0;
-                    v = gate_truth(op.gate, a, b, c3);
+                    const int c4 = op.off_d >= 0 ? ws[c->h_idx[op.off_d + g]] : 0;
+                    v = gate_truth(op.gate, a, b, c3, c4);
                 } else if (lv.type == LV_MUX) {
                     v = ws[c->h_idx[op.off_a + g]] ? ws[c->h_idx[op.off_b + g]] : ws[c->h_idx[op.off_c + g]];
                 } else {

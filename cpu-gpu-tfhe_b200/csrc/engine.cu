@@ -59,6 +59,7 @@ struct GateDef {
     int32_t cst;
     int sa, sb;
     int sc = 0;  // weight of the optional third operand
+    int sd = 0;  // ... and of the fourth
 };
 
 // modSwitchToTorus32(+-1, 8) = +-0x20000000, (+-1, 4) = +-0x40000000 (numeric-functions.cu:72-77)
@@ -83,6 +84,11 @@ const GateDef kGates[TFHE_B200_NUM_GATES_EXT] = {
     // majority; -2 (a + b + c) = +-1/4 mod 1, positive for an odd number of ones.
     /* XOR3  */ {0, -2, -2, -2},
     /* MAJ   */ {0, 1, 1, 1},
+    // Sum bit of a parallel-prefix adder fused with the last carry operator: p ^ (g | (pp & c)), g and pp
+    // mutually exclusive.  v = 2p + 2g + pp + c in {0..5}; the sum is 1 exactly for v in {2, 3}; the phase
+    // (v - 1.5) / 4 mod 1 puts those two values at +1/8, +3/8 and the other four at -3/8, -1/8: the
+    // standard 1/8 margin, noise weight 10 sigma^2.  Operands a = p, b = g, c = pp, d = c.
+    /* SUMC  */ {3 * kMu, 2, 2, 1, 1},
 };
 
 BrLaunch base_launch(const tfhe_b200_ctx *c) {
@@ -510,6 +516,7 @@ int tfhe_b200_gate_multi(tfhe_b200_ctx *c, const tfhe_b200_gate_op *ops, int nop
         if (o.count < 0) return fail("negative count");
         if (o.count == 0) continue;
         if ((kGates[o.gate].sc != 0) != (o.c != nullptr)) return fail("gate %d: third operand mismatch", o.gate);
+        if ((kGates[o.gate].sd != 0) != (o.d != nullptr)) return fail("gate %d: fourth operand mismatch", o.gate);
         BrSegment &sg = L.seg[nseg];
         sg.in0 = o.a;
         sg.in1 = o.b;
@@ -525,6 +532,10 @@ int tfhe_b200_gate_multi(tfhe_b200_ctx *c, const tfhe_b200_gate_op *ops, int nop
         sg.stride2 = o.stride_c;
         sg.idx2 = o.idx_c;
         sg.sc = kGates[o.gate].sc;
+        sg.in3 = o.d;
+        sg.stride3 = o.stride_d;
+        sg.idx3 = o.idx_d;
+        sg.sd = kGates[o.gate].sd;
         dst[nseg].out = o.out;
         dst[nseg].stride = o.stride_out;
         dst[nseg].count = o.count;

@@ -9,7 +9,7 @@ namespace tfhe_b200 {
 
 struct cpx;
 
-// One homogeneous run of bootstraps inside a batch: x = (0,cst) + sa*in0 + sb*in1 [+ sc*in2]
+// One homogeneous run of bootstraps inside a batch: x = (0,cst) + sa*in0 + sb*in1 [+ sc*in2 [+ sd*in3]]
 // (gate prologues, boot-gates.cu:98-448).  Samples are int32[n+1] rows.
 struct BrSegment {
     const int32_t *in0;
@@ -23,6 +23,11 @@ struct BrSegment {
     const int32_t *in2;
     long long stride2;
     const int32_t *idx2;
+    // optional fourth operand (the fused sum bit of the prefix adder, TFHE_B200_SUMC)
+    const int32_t *in3;
+    long long stride3;
+    const int32_t *idx3;
+    int sd;
     int sc;
     int sa, sb;
     int32_t cst;

@@ -69,7 +69,12 @@ enum {
      * -1/4 for an even one (the sum bit).  Margins 1/8 and 1/4, input noise 3 and 12 sigma^2. */
     TFHE_B200_XOR3 = 11, /* a ^ b ^ c */
     TFHE_B200_MAJ = 12,  /* majority(a, b, c) */
-    TFHE_B200_NUM_GATES_EXT = 13
+    /* extension: sum bit of a parallel-prefix adder fused with its last carry operator,
+     * a ^ (b | (c & d)) for mutually exclusive b, c (a = propagate of the bit, b / c = generate / propagate
+     * of the group below it, d = carry into that group): one bootstrap of 3/8 + 2a + 2b + c + d; saves the
+     * last level of every addition.  Four operands (tfhe_b200_gate_op.d). */
+    TFHE_B200_SUMC = 13,
+    TFHE_B200_NUM_GATES_EXT = 14
 };
 
 const char *tfhe_b200_last_error(void);
@@ -128,9 +133,12 @@ typedef struct {
     int32_t *out;
     int64_t stride_a, stride_b, stride_out;
     const int32_t *idx_a, *idx_b, *idx_out; /* optional, device memory */
-    const int32_t *c;                       /* third operand, only for three-input gates (else NULL) */
+    const int32_t *c;                       /* third operand, only for three- / four-input gates (else NULL) */
     int64_t stride_c;
     const int32_t *idx_c;
+    const int32_t *d;                       /* fourth operand, only for TFHE_B200_SUMC (else NULL) */
+    int64_t stride_d;
+    const int32_t *idx_d;
 } tfhe_b200_gate_op;
 /* Up to TFHE_B200_MAX_RUNS runs in ONE bootstrap batch (one blind-rotate launch + one key-switch launch). */
 #define TFHE_B200_MAX_RUNS 16
@@ -181,13 +189,14 @@ typedef struct tfhe_b200_circuit tfhe_b200_circuit;
 tfhe_b200_circuit *tfhe_b200_circuit_add(tfhe_b200_ctx *ctx, int nbits, int count, int mode);
 /* Adder used inside the multiplier / matrix-multiply trees.  RIPPLE is the reference's schedule
  * (3*nbits-3 levels per addition); PREFIX is a Kogge-Stone adder whose carry operator is one
- * three-input bootstrap (TFHE_B200_GPC): 2 + ceil(log2(nbits-1)) levels per addition (SURVEY
+ * three-input bootstrap (TFHE_B200_GPC) and whose last level yields the sum bits themselves
+ * (TFHE_B200_SUMC): 1 + ceil(log2(nbits-1)) levels per addition (SURVEY
  * 8f rank 4, not in the reference).  tfhe_b200_circuit_add mode 2 is the PREFIX adder. */
 enum { TFHE_B200_ADDER_RIPPLE = 0, TFHE_B200_ADDER_PREFIX = 1,
        /* multipliers / matrix products only: all partial-product bits of a result go through a
         * carry-save (Wallace) tree of full adders — one level per 3:2 compression, two bootstraps per
         * full adder (TFHE_B200_XOR3 / TFHE_B200_MAJ) — down to two rows, then ONE parallel-prefix
-        * addition.  32 bits: 16 levels and 2.5 k gates instead of 36 levels and 10.2 k (prefix adders)
+        * addition.  32 bits: 15 levels and 1.7 k gates instead of 31 levels and 10 k (prefix adders)
         * or 466 levels (the reference's schedule, multiplyLweSamples main.cu:1483-1579). */
        TFHE_B200_ADDER_CARRY_SAVE = 2 };
 /* a * b mod 2^nbits for count pairs (multiplyLweSamples main.cu:1483, BOOTS_vectorMultiplication

@@ -32,15 +32,17 @@ def test_addition_schedules(pkg, nbits, mode):
     assert np.array_equal(from_bits(out, nbits), (a + b) % 2 ** nbits)
     if nbits > 1:
         expect = {0: 3 * nbits - 3, 1: nbits,
-                  2: 2 + (int(np.ceil(np.log2(nbits - 1))) if nbits > 2 else 0)}[mode]
+                  # prefix adder: g/p level + scan levels, the last of which produces the sum bits (SUMC)
+                  2: (1 + int(np.ceil(np.log2(nbits - 1)))) if nbits > 2 else 2}[mode]
         assert circ.levels == expect
     circ.close()
 
 
 def test_16_bit_depths(pkg):
     """BASELINE config 2: the reference's schedules are 45 / 16 sequential bootstrap batches,
-    the prefix adder 6."""
-    assert [pkg.Circuit(None, "add", 16, 1, m).levels for m in (0, 1, 2)] == [45, 16, 6]
+    the prefix adder 5 (one level of generate / propagate, four scan levels of which the last one
+    produces the sum bits)."""
+    assert [pkg.Circuit(None, "add", 16, 1, m).levels for m in (0, 1, 2)] == [45, 16, 5]
 
 
 @pytest.mark.parametrize("adder", [0, 1])
@@ -58,10 +60,10 @@ def test_multiplication_schedules(pkg, nbits, adder):
 
 
 def test_32_bit_multiplication_depth(pkg):
-    """BASELINE config 4: 1 + 5 adder-tree levels; ripple 5*93 = 465 levels, prefix 5*7 = 35."""
+    """BASELINE config 4: 1 + 5 adder-tree levels; ripple 5*93 = 465 levels, prefix 5*6 = 30."""
     ripple = pkg.Circuit(None, "mul_ex", 32, 1, 0)
     prefix = pkg.Circuit(None, "mul_ex", 32, 1, 1)
-    assert ripple.levels == 1 + 5 * 93 and prefix.levels == 1 + 5 * 7
+    assert ripple.levels == 1 + 5 * 93 and prefix.levels == 1 + 5 * 6
     a, b = np.array([40000]), np.array([50000])
     for c in (ripple, prefix):
         assert from_bits(c.simulate(to_bits(a, 32), to_bits(b, 32)), 32)[0] == (40000 * 50000) % 2 ** 32
@@ -268,10 +270,10 @@ def test_carry_save_multiplication_schedule(pkg, nbits):
 
 
 def test_carry_save_depth_and_size(pkg):
-    """32 bits: 1 AND level + 8 compression levels + 7 levels of the final prefix addition = 16, with a
+    """32 bits: 1 AND level + 8 compression levels + 6 levels of the final prefix addition = 15, with a
     quarter of the gates of the prefix-adder tree (BASELINE config 4)."""
     cs, prefix = pkg.Circuit(None, "mul_ex", 32, 1, 2), pkg.Circuit(None, "mul_ex", 32, 1, 1)
-    assert cs.levels == 16 and prefix.levels == 36
+    assert cs.levels == 15 and prefix.levels == 31
     assert cs.gates < prefix.gates / 3
     a, b = np.array([40000]), np.array([50000])
     assert from_bits(cs.simulate(to_bits(a, 32), to_bits(b, 32)), 32)[0] == (40000 * 50000) % 2 ** 32
