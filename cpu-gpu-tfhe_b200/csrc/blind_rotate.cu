@@ -586,10 +586,12 @@ __global__ void __launch_bounds__(kThreads, 1) blind_rotate_kernel(const BrLaunc
 // runs pass 1 (split over lane pairs: a lone warp issues one fp64 instruction per ~3.4 cycles, so the
 // length of the per-lane instruction stream is what counts), pass 2 and the Fourier multiply of ITS ONE
 // decomposed row (o, q) against BK row 2o+q (two key chunks instead of four: one ring of three stages per row); the partial sums meet in shared
-// memory, warp (o, 0) reduces the four contributions to result polynomial o and runs the inverse
-// transform and the accumulator update as in the throughput kernel.  The second half of the CTA
-// (warps 4..7) keeps the four key rings filled (one helper warp per ring) so that no computing warp
-// ever pays a proxy fence or a TMA issue.  Two CTA-half barriers (128 threads) per iteration.
+// memory; the inverse transform of result polynomial o is shared by the warps (o, 0) and (o, 1): inverse
+// pass 2 by halves of the frequency classes (8 positions per lane, last stage through lane ^ 16), inverse
+// pass 1 + conversion + accumulator update by halves of the slices (8 positions per lane, the last two
+// stages through lane ^ 8 and lane ^ 16).  The second half of the CTA (warps 4..7) keeps the four key
+// rings filled (one helper warp per ring) so that no computing warp ever pays a proxy fence or a TMA
+// issue.  Two CTA-half barriers (128 threads) and one pair barrier per iteration.
 // Results are the same Torus32 words as the throughput kernel's: both return the exact integer
 // product (the fp64 sums are taken in a different order, far inside the rounding margin;
 // tests/test_gpu_parity.py compares the two kernels word for word).
@@ -788,30 +790,49 @@ __global__ void __launch_bounds__(kThreads, 1) blind_rotate_quad_kernel(const Br
             }
             __syncwarp();  // every lane has read its pass-1 output
             phase_part_store(lane, W.exch[r], give);
-            if (q == 1) phase_part_store(lane, W.red[o], keep);
+            phase_part_store(lane, W.keep[r], keep);
             PHASE_MARK(4);
             quad_sync(1);
             PHASE_MARK(5);
-            if (q == 0) {
-                phase_part_add(lane, W.red[o], keep);                     // warp (o, 1): rows of polynomial o
-                phase_part_add(lane, W.exch[2 * (1 - o)], keep);          // the two warps of polynomial 1-o
-                phase_part_add(lane, W.exch[2 * (1 - o) + 1], keep);
-                if (!rotate) phase_acc_clear_p(lane, W.acc[o]);          // external product only: result replaces ACC
-                __syncwarp();
+            // ---- the inverse of result polynomial o, shared by the warps (o, 0) and (o, 1) ----
+            {
+                // inverse pass 2: this warp's 16 frequency classes, 8 positions per lane
+                const int ph = lane >> 4;
+                const cpx *e = S.e2 + (16 * q + (lane & 15)) * kE2Row;
+                cpx z[8], recv[8];
+                phase_q_reduce8(lane, q, W.keep[2 * o], W.keep[2 * o + 1], W.exch[2 * (1 - o)], W.exch[2 * (1 - o) + 1], z);
                 PHASE_MARK(6);
-                phase_inv16_store_p(lane, W.red[o], S.e2, keep);
-                __syncwarp();
-                PHASE_MARK(7);
-                cpx x[16], send[8], recv[8];
-                phase_i2_inner_p(lane, W.red[o], x);
-                PHASE_MARK(8);
-                phase_i2_send(lane, x, send);
+                phase_q_inv8_local(ph, e, z);
 #pragma unroll
-                for (int b = 0; b < 8; b++) {
-                    recv[b].x = __shfl_xor_sync(0xffffffffu, send[b].x, 16);
-                    recv[b].y = __shfl_xor_sync(0xffffffffu, send[b].y, 16);
+                for (int i = 0; i < 8; i++) {
+                    recv[i].x = __shfl_xor_sync(0xffffffffu, z[i].x, 16);
+                    recv[i].y = __shfl_xor_sync(0xffffffffu, z[i].y, 16);
                 }
-                phase_i2_final_p(lane, W.acc[o], W.ext[o], x, recv);
+                phase_q_inv8_cross(ph, e, recv, z);
+                phase_q_inv8_store(lane, q, W.inv[o], z);
+            }
+            PHASE_MARK(7);
+            named_sync(3 + o, 64);  // both halves of the inverse pass-2 output are in place
+            {
+                // inverse pass 1 + conversion + update: this warp's 8 slices, 8 positions per lane
+                const int qq = lane >> 3;
+                cpx x[8], recv[8];
+                phase_q_i2_local(lane, q, W.inv[o], x);
+                PHASE_MARK(8);
+#pragma unroll
+                for (int i = 0; i < 8; i++) {
+                    recv[i].x = __shfl_xor_sync(0xffffffffu, x[i].x, 8);
+                    recv[i].y = __shfl_xor_sync(0xffffffffu, x[i].y, 8);
+                }
+                phase_q_i2_cross((qq & 1) != 0, 1 + (qq >> 1), recv, x);
+#pragma unroll
+                for (int i = 0; i < 8; i++) {
+                    recv[i].x = __shfl_xor_sync(0xffffffffu, x[i].x, 16);
+                    recv[i].y = __shfl_xor_sync(0xffffffffu, x[i].y, 16);
+                }
+                phase_q_i2_cross((qq >> 1) != 0, 0, recv, x);
+                if (!rotate) phase_q_acc_clear(lane, q, W.acc[o]);  // external product only: result replaces ACC
+                phase_q_final(lane, q, W.acc[o], W.ext[o], x);
                 PHASE_MARK(9);
             }
             quad_sync(2);  // ACC and its extended copy are final; every partial-sum buffer is free again

@@ -115,7 +115,8 @@ static_assert(16 * kExtRow + kExtGapThroughput <= kExchPoly * 4, "extended copy 
 constexpr int kExtPolyWords = 2048;   // 16 rows of 127 words, padded
 struct QuadSmem {
     cpx exch[kKpl][kExchPoly];          // row (o, q): pass-1 output, then that warp's `give` partial sums
-    cpx red[kK + 1][kExchPoly];         // polynomial o: `keep` partial sums of warp (o, 1), then inverse pass-2 output
+    cpx keep[kKpl][kExchPoly];          // row (o, q): that warp's `keep` partial sums
+    cpx inv[kK + 1][kExchPoly];         // polynomial o: inverse pass-2 output (written by both of its warps)
     int32_t acc[kK + 1][kAccPoly];
     int32_t ext[kK + 1][kExtPolyWords];
 };
@@ -699,6 +700,167 @@ TFHE_HD void phase_i2_final_p(int lane, int32_t *acc_o, int32_t *ext_o, const cp
 
 TFHE_HD void phase_i2_final(int lane, WarpSmem &ws, int o, const cpx (&x)[16], const cpx (&p)[8]) {
     phase_i2_final_p<kExtGapThroughput>(lane, ws.acc[o], ext_poly(ws, o), x, p);
+}
+
+// ---- the inverse transform split over TWO warps (latency kernel) ------------------------------
+// Result polynomial o is finished by the warps (o, 0) and (o, 1) together.
+//
+// Inverse pass 2 (16 points per frequency class m1): warp h takes the classes m1 = 16 h .. 16 h + 15,
+// lane (ph, m1') the positions 8 ph .. 8 ph + 7 of class 16 h + m1': it adds the four partial sums of
+// its 8 positions, runs the three inner stages locally (the blocks of its half: multipliers chosen by
+// ph) and the last stage — position i of lane (0, m1') with position i of lane (1, m1') — through
+// lane ^ 16.  144 instead of 256 fp64 instructions per lane, half the additions.
+TFHE_HD void phase_q_reduce8(int lane, int h, const cpx *p0, const cpx *p1, const cpx *p2, const cpx *p3, cpx (&z)[8]) {
+    const int ph = lane >> 4, m1 = 16 * h + (lane & 15);
+    const int off = m1 * kExchRow + 8 * ph;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        const cpx a = p0[off + i], b = p1[off + i], c = p2[off + i], d = p3[off + i];
+        z[i].x = (a.x + b.x) + (c.x + d.x);
+        z[i].y = (a.y + b.y) + (c.y + d.y);
+    }
+}
+
+// inner stages 3, 2, 1 of inv16 on the 8 positions of half ph; e: the class's four base multipliers
+TFHE_HD void phase_q_inv8_local(int ph, const cpx *e, cpx (&z)[8]) {
+    {   // stage 3: pairs (2b, 2b+1); block B = 4 ph + b: multiplier base B >> 1, odd blocks times i
+        const cpx g = e[3];
+        cpx h4, h8, h38;
+        h4.x = (g.x - g.y) * kSqrtHalf;
+        h4.y = (g.x + g.y) * kSqrtHalf;
+        h8 = cmul_const(g, kCosPi8, kSinPi8);
+        h38 = cmul_const(g, kSinPi8, kCosPi8);
+        cpx c0, c2;
+        c0.x = ph ? h8.x : g.x;
+        c0.y = ph ? h8.y : g.y;
+        c2.x = ph ? h38.x : h4.x;
+        c2.y = ph ? h38.y : h4.y;
+        bf_inv(z[0], z[1], c0.x, c0.y);
+        bf_inv(z[2], z[3], -c0.y, c0.x);
+        bf_inv(z[4], z[5], c2.x, c2.y);
+        bf_inv(z[6], z[7], -c2.y, c2.x);
+    }
+    {   // stage 2: blocks of 4; block B = 2 ph + b: base ph (g or g * e^{i pi/4}), odd block times i
+        const cpx g = e[2];
+        cpx c;
+        c.x = ph ? (g.x - g.y) * kSqrtHalf : g.x;
+        c.y = ph ? (g.x + g.y) * kSqrtHalf : g.y;
+#pragma unroll
+        for (int i = 0; i < 2; i++) {
+            bf_inv(z[i], z[i + 2], c.x, c.y);
+            bf_inv(z[4 + i], z[6 + i], -c.y, c.x);
+        }
+    }
+    {   // stage 1: one block of 8 per half; block B = ph: g, times i for the odd block
+        const cpx g = e[1];
+        const double cx = ph ? -g.y : g.x, cy = ph ? g.x : g.y;
+#pragma unroll
+        for (int i = 0; i < 4; i++) bf_inv(z[i], z[i + 4], cx, cy);
+    }
+}
+
+// last stage of inv16: recv = the partner lane's z; lane ph = 0 keeps u + v (output j2 = i), lane ph = 1
+// conj(g0) (u - v) (output j2 = 8 + i).  One code path: d = recv +- z, out = kappa * d, kappa = 1 or conj(g0).
+TFHE_HD void phase_q_inv8_cross(int ph, const cpx *e, const cpx (&recv)[8], cpx (&z)[8]) {
+    const double sg = ph ? -1.0 : 1.0;
+    const double kx = ph ? e[0].x : 1.0, ky = ph ? e[0].y : 0.0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        const double dx = fma(sg, z[i].x, recv[i].x), dy = fma(sg, z[i].y, recv[i].y);
+        z[i].x = fma(kx, dx, ky * dy);
+        z[i].y = fma(kx, dy, -(ky * dx));
+    }
+}
+
+TFHE_HD void phase_q_inv8_store(int lane, int h, cpx *buf, const cpx (&z)[8]) {
+    const int ph = lane >> 4, m1 = 16 * h + (lane & 15);
+    cpx *d = buf + m1 * kExchRow + 8 * ph;
+#pragma unroll
+    for (int i = 0; i < 8; i++) d[i] = z[i];
+}
+
+// Inverse pass 1 (32 points per slice j2): warp h takes the slices j2 = 8 h .. 8 h + 7, lane (qq, j2') the
+// positions 8 qq .. 8 qq + 7 of slice 8 h + j2'.  Stages 4, 3, 2 are local (multipliers of the lane's
+// blocks: run-time index into the pass-1 table), stage 1 pairs qq with qq ^ 1 (lane ^ 8), stage 0 qq with
+// qq ^ 2 (lane ^ 16).  After stage 0 the lane holds the coefficients j1 = 8 qq .. 8 qq + 7 of the slice.
+TFHE_HD void phase_q_i2_local(int lane, int h, const cpx *buf, cpx (&x)[8]) {
+    const int qq = lane >> 3, j2 = 8 * h + (lane & 7);
+    // position 8 qq + k holds frequency class bitrev5(8 qq + k) = 4 bitrev3(k) + bitrev2(qq)
+    const cpx *src = buf + j2 + (((qq & 1) << 1) | (qq >> 1)) * kExchRow;
+#pragma unroll
+    for (int k = 0; k < 8; k++) x[k] = src[4 * (((k & 1) << 2) | (k & 2) | (k >> 2)) * kExchRow];
+#pragma unroll
+    for (int b = 0; b < 4; b++) {  // stage 4: blocks 4 qq + b
+        const int ci = 15 + 4 * qq + b;
+        bf_inv(x[2 * b], x[2 * b + 1], c1_re_rt(ci), c1_im_rt(ci));
+    }
+#pragma unroll
+    for (int b = 0; b < 2; b++) {  // stage 3: blocks 2 qq + b
+        const int ci = 7 + 2 * qq + b;
+        const double er = c1_re_rt(ci), ei = c1_im_rt(ci);
+        bf_inv(x[4 * b], x[4 * b + 2], er, ei);
+        bf_inv(x[4 * b + 1], x[4 * b + 3], er, ei);
+    }
+    {   // stage 2: block qq
+        const double er = c1_re_rt(3 + qq), ei = c1_im_rt(3 + qq);
+#pragma unroll
+        for (int i = 0; i < 4; i++) bf_inv(x[i], x[i + 4], er, ei);
+    }
+}
+
+// one cross-lane stage: is_v = this lane holds the v's of the pairs; ci = the stage's multiplier
+TFHE_HD void phase_q_i2_cross(bool is_v, int ci, const cpx (&recv)[8], cpx (&x)[8]) {
+    const double sg = is_v ? -1.0 : 1.0;
+    const double kx = is_v ? c1_re_rt(ci) : 1.0, ky = is_v ? c1_im_rt(ci) : 0.0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        const double dx = fma(sg, x[i].x, recv[i].x), dy = fma(sg, x[i].y, recv[i].y);
+        x[i].x = fma(kx, dx, ky * dy);
+        x[i].y = fma(kx, dy, -(ky * dx));
+    }
+}
+
+// conversion to Torus32 and accumulator update of the 16 coefficients of lane (qq, j2'):
+// words 8 qq .. 8 qq + 7 (real parts) and 32 + 8 qq .. (imaginary parts) of row j2; extended copy (GAP = 0)
+TFHE_HD void phase_q_final(int lane, int h, int32_t *acc_o, int32_t *ext_o, const cpx (&x)[8]) {
+    const int qq = lane >> 3, j2 = 8 * h + (lane & 7);
+    int32_t *row = acc_o + j2 * kAccRow + 8 * qq;
+    int32_t *ext = ext_o + j2 * kExtRow + 8 * qq;
+    word4 w[2][2];  // [real / imaginary][quad]
+#pragma unroll
+    for (int part = 0; part < 2; part++)
+#pragma unroll
+        for (int v = 0; v < 2; v++) w[part][v] = *reinterpret_cast<const word4 *>(row + 32 * part + 4 * v);
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        int32_t &re = w[0][k >> 2].v[k & 3], &im = w[1][k >> 2].v[k & 3];
+        re = (int32_t) ((uint32_t) re + double_to_torus32(x[k].x));
+        im = (int32_t) ((uint32_t) im + double_to_torus32(x[k].y));
+    }
+#pragma unroll
+    for (int part = 0; part < 2; part++) {
+#pragma unroll
+        for (int v = 0; v < 2; v++) *reinterpret_cast<word4 *>(row + 32 * part + 4 * v) = w[part][v];
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            const uint32_t nv = (uint32_t) w[part][k >> 2].v[k & 3];
+            ext[kExtOrg + 32 * part + k] = (int32_t) nv;
+            if (part != 0 || k > 0 || qq != 0) ext[32 * part + k - 1] = (int32_t) (0u - nv);
+        }
+    }
+}
+
+// external product only: clear the 16 coefficients this lane will set
+TFHE_HD void phase_q_acc_clear(int lane, int h, int32_t *acc_o) {
+    const int qq = lane >> 3, j2 = 8 * h + (lane & 7);
+    int32_t *row = acc_o + j2 * kAccRow + 8 * qq;
+    word4 z;
+#pragma unroll
+    for (int k = 0; k < 4; k++) z.v[k] = 0;
+#pragma unroll
+    for (int part = 0; part < 2; part++)
+#pragma unroll
+        for (int v = 0; v < 2; v++) *reinterpret_cast<word4 *>(row + 32 * part + 4 * v) = z;
 }
 
 // Stand-alone external product: the result REPLACES the accumulator, so the master copy is

@@ -254,23 +254,35 @@ int main() {
             for (int w = 0; w < 4; w++)
                 for (int lane = 0; lane < 32; lane++) {
                     phase_part_store(lane, qs->exch[w], giveq[w][lane]);
-                    if (w & 1) phase_part_store(lane, qs->red[w >> 1], keepq[w][lane]);
+                    phase_part_store(lane, qs->keep[w], keepq[w][lane]);
                 }
-            static cpx xhq[2][32][16], sndq[2][32][8];
-            for (int o = 0; o < 2; o++) {
+            // the inverse of result polynomial o split over the warps (o, 0), (o, 1)
+            static cpx z8[4][32][8], x8[4][32][8];
+            for (int w = 0; w < 4; w++) {
+                const int o = w >> 1, h = w & 1;
                 for (int lane = 0; lane < 32; lane++) {
-                    cpx(&k)[16] = keepq[2 * o][lane];
-                    phase_part_add(lane, qs->red[o], k);
-                    phase_part_add(lane, qs->exch[2 * (1 - o)], k);
-                    phase_part_add(lane, qs->exch[2 * (1 - o) + 1], k);
+                    phase_q_reduce8(lane, h, qs->keep[2 * o], qs->keep[2 * o + 1], qs->exch[2 * (1 - o)],
+                                    qs->exch[2 * (1 - o) + 1], z8[w][lane]);
+                    phase_q_inv8_local(lane >> 4, e2.data() + (16 * h + (lane & 15)) * kE2Row, z8[w][lane]);
                 }
-                for (int lane = 0; lane < 32; lane++) phase_inv16_store_p(lane, qs->red[o], e2.data(), keepq[2 * o][lane]);
+                static cpx zc[32][8];
+                memcpy(zc, z8[w], sizeof(zc));
                 for (int lane = 0; lane < 32; lane++) {
-                    phase_i2_inner_p(lane, qs->red[o], xhq[o][lane]);
-                    phase_i2_send(lane, xhq[o][lane], sndq[o][lane]);
+                    phase_q_inv8_cross(lane >> 4, e2.data() + (16 * h + (lane & 15)) * kE2Row, zc[lane ^ 16], z8[w][lane]);
+                    phase_q_inv8_store(lane, h, qs->inv[o], z8[w][lane]);
                 }
-                for (int lane = 0; lane < 32; lane++)
-                    phase_i2_final_p(lane, qs->acc[o], qs->ext[o], xhq[o][lane], sndq[o][lane ^ 16]);
+            }
+            for (int w = 0; w < 4; w++) {
+                const int o = w >> 1, h = w & 1;
+                for (int lane = 0; lane < 32; lane++) phase_q_i2_local(lane, h, qs->inv[o], x8[w][lane]);
+                static cpx xc[32][8];
+                memcpy(xc, x8[w], sizeof(xc));
+                for (int lane = 0; lane < 32; lane++)   // stage 1: lane ^ 8, blocks of 16: multiplier 1 + (qq >> 1)
+                    phase_q_i2_cross(((lane >> 3) & 1) != 0, 1 + (lane >> 4), xc[lane ^ 8], x8[w][lane]);
+                memcpy(xc, x8[w], sizeof(xc));
+                for (int lane = 0; lane < 32; lane++)   // stage 0: lane ^ 16, multiplier 0
+                    phase_q_i2_cross((lane >> 4) != 0, 0, xc[lane ^ 16], x8[w][lane]);
+                for (int lane = 0; lane < 32; lane++) phase_q_final(lane, h, qs->acc[o], qs->ext[o], x8[w][lane]);
             }
             std::vector<int32_t> got(2 * kN);
             for (int lane = 0; lane < 32; lane++) phase_dump_acc_p(lane, 32, qs->acc, got.data());
