@@ -119,19 +119,26 @@ int check_ctx(const tfhe_b200_ctx *c, bool need_bk, bool need_ks) {
     return 0;
 }
 
-// large batches: the contraction runs on the tensor cores (128-gate tiles); small ones stay on
-// the SIMT kernel, which splits a single gate over the whole chip
+// The contraction runs on the tensor cores (128-gate tiles; small batches split it over the chip, see
+// keyswitch_mma.cu).  Measured in round 2 (tools/ks_bench.py), tensor-core / SIMT kernel: 1 gate 0.034 / 0.093 ms,
+// 148 gates 0.041 / 0.208, 1024 gates 0.091 / 0.950, 4736 gates 0.433 / 3.93 — so the SIMT kernel only serves
+// parameter sets the byte-limb table does not cover (ks_mma_supported) and TFHE_B200_KS_MMA_MIN (tests).
+std::atomic<int> g_ks_mma_min{-1};
+int ks_mma_min() {
+    int v = g_ks_mma_min.load(std::memory_order_relaxed);
+    if (v < 0) {
+        const char *e = getenv("TFHE_B200_KS_MMA_MIN");
+        v = e ? atoi(e) : 1;
+        g_ks_mma_min.store(v, std::memory_order_relaxed);
+    }
+    return v;
+}
+
 int run_keyswitch(tfhe_b200_ctx *c, const KsLaunch &K, cudaStream_t st) {
-    // crossover measured in round 2 (tools/ks_bench.py): the tensor-core kernel costs a flat 0.285 ms up
-    // to 1024 gates (one pass over its quarter of the table per CTA), the SIMT kernel 0.09 ms (1 gate),
-    // 0.27 ms (256), 0.38 ms (296), 0.72 ms (592), 0.96 ms (1024)
-    static const int mma_min = [] {
-        const char *v = getenv("TFHE_B200_KS_MMA_MIN");
-        return v ? atoi(v) : 272;
-    }();
+    const int mma_min = ks_mma_min();
     if (c->d_ks_mma && mma_min > 0 && K.count >= mma_min) {
-        CU(launch_keyswitch_mma(K, c->d_ks_mma, st));
-        c->launches += 1;
+        CU(launch_keyswitch_mma(K, c->d_ks_mma, c->sm_count, st));
+        c->launches += (((K.count + 127) / 128) * 4 * 2 <= c->sm_count) ? 2 : 1;  // + the zeroing launch when split
     } else {
         CU(launch_keyswitch(K, c->sm_count, st));
         c->launches += (K.count > 0 && ((K.count + kKsTile - 1) / kKsTile) < 2 * c->sm_count) ? 2 : 1;
@@ -206,6 +213,13 @@ void engine_set_thread_scratch(int32_t *d_u, size_t bytes) {
 extern "C" {
 
 const char *tfhe_b200_last_error(void) { return g_err; }
+
+// test hook (not in include/): batches below `min_count` take the SIMT key switch; returns the previous value
+int tfhe_b200_debug_set_ks_mma_min(int min_count) {
+    const int prev = ks_mma_min();
+    g_ks_mma_min.store(min_count < 0 ? 0 : min_count, std::memory_order_relaxed);
+    return prev;
+}
 
 void tfhe_b200_default_params(tfhe_b200_params *p) {
     p->n = 500;

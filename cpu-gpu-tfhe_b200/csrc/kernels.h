@@ -103,7 +103,8 @@ cudaError_t launch_lwe_linear(int32_t *out, long long out_stride, const int32_t 
 size_t ks_mma_table_bytes();
 bool ks_mma_supported(int N, int t, int basebit, int n);
 cudaError_t launch_ks_mma_relayout(const int32_t *src, uint8_t *dst, int base, int n, cudaStream_t stream);
-cudaError_t launch_keyswitch_mma(const KsLaunch &L, const uint8_t *tbl, cudaStream_t stream);
+cudaError_t launch_keyswitch_mma(const KsLaunch &L, const uint8_t *tbl, int sm_count, cudaStream_t stream);
+cudaError_t launch_ks_zero(const KsLaunch &L, cudaStream_t stream);
 
 // Scratch for the extracted samples of the calling thread's NEXT bootstrap launches (engine.cu
 // run_bootstrap_ks): circuit plans own their scratch so that a captured CUDA graph holds no

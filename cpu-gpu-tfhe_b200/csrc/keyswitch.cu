@@ -189,6 +189,14 @@ cudaError_t launch_lwe_linear_idx(int32_t *out, const int32_t *in, long long str
     return cudaGetLastError();
 }
 
+// zeroes the output rows of a key switch (split launches accumulate into them with atomics)
+cudaError_t launch_ks_zero(const KsLaunch &L, cudaStream_t stream) {
+    const long long total = (long long) L.count * (L.n + 1);
+    if (total <= 0) return cudaSuccess;
+    ks_zero_kernel<<<(unsigned) ((total + 255) / 256), 256, 0, stream>>>(L, L.n + 1);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_keyswitch(const KsLaunch &L, int sm_count, cudaStream_t stream) {
     if (L.count <= 0) return cudaSuccess;
     if (L.basebit != 2 || L.t > kMaxT || L.n + 1 > 2 * kKsThreads) return cudaErrorInvalidValue;

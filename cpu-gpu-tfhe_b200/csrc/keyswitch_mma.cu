@@ -143,12 +143,19 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
         : "memory");
 }
 
-__global__ void __launch_bounds__(kMmaThreads, 1) keyswitch_mma_kernel(const KsLaunch L, const uint8_t *__restrict__ tbl) {
+// nsplit > 1 (small batches): blockIdx.z takes the stages [z * kStages / nsplit, (z + 1) * kStages / nsplit)
+// of the contraction and ADDS its partial result to the (pre-zeroed) output with integer atomics — exact
+// whatever the order — so that a few hundred gates do not wait for one CTA per column tile to stream its
+// whole quarter of the table (a flat 0.285 ms): the table pass is spread over up to 148 / (4 * tiles) CTAs.
+__global__ void __launch_bounds__(kMmaThreads, 1) keyswitch_mma_kernel(const KsLaunch L, const uint8_t *__restrict__ tbl,
+                                                                       const int nsplit) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     MmaSmem &S = *reinterpret_cast<MmaSmem *>(smem_raw);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int g0 = blockIdx.x * kMmaM;
     const int nt = blockIdx.y;
+    const int nst = kStages / nsplit;            // stages of this CTA (a multiple of kPrefetch)
+    const int st_first = (int) blockIdx.z * nst;
 
     // lookup: four digits (one byte of the 16 digit bits of a coefficient) -> 0/1 bytes for h
     for (int e = threadIdx.x; e < 3 * 256; e += kMmaThreads) {
@@ -203,17 +210,17 @@ __global__ void __launch_bounds__(kMmaThreads, 1) keyswitch_mma_kernel(const KsL
         };
         uint32_t ring[kPrefetch][kCoefStage];
 #pragma unroll
-        for (int p = 0; p < kPrefetch; p++) load_digits(p, ring[p]);
-        for (int st0 = 0; st0 < kStages; st0 += kPrefetch) {
+        for (int p = 0; p < kPrefetch; p++) load_digits(st_first + p, ring[p]);
+        for (int st0 = 0; st0 < nst; st0 += kPrefetch) {
 #pragma unroll
             for (int p = 0; p < kPrefetch; p++) {
-                const int st = st0 + p;
+                const int st = st0 + p;   // local stage number: slot and phase arithmetic
                 const int slot = st % kSlots;
                 const uint32_t phase = (uint32_t) (st / kSlots) & 1u;
                 uint32_t dg[kCoefStage];
 #pragma unroll
                 for (int k = 0; k < kCoefStage; k++) dg[k] = ring[p][k];
-                if (st + kPrefetch < kStages) load_digits(st + kPrefetch, ring[p]);
+                if (st + kPrefetch < nst) load_digits(st_first + st + kPrefetch, ring[p]);
                 mbar_wait(&S.empty[slot], phase ^ 1u);
                 uint8_t *abase = S.a[slot] + row_off;
 #pragma unroll
@@ -246,8 +253,10 @@ __global__ void __launch_bounds__(kMmaThreads, 1) keyswitch_mma_kernel(const KsL
             }
             const long long orow = L.dst[di].idx ? (long long) __ldg(L.dst[di].idx + local) : (long long) local;
             row = L.dst[di].out + orow * L.dst[di].stride;
-            bval = (uint32_t) __ldg(u0 + L.N) + (uint32_t) L.cst;
-            if (u1) bval += (uint32_t) __ldg(u1 + L.N);
+            if (blockIdx.z == 0) {  // the body (and the constant) are added once
+                bval = (uint32_t) __ldg(u0 + L.N) + (uint32_t) L.cst;
+                if (u1) bval += (uint32_t) __ldg(u1 + L.N);
+            }
         }
         const uint32_t lane_base = (uint32_t) (warp * 32) << 16;
         for (int c0 = 0; c0 < kColsPerCta; c0 += 16) {
@@ -264,7 +273,8 @@ __global__ void __launch_bounds__(kMmaThreads, 1) keyswitch_mma_kernel(const KsL
                     if (col > L.n) continue;
                     uint32_t v = 0u - (d0[k] + (d1[k] << 8) + (d2[k] << 16) + (d3[k] << 24));
                     if (col == L.n) v += bval;
-                    row[col] = (int32_t) v;
+                    if (nsplit > 1) atomicAdd(reinterpret_cast<unsigned int *>(row + col), v);
+                    else row[col] = (int32_t) v;
                 }
             }
         }
@@ -272,8 +282,8 @@ __global__ void __launch_bounds__(kMmaThreads, 1) keyswitch_mma_kernel(const KsL
     } else if (warp == 4) {
         // ================= table loader =================
         if (lane == 0) {
-            const uint8_t *src = tbl + (size_t) nt * kSteps * kBBytesStep;
-            for (int st = 0; st < kStages; st++) {
+            const uint8_t *src = tbl + ((size_t) nt * kSteps + (size_t) st_first * kStepsPerStage) * kBBytesStep;
+            for (int st = 0; st < nst; st++) {
                 const int slot = st % kSlots;
                 const uint32_t phase = (uint32_t) (st / kSlots) & 1u;
                 mbar_wait(&S.empty[slot], phase ^ 1u);
@@ -287,7 +297,7 @@ __global__ void __launch_bounds__(kMmaThreads, 1) keyswitch_mma_kernel(const KsL
     } else {
         // ================= MMA issuer =================
         if (lane == 0) {
-            for (int st = 0; st < kStages; st++) {
+            for (int st = 0; st < nst; st++) {
                 const int slot = st % kSlots;
                 const uint32_t phase = (uint32_t) (st / kSlots) & 1u;
                 mbar_wait(&S.full_a[slot], phase);
@@ -354,13 +364,21 @@ cudaError_t launch_ks_mma_relayout(const int32_t *src, uint8_t *dst, int base, i
     return cudaGetLastError();
 }
 
-cudaError_t launch_keyswitch_mma(const KsLaunch &L, const uint8_t *tbl, cudaStream_t stream) {
+cudaError_t launch_keyswitch_mma(const KsLaunch &L, const uint8_t *tbl, int sm_count, cudaStream_t stream) {
     if (L.count <= 0) return cudaSuccess;
     cudaError_t e = cudaFuncSetAttribute(keyswitch_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int) sizeof(MmaSmem) + 1024);
     if (e != cudaSuccess) return e;
-    dim3 grid((L.count + kMmaM - 1) / kMmaM, kNTiles);
-    keyswitch_mma_kernel<<<grid, kMmaThreads, sizeof(MmaSmem) + 1024, stream>>>(L, tbl);
+    const int tiles = (L.count + kMmaM - 1) / kMmaM;
+    // split the contraction while all CTAs still fit one wave (one CTA per SM: 240 KB of shared memory)
+    int nsplit = 1;
+    while (nsplit < kStages / kPrefetch && tiles * kNTiles * nsplit * 2 <= sm_count) nsplit *= 2;
+    if (nsplit > 1) {
+        e = launch_ks_zero(L, stream);
+        if (e != cudaSuccess) return e;
+    }
+    dim3 grid(tiles, kNTiles, nsplit);
+    keyswitch_mma_kernel<<<grid, kMmaThreads, sizeof(MmaSmem) + 1024, stream>>>(L, tbl, nsplit);
     return cudaGetLastError();
 }
 

@@ -123,7 +123,8 @@ def test_init_and_extract_exact(engine, oracle, ctx_ref):
         assert np.array_equal(u[r], expect), barb
 
 
-@pytest.mark.parametrize("count", [1, 3, 16, 17, 271, 272, 300, 5000])
+# 1..17: the contraction is split 32 ways, 271..300: 8, 600: 4, 2304: 2, 5000: not split (keyswitch_mma.cu)
+@pytest.mark.parametrize("count", [1, 3, 16, 17, 271, 272, 300, 600, 2304, 5000])
 def test_keyswitch_bit_exact(engine, ctx_ref, count):
     rng = np.random.default_rng(15 + count)
     u = _rand_i32(rng, (count, 1025))
@@ -133,17 +134,23 @@ def test_keyswitch_bit_exact(engine, ctx_ref, count):
         assert np.array_equal(got[i], ctx_ref.keyswitch(u[i])), i
 
 
-def test_tensor_core_keyswitch_equals_simt_kernel(engine):
-    """Batches of >= 272 samples take the tcgen05 int8 path (keyswitch_mma.cu); smaller ones the
-    SIMT kernel.  Same integers, bit for bit, on a ragged batch (not a multiple of the 128-gate tile)."""
+@pytest.mark.parametrize("count", [1, 37, 148, 300, 1000, 2309, 4800])
+def test_tensor_core_keyswitch_equals_simt_kernel(engine, pkg, count):
+    """The key switch runs on the tcgen05 int8 path (keyswitch_mma.cu; batches that leave SMs idle split the
+    contraction and add the parts with integer atomics); the SIMT kernel serves other parameter sets.  Same
+    integers, bit for bit, on ragged batches (not multiples of the 128-gate tile) of every split factor."""
     import torch
 
-    rng = np.random.default_rng(77)
-    count = 2309
+    rng = np.random.default_rng(77 + count)
     u = engine.to_device(_rand_i32(rng, (count, 1025)))
     got = engine.keyswitch(u)
-    parts = [engine.keyswitch(u[lo:lo + 250].contiguous()) for lo in range(0, count, 250)]   # SIMT kernel
-    assert torch.equal(got, torch.cat(parts, 0))
+    prev = pkg.lib().tfhe_b200_debug_set_ks_mma_min(1 << 30)
+    try:
+        simt = engine.keyswitch(u)
+    finally:
+        pkg.lib().tfhe_b200_debug_set_ks_mma_min(prev)
+    assert torch.equal(got, simt)
+    assert torch.equal(got, engine.keyswitch(u))   # atomics in any order: the same integers
 
 
 def test_large_mux_batch_through_tensor_core_keyswitch(engine, oracle, keys):
