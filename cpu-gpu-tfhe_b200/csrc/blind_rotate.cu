@@ -598,6 +598,7 @@ __global__ void __launch_bounds__(kThreads, 1) blind_rotate_kernel(const BrLaunc
 constexpr uint32_t kQStages = 3;          // per ring
 constexpr uint32_t kQChunksPerIter = 2;   // per ring: (row, half o) then (row, half 1-o)
 constexpr int kQRings = kKpl;
+constexpr unsigned int kQReleases = 5;    // per chunk: the four computing warps + the ring's helper warp
 
 struct __align__(128) QuadCtaSmem {
     QuadSmem w;
@@ -630,34 +631,44 @@ struct QuadPos {
     }
 };
 
-// a computing warp gives its current stage back (lane 0); the ring's helper warp refills it
-__device__ __forceinline__ void quad_release(QuadCtaSmem &S, uint32_t st, int lane) {
-    if (lane == 0) atomicAdd(&S.drained[st], 1u);
-}
-
-// Fourier multiply of z against the current chunk of ring r, stage released right behind the last load
-// (see mac_consume above; same hardware-ordered early release)
-__device__ __forceinline__ void quad_mac(QuadCtaSmem &S, uint32_t r, int lane, QuadPos &qp, const cpx (&z)[16],
-                                         cpx (&acc)[16]) {
-    const uint32_t st = r * kQStages + qp.stage;
-    mbar_wait(&S.full[st], qp.phase);
-    const cpx *part = S.ring[st];
-    constexpr int kTail = TFHE_B200_BR_MAC_TAIL, kHead = kChunkPos - kTail;
-    phase_mac_part<0, kHead>(lane, z, part, acc);
-    cpx w[kTail];
-#pragma unroll
-    for (int p = 0; p < kTail; p++) w[p] = part[(kHead + p) * 32 + lane];
+// Every computing warp reads its quarter of every ring; lane l < 4 gives the warp's share of the current
+// stage of ring l back right behind the last load (see mac_consume above: same hardware-ordered early
+// release); the ring's helper warp refills the stage when all four warps have done so.
+__device__ __forceinline__ void quad_release(QuadCtaSmem &S, uint32_t stage, int lane) {
     asm volatile(
         "{\n"
         ".reg .pred p;\n"
         ".reg .u32 t;\n"
-        "setp.eq.u32 p, %1, 0;\n"
+        "setp.lt.u32 p, %1, 4;\n"
         "@p atom.shared.add.u32 t, [%0], 1;\n"
-        "}\n" ::"r"(smem_u32(&S.drained[st])),
+        "}\n" ::"r"(smem_u32(&S.drained[((uint32_t) lane & 3u) * kQStages + stage])),
         "r"(lane)
         : "memory");
+}
+
+// acc[half][i] += zr[row][i] * key, over the current chunk of all four rings (chunk SUB of an iteration:
+// ring `row` holds result-polynomial half row >> 1 first, then the other one); lane (g, c): positions
+// 4 g .. 4 g + 3 of class m1
+template <int SUB>
+__device__ __forceinline__ void quad_mac(QuadCtaSmem &S, int g, int m1, int lane, QuadPos &qp,
+                                         const cpx (&zr)[kKpl][4], cpx (&acc)[kK + 1][4]) {
 #pragma unroll
-    for (int p = 0; p < kTail; p++) cmac(acc[kHead + p], z[kHead + p], w[p]);
+    for (int row = 0; row < kKpl; row++) mbar_wait(&S.full[row * kQStages + qp.stage], qp.phase);
+    __syncwarp();
+    cpx k[kKpl][4];
+#pragma unroll
+    for (int row = 0; row < kKpl; row++) {
+        const cpx *part = S.ring[row * kQStages + qp.stage] + (4 * g) * 32 + m1;
+#pragma unroll
+        for (int i = 0; i < 4; i++) k[row][i] = part[i * 32];
+    }
+    quad_release(S, qp.stage, lane);
+#pragma unroll
+    for (int row = 0; row < kKpl; row++) {
+        const int half = SUB ? 1 - (row >> 1) : (row >> 1);
+#pragma unroll
+        for (int i = 0; i < 4; i++) cmac(acc[half][i], zr[row][i], k[row][i]);
+    }
     qp.advance();
 }
 
@@ -683,8 +694,8 @@ __global__ void __launch_bounds__(kThreads, 1) blind_rotate_quad_kernel(const Br
     const bool rotate = (L.extern_only == 0);
 
     if (warp >= 4) {
-        // ---- helper warp of ring r: every chunk is released twice (by the computing warp and here);
-        //      when both have happened the stage is refilled with the chunk kQStages ahead
+        // ---- helper warp of ring r: every chunk is released five times (by the four computing warps and
+        //      here); when all have happened the stage is refilled with the chunk kQStages ahead
         const uint32_t r = (uint32_t) warp - 4u;
         QuadPos qp;
         if (lane == 0) {
@@ -692,7 +703,7 @@ __global__ void __launch_bounds__(kThreads, 1) blind_rotate_quad_kernel(const Br
                 const uint32_t st = r * kQStages + qp.stage;
                 mbar_wait(&S.full[st], qp.phase);
                 const unsigned int seen = atomicAdd(&S.drained[st], 1u);
-                const unsigned int target = seen - (seen % 2u) + 2u;
+                const unsigned int target = seen - (seen % kQReleases) + kQReleases;
                 unsigned int v;
                 do {
                     asm volatile("ld.acquire.cta.shared.u32 %0, [%1];" : "=r"(v) : "r"(smem_u32(&S.drained[st])) : "memory");
@@ -710,11 +721,15 @@ __global__ void __launch_bounds__(kThreads, 1) blind_rotate_quad_kernel(const Br
 
     // ---- computing warps (o, q) --------------------------------------------------------------
     const int o = warp >> 1, q = warp & 1;
-    const uint32_t r = (uint32_t) warp;  // ring = decomposed row = 2o + q
+    const uint32_t r = (uint32_t) warp;  // decomposed row of pass 1 = 2o + q
+    const int rr = lane >> 3, m1 = 8 * warp + (lane & 7);  // Fourier section: lane (rr, c), class m1 = 8 w + c
     QuadSmem &W = S.w;
     const int tid4 = threadIdx.x;        // 0..127 over the four computing warps
     auto quad_sync = [](int id) { named_sync(id, 128); };
     QuadPos qp;
+    cpx ic3, ic2;  // this lane's multipliers of the inverse pass-2 stages (class m1, position block rr)
+    phase_c_inv_consts(rr, S.e2 + m1 * kE2Row, ic3, ic2);
+    const cpx ig1 = S.e2[m1 * kE2Row + 1], ig0 = S.e2[m1 * kE2Row];
     for (int g = blockIdx.x; g < L.total; g += gridDim.x) {
         const GateIn I = resolve_inputs(L, g);
         // ---- accumulator initialisation (all four warps share the copies)
@@ -746,16 +761,14 @@ __global__ void __launch_bounds__(kThreads, 1) blind_rotate_quad_kernel(const Br
             const int a = __shfl_sync(0xffffffffu, a_blk, it & 31);
             if (a == 0 && rotate) {  // tfhe_blindRotate_FFT :705: nothing to do; keep the place in the key stream
 #pragma unroll 1
-                for (uint32_t c = 0; c < kQChunksPerIter; c++) {
-                    const uint32_t st = r * kQStages + qp.stage;
-                    mbar_wait(&S.full[st], qp.phase);
+                for (uint32_t ch = 0; ch < kQChunksPerIter; ch++) {
+                    for (int row = 0; row < kKpl; row++) mbar_wait(&S.full[row * kQStages + qp.stage], qp.phase);
                     __syncwarp();
-                    quad_release(S, st, lane);
+                    quad_release(S, qp.stage, lane);
                     qp.advance();
                 }
                 continue;
             }
-            cpx keep[16], give[16];
             PHASE_T0();
             {
                 // pass 1 of row (o, q) split over lane pairs: lane (hh, j2) transforms points
@@ -770,51 +783,45 @@ __global__ void __launch_bounds__(kThreads, 1) blind_rotate_quad_kernel(const Br
                     recv[i].y = __shfl_xor_sync(0xffffffffu, w[i].y, 16);
                 }
                 phase_f1h_finish(hh, w, recv, x);
-                phase_f1h_store_p(hh, j2, W.exch[r], x);  // own buffer: free since the barrier that ended the last iteration
-                __syncwarp();
+                phase_f1h_store_p(hh, j2, W.exch[r], x);  // own buffer: every warp has read it before barrier 2 of the last iteration
             }
             PHASE_MARK(0);
-#pragma unroll
-            for (int i = 0; i < 16; i++) {
-                keep[i].x = 0.0; keep[i].y = 0.0;
-                give[i].x = 0.0; give[i].y = 0.0;
-            }
+            quad_sync(1);  // the pass-1 output of all four rows is in place
+            PHASE_MARK(1);
             {
-                cpx z[16];
-                phase_f2_fft_p(lane, W.exch[r], S.e2, z);
-                PHASE_MARK(1);
-                quad_mac(S, r, lane, qp, z, keep);
+                // pass 2 + Fourier multiply + inverse pass 2 for this warp's quarter of the frequency classes
+                // (br_core.cuh "by quarters of the frequency classes"): nothing here leaves the warp
+                phase_c_f2_inplace(rr, m1, W.exch, S.e2);
+                __syncwarp();
                 PHASE_MARK(2);
-                quad_mac(S, r, lane, qp, z, give);
-                PHASE_MARK(3);
-            }
-            __syncwarp();  // every lane has read its pass-1 output
-            phase_part_store(lane, W.exch[r], give);
-            phase_part_store(lane, W.keep[r], keep);
-            PHASE_MARK(4);
-            quad_sync(1);
-            PHASE_MARK(5);
-            // ---- the inverse of result polynomial o, shared by the warps (o, 0) and (o, 1) ----
-            {
-                // inverse pass 2: this warp's 16 frequency classes, 8 positions per lane
-                const int ph = lane >> 4;
-                const cpx *e = S.e2 + (16 * q + (lane & 15)) * kE2Row;
-                cpx z[8], recv[8];
-                phase_q_reduce8(lane, q, W.keep[2 * o], W.keep[2 * o + 1], W.exch[2 * (1 - o)], W.exch[2 * (1 - o) + 1], z);
-                PHASE_MARK(6);
-                phase_q_inv8_local(ph, e, z);
+                cpx acc[kK + 1][4];
 #pragma unroll
-                for (int i = 0; i < 8; i++) {
-                    recv[i].x = __shfl_xor_sync(0xffffffffu, z[i].x, 16);
-                    recv[i].y = __shfl_xor_sync(0xffffffffu, z[i].y, 16);
+                for (int oo = 0; oo <= kK; oo++)
+#pragma unroll
+                    for (int i = 0; i < 4; i++) acc[oo][i].x = 0.0, acc[oo][i].y = 0.0;
+                {
+                    cpx zr[kKpl][4];
+                    phase_c_load_rows(rr, m1, W.exch, zr);
+                    quad_mac<0>(S, rr, m1, lane, qp, zr, acc);
+                    PHASE_MARK(3);
+                    quad_mac<1>(S, rr, m1, lane, qp, zr, acc);
+                    PHASE_MARK(4);
                 }
-                phase_q_inv8_cross(ph, e, recv, z);
-                phase_q_inv8_store(lane, q, W.inv[o], z);
+#pragma unroll
+                for (int oo = 0; oo <= kK; oo++) {
+                    phase_c_inv_a(ic3, ic2, acc[oo]);
+                    phase_c_inv_a_store(rr, m1, W.inv[oo], acc[oo]);
+                }
+                __syncwarp();
+                PHASE_MARK(5);
+                phase_c_inv_b_inplace(rr & 1, m1, W.inv[rr >> 1], ig1, ig0);
             }
+            PHASE_MARK(6);
+            quad_sync(2);  // the inverse pass-2 output of both result polynomials is in place
             PHASE_MARK(7);
-            named_sync(3 + o, 64);  // both halves of the inverse pass-2 output are in place
             {
-                // inverse pass 1 + conversion + update: this warp's 8 slices, 8 positions per lane
+                // inverse pass 1 + conversion + update of result polynomial o, shared by the warps (o, 0) and
+                // (o, 1): this warp's 8 slices, 8 positions per lane
                 const int qq = lane >> 3;
                 cpx x[8], recv[8];
                 phase_q_i2_local(lane, q, W.inv[o], x);
@@ -835,12 +842,13 @@ __global__ void __launch_bounds__(kThreads, 1) blind_rotate_quad_kernel(const Br
                 phase_q_final(lane, q, W.acc[o], W.ext[o], x);
                 PHASE_MARK(9);
             }
-            quad_sync(2);  // ACC and its extended copy are final; every partial-sum buffer is free again
+            named_sync(3 + o, 64);  // polynomial o and its extended copy are final for its two warps
             PHASE_MARK(10);
         }
+        quad_sync(1);  // both polynomials are final for all four warps
         if (L.u_out != nullptr) phase_extract_p(tid4, 128, W.acc, L.u_out + (size_t) g * (kN + 1));
         if (L.acc_out != nullptr) phase_dump_acc_p(tid4, 128, W.acc, L.acc_out + (size_t) g * (kK + 1) * kN);
-        quad_sync(1);
+        quad_sync(2);
     }
 }
 

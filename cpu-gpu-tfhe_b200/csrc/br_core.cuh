@@ -111,12 +111,11 @@ static_assert(16 * kExtRow + kExtGapThroughput <= kExchPoly * 4, "extended copy 
 // Working set of the LATENCY kernel (four warps per ciphertext, one ciphertext per CTA: blind_rotate.cu
 // blind_rotate_quad_kernel): the extended accumulator copies have buffers of their own (both warps of
 // a polynomial read them while the exchange buffers are being rewritten), and two more buffers take
-// the partial sums of the q = 1 warps / the inverse pass-2 output.
+// the inverse pass-2 output.
 constexpr int kExtPolyWords = 2048;   // 16 rows of 127 words, padded
 struct QuadSmem {
-    cpx exch[kKpl][kExchPoly];          // row (o, q): pass-1 output, then that warp's `give` partial sums
-    cpx keep[kKpl][kExchPoly];          // row (o, q): that warp's `keep` partial sums
-    cpx inv[kK + 1][kExchPoly];         // polynomial o: inverse pass-2 output (written by both of its warps)
+    cpx exch[kKpl][kExchPoly];          // row (o, q): pass-1 output of warp (o, q), read by all four warps
+    cpx inv[kK + 1][kExchPoly];         // polynomial o: inverse pass-2 output (written by all four warps)
     int32_t acc[kK + 1][kAccPoly];
     int32_t ext[kK + 1][kExtPolyWords];
 };
@@ -702,81 +701,92 @@ TFHE_HD void phase_i2_final(int lane, WarpSmem &ws, int o, const cpx (&x)[16], c
     phase_i2_final_p<kExtGapThroughput>(lane, ws.acc[o], ext_poly(ws, o), x, p);
 }
 
-// ---- the inverse transform split over TWO warps (latency kernel) ------------------------------
-// Result polynomial o is finished by the warps (o, 0) and (o, 1) together.
-//
-// Inverse pass 2 (16 points per frequency class m1): warp h takes the classes m1 = 16 h .. 16 h + 15,
-// lane (ph, m1') the positions 8 ph .. 8 ph + 7 of class 16 h + m1': it adds the four partial sums of
-// its 8 positions, runs the three inner stages locally (the blocks of its half: multipliers chosen by
-// ph) and the last stage — position i of lane (0, m1') with position i of lane (1, m1') — through
-// lane ^ 16.  144 instead of 256 fp64 instructions per lane, half the additions.
-TFHE_HD void phase_q_reduce8(int lane, int h, const cpx *p0, const cpx *p1, const cpx *p2, const cpx *p3, cpx (&z)[8]) {
-    const int ph = lane >> 4, m1 = 16 * h + (lane & 15);
-    const int off = m1 * kExchRow + 8 * ph;
+// ---- Fourier multiply and inverse pass 2 by QUARTERS OF THE FREQUENCY CLASSES (latency kernel) -----
+// After pass 1 (warp r = decomposed row r) and a barrier, warp w takes the classes m1 = 8 w .. 8 w + 7 of
+// ALL FOUR rows, and nothing in this section leaves the warp:
+//   pass 2:   lane (rr, c) transforms row rr of class m1 = 8 w + c IN PLACE in the exchange buffer
+//             (16 positions, as phase_f2_fft_p);
+//   multiply: lane (g, c) re-reads positions 4 g .. 4 g + 3 of all four rows of its class (written by the
+//             lanes (0..3, c) of the same warp: a transposition through shared memory, one __syncwarp) and
+//             accumulates both result polynomials over the four key rows: the sum over rows is a sum in
+//             registers;
+//   inverse pass 2: stages 3 and 2 stay inside a block of four positions (lane (g, c), both result
+//             polynomials), the values go to the inverse buffer; lane (oo, k2, c) re-reads positions
+//             {2 k2, 2 k2 + 1} + {0, 4, 8, 12} of result polynomial oo, runs stages 1 and 0 and writes them back.
+// The first version of this kernel parked the partial sums of each warp's row in shared memory and read
+// three quarters of them back (18 % of its iteration); a second one summed over rows with warp shuffles:
+// a 64-bit shuffle pair moves 8 bytes per lane where a 128-bit shared-memory access moves 16, and the
+// shuffles measured ~10 cycles each for a lone warp.
+TFHE_HD void phase_c_f2_inplace(int rr, int m1, cpx (*exch)[kExchPoly], const cpx *e2) {
+    cpx *row = exch[rr] + m1 * kExchRow;
+    cpx z[16];
 #pragma unroll
-    for (int i = 0; i < 8; i++) {
-        const cpx a = p0[off + i], b = p1[off + i], c = p2[off + i], d = p3[off + i];
-        z[i].x = (a.x + b.x) + (c.x + d.x);
-        z[i].y = (a.y + b.y) + (c.y + d.y);
+    for (int j2 = 0; j2 < 16; j2++) z[j2] = row[j2];
+    fwd16(z, e2 + m1 * kE2Row);
+#pragma unroll
+    for (int pos = 0; pos < 16; pos++) row[pos] = z[pos];
+}
+
+// positions 4 g .. 4 g + 3 of class m1 of the four transformed rows
+TFHE_HD void phase_c_load_rows(int g, int m1, const cpx (*exch)[kExchPoly], cpx (&zr)[kKpl][4]) {
+#pragma unroll
+    for (int row = 0; row < kKpl; row++) {
+        const cpx *src = exch[row] + m1 * kExchRow + 4 * g;
+#pragma unroll
+        for (int i = 0; i < 4; i++) zr[row][i] = src[i];
     }
 }
 
-// inner stages 3, 2, 1 of inv16 on the 8 positions of half ph; e: the class's four base multipliers
-TFHE_HD void phase_q_inv8_local(int ph, const cpx *e, cpx (&z)[8]) {
-    {   // stage 3: pairs (2b, 2b+1); block B = 4 ph + b: multiplier base B >> 1, odd blocks times i
-        const cpx g = e[3];
-        cpx h4, h8, h38;
-        h4.x = (g.x - g.y) * kSqrtHalf;
-        h4.y = (g.x + g.y) * kSqrtHalf;
-        h8 = cmul_const(g, kCosPi8, kSinPi8);
-        h38 = cmul_const(g, kSinPi8, kCosPi8);
-        cpx c0, c2;
-        c0.x = ph ? h8.x : g.x;
-        c0.y = ph ? h8.y : g.y;
-        c2.x = ph ? h38.x : h4.x;
-        c2.y = ph ? h38.y : h4.y;
-        bf_inv(z[0], z[1], c0.x, c0.y);
-        bf_inv(z[2], z[3], -c0.y, c0.x);
-        bf_inv(z[4], z[5], c2.x, c2.y);
-        bf_inv(z[6], z[7], -c2.y, c2.x);
-    }
-    {   // stage 2: blocks of 4; block B = 2 ph + b: base ph (g or g * e^{i pi/4}), odd block times i
-        const cpx g = e[2];
-        cpx c;
-        c.x = ph ? (g.x - g.y) * kSqrtHalf : g.x;
-        c.y = ph ? (g.x + g.y) * kSqrtHalf : g.y;
-#pragma unroll
-        for (int i = 0; i < 2; i++) {
-            bf_inv(z[i], z[i + 2], c.x, c.y);
-            bf_inv(z[4 + i], z[6 + i], -c.y, c.x);
-        }
-    }
-    {   // stage 1: one block of 8 per half; block B = ph: g, times i for the odd block
-        const cpx g = e[1];
-        const double cx = ph ? -g.y : g.x, cy = ph ? g.x : g.y;
-#pragma unroll
-        for (int i = 0; i < 4; i++) bf_inv(z[i], z[i + 4], cx, cy);
-    }
+// lane constants of the inverse stages 3 and 2 for the block of four positions g (pass2_const)
+TFHE_HD void phase_c_inv_consts(int g, const cpx *e, cpx &c3, cpx &c2) {
+    const cpx g3 = e[3], g2 = e[2];
+    cpx h4, h8, h38;
+    h4.x = (g3.x - g3.y) * kSqrtHalf;
+    h4.y = (g3.x + g3.y) * kSqrtHalf;
+    h8 = cmul_const(g3, kCosPi8, kSinPi8);
+    h38 = cmul_const(g3, kSinPi8, kCosPi8);
+    c3 = g == 0 ? g3 : (g == 1 ? h4 : (g == 2 ? h8 : h38));  // stage 3, blocks 2g (c3) and 2g + 1 (i * c3)
+    cpx b;
+    b.x = (g >> 1) ? (g2.x - g2.y) * kSqrtHalf : g2.x;       // stage 2, block g: base g >> 1, odd block times i
+    b.y = (g >> 1) ? (g2.x + g2.y) * kSqrtHalf : g2.y;
+    c2.x = (g & 1) ? -b.y : b.x;
+    c2.y = (g & 1) ? b.x : b.y;
 }
 
-// last stage of inv16: recv = the partner lane's z; lane ph = 0 keeps u + v (output j2 = i), lane ph = 1
-// conj(g0) (u - v) (output j2 = 8 + i).  One code path: d = recv +- z, out = kappa * d, kappa = 1 or conj(g0).
-TFHE_HD void phase_q_inv8_cross(int ph, const cpx *e, const cpx (&recv)[8], cpx (&z)[8]) {
-    const double sg = ph ? -1.0 : 1.0;
-    const double kx = ph ? e[0].x : 1.0, ky = ph ? e[0].y : 0.0;
-#pragma unroll
-    for (int i = 0; i < 8; i++) {
-        const double dx = fma(sg, z[i].x, recv[i].x), dy = fma(sg, z[i].y, recv[i].y);
-        z[i].x = fma(kx, dx, ky * dy);
-        z[i].y = fma(kx, dy, -(ky * dx));
-    }
+// inverse stages 3 and 2 on positions 4 g .. 4 g + 3
+TFHE_HD void phase_c_inv_a(const cpx &c3, const cpx &c2, cpx (&z)[4]) {
+    bf_inv(z[0], z[1], c3.x, c3.y);
+    bf_inv(z[2], z[3], -c3.y, c3.x);
+    bf_inv(z[0], z[2], c2.x, c2.y);
+    bf_inv(z[1], z[3], c2.x, c2.y);
 }
 
-TFHE_HD void phase_q_inv8_store(int lane, int h, cpx *buf, const cpx (&z)[8]) {
-    const int ph = lane >> 4, m1 = 16 * h + (lane & 15);
-    cpx *d = buf + m1 * kExchRow + 8 * ph;
+TFHE_HD void phase_c_inv_a_store(int g, int m1, cpx *inv_o, const cpx (&z)[4]) {
+    cpx *d = inv_o + m1 * kExchRow + 4 * g;
 #pragma unroll
-    for (int i = 0; i < 8; i++) d[i] = z[i];
+    for (int i = 0; i < 4; i++) d[i] = z[i];
+}
+
+// inverse stages 1 and 0 on positions {2 k2, 2 k2 + 1} + {0, 4, 8, 12} of class m1, in place; g1, g0: the
+// class's base multipliers of those stages
+TFHE_HD void phase_c_inv_b_inplace(int k2, int m1, cpx *inv_o, const cpx &g1, const cpx &g0) {
+    cpx *d = inv_o + m1 * kExchRow + 2 * k2;
+    cpx z[2][4];
+#pragma unroll
+    for (int e = 0; e < 2; e++)
+#pragma unroll
+        for (int m = 0; m < 4; m++) z[e][m] = d[e + 4 * m];
+#pragma unroll
+    for (int e = 0; e < 2; e++) {
+        bf_inv(z[e][0], z[e][1], g1.x, g1.y);    // stage 1, block 0
+        bf_inv(z[e][2], z[e][3], -g1.y, g1.x);   // stage 1, block 1: times i
+        bf_inv(z[e][0], z[e][2], g0.x, g0.y);    // stage 0
+        bf_inv(z[e][1], z[e][3], g0.x, g0.y);
+    }
+#pragma unroll
+    for (int e = 0; e < 2; e++)
+#pragma unroll
+        for (int m = 0; m < 4; m++) d[e + 4 * m] = z[e][m];
 }
 
 // Inverse pass 1 (32 points per slice j2): warp h takes the slices j2 = 8 h .. 8 h + 7, lane (qq, j2') the

@@ -213,8 +213,8 @@ int main() {
 #endif
 
     // ---- B3. the same steps through the LATENCY kernel's split (four warps per ciphertext) ----------
-    // warp (o, q): decomposition + pass 1 + pass 2 + MAC of row (o, q); partial sums reduced by warp (o, 0)
-    // (own keep + keep of (o, 1) + the two gives of polynomial 1-o), which also runs the inverse.
+    // warp (o, q): decomposition + pass 1 of row (o, q); pass 2, multiply and inverse pass 2 by quarters of the
+    // frequency classes (the sum over rows through lane exchanges); inverse pass 1 by halves of the slices.
     {
         QuadSmem *qs = new QuadSmem();
         std::vector<int32_t> accq = acc0;
@@ -238,38 +238,32 @@ int main() {
                     phase_f1h_finish(lane >> 4, wq[w][lane], wq[w][lane ^ 16], xq[w][lane]);
                     phase_f1h_store_p(lane >> 4, lane & 15, qs->exch[w], xq[w][lane]);
                 }
-            static cpx keepq[4][32][16], giveq[4][32][16];
-            memset(keepq, 0, sizeof(keepq));
-            memset(giveq, 0, sizeof(giveq));
+            // pass 2 + Fourier multiply + inverse pass 2 by quarters of the frequency classes: warp w, lane
+            // (rr, c): class 8 w + c; transpositions through the exchange / inverse buffers inside the warp
+            static cpx x8[4][32][8];
             for (int w = 0; w < 4; w++) {
-                const int o = w >> 1;
-                const cpx *bkrow = bkdev.data() + ((size_t) i * kKpl + w) * kBkRowCplx;
+                for (int lane = 0; lane < 32; lane++) phase_c_f2_inplace(lane >> 3, 8 * w + (lane & 7), qs->exch, e2.data());
                 for (int lane = 0; lane < 32; lane++) {
-                    cpx z[16];
-                    phase_f2_fft_p(lane, qs->exch[w], e2.data(), z);
-                    phase_mac_half(lane, z, bkrow + o * kBkHalfCplx, keepq[w][lane]);
-                    phase_mac_half(lane, z, bkrow + (1 - o) * kBkHalfCplx, giveq[w][lane]);
+                    const int g = lane >> 3, m1 = 8 * w + (lane & 7);
+                    cpx zr[kKpl][4], accv[2][4];
+                    memset(accv, 0, sizeof(accv));
+                    phase_c_load_rows(g, m1, qs->exch, zr);
+                    for (int row = 0; row < kKpl; row++) {
+                        const cpx *bkrow = bkdev.data() + ((size_t) i * kKpl + row) * kBkRowCplx;
+                        for (int oo = 0; oo < 2; oo++)
+                            for (int p4 = 0; p4 < 4; p4++)
+                                cmac(accv[oo][p4], zr[row][p4], bkrow[oo * kBkHalfCplx + (4 * g + p4) * 32 + m1]);
+                    }
+                    cpx c3, c2;
+                    phase_c_inv_consts(g, e2.data() + m1 * kE2Row, c3, c2);
+                    for (int oo = 0; oo < 2; oo++) {
+                        phase_c_inv_a(c3, c2, accv[oo]);
+                        phase_c_inv_a_store(g, m1, qs->inv[oo], accv[oo]);
+                    }
                 }
-            }
-            for (int w = 0; w < 4; w++)
                 for (int lane = 0; lane < 32; lane++) {
-                    phase_part_store(lane, qs->exch[w], giveq[w][lane]);
-                    phase_part_store(lane, qs->keep[w], keepq[w][lane]);
-                }
-            // the inverse of result polynomial o split over the warps (o, 0), (o, 1)
-            static cpx z8[4][32][8], x8[4][32][8];
-            for (int w = 0; w < 4; w++) {
-                const int o = w >> 1, h = w & 1;
-                for (int lane = 0; lane < 32; lane++) {
-                    phase_q_reduce8(lane, h, qs->keep[2 * o], qs->keep[2 * o + 1], qs->exch[2 * (1 - o)],
-                                    qs->exch[2 * (1 - o) + 1], z8[w][lane]);
-                    phase_q_inv8_local(lane >> 4, e2.data() + (16 * h + (lane & 15)) * kE2Row, z8[w][lane]);
-                }
-                static cpx zc[32][8];
-                memcpy(zc, z8[w], sizeof(zc));
-                for (int lane = 0; lane < 32; lane++) {
-                    phase_q_inv8_cross(lane >> 4, e2.data() + (16 * h + (lane & 15)) * kE2Row, zc[lane ^ 16], z8[w][lane]);
-                    phase_q_inv8_store(lane, h, qs->inv[o], z8[w][lane]);
+                    const int rr = lane >> 3, m1 = 8 * w + (lane & 7);
+                    phase_c_inv_b_inplace(rr & 1, m1, qs->inv[rr >> 1], e2[m1 * kE2Row + 1], e2[m1 * kE2Row]);
                 }
             }
             for (int w = 0; w < 4; w++) {
