@@ -577,279 +577,197 @@ __global__ void __launch_bounds__(kThreads, 1) blind_rotate_kernel(const BrLaunc
 }
 
 // =================================================================================
-// LATENCY kernel: FOUR warps per ciphertext, one ciphertext per CTA (batches of at most one
-// ciphertext per SM: a single gate, the narrow levels of an adder or multiplier).
+// LATENCY kernel: one ciphertext per CTA, eight warps (batches of at most one ciphertext per SM: a single
+// gate, the narrow levels of an adder or multiplier).
 //
 // The throughput kernel gives a ciphertext two warps because eight 255-register warps fill an SM with
 // four ciphertexts.  A lone ciphertext on an SM leaves six warps idle, and its iteration is a chain of
-// dependent phases.  Here warp (o, q) decomposes accumulator polynomial o at digit level q only and
-// runs pass 1 (split over lane pairs: a lone warp issues one fp64 instruction per ~3.4 cycles, so the
-// length of the per-lane instruction stream is what counts), pass 2 and the Fourier multiply of ITS ONE
-// decomposed row (o, q) against BK row 2o+q (two key chunks instead of four: one ring of three stages per row); the partial sums meet in shared
-// memory; the inverse transform of result polynomial o is shared by the warps (o, 0) and (o, 1): inverse
-// pass 2 by halves of the frequency classes (8 positions per lane, last stage through lane ^ 16), inverse
-// pass 1 + conversion + accumulator update by halves of the slices (8 positions per lane, the last two
-// stages through lane ^ 8 and lane ^ 16).  The second half of the CTA (warps 4..7) keeps the four key
-// rings filled (one helper warp per ring) so that no computing warp ever pays a proxy fence or a TMA
-// issue.  Two CTA-half barriers (128 threads) and one pair barrier per iteration.
-// Results are the same Torus32 words as the throughput kernel's: both return the exact integer
-// product (the fp64 sums are taken in a different order, far inside the rounding margin;
-// tests/test_gpu_parity.py compares the two kernels word for word).
-constexpr uint32_t kQStages = 3;          // per ring
-constexpr uint32_t kQChunksPerIter = 2;   // per ring: (row, half o) then (row, half 1-o)
-constexpr int kQRings = kKpl;
-constexpr unsigned int kQReleases = 5;    // per chunk: the four computing warps + the ring's helper warp
-
-struct __align__(128) QuadCtaSmem {
-    QuadSmem w;
+// dependent phases; a lone warp on a sub-partition issues an fp64 instruction every ~3.4 cycles and ~0.45
+// instructions per cycle over all, so the length of the per-lane instruction stream is what counts.  Here:
+//   - warp (o, q) (warps 0..3) decomposes accumulator polynomial o at digit level q only and runs pass 1 of
+//     that ONE row, split over lane pairs (br_core.cuh phase_f1h_*);
+//   - the key of an iteration (64 KiB) is double buffered whole in shared memory: one thread re-arms the
+//     buffer of iteration it for iteration it + 2 right behind the barrier that ends the Fourier section
+//     (one bulk-copy issue per iteration; no helper warps, no release counters, no polling);
+//   - the Fourier section (pass 2, multiply, inverse pass 2) runs on eight warps: warp v = frequency-class
+//     octet v >> 1, position half v & 1 (br_core.cuh "the same section on EIGHT warps");
+//   - the inverse pass 1 + conversion + accumulator update of result polynomial o is shared by the warps
+//     (o, 0) and (o, 1) by halves of the slices (8 positions per lane, the last two stages through lane ^ 8
+//     and lane ^ 16); warps 4..7 wait at the next barrier during pass 1 and this part.
+// Two CTA barriers and three 64-thread barriers per iteration.  History (single gate, blind rotation):
+// two-warp kernel 2.30 ms; four warps by decomposed row with partial sums in shared memory and four helper
+// warps on the key rings 1.60 ms; sums over rows in registers 1.55 ms; this kernel 1.50 ms.
+// Results are the same Torus32 words as the throughput kernel's: both return the exact integer product
+// (the fp64 sums are taken in a different order, far inside the rounding margin; tests/test_gpu_parity.py
+// compares the two kernels word for word).
+struct __align__(128) OctoCtaSmem {
+    LatencySmem w;
     cpx e2[32 * kE2Row];
-    cpx ring[kQRings * kQStages][kChunkCplx];
-    unsigned long long full[kQRings * kQStages];
-    unsigned int drained[kQRings * kQStages];
+    cpx key[2][kBkIterCplx];
+    unsigned long long full[2];
 };
-static_assert(offsetof(QuadCtaSmem, ring) % 128 == 0, "TMA destination alignment");
-static_assert(sizeof(QuadCtaSmem) <= 227 * 1024, "shared memory budget");
+static_assert(offsetof(OctoCtaSmem, key) % 128 == 0, "TMA destination alignment");
+static_assert(sizeof(OctoCtaSmem) <= 227 * 1024, "shared memory budget");
 
-// chunk `c` (ring-local running number) of ring r = 2o + q
-__device__ __forceinline__ void quad_fill(QuadCtaSmem &S, const BrLaunch &L, uint32_t r, uint32_t c, uint32_t stage) {
-    const uint32_t it = (c / kQChunksPerIter) % (uint32_t) L.n_iter, sub = c % kQChunksPerIter;
-    const uint32_t o = r >> 1, half = sub ? 1u - o : o;
-    const cpx *src = L.bk + ((size_t) (L.bk_first + it) * kKpl + r) * kBkRowCplx + half * kBkHalfCplx;
-    const uint32_t st = r * kQStages + stage;
-    mbar_arrive_expect_tx(&S.full[st], kStageBytes);
-    tma_load_1d(S.ring[st], src, kStageBytes, &S.full[st]);
+// key of iteration `it` into buffer it & 1 (four 16 KiB bulk copies, one per TGSW row)
+__device__ __forceinline__ void octo_fill(OctoCtaSmem &S, const BrLaunch &L, int it) {
+    unsigned long long *bar = &S.full[it & 1];
+    const cpx *src = L.bk + (size_t) (L.bk_first + it) * kBkIterCplx;
+    mbar_arrive_expect_tx(bar, (uint32_t) (kBkIterCplx * sizeof(cpx)));
+#pragma unroll
+    for (int row = 0; row < kKpl; row++)
+        tma_load_1d(S.key[it & 1] + row * kBkRowCplx, src + row * kBkRowCplx, (uint32_t) (kBkRowCplx * sizeof(cpx)), bar);
 }
 
-struct QuadPos {
-    uint32_t stage = 0, phase = 0, chunk = 0;
-    __device__ __forceinline__ void advance() {
-        chunk++;
-        if (++stage == kQStages) {
-            stage = 0;
-            phase ^= 1;
-        }
-    }
-};
-
-// Every computing warp reads its quarter of every ring; lane l < 4 gives the warp's share of the current
-// stage of ring l back right behind the last load (see mac_consume above: same hardware-ordered early
-// release); the ring's helper warp refills the stage when all four warps have done so.
-__device__ __forceinline__ void quad_release(QuadCtaSmem &S, uint32_t stage, int lane) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        ".reg .u32 t;\n"
-        "setp.lt.u32 p, %1, 4;\n"
-        "@p atom.shared.add.u32 t, [%0], 1;\n"
-        "}\n" ::"r"(smem_u32(&S.drained[((uint32_t) lane & 3u) * kQStages + stage])),
-        "r"(lane)
-        : "memory");
-}
-
-// acc[half][i] += zr[row][i] * key, over the current chunk of all four rings (chunk SUB of an iteration:
-// ring `row` holds result-polynomial half row >> 1 first, then the other one); lane (g, c): positions
-// 4 g .. 4 g + 3 of class m1
-template <int SUB>
-__device__ __forceinline__ void quad_mac(QuadCtaSmem &S, int g, int m1, int lane, QuadPos &qp,
-                                         const cpx (&zr)[kKpl][4], cpx (&acc)[kK + 1][4]) {
-#pragma unroll
-    for (int row = 0; row < kKpl; row++) mbar_wait(&S.full[row * kQStages + qp.stage], qp.phase);
-    __syncwarp();
-    cpx k[kKpl][4];
-#pragma unroll
-    for (int row = 0; row < kKpl; row++) {
-        const cpx *part = S.ring[row * kQStages + qp.stage] + (4 * g) * 32 + m1;
-#pragma unroll
-        for (int i = 0; i < 4; i++) k[row][i] = part[i * 32];
-    }
-    quad_release(S, qp.stage, lane);
-#pragma unroll
-    for (int row = 0; row < kKpl; row++) {
-        const int half = SUB ? 1 - (row >> 1) : (row >> 1);
-#pragma unroll
-        for (int i = 0; i < 4; i++) cmac(acc[half][i], zr[row][i], k[row][i]);
-    }
-    qp.advance();
-}
-
-__global__ void __launch_bounds__(kThreads, 1) blind_rotate_quad_kernel(const BrLaunch L) {
+__global__ void __launch_bounds__(kThreads, 1) blind_rotate_octo_kernel(const BrLaunch L) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    QuadCtaSmem &S = *reinterpret_cast<QuadCtaSmem *>(smem_raw);
+    OctoCtaSmem &S = *reinterpret_cast<OctoCtaSmem *>(smem_raw);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n_iter = L.n_iter;
-    const int my_groups = (L.total - (int) blockIdx.x + (int) gridDim.x - 1) / (int) gridDim.x;  // one ciphertext per group
-    const uint32_t ring_chunks = kQChunksPerIter * (uint32_t) my_groups * (uint32_t) n_iter;
+    const int g = blockIdx.x;  // one ciphertext per CTA
+    const bool rotate = (L.extern_only == 0);
 
     build_e2(S.e2);
     if (threadIdx.x == 0) {
-        for (uint32_t s = 0; s < kQRings * kQStages; s++) {
-            mbar_init(&S.full[s], 1);
-            S.drained[s] = 0;
-        }
+        mbar_init(&S.full[0], 1);
+        mbar_init(&S.full[1], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        for (uint32_t r = 0; r < (uint32_t) kQRings; r++)
-            for (uint32_t c = 0; c < kQStages && c < ring_chunks; c++) quad_fill(S, L, r, c, c);
+        for (int it = 0; it < 2 && it < n_iter; it++) octo_fill(S, L, it);
     }
     __syncthreads();
-    const bool rotate = (L.extern_only == 0);
 
-    if (warp >= 4) {
-        // ---- helper warp of ring r: every chunk is released five times (by the four computing warps and
-        //      here); when all have happened the stage is refilled with the chunk kQStages ahead
-        const uint32_t r = (uint32_t) warp - 4u;
-        QuadPos qp;
-        if (lane == 0) {
-            for (uint32_t c = 0; c < ring_chunks; c++) {
-                const uint32_t st = r * kQStages + qp.stage;
-                mbar_wait(&S.full[st], qp.phase);
-                const unsigned int seen = atomicAdd(&S.drained[st], 1u);
-                const unsigned int target = seen - (seen % kQReleases) + kQReleases;
-                unsigned int v;
-                do {
-                    asm volatile("ld.acquire.cta.shared.u32 %0, [%1];" : "=r"(v) : "r"(smem_u32(&S.drained[st])) : "memory");
-                    if ((int) (v - target) < 0) __nanosleep(32);
-                } while ((int) (v - target) < 0);
-                if (c + kQStages < ring_chunks) {
-                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                    quad_fill(S, L, r, c + kQStages, qp.stage);
-                }
-                qp.advance();
-            }
-        }
-        return;
-    }
-
-    // ---- computing warps (o, q) --------------------------------------------------------------
-    const int o = warp >> 1, q = warp & 1;
-    const uint32_t r = (uint32_t) warp;  // decomposed row of pass 1 = 2o + q
-    const int rr = lane >> 3, m1 = 8 * warp + (lane & 7);  // Fourier section: lane (rr, c), class m1 = 8 w + c
-    QuadSmem &W = S.w;
-    const int tid4 = threadIdx.x;        // 0..127 over the four computing warps
-    auto quad_sync = [](int id) { named_sync(id, 128); };
-    QuadPos qp;
-    cpx ic3, ic2;  // this lane's multipliers of the inverse pass-2 stages (class m1, position block rr)
-    phase_c_inv_consts(rr, S.e2 + m1 * kE2Row, ic3, ic2);
+    LatencySmem &W = S.w;
+    const int tid = threadIdx.x;
+    auto sync_all = [](int id) { named_sync(id, kThreads); };
+    // pass 1 / inverse pass 1 (warps 0..3): decomposed row r = 2o + q
+    const int o = (warp >> 1) & 1, q = warp & 1, r = warp & 3;
+    const bool edge = warp < 4;
+    // Fourier section: class octet cq, position half ph; lane (rr, c) / (g2, oo, c) / (kk, oo, c)
+    const int cq = warp >> 1, ph = warp & 1;
+    const int rr = lane >> 3, m1 = 8 * cq + (lane & 7);
+    const int g2 = lane >> 4, oo = (lane >> 3) & 1, gb = 2 * ph + g2;
+    OctoFwdConsts fk;
+    phase_o_fwd_consts(ph, S.e2 + m1 * kE2Row, fk);
+    cpx ic3, ic2;
+    phase_c_inv_consts(gb, S.e2 + m1 * kE2Row, ic3, ic2);
     const cpx ig1 = S.e2[m1 * kE2Row + 1], ig0 = S.e2[m1 * kE2Row];
-    for (int g = blockIdx.x; g < L.total; g += gridDim.x) {
-        const GateIn I = resolve_inputs(L, g);
-        // ---- accumulator initialisation (all four warps share the copies)
-        if (L.acc_in != nullptr) {
-            phase_load_acc_p(tid4, 128, W.acc, L.acc_in + (size_t) g * (kK + 1) * kN);
-        } else if (L.testvect != nullptr) {
-            const int barb = L.barb ? (__ldg(L.barb + g) & (2 * kN - 1)) : 0;
-            for (int j = tid4; j < kN; j += 128) {
-                const int s = (j + barb) & (2 * kN - 1);
-                const uint32_t v = (uint32_t) __ldg(L.testvect + (s & (kN - 1)));
-                W.acc[0][(j & 15) * kAccRow + (j >> 4)] = 0;
-                W.acc[kK][(j & 15) * kAccRow + (j >> 4)] = (int32_t) (s < kN ? v : 0u - v);
-            }
-        } else if (q == 0) {
-            int barb;
-            if (L.explicit_inputs != 0) barb = L.barb ? (__ldg(L.barb + g) & (2 * kN - 1)) : 0;
-            else {
-                barb = modswitch_2N(prologue_word(I, L.n, I.cst));
-            }
-            phase_init_p(lane, W.acc[o], o, barb, L.mu);
-        }
-        quad_sync(1);
-        if (q == 0) phase_ext_build_p(lane, W.acc[o], W.ext[o]);
-        quad_sync(2);
 
-        int a_blk = 0;  // lane l holds bara of iteration (it & ~31) + l
-        for (int it = 0; it < n_iter; it++) {
-            if ((it & 31) == 0) a_blk = load_bara(L, I, g, it + lane, n_iter, rotate);
-            const int a = __shfl_sync(0xffffffffu, a_blk, it & 31);
-            if (a == 0 && rotate) {  // tfhe_blindRotate_FFT :705: nothing to do; keep the place in the key stream
-#pragma unroll 1
-                for (uint32_t ch = 0; ch < kQChunksPerIter; ch++) {
-                    for (int row = 0; row < kKpl; row++) mbar_wait(&S.full[row * kQStages + qp.stage], qp.phase);
-                    __syncwarp();
-                    quad_release(S, qp.stage, lane);
-                    qp.advance();
-                }
-                continue;
+    const GateIn I = resolve_inputs(L, g);
+    // ---- accumulator initialisation
+    if (L.acc_in != nullptr) {
+        phase_load_acc_p(tid, kThreads, W.acc, L.acc_in + (size_t) g * (kK + 1) * kN);
+    } else if (L.testvect != nullptr) {
+        const int barb = L.barb ? (__ldg(L.barb + g) & (2 * kN - 1)) : 0;
+        for (int j = tid; j < kN; j += kThreads) {
+            const int s = (j + barb) & (2 * kN - 1);
+            const uint32_t v = (uint32_t) __ldg(L.testvect + (s & (kN - 1)));
+            W.acc[0][(j & 15) * kAccRow + (j >> 4)] = 0;
+            W.acc[kK][(j & 15) * kAccRow + (j >> 4)] = (int32_t) (s < kN ? v : 0u - v);
+        }
+    } else if (edge && q == 0) {
+        int barb;
+        if (L.explicit_inputs != 0) barb = L.barb ? (__ldg(L.barb + g) & (2 * kN - 1)) : 0;
+        else barb = modswitch_2N(prologue_word(I, L.n, I.cst));
+        phase_init_p(lane, W.acc[o], o, barb, L.mu);
+    }
+    sync_all(1);
+    if (edge && q == 0) phase_ext_build_p(lane, W.acc[o], W.ext[o]);
+    sync_all(2);
+
+    int a_blk = 0;  // lane l holds bara of iteration (it & ~31) + l
+    for (int it = 0; it < n_iter; it++) {
+        if ((it & 31) == 0) a_blk = load_bara(L, I, g, it + lane, n_iter, rotate);
+        const int a = __shfl_sync(0xffffffffu, a_blk, it & 31);
+        unsigned long long *full = &S.full[it & 1];
+        const uint32_t parity = (uint32_t) (it >> 1) & 1u;
+        if (a == 0 && rotate) {  // tfhe_blindRotate_FFT :705: nothing to do; the key buffer moves on
+            if (threadIdx.x == 0) {
+                mbar_wait(full, parity);
+                if (it + 2 < n_iter) octo_fill(S, L, it + 2);
             }
-            PHASE_T0();
-            {
-                // pass 1 of row (o, q) split over lane pairs: lane (hh, j2) transforms points
-                // 16 hh .. 16 hh + 15 of slice j2, stage 0 through lane ^ 16 (br_core.cuh phase_f1h_*)
-                const int hh = lane >> 4, j2 = lane & 15;
-                cpx x[16], w[16], recv[16];
-                phase_f1h_decomp_p(hh, j2, q, W.acc[o], W.ext[o], a, rotate, x);
-                phase_f1h_cross_send(hh, x, w);
+            continue;
+        }
+        PHASE_T0();
+        if (edge) {
+            // pass 1 of row (o, q) split over lane pairs (br_core.cuh phase_f1h_*)
+            const int hh = lane >> 4, j2 = lane & 15;
+            cpx x[16], w[16], recv[16];
+            phase_f1h_decomp_p(hh, j2, q, W.acc[o], W.ext[o], a, rotate, x);
+            phase_f1h_cross_send(hh, x, w);
 #pragma unroll
-                for (int i = 0; i < 16; i++) {
-                    recv[i].x = __shfl_xor_sync(0xffffffffu, w[i].x, 16);
-                    recv[i].y = __shfl_xor_sync(0xffffffffu, w[i].y, 16);
-                }
-                phase_f1h_finish(hh, w, recv, x);
-                phase_f1h_store_p(hh, j2, W.exch[r], x);  // own buffer: every warp has read it before barrier 2 of the last iteration
+            for (int i = 0; i < 16; i++) {
+                recv[i].x = __shfl_xor_sync(0xffffffffu, w[i].x, 16);
+                recv[i].y = __shfl_xor_sync(0xffffffffu, w[i].y, 16);
             }
-            PHASE_MARK(0);
-            quad_sync(1);  // the pass-1 output of all four rows is in place
-            PHASE_MARK(1);
-            {
-                // pass 2 + Fourier multiply + inverse pass 2 for this warp's quarter of the frequency classes
-                // (br_core.cuh "by quarters of the frequency classes"): nothing here leaves the warp
-                phase_c_f2_inplace(rr, m1, W.exch, S.e2);
-                __syncwarp();
-                PHASE_MARK(2);
-                cpx acc[kK + 1][4];
+            phase_f1h_finish(hh, w, recv, x);
+            phase_f1h_store_p(hh, j2, W.exch[r], x);
+        }
+        PHASE_MARK(0);
+        sync_all(1);  // the pass-1 output of all four rows is in place
+        PHASE_MARK(1);
+        {
+            cpx *row = W.exch[rr] + m1 * kExchRow;
+            cpx z[8];
+            phase_o_f2_half(row, fk, z);
+            named_sync(3 + cq, 64);  // the other position half's warp has read its inputs too
+            phase_o_f2_store(ph, row, z);
+            __syncwarp();
+        }
+        PHASE_MARK(2);
+        {
+            cpx zr[kKpl][4], acc[4];
+            phase_c_load_rows(gb, m1, W.exch, zr);
 #pragma unroll
-                for (int oo = 0; oo <= kK; oo++)
+            for (int i = 0; i < 4; i++) acc[i].x = 0.0, acc[i].y = 0.0;
+            mbar_wait(full, parity);
+            const cpx *kb = S.key[it & 1] + oo * kBkHalfCplx + (4 * gb) * 32 + m1;
 #pragma unroll
-                    for (int i = 0; i < 4; i++) acc[oo][i].x = 0.0, acc[oo][i].y = 0.0;
-                {
-                    cpx zr[kKpl][4];
-                    phase_c_load_rows(rr, m1, W.exch, zr);
-                    quad_mac<0>(S, rr, m1, lane, qp, zr, acc);
-                    PHASE_MARK(3);
-                    quad_mac<1>(S, rr, m1, lane, qp, zr, acc);
-                    PHASE_MARK(4);
-                }
+            for (int row = 0; row < kKpl; row++)
 #pragma unroll
-                for (int oo = 0; oo <= kK; oo++) {
-                    phase_c_inv_a(ic3, ic2, acc[oo]);
-                    phase_c_inv_a_store(rr, m1, W.inv[oo], acc[oo]);
-                }
-                __syncwarp();
-                PHASE_MARK(5);
-                phase_c_inv_b_inplace(rr & 1, m1, W.inv[rr >> 1], ig1, ig0);
+                for (int i = 0; i < 4; i++) cmac(acc[i], zr[row][i], kb[row * kBkRowCplx + i * 32]);
+            PHASE_MARK(3);
+            phase_c_inv_a(ic3, ic2, acc);
+            phase_c_inv_a_store(gb, m1, W.inv[oo], acc);
+        }
+        PHASE_MARK(4);
+        named_sync(3 + cq, 64);  // stages 3, 2 of both position halves of this class octet are in place
+        PHASE_MARK(5);
+        phase_o_inv_b_inplace(gb, m1, W.inv[oo], ig1, ig0);  // positions {k, k + 4, k + 8, k + 12}, k = 2 ph + (lane >> 4)
+        PHASE_MARK(6);
+        sync_all(2);  // the inverse pass-2 output is complete; nobody reads this iteration's key any more
+        PHASE_MARK(7);
+        if (threadIdx.x == 0 && it + 2 < n_iter) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            octo_fill(S, L, it + 2);
+        }
+        if (edge) {
+            // inverse pass 1 + conversion + update of result polynomial o, shared by the warps (o, 0) and (o, 1)
+            const int qq = lane >> 3;
+            cpx x[8], recv[8];
+            phase_q_i2_local(lane, q, W.inv[o], x);
+            PHASE_MARK(8);
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                recv[i].x = __shfl_xor_sync(0xffffffffu, x[i].x, 8);
+                recv[i].y = __shfl_xor_sync(0xffffffffu, x[i].y, 8);
             }
-            PHASE_MARK(6);
-            quad_sync(2);  // the inverse pass-2 output of both result polynomials is in place
-            PHASE_MARK(7);
-            {
-                // inverse pass 1 + conversion + update of result polynomial o, shared by the warps (o, 0) and
-                // (o, 1): this warp's 8 slices, 8 positions per lane
-                const int qq = lane >> 3;
-                cpx x[8], recv[8];
-                phase_q_i2_local(lane, q, W.inv[o], x);
-                PHASE_MARK(8);
+            phase_q_i2_cross((qq & 1) != 0, 1 + (qq >> 1), recv, x);
 #pragma unroll
-                for (int i = 0; i < 8; i++) {
-                    recv[i].x = __shfl_xor_sync(0xffffffffu, x[i].x, 8);
-                    recv[i].y = __shfl_xor_sync(0xffffffffu, x[i].y, 8);
-                }
-                phase_q_i2_cross((qq & 1) != 0, 1 + (qq >> 1), recv, x);
-#pragma unroll
-                for (int i = 0; i < 8; i++) {
-                    recv[i].x = __shfl_xor_sync(0xffffffffu, x[i].x, 16);
-                    recv[i].y = __shfl_xor_sync(0xffffffffu, x[i].y, 16);
-                }
-                phase_q_i2_cross((qq >> 1) != 0, 0, recv, x);
-                if (!rotate) phase_q_acc_clear(lane, q, W.acc[o]);  // external product only: result replaces ACC
-                phase_q_final(lane, q, W.acc[o], W.ext[o], x);
-                PHASE_MARK(9);
+            for (int i = 0; i < 8; i++) {
+                recv[i].x = __shfl_xor_sync(0xffffffffu, x[i].x, 16);
+                recv[i].y = __shfl_xor_sync(0xffffffffu, x[i].y, 16);
             }
-            named_sync(3 + o, 64);  // polynomial o and its extended copy are final for its two warps
+            phase_q_i2_cross((qq >> 1) != 0, 0, recv, x);
+            if (!rotate) phase_q_acc_clear(lane, q, W.acc[o]);  // external product only: result replaces ACC
+            phase_q_final(lane, q, W.acc[o], W.ext[o], x);
+            PHASE_MARK(9);
+            named_sync(7 + o, 64);  // polynomial o and its extended copy are final for its two warps
             PHASE_MARK(10);
         }
-        quad_sync(1);  // both polynomials are final for all four warps
-        if (L.u_out != nullptr) phase_extract_p(tid4, 128, W.acc, L.u_out + (size_t) g * (kN + 1));
-        if (L.acc_out != nullptr) phase_dump_acc_p(tid4, 128, W.acc, L.acc_out + (size_t) g * (kK + 1) * kN);
-        quad_sync(2);
     }
+    sync_all(1);  // both polynomials are final for everybody
+    if (L.u_out != nullptr) phase_extract_p(tid, kThreads, W.acc, L.u_out + (size_t) g * (kN + 1));
+    if (L.acc_out != nullptr) phase_dump_acc_p(tid, kThreads, W.acc, L.acc_out + (size_t) g * (kK + 1) * kN);
 }
 
 // ------------------------------------------------------------ key conversion
@@ -903,8 +821,8 @@ cudaError_t blind_rotate_configure() {
     e = cudaFuncSetAttribute(blind_rotate_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              (int) sizeof(CtaSmem));
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(blind_rotate_quad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             (int) sizeof(QuadCtaSmem));
+    e = cudaFuncSetAttribute(blind_rotate_octo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int) sizeof(OctoCtaSmem));
     if (e != cudaSuccess) return e;
     return cudaFuncSetAttribute(forward_polys_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 (int) sizeof(FwdSmem));
@@ -917,14 +835,15 @@ cudaError_t launch_blind_rotate(const BrLaunch &L_in, int sm_count, cudaStream_t
     L.cts_per_group = cpg < 1 ? 1 : (cpg > kCtWarps ? kCtWarps : cpg);
     const int ngroups = (L.total + L.cts_per_group - 1) / L.cts_per_group;
     const int grid = ngroups < sm_count ? ngroups : sm_count;
-    // at most one ciphertext per SM: the latency kernel (four warps per ciphertext).
+    // at most one ciphertext per SM: the latency kernel (one ciphertext per CTA, eight warps).
     // TFHE_B200_BR_QUAD=0 keeps such batches on the two-warp kernel (A/B measurements).
-    static const bool use_quad = [] {
-        const char *v = getenv("TFHE_B200_BR_QUAD");
+    // TFHE_B200_BR_LATENCY=0 keeps such batches on the two-warp kernel (A/B measurements)
+    static const bool use_latency = [] {
+        const char *v = getenv("TFHE_B200_BR_LATENCY");
         return v == nullptr || atoi(v) != 0;
     }();
-    if (use_quad && L.total <= sm_count) {
-        blind_rotate_quad_kernel<<<L.total, kThreads, sizeof(QuadCtaSmem), stream>>>(L);
+    if (use_latency && L.total <= sm_count) {
+        blind_rotate_octo_kernel<<<L.total, kThreads, sizeof(OctoCtaSmem), stream>>>(L);
         return cudaGetLastError();
     }
     // small batches: the always-idle last slot of every CTA refills the key rings (ring_skip<true>)

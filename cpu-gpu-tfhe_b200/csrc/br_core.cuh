@@ -108,14 +108,14 @@ struct WarpSmem {
 };
 static_assert(16 * kExtRow + kExtGapThroughput <= kExchPoly * 4, "extended copy must fit an exchange buffer");
 
-// Working set of the LATENCY kernel (four warps per ciphertext, one ciphertext per CTA: blind_rotate.cu
-// blind_rotate_quad_kernel): the extended accumulator copies have buffers of their own (both warps of
+// Working set of the LATENCY kernel (one ciphertext per CTA, eight warps: blind_rotate.cu
+// blind_rotate_octo_kernel): the extended accumulator copies have buffers of their own (both warps of
 // a polynomial read them while the exchange buffers are being rewritten), and two more buffers take
 // the inverse pass-2 output.
 constexpr int kExtPolyWords = 2048;   // 16 rows of 127 words, padded
-struct QuadSmem {
-    cpx exch[kKpl][kExchPoly];          // row (o, q): pass-1 output of warp (o, q), read by all four warps
-    cpx inv[kK + 1][kExchPoly];         // polynomial o: inverse pass-2 output (written by all four warps)
+struct LatencySmem {
+    cpx exch[kKpl][kExchPoly];          // row (o, q): pass-1 output of warp (o, q), read by all eight warps
+    cpx inv[kK + 1][kExchPoly];         // polynomial o: inverse pass-2 output (written by all eight warps)
     int32_t acc[kK + 1][kAccPoly];
     int32_t ext[kK + 1][kExtPolyWords];
 };
@@ -701,32 +701,23 @@ TFHE_HD void phase_i2_final(int lane, WarpSmem &ws, int o, const cpx (&x)[16], c
     phase_i2_final_p<kExtGapThroughput>(lane, ws.acc[o], ext_poly(ws, o), x, p);
 }
 
-// ---- Fourier multiply and inverse pass 2 by QUARTERS OF THE FREQUENCY CLASSES (latency kernel) -----
-// After pass 1 (warp r = decomposed row r) and a barrier, warp w takes the classes m1 = 8 w .. 8 w + 7 of
-// ALL FOUR rows, and nothing in this section leaves the warp:
-//   pass 2:   lane (rr, c) transforms row rr of class m1 = 8 w + c IN PLACE in the exchange buffer
-//             (16 positions, as phase_f2_fft_p);
-//   multiply: lane (g, c) re-reads positions 4 g .. 4 g + 3 of all four rows of its class (written by the
-//             lanes (0..3, c) of the same warp: a transposition through shared memory, one __syncwarp) and
-//             accumulates both result polynomials over the four key rows: the sum over rows is a sum in
-//             registers;
-//   inverse pass 2: stages 3 and 2 stay inside a block of four positions (lane (g, c), both result
-//             polynomials), the values go to the inverse buffer; lane (oo, k2, c) re-reads positions
-//             {2 k2, 2 k2 + 1} + {0, 4, 8, 12} of result polynomial oo, runs stages 1 and 0 and writes them back.
-// The first version of this kernel parked the partial sums of each warp's row in shared memory and read
-// three quarters of them back (18 % of its iteration); a second one summed over rows with warp shuffles:
-// a 64-bit shuffle pair moves 8 bytes per lane where a 128-bit shared-memory access moves 16, and the
-// shuffles measured ~10 cycles each for a lone warp.
-TFHE_HD void phase_c_f2_inplace(int rr, int m1, cpx (*exch)[kExchPoly], const cpx *e2) {
-    cpx *row = exch[rr] + m1 * kExchRow;
-    cpx z[16];
-#pragma unroll
-    for (int j2 = 0; j2 < 16; j2++) z[j2] = row[j2];
-    fwd16(z, e2 + m1 * kE2Row);
-#pragma unroll
-    for (int pos = 0; pos < 16; pos++) row[pos] = z[pos];
-}
-
+// ---- Fourier section of the latency kernel: pass 2, multiply, inverse pass 2 on EIGHT warps ------------
+// After pass 1 (warp r = decomposed row r) and a CTA barrier, warp v takes the frequency classes
+// 8 (v >> 1) .. + 7 and the position half ph = v & 1 of ALL FOUR rows and both result polynomials; the two
+// warps of a class octet meet at two 64-thread barriers, nothing else leaves a warp:
+//   pass 2:   lane (rr, c) reads all 16 inputs of (row rr, class m1) and produces the 8 outputs of half ph:
+//             stage 0 one-sided (u = a + g0 b for ph = 0, v = a - g0 b for ph = 1: 4 fp64 per point, the
+//             same as half a butterfly), stages 1-3 inside the half; written back IN PLACE after the
+//             partner warp has read its inputs (pair barrier);
+//   multiply: lane (g2, oo, c) re-reads positions 8 ph + 4 g2 .. + 3 of all four rows of its class (written
+//             by lanes of the same warp: a transposition through shared memory, one __syncwarp) and
+//             accumulates result polynomial oo over the four key rows: the sum over rows is a sum in registers;
+//   inverse:  stages 3, 2 inside that block of four positions, values to the inverse buffer; (pair barrier);
+//             stages 1, 0 on the four positions {k, k + 4, k + 8, k + 12}, k = 2 ph + kk, lane (kk, oo, c),
+//             in place.
+// Earlier versions: one warp per decomposed row all the way, the partial sums parked in shared memory and
+// three quarters of them read back (18 % of the iteration); then a sum over rows by warp shuffles (a 64-bit
+// shuffle pair moves 8 bytes per lane where a 128-bit shared-memory access moves 16).
 // positions 4 g .. 4 g + 3 of class m1 of the four transformed rows
 TFHE_HD void phase_c_load_rows(int g, int m1, const cpx (*exch)[kExchPoly], cpx (&zr)[kKpl][4]) {
 #pragma unroll
@@ -767,26 +758,75 @@ TFHE_HD void phase_c_inv_a_store(int g, int m1, cpx *inv_o, const cpx (&z)[4]) {
     for (int i = 0; i < 4; i++) d[i] = z[i];
 }
 
-// inverse stages 1 and 0 on positions {2 k2, 2 k2 + 1} + {0, 4, 8, 12} of class m1, in place; g1, g0: the
-// class's base multipliers of those stages
-TFHE_HD void phase_c_inv_b_inplace(int k2, int m1, cpx *inv_o, const cpx &g1, const cpx &g0) {
-    cpx *d = inv_o + m1 * kExchRow + 2 * k2;
-    cpx z[2][4];
+// lane constants of the forward half transform (position half ph of class m1; e: the class's base multipliers)
+struct OctoFwdConsts {
+    cpx c0, c1, c2, c3a, c3b;  // stage 0 (signed), stage 1, stage 2 (block 2 ph), stage 3 (blocks 4 ph, 4 ph + 2)
+};
+
+TFHE_HD cpx times_i(const cpx &c) {
+    cpx r;
+    r.x = -c.y;
+    r.y = c.x;
+    return r;
+}
+
+TFHE_HD void phase_o_fwd_consts(int ph, const cpx *e, OctoFwdConsts &k) {
+    const cpx g0 = e[0], g1 = e[1], g2 = e[2], g3 = e[3];
+    k.c0.x = ph ? -g0.x : g0.x;
+    k.c0.y = ph ? -g0.y : g0.y;
+    k.c1 = ph ? times_i(g1) : g1;
+    cpx h4;
+    h4.x = (g2.x - g2.y) * kSqrtHalf;
+    h4.y = (g2.x + g2.y) * kSqrtHalf;
+    k.c2 = ph ? h4 : g2;
+    cpx q4, q8, q38;
+    q4.x = (g3.x - g3.y) * kSqrtHalf;
+    q4.y = (g3.x + g3.y) * kSqrtHalf;
+    q8 = cmul_const(g3, kCosPi8, kSinPi8);
+    q38 = cmul_const(g3, kSinPi8, kCosPi8);
+    k.c3a = ph ? q8 : g3;
+    k.c3b = ph ? q38 : q4;
+}
+
+// outputs 8 ph .. 8 ph + 7 of the 16-point pass 2 of one (row, class); row: its 16 inputs
+TFHE_HD void phase_o_f2_half(const cpx *row, const OctoFwdConsts &k, cpx (&z)[8]) {
 #pragma unroll
-    for (int e = 0; e < 2; e++)
-#pragma unroll
-        for (int m = 0; m < 4; m++) z[e][m] = d[e + 4 * m];
-#pragma unroll
-    for (int e = 0; e < 2; e++) {
-        bf_inv(z[e][0], z[e][1], g1.x, g1.y);    // stage 1, block 0
-        bf_inv(z[e][2], z[e][3], -g1.y, g1.x);   // stage 1, block 1: times i
-        bf_inv(z[e][0], z[e][2], g0.x, g0.y);    // stage 0
-        bf_inv(z[e][1], z[e][3], g0.x, g0.y);
+    for (int i = 0; i < 8; i++) {
+        const cpx a = row[i], b = row[i + 8];
+        double zx = fma(k.c0.x, b.x, a.x), zy = fma(k.c0.x, b.y, a.y);
+        z[i].x = fma(-k.c0.y, b.y, zx);
+        z[i].y = fma(k.c0.y, b.x, zy);
     }
 #pragma unroll
-    for (int e = 0; e < 2; e++)
+    for (int i = 0; i < 4; i++) bf_fwd(z[i], z[i + 4], k.c1.x, k.c1.y);
 #pragma unroll
-        for (int m = 0; m < 4; m++) d[e + 4 * m] = z[e][m];
+    for (int i = 0; i < 2; i++) {
+        bf_fwd(z[i], z[i + 2], k.c2.x, k.c2.y);
+        bf_fwd(z[4 + i], z[6 + i], -k.c2.y, k.c2.x);
+    }
+    bf_fwd(z[0], z[1], k.c3a.x, k.c3a.y);
+    bf_fwd(z[2], z[3], -k.c3a.y, k.c3a.x);
+    bf_fwd(z[4], z[5], k.c3b.x, k.c3b.y);
+    bf_fwd(z[6], z[7], -k.c3b.y, k.c3b.x);
+}
+
+TFHE_HD void phase_o_f2_store(int ph, cpx *row, const cpx (&z)[8]) {
+#pragma unroll
+    for (int i = 0; i < 8; i++) row[8 * ph + i] = z[i];
+}
+
+// inverse stages 1 and 0 on positions {k, k + 4, k + 8, k + 12} of class m1, in place
+TFHE_HD void phase_o_inv_b_inplace(int k, int m1, cpx *inv_o, const cpx &g1, const cpx &g0) {
+    cpx *d = inv_o + m1 * kExchRow + k;
+    cpx z[4];
+#pragma unroll
+    for (int m = 0; m < 4; m++) z[m] = d[4 * m];
+    bf_inv(z[0], z[1], g1.x, g1.y);    // stage 1, block 0
+    bf_inv(z[2], z[3], -g1.y, g1.x);   // stage 1, block 1: times i
+    bf_inv(z[0], z[2], g0.x, g0.y);    // stage 0
+    bf_inv(z[1], z[3], g0.x, g0.y);
+#pragma unroll
+    for (int m = 0; m < 4; m++) d[4 * m] = z[m];
 }
 
 // Inverse pass 1 (32 points per slice j2): warp h takes the slices j2 = 8 h .. 8 h + 7, lane (qq, j2') the
@@ -897,7 +937,7 @@ TFHE_HD int32_t acc_coef_p(const int32_t (*acc)[kAccPoly], int o, int j) {
 
 // Sample extraction at index 0 (tLweExtractLweSampleIndex, lwe.cu:41-56):
 // u.a[0] = ACC.a[0], u.a[j] = -ACC.a[N-j], u.b = ACC.b[0].  u: int32[N+1].
-// `step` lanes share the work (32: one warp; 128: the four warps of the latency kernel).
+// `step` lanes share the work (32: one warp; 256: the eight warps of the latency kernel).
 TFHE_HD void phase_extract_p(int lane, int step, const int32_t (*acc)[kAccPoly], int32_t *u) {
     for (int j = lane; j < kN; j += step) {
         const int32_t v = (j == 0) ? acc_coef_p(acc, 0, 0) : (int32_t) (0u - (uint32_t) acc_coef_p(acc, 0, kN - j));

@@ -212,11 +212,11 @@ int main() {
     CHECK(g_max_frac < 0.25, "fp64 rounding error too close to 1/2");
 #endif
 
-    // ---- B3. the same steps through the LATENCY kernel's split (four warps per ciphertext) ----------
-    // warp (o, q): decomposition + pass 1 of row (o, q); pass 2, multiply and inverse pass 2 by quarters of the
-    // frequency classes (the sum over rows through lane exchanges); inverse pass 1 by halves of the slices.
+    // ---- B3. the same steps through the LATENCY kernel's split (eight warps per ciphertext) ---------
+    // warp (o, q): decomposition + pass 1 of row (o, q); pass 2, multiply and inverse pass 2 on eight warps by
+    // class octets and position halves; inverse pass 1 by halves of the slices on warps (o, 0), (o, 1).
     {
-        QuadSmem *qs = new QuadSmem();
+        LatencySmem *qs = new LatencySmem();
         std::vector<int32_t> accq = acc0;
         int maxdiffq = 0;
         for (int it = 0; it < 12; it++) {
@@ -238,33 +238,42 @@ int main() {
                     phase_f1h_finish(lane >> 4, wq[w][lane], wq[w][lane ^ 16], xq[w][lane]);
                     phase_f1h_store_p(lane >> 4, lane & 15, qs->exch[w], xq[w][lane]);
                 }
-            // pass 2 + Fourier multiply + inverse pass 2 by quarters of the frequency classes: warp w, lane
-            // (rr, c): class 8 w + c; transpositions through the exchange / inverse buffers inside the warp
+            // pass 2 + Fourier multiply + inverse pass 2 on eight warps: warp v = (class octet v >> 1, position
+            // half v & 1); transpositions through the exchange / inverse buffers
             static cpx x8[4][32][8];
-            for (int w = 0; w < 4; w++) {
-                for (int lane = 0; lane < 32; lane++) phase_c_f2_inplace(lane >> 3, 8 * w + (lane & 7), qs->exch, e2.data());
-                for (int lane = 0; lane < 32; lane++) {
-                    const int g = lane >> 3, m1 = 8 * w + (lane & 7);
-                    cpx zr[kKpl][4], accv[2][4];
-                    memset(accv, 0, sizeof(accv));
-                    phase_c_load_rows(g, m1, qs->exch, zr);
-                    for (int row = 0; row < kKpl; row++) {
-                        const cpx *bkrow = bkdev.data() + ((size_t) i * kKpl + row) * kBkRowCplx;
-                        for (int oo = 0; oo < 2; oo++)
+            {
+                static cpx zh[8][32][8];
+                for (int v = 0; v < 8; v++)
+                    for (int lane = 0; lane < 32; lane++) {
+                        const int rr = lane >> 3, m1 = 8 * (v >> 1) + (lane & 7);
+                        OctoFwdConsts k;
+                        phase_o_fwd_consts(v & 1, e2.data() + m1 * kE2Row, k);
+                        phase_o_f2_half(qs->exch[rr] + m1 * kExchRow, k, zh[v][lane]);
+                    }
+                for (int v = 0; v < 8; v++)   // (pair barrier: both warps of an octet have read their inputs)
+                    for (int lane = 0; lane < 32; lane++)
+                        phase_o_f2_store(v & 1, qs->exch[lane >> 3] + (8 * (v >> 1) + (lane & 7)) * kExchRow, zh[v][lane]);
+                for (int v = 0; v < 8; v++)
+                    for (int lane = 0; lane < 32; lane++) {
+                        const int g2 = lane >> 4, oo = (lane >> 3) & 1, m1 = 8 * (v >> 1) + (lane & 7), gb = 2 * (v & 1) + g2;
+                        cpx zr[kKpl][4], accv[4];
+                        memset(accv, 0, sizeof(accv));
+                        phase_c_load_rows(gb, m1, qs->exch, zr);
+                        for (int row = 0; row < kKpl; row++) {
+                            const cpx *bkrow = bkdev.data() + ((size_t) i * kKpl + row) * kBkRowCplx;
                             for (int p4 = 0; p4 < 4; p4++)
-                                cmac(accv[oo][p4], zr[row][p4], bkrow[oo * kBkHalfCplx + (4 * g + p4) * 32 + m1]);
+                                cmac(accv[p4], zr[row][p4], bkrow[oo * kBkHalfCplx + (4 * gb + p4) * 32 + m1]);
+                        }
+                        cpx c3, c2;
+                        phase_c_inv_consts(gb, e2.data() + m1 * kE2Row, c3, c2);
+                        phase_c_inv_a(c3, c2, accv);
+                        phase_c_inv_a_store(gb, m1, qs->inv[oo], accv);
                     }
-                    cpx c3, c2;
-                    phase_c_inv_consts(g, e2.data() + m1 * kE2Row, c3, c2);
-                    for (int oo = 0; oo < 2; oo++) {
-                        phase_c_inv_a(c3, c2, accv[oo]);
-                        phase_c_inv_a_store(g, m1, qs->inv[oo], accv[oo]);
+                for (int v = 0; v < 8; v++)   // (pair barrier)
+                    for (int lane = 0; lane < 32; lane++) {
+                        const int kk = lane >> 4, oo = (lane >> 3) & 1, m1 = 8 * (v >> 1) + (lane & 7);
+                        phase_o_inv_b_inplace(2 * (v & 1) + kk, m1, qs->inv[oo], e2[m1 * kE2Row + 1], e2[m1 * kE2Row]);
                     }
-                }
-                for (int lane = 0; lane < 32; lane++) {
-                    const int rr = lane >> 3, m1 = 8 * w + (lane & 7);
-                    phase_c_inv_b_inplace(rr & 1, m1, qs->inv[rr >> 1], e2[m1 * kE2Row + 1], e2[m1 * kE2Row]);
-                }
             }
             for (int w = 0; w < 4; w++) {
                 const int o = w >> 1, h = w & 1;
@@ -290,17 +299,17 @@ int main() {
             }
             accq = got;
         }
-        printf("B3. latency-kernel split (4 warps per ciphertext) vs exact: max |diff| = %d LSB\n", maxdiffq);
+        printf("B3. latency-kernel split (eight warps per ciphertext) vs exact: max |diff| = %d LSB\n", maxdiffq);
 #if TFHE_B200_TRUNCATE_LIKE_REFERENCE
         CHECK(maxdiffq <= 1, "latency-kernel split differs from exact result by more than truncation");
 #else
         CHECK(maxdiffq == 0, "latency-kernel split differs from the exact integer product");
 #endif
         std::vector<int32_t> u(kN + 1), u2(kN + 1);
-        for (int lane = 0; lane < 128; lane++) phase_extract_p(lane, 128, qs->acc, u.data());
+        for (int lane = 0; lane < 256; lane++) phase_extract_p(lane, 256, qs->acc, u.data());
         for (int lane = 0; lane < 32; lane++) phase_load_acc(lane, *ws, accq.data());
         for (int lane = 0; lane < 32; lane++) phase_extract(lane, *ws, u2.data());
-        CHECK(u == u2, "extraction by 128 lanes");
+        CHECK(u == u2, "extraction by 256 lanes");
         delete qs;
     }
 

@@ -16,9 +16,9 @@ rng = np.random.default_rng(12)
 names = ["f1 (decomp, pass 1, store)", "f2_fft (2 rows)", "mac keep (+wait)", "mac give (+wait)", "xchg_store",
          "pair barrier", "xchg_load + inv16", "i2_inner", "i2 shuffles", "i2_final", "-", "-", "-", "-", "-", "-"]
 if os.environ.get("QUAD_NAMES"):
-    names = ["f1 (decomp, pass 1, store)", "barrier 1", "pass 2 in place", "load rows + mac chunk 0 (+wait)",
-             "mac chunk 1", "inverse stages 3, 2 + store", "inverse stages 1, 0 in place", "barrier 2", "i2_local",
-             "shuffles + final", "pair barrier", "-", "-", "-", "-", "-"]
+    names = ["f1 (decomp, pass 1, store)", "barrier 1", "pass 2 half + pair barrier + store", "load rows + mac (+wait)",
+             "inverse stages 3, 2 + store", "pair barrier", "inverse stages 1, 0 in place", "barrier 2", "i2_local",
+             "shuffles + final", "pair barrier (i2)", "-", "-", "-", "-", "-"]
 n_iter = 100
 buf = (ctypes.c_longlong * 16)()
 for count in [int(x) for x in sys.argv[1:]] or [148, 592]:
