@@ -609,14 +609,12 @@ struct __align__(128) OctoCtaSmem {
 static_assert(offsetof(OctoCtaSmem, key) % 128 == 0, "TMA destination alignment");
 static_assert(sizeof(OctoCtaSmem) <= 227 * 1024, "shared memory budget");
 
-// key of iteration `it` into buffer it & 1 (four 16 KiB bulk copies, one per TGSW row)
+// key of iteration `it` into buffer it & 1 (one 64 KiB bulk copy)
 __device__ __forceinline__ void octo_fill(OctoCtaSmem &S, const BrLaunch &L, int it) {
     unsigned long long *bar = &S.full[it & 1];
     const cpx *src = L.bk + (size_t) (L.bk_first + it) * kBkIterCplx;
     mbar_arrive_expect_tx(bar, (uint32_t) (kBkIterCplx * sizeof(cpx)));
-#pragma unroll
-    for (int row = 0; row < kKpl; row++)
-        tma_load_1d(S.key[it & 1] + row * kBkRowCplx, src + row * kBkRowCplx, (uint32_t) (kBkRowCplx * sizeof(cpx)), bar);
+    tma_load_1d(S.key[it & 1], src, (uint32_t) (kBkIterCplx * sizeof(cpx)), bar);
 }
 
 __global__ void __launch_bounds__(kThreads, 1) blind_rotate_octo_kernel(const BrLaunch L) {
@@ -681,7 +679,7 @@ __global__ void __launch_bounds__(kThreads, 1) blind_rotate_octo_kernel(const Br
         unsigned long long *full = &S.full[it & 1];
         const uint32_t parity = (uint32_t) (it >> 1) & 1u;
         if (a == 0 && rotate) {  // tfhe_blindRotate_FFT :705: nothing to do; the key buffer moves on
-            if (threadIdx.x == 0) {
+            if (threadIdx.x == 4 * 32) {
                 mbar_wait(full, parity);
                 if (it + 2 < n_iter) octo_fill(S, L, it + 2);
             }
@@ -736,7 +734,10 @@ __global__ void __launch_bounds__(kThreads, 1) blind_rotate_octo_kernel(const Br
         PHASE_MARK(6);
         sync_all(2);  // the inverse pass-2 output is complete; nobody reads this iteration's key any more
         PHASE_MARK(7);
-        if (threadIdx.x == 0 && it + 2 < n_iter) {
+        // this iteration's key buffer is free: re-arm it for iteration it + 2 from a warp that is idle until
+        // the next barrier 1 (on a computing warp the proxy fence and the bulk-copy issue cost ~700 cycles of
+        // the iteration: measured)
+        if (threadIdx.x == 4 * 32 && it + 2 < n_iter) {
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             octo_fill(S, L, it + 2);
         }
