@@ -762,41 +762,35 @@ int tfhe_b200_extern_mul(tfhe_b200_ctx *c, int32_t *d_acc, int bk_index, int cou
 // ------------------------------------------------------ host-buffer variants --
 
 // Host-buffer gate batch (the reference-facing call: inputs and outputs are host arrays).
-// Large batches are cut into chunks of whole waves (16 x 4 ciphertexts per SM) and pipelined over
-// three streams: the H2D copy of chunk i+1 and the D2H copy of chunk i-1 run under the kernels of
-// chunk i, so the call costs the kernels plus one chunk's copies instead of all of them.
+// Batches of four waves or more are cut into chunks of whole waves (4 ciphertexts per SM) and pipelined
+// over three streams: the H2D copy of chunk i+1 and the D2H copy of chunk i-1 run under the kernels of
+// chunk i, so the call costs the kernels plus the copies of one wave instead of all of them.
 static int host_gate_common(tfhe_b200_ctx *c, int gate, bool mux, int32_t *out, const int32_t *a, const int32_t *b,
                             const int32_t *cc, int count) {
     if (check_ctx(c, true, true)) return 1;
     if (count <= 0) return count < 0 ? fail("negative count") : 0;
     CU(cudaSetDevice(c->device));
     const size_t row = (size_t) (c->p.n + 1);
-    {
-        // Memory-capped sub-batching (the reference: cudaMemGetInfo -> bootsLimit -> loop over
-        // sub-batches, boot-gates.cu:2869-2907): operands, result and the extracted samples of a
-        // sub-batch must fit in 80 % of the free device memory.  TFHE_B200_HOST_BATCH_LIMIT (gates)
-        // lowers the cap (tests).
-        size_t free_b = 0, total_b = 0;
-        CU(cudaMemGetInfo(&free_b, &total_b));
-        const size_t per_gate = ((mux ? 4 : 3) * row + (mux ? 2 : 1) * (size_t) (kN + 1)) * sizeof(int32_t);
-        size_t cap = (size_t) ((double) free_b * 0.8 / (double) per_gate);
-        static const long long env_cap = [] {
-            const char *v = getenv("TFHE_B200_HOST_BATCH_LIMIT");
-            return v ? atoll(v) : 0ll;
-        }();
-        if (env_cap > 0 && (size_t) env_cap < cap) cap = (size_t) env_cap;
+    // Memory-capped sub-batching (the reference: cudaMemGetInfo -> bootsLimit -> loop over sub-batches,
+    // boot-gates.cu:2869-2907): operands, result and the extracted samples of a sub-batch must fit in 80 % of
+    // the free device memory.  The query costs milliseconds (it was 4 % of a 65536-gate call when made
+    // unconditionally), so it is made only when the whole batch could not be allocated, or when
+    // TFHE_B200_HOST_BATCH_LIMIT (gates; tests) sets a cap.
+    static const long long env_cap = [] {
+        const char *v = getenv("TFHE_B200_HOST_BATCH_LIMIT");
+        return v ? atoll(v) : 0ll;
+    }();
+    auto sub_batches = [&](size_t cap) -> int {
         const size_t wave = 4 * (size_t) c->sm_count;
         if (cap > wave) cap -= cap % wave;  // whole waves
-        if (cap == 0) return fail("not enough free device memory for a single gate (%zu bytes free)", free_b);
-        if ((size_t) count > cap) {
-            for (size_t g0 = 0; g0 < (size_t) count; g0 += cap) {
-                const int nsub = (int) ((size_t) count - g0 < cap ? (size_t) count - g0 : cap);
-                const size_t off = g0 * row;
-                if (host_gate_common(c, gate, mux, out + off, a + off, b + off, mux ? cc + off : nullptr, nsub)) return 1;
-            }
-            return 0;
+        for (size_t g0 = 0; g0 < (size_t) count; g0 += cap) {
+            const int nsub = (int) ((size_t) count - g0 < cap ? (size_t) count - g0 : cap);
+            const size_t off = g0 * row;
+            if (host_gate_common(c, gate, mux, out + off, a + off, b + off, mux ? cc + off : nullptr, nsub)) return 1;
         }
-    }
+        return 0;
+    };
+    if (env_cap > 0 && (long long) count > env_cap) return sub_batches((size_t) env_cap);
     const size_t bytes = (size_t) count * row * sizeof(int32_t);
     int32_t *d_a = nullptr, *d_b = nullptr, *d_c = nullptr, *d_o = nullptr;
     cudaStream_t st = c->stream;
@@ -811,10 +805,42 @@ static int host_gate_common(tfhe_b200_ctx *c, int gate, bool mux, int32_t *out, 
         cudaMallocAsync(&d_o, bytes, st) != cudaSuccess || (mux && cudaMallocAsync(&d_c, bytes, st) != cudaSuccess)) {
         const cudaError_t e = cudaGetLastError();
         release();
-        return fail("device allocation of %zu bytes per operand failed: %s", bytes, cudaGetErrorString(e));
+        d_a = d_b = d_c = d_o = nullptr;
+        // the whole batch does not fit: size sub-batches from the free memory
+        size_t free_b = 0, total_b = 0;
+        CU(cudaMemGetInfo(&free_b, &total_b));
+        const size_t per_gate = ((mux ? 4 : 3) * row + (mux ? 2 : 1) * (size_t) (kN + 1)) * sizeof(int32_t);
+        const size_t cap = (size_t) ((double) free_b * 0.8 / (double) per_gate);
+        if (cap == 0 || cap >= (size_t) count)
+            return fail("device allocation of %zu bytes per operand failed: %s", bytes, cudaGetErrorString(e));
+        return sub_batches(cap);
     }
-    const int chunk = 16 * 4 * c->sm_count;  // 16 waves
-    const int nchunks = count >= 2 * chunk ? (count + chunk - 1) / chunk : 1;
+    // chunk boundaries in whole waves (4 ciphertexts per SM): 1, 3, 8, 16, 16, ..., 8, 3, 1.  Only the H2D
+    // copy of the first chunk and the D2H copy of the last one are exposed, so both are small; every other
+    // copy runs under a kernel at least as long as itself even at a tenth of the nominal PCIe rate (one wave
+    // = 3.5 ms of kernel and 2.4 MB in / 1.2 MB out).  Batches below four waves go in one piece.
+    const int wave = 4 * c->sm_count;
+    std::vector<int> bounds;  // chunk i = gates [bounds[i], bounds[i + 1])
+    {
+        int rem = (count + wave - 1) / wave;
+        std::vector<int> head, tail, waves;
+        for (int s : {1, 3, 8})
+            if (rem >= 2 * s + 2) {
+                head.push_back(s);
+                tail.push_back(s);
+                rem -= 2 * s;
+            }
+        waves = head;
+        for (; rem > 0; rem -= 16) waves.push_back(rem < 16 ? rem : 16);
+        for (size_t i = tail.size(); i-- > 0;) waves.push_back(tail[i]);
+        long long g = 0;
+        bounds.push_back(0);
+        for (int w : waves) {
+            g += (long long) w * wave;
+            bounds.push_back(g < count ? (int) g : count);
+        }
+    }
+    const int nchunks = (int) bounds.size() - 1;
     int rc = 0;
     if (nchunks == 1) {
         cudaError_t e = cudaMemcpyAsync(d_a, a, bytes, cudaMemcpyHostToDevice, st);
@@ -836,7 +862,7 @@ static int host_gate_common(tfhe_b200_ctx *c, int gate, bool mux, int32_t *out, 
                     cudaStreamWaitEvent(c->copy_in, ev[2 * nchunks], 0) != cudaSuccess))
             rc = fail("stream setup failed");
         for (int i = 0; i < nchunks && !rc; i++) {
-            const int g0 = i * chunk, n = (count - g0 < chunk) ? count - g0 : chunk;
+            const int g0 = bounds[i], n = bounds[i + 1] - g0;
             const size_t off = (size_t) g0 * row, nb = (size_t) n * row * sizeof(int32_t);
             cudaError_t e = cudaMemcpyAsync(d_a + off, a + off, nb, cudaMemcpyHostToDevice, c->copy_in);
             if (e == cudaSuccess) e = cudaMemcpyAsync(d_b + off, b + off, nb, cudaMemcpyHostToDevice, c->copy_in);

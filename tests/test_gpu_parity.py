@@ -292,11 +292,12 @@ def test_host_buffer_entry_points(engine, oracle, keys):
     assert engine.gate_host("AND", ca[:0], cb[:0]).shape == (0, 501)  # empty batch is a no-op
 
 
-def test_host_buffer_entry_point_pipelined_chunks(engine, oracle, keys):
-    """Batches of two or more 16-wave chunks go through the three-stream pipeline of the host-buffer
-    entry point (copies of neighbouring chunks under the kernels): ragged last chunk, results in
-    place and identical to the device-resident call."""
-    n = 2 * 16 * 4 * engine.sm_count + 777
+@pytest.mark.parametrize("waves", [5, 32])
+def test_host_buffer_entry_point_pipelined_chunks(engine, oracle, keys, waves):
+    """Batches of four waves or more go through the three-stream pipeline of the host-buffer entry point
+    (chunks of 1, 3, 8, 16 ... 8, 3, 1 waves, copies of neighbouring chunks under the kernels): ragged
+    last chunk, results in place and identical to the device-resident call."""
+    n = waves * 4 * engine.sm_count + 777
     r = np.random.default_rng(77)
     a, b = r.integers(0, 2, n).astype(np.int32), r.integers(0, 2, n).astype(np.int32)
     rng = oracle.rng(701)
