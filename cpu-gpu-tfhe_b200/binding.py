@@ -128,6 +128,8 @@ def lib():
         L.tfhe_b200_circuit_levels.argtypes = [_vp]
         L.tfhe_b200_circuit_gates.argtypes = [_vp]
         L.tfhe_b200_circuit_gates.restype = ctypes.c_longlong
+        L.tfhe_b200_circuit_level_gates.argtypes = [_vp, ctypes.c_int]
+        L.tfhe_b200_circuit_level_gates.restype = ctypes.c_longlong
         L.tfhe_b200_circuit_operands.argtypes = [_vp]
         L.tfhe_b200_circuit_operand_rows.argtypes = [_vp, _i]
         L.tfhe_b200_circuit_output_rows.argtypes = [_vp]
@@ -561,6 +563,7 @@ class Circuit:
         self.h = _vp(h)
         self.levels = int(self.L.tfhe_b200_circuit_levels(self.h))
         self.gates = int(self.L.tfhe_b200_circuit_gates(self.h))
+        self.level_gates = [int(self.L.tfhe_b200_circuit_level_gates(self.h, i)) for i in range(self.levels)]
         self.out_rows = int(self.L.tfhe_b200_circuit_output_rows(self.h))
         self.operand_rows = [int(self.L.tfhe_b200_circuit_operand_rows(self.h, o))
                              for o in range(int(self.L.tfhe_b200_circuit_operands(self.h)))]

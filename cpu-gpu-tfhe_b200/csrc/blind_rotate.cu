@@ -55,6 +55,9 @@ constexpr uint32_t kRingStages = 3;                    // per role
 constexpr uint32_t kChunksPerIter = 4;                 // per role
 constexpr int kStages = 2 * (int) kRingStages;
 // positions of a chunk multiplied AFTER its stage release has been issued (mac_consume)
+#ifndef TFHE_B200_NO_REFILL_FENCE
+#define TFHE_B200_NO_REFILL_FENCE 0   // 1: experiment, no proxy fence in front of a ring refill
+#endif
 #ifndef TFHE_B200_BR_MAC_TAIL
 #define TFHE_B200_BR_MAC_TAIL 6
 #endif
@@ -232,7 +235,9 @@ __device__ __forceinline__ void ring_refill_if_last(CtaSmem &S, const BrLaunch &
 #if TFHE_B200_RING_STRICT
         asm volatile("fence.acq_rel.cta;" ::: "memory");  // acquire: the other consumers' releases
 #endif
+#if !TFHE_B200_NO_REFILL_FENCE
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+#endif
         ring_fill_at(S, L, role, fit, fsub, st);
     }
 }
@@ -400,7 +405,9 @@ __device__ __forceinline__ void mac_consume(CtaSmem &S, const BrLaunch &L, int r
 #if TFHE_B200_RING_STRICT
         asm volatile("fence.acq_rel.cta;" ::: "memory");  // acquire: the other consumers' releases
 #endif
+#if !TFHE_B200_NO_REFILL_FENCE
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+#endif
         ring_fill_at(S, L, role, fit, fsub, st);
     }
     sp.advance((uint32_t) L.n_iter);
@@ -735,8 +742,8 @@ __global__ void __launch_bounds__(kThreads, 1) blind_rotate_octo_kernel(const Br
         sync_all(2);  // the inverse pass-2 output is complete; nobody reads this iteration's key any more
         PHASE_MARK(7);
         // this iteration's key buffer is free: re-arm it for iteration it + 2 from a warp that is idle until
-        // the next barrier 1 (on a computing warp the proxy fence and the bulk-copy issue cost ~700 cycles of
-        // the iteration: measured)
+        // the next barrier 1 (on warp 0 the proxy fence and the bulk-copy issue were ~175 cycles of its
+        // inverse pass 1: measured with the phase timers)
         if (threadIdx.x == 4 * 32 && it + 2 < n_iter) {
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             octo_fill(S, L, it + 2);

@@ -1157,6 +1157,18 @@ void tfhe_b200_circuit_destroy(tfhe_b200_circuit *c) {
 }
 
 int tfhe_b200_circuit_levels(const tfhe_b200_circuit *c) { return c ? c->depth : 0; }
+// bootstraps of the level-th sequential bootstrap batch (0 .. levels - 1); a MUX group counts two per row
+long long tfhe_b200_circuit_level_gates(const tfhe_b200_circuit *c, int level) {
+    if (!c || level < 0) return 0;
+    for (const Level &lv : c->levels) {
+        if (lv.type == LV_LINEAR) continue;
+        if (level-- > 0) continue;
+        long long n = 0;
+        for (int i = 0; i < lv.nops; i++) n += lv.ops[i].count;
+        return lv.type == LV_MUX ? 2 * n : n;
+    }
+    return 0;
+}
 long long tfhe_b200_circuit_gates(const tfhe_b200_circuit *c) { return c ? c->n_gates : 0; }
 int tfhe_b200_circuit_operands(const tfhe_b200_circuit *c) { return c ? (int) c->in_row0.size() : 0; }
 int tfhe_b200_circuit_operand_rows(const tfhe_b200_circuit *c, int o) {

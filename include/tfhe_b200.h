@@ -239,6 +239,8 @@ tfhe_b200_circuit *tfhe_b200_circuit_shift(tfhe_b200_ctx *ctx, int nbits, int co
 tfhe_b200_circuit *tfhe_b200_circuit_div(tfhe_b200_ctx *ctx, int nbits, int count, int is_signed, int adder);
 void tfhe_b200_circuit_destroy(tfhe_b200_circuit *c);
 int tfhe_b200_circuit_levels(const tfhe_b200_circuit *c);      /* sequential bootstrap batches */
+/* bootstraps in batch `level` (0 .. levels - 1): the width the latency of that level depends on */
+long long tfhe_b200_circuit_level_gates(const tfhe_b200_circuit *c, int level);
 long long tfhe_b200_circuit_gates(const tfhe_b200_circuit *c); /* bootstrapped gates per run   */
 int tfhe_b200_circuit_operands(const tfhe_b200_circuit *c);
 int tfhe_b200_circuit_operand_rows(const tfhe_b200_circuit *c, int operand);

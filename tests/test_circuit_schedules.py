@@ -275,6 +275,10 @@ def test_carry_save_depth_and_size(pkg):
     cs, prefix = pkg.Circuit(None, "mul_ex", 32, 1, 2), pkg.Circuit(None, "mul_ex", 32, 1, 1)
     assert cs.levels == 15 and prefix.levels == 31
     assert cs.gates < prefix.gates / 3
+    # per-level widths (tfhe_b200_circuit_level_gates): the AND level, then the narrow reduction levels
+    for c in (cs, prefix):
+        assert len(c.level_gates) == c.levels and sum(c.level_gates) == c.gates
+    assert cs.level_gates[0] == 32 * 33 // 2 and max(cs.level_gates[1:]) < 200
     a, b = np.array([40000]), np.array([50000])
     assert from_bits(cs.simulate(to_bits(a, 32), to_bits(b, 32)), 32)[0] == (40000 * 50000) % 2 ** 32
 
