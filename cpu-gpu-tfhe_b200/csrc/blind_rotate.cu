@@ -596,8 +596,8 @@ __global__ void __launch_bounds__(kThreads, 1) blind_rotate_kernel(const BrLaunc
 //   - the key of an iteration (64 KiB) is double buffered whole in shared memory: one thread re-arms the
 //     buffer of iteration it for iteration it + 2 right behind the barrier that ends the Fourier section
 //     (one bulk-copy issue per iteration; no helper warps, no release counters, no polling);
-//   - the Fourier section (pass 2, multiply, inverse pass 2) runs on eight warps: warp v = frequency-class
-//     octet v >> 1, position half v & 1 (br_core.cuh "the same section on EIGHT warps");
+//   - the Fourier section: pass 2 by warp cq (class octet cq, all four rows, in place), multiply and inverse
+//     pass 2 by the warps cq (position half 0) and cq + 4 (half 1) (br_core.cuh "Fourier section");
 //   - the inverse pass 1 + conversion + accumulator update of result polynomial o is shared by the warps
 //     (o, 0) and (o, 1) by halves of the slices (8 positions per lane, the last two stages through lane ^ 8
 //     and lane ^ 16); warps 4..7 wait at the next barrier during pass 1 and this part.
@@ -648,11 +648,9 @@ __global__ void __launch_bounds__(kThreads, 1) blind_rotate_octo_kernel(const Br
     const int o = (warp >> 1) & 1, q = warp & 1, r = warp & 3;
     const bool edge = warp < 4;
     // Fourier section: class octet cq, position half ph; lane (rr, c) / (g2, oo, c) / (kk, oo, c)
-    const int cq = warp >> 1, ph = warp & 1;
+    const int cq = warp & 3, ph = warp >> 2;   // the octet's warps (cq, cq + 4) sit on the same sub-partition
     const int rr = lane >> 3, m1 = 8 * cq + (lane & 7);
     const int g2 = lane >> 4, oo = (lane >> 3) & 1, gb = 2 * ph + g2;
-    OctoFwdConsts fk;
-    phase_o_fwd_consts(ph, S.e2 + m1 * kE2Row, fk);
     cpx ic3, ic2;
     phase_c_inv_consts(gb, S.e2 + m1 * kE2Row, ic3, ic2);
     const cpx ig1 = S.e2[m1 * kE2Row + 1], ig0 = S.e2[m1 * kE2Row];
@@ -710,14 +708,11 @@ __global__ void __launch_bounds__(kThreads, 1) blind_rotate_octo_kernel(const Br
         PHASE_MARK(0);
         sync_all(1);  // the pass-1 output of all four rows is in place
         PHASE_MARK(1);
-        {
-            cpx *row = W.exch[rr] + m1 * kExchRow;
-            cpx z[8];
-            phase_o_f2_half(row, fk, z);
-            named_sync(3 + cq, 64);  // the other position half's warp has read its inputs too
-            phase_o_f2_store(ph, row, z);
-            __syncwarp();
-        }
+        // pass 2 of the octet's 32 (row, class) transforms by warp cq alone, in place (16 positions per lane; an
+        // eight-warp version that produced 8 positions per lane from all 16 inputs read every input twice: 256
+        // more shared-memory wavefronts, +3 % time); warp cq + 4 waits for it
+        if (edge) phase_c_f2_inplace(rr, m1, W.exch, S.e2);
+        named_sync(3 + cq, 64);
         PHASE_MARK(2);
         {
             cpx zr[kKpl][4], acc[4];

@@ -701,23 +701,32 @@ TFHE_HD void phase_i2_final(int lane, WarpSmem &ws, int o, const cpx (&x)[16], c
     phase_i2_final_p<kExtGapThroughput>(lane, ws.acc[o], ext_poly(ws, o), x, p);
 }
 
-// ---- Fourier section of the latency kernel: pass 2, multiply, inverse pass 2 on EIGHT warps ------------
-// After pass 1 (warp r = decomposed row r) and a CTA barrier, warp v takes the frequency classes
-// 8 (v >> 1) .. + 7 and the position half ph = v & 1 of ALL FOUR rows and both result polynomials; the two
-// warps of a class octet meet at two 64-thread barriers, nothing else leaves a warp:
-//   pass 2:   lane (rr, c) reads all 16 inputs of (row rr, class m1) and produces the 8 outputs of half ph:
-//             stage 0 one-sided (u = a + g0 b for ph = 0, v = a - g0 b for ph = 1: 4 fp64 per point, the
-//             same as half a butterfly), stages 1-3 inside the half; written back IN PLACE after the
-//             partner warp has read its inputs (pair barrier);
-//   multiply: lane (g2, oo, c) re-reads positions 8 ph + 4 g2 .. + 3 of all four rows of its class (written
-//             by lanes of the same warp: a transposition through shared memory, one __syncwarp) and
-//             accumulates result polynomial oo over the four key rows: the sum over rows is a sum in registers;
+// ---- Fourier section of the latency kernel: pass 2, multiply, inverse pass 2 by CLASS OCTETS ---------
+// After pass 1 (warp r = decomposed row r) and a CTA barrier, the warps cq and cq + 4 take the frequency
+// classes 8 cq .. 8 cq + 7 of ALL FOUR rows and both result polynomials; they meet at two 64-thread
+// barriers, nothing else leaves the pair:
+//   pass 2:   warp cq, lane (rr, c): the 16-point transform of (row rr, class m1 = 8 cq + c) IN PLACE in the
+//             exchange buffer;
+//   multiply: warp cq + 4 ph (position half ph), lane (g2, oo, c) re-reads positions 8 ph + 4 g2 .. + 3 of all
+//             four rows of its class (a transposition through shared memory) and accumulates result
+//             polynomial oo over the four key rows: the sum over rows is a sum in registers;
 //   inverse:  stages 3, 2 inside that block of four positions, values to the inverse buffer; (pair barrier);
 //             stages 1, 0 on the four positions {k, k + 4, k + 8, k + 12}, k = 2 ph + kk, lane (kk, oo, c),
 //             in place.
 // Earlier versions: one warp per decomposed row all the way, the partial sums parked in shared memory and
 // three quarters of them read back (18 % of the iteration); then a sum over rows by warp shuffles (a 64-bit
 // shuffle pair moves 8 bytes per lane where a 128-bit shared-memory access moves 16).
+// pass 2 of (row rr, class m1) in place in the exchange buffer (all 16 positions by one lane)
+TFHE_HD void phase_c_f2_inplace(int rr, int m1, cpx (*exch)[kExchPoly], const cpx *e2) {
+    cpx *row = exch[rr] + m1 * kExchRow;
+    cpx z[16];
+#pragma unroll
+    for (int j2 = 0; j2 < 16; j2++) z[j2] = row[j2];
+    fwd16(z, e2 + m1 * kE2Row);
+#pragma unroll
+    for (int pos = 0; pos < 16; pos++) row[pos] = z[pos];
+}
+
 // positions 4 g .. 4 g + 3 of class m1 of the four transformed rows
 TFHE_HD void phase_c_load_rows(int g, int m1, const cpx (*exch)[kExchPoly], cpx (&zr)[kKpl][4]) {
 #pragma unroll
@@ -756,63 +765,6 @@ TFHE_HD void phase_c_inv_a_store(int g, int m1, cpx *inv_o, const cpx (&z)[4]) {
     cpx *d = inv_o + m1 * kExchRow + 4 * g;
 #pragma unroll
     for (int i = 0; i < 4; i++) d[i] = z[i];
-}
-
-// lane constants of the forward half transform (position half ph of class m1; e: the class's base multipliers)
-struct OctoFwdConsts {
-    cpx c0, c1, c2, c3a, c3b;  // stage 0 (signed), stage 1, stage 2 (block 2 ph), stage 3 (blocks 4 ph, 4 ph + 2)
-};
-
-TFHE_HD cpx times_i(const cpx &c) {
-    cpx r;
-    r.x = -c.y;
-    r.y = c.x;
-    return r;
-}
-
-TFHE_HD void phase_o_fwd_consts(int ph, const cpx *e, OctoFwdConsts &k) {
-    const cpx g0 = e[0], g1 = e[1], g2 = e[2], g3 = e[3];
-    k.c0.x = ph ? -g0.x : g0.x;
-    k.c0.y = ph ? -g0.y : g0.y;
-    k.c1 = ph ? times_i(g1) : g1;
-    cpx h4;
-    h4.x = (g2.x - g2.y) * kSqrtHalf;
-    h4.y = (g2.x + g2.y) * kSqrtHalf;
-    k.c2 = ph ? h4 : g2;
-    cpx q4, q8, q38;
-    q4.x = (g3.x - g3.y) * kSqrtHalf;
-    q4.y = (g3.x + g3.y) * kSqrtHalf;
-    q8 = cmul_const(g3, kCosPi8, kSinPi8);
-    q38 = cmul_const(g3, kSinPi8, kCosPi8);
-    k.c3a = ph ? q8 : g3;
-    k.c3b = ph ? q38 : q4;
-}
-
-// outputs 8 ph .. 8 ph + 7 of the 16-point pass 2 of one (row, class); row: its 16 inputs
-TFHE_HD void phase_o_f2_half(const cpx *row, const OctoFwdConsts &k, cpx (&z)[8]) {
-#pragma unroll
-    for (int i = 0; i < 8; i++) {
-        const cpx a = row[i], b = row[i + 8];
-        double zx = fma(k.c0.x, b.x, a.x), zy = fma(k.c0.x, b.y, a.y);
-        z[i].x = fma(-k.c0.y, b.y, zx);
-        z[i].y = fma(k.c0.y, b.x, zy);
-    }
-#pragma unroll
-    for (int i = 0; i < 4; i++) bf_fwd(z[i], z[i + 4], k.c1.x, k.c1.y);
-#pragma unroll
-    for (int i = 0; i < 2; i++) {
-        bf_fwd(z[i], z[i + 2], k.c2.x, k.c2.y);
-        bf_fwd(z[4 + i], z[6 + i], -k.c2.y, k.c2.x);
-    }
-    bf_fwd(z[0], z[1], k.c3a.x, k.c3a.y);
-    bf_fwd(z[2], z[3], -k.c3a.y, k.c3a.x);
-    bf_fwd(z[4], z[5], k.c3b.x, k.c3b.y);
-    bf_fwd(z[6], z[7], -k.c3b.y, k.c3b.x);
-}
-
-TFHE_HD void phase_o_f2_store(int ph, cpx *row, const cpx (&z)[8]) {
-#pragma unroll
-    for (int i = 0; i < 8; i++) row[8 * ph + i] = z[i];
 }
 
 // inverse stages 1 and 0 on positions {k, k + 4, k + 8, k + 12} of class m1, in place

@@ -238,24 +238,15 @@ int main() {
                     phase_f1h_finish(lane >> 4, wq[w][lane], wq[w][lane ^ 16], xq[w][lane]);
                     phase_f1h_store_p(lane >> 4, lane & 15, qs->exch[w], xq[w][lane]);
                 }
-            // pass 2 + Fourier multiply + inverse pass 2 on eight warps: warp v = (class octet v >> 1, position
-            // half v & 1); transpositions through the exchange / inverse buffers
+            // pass 2 by warp cq; Fourier multiply + inverse pass 2 on eight warps: warp v = (class octet v & 3,
+            // position half v >> 2); transpositions through the exchange / inverse buffers
             static cpx x8[4][32][8];
             {
-                static cpx zh[8][32][8];
+                for (int w = 0; w < 4; w++)   // pass 2 by warp w = class octet w, in place
+                    for (int lane = 0; lane < 32; lane++) phase_c_f2_inplace(lane >> 3, 8 * w + (lane & 7), qs->exch, e2.data());
                 for (int v = 0; v < 8; v++)
                     for (int lane = 0; lane < 32; lane++) {
-                        const int rr = lane >> 3, m1 = 8 * (v >> 1) + (lane & 7);
-                        OctoFwdConsts k;
-                        phase_o_fwd_consts(v & 1, e2.data() + m1 * kE2Row, k);
-                        phase_o_f2_half(qs->exch[rr] + m1 * kExchRow, k, zh[v][lane]);
-                    }
-                for (int v = 0; v < 8; v++)   // (pair barrier: both warps of an octet have read their inputs)
-                    for (int lane = 0; lane < 32; lane++)
-                        phase_o_f2_store(v & 1, qs->exch[lane >> 3] + (8 * (v >> 1) + (lane & 7)) * kExchRow, zh[v][lane]);
-                for (int v = 0; v < 8; v++)
-                    for (int lane = 0; lane < 32; lane++) {
-                        const int g2 = lane >> 4, oo = (lane >> 3) & 1, m1 = 8 * (v >> 1) + (lane & 7), gb = 2 * (v & 1) + g2;
+                        const int g2 = lane >> 4, oo = (lane >> 3) & 1, m1 = 8 * (v & 3) + (lane & 7), gb = 2 * (v >> 2) + g2;
                         cpx zr[kKpl][4], accv[4];
                         memset(accv, 0, sizeof(accv));
                         phase_c_load_rows(gb, m1, qs->exch, zr);
@@ -271,8 +262,8 @@ int main() {
                     }
                 for (int v = 0; v < 8; v++)   // (pair barrier)
                     for (int lane = 0; lane < 32; lane++) {
-                        const int kk = lane >> 4, oo = (lane >> 3) & 1, m1 = 8 * (v >> 1) + (lane & 7);
-                        phase_o_inv_b_inplace(2 * (v & 1) + kk, m1, qs->inv[oo], e2[m1 * kE2Row + 1], e2[m1 * kE2Row]);
+                        const int kk = lane >> 4, oo = (lane >> 3) & 1, m1 = 8 * (v & 3) + (lane & 7);
+                        phase_o_inv_b_inplace(2 * (v >> 2) + kk, m1, qs->inv[oo], e2[m1 * kE2Row + 1], e2[m1 * kE2Row]);
                     }
             }
             for (int w = 0; w < 4; w++) {
