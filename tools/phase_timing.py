@@ -16,7 +16,7 @@ rng = np.random.default_rng(12)
 names = ["f1 (decomp, pass 1, store)", "f2_fft (2 rows)", "mac keep (+wait)", "mac give (+wait)", "xchg_store",
          "pair barrier", "xchg_load + inv16", "i2_inner", "i2 shuffles", "i2_final", "-", "-", "-", "-", "-", "-"]
 if os.environ.get("QUAD_NAMES"):
-    names = ["f1 (decomp, pass 1, store)", "barrier 1", "pass 2 half + pair barrier + store", "load rows + mac (+wait)",
+    names = ["f1 (decomp, pass 1, store)", "barrier 1", "pass 2 in place (warp cq) + pair barrier", "load rows + mac (+wait)",
              "inverse stages 3, 2 + store", "pair barrier", "inverse stages 1, 0 in place", "barrier 2", "i2_local",
              "shuffles + final", "pair barrier (i2)", "-", "-", "-", "-", "-"]
 n_iter = 100
