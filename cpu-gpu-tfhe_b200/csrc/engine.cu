@@ -861,6 +861,19 @@ static int host_gate_common(tfhe_b200_ctx *c, int gate, bool mux, int32_t *out, 
         if (!rc && (cudaEventRecord(ev[2 * nchunks], st) != cudaSuccess ||
                     cudaStreamWaitEvent(c->copy_in, ev[2 * nchunks], 0) != cudaSuccess))
             rc = fail("stream setup failed");
+        // Issue order: H2D(i), kernels(i), D2H(i - 1).  With PAGEABLE host memory cudaMemcpyAsync blocks the
+        // calling thread (the driver stages the data itself; a D2H additionally waits for its kernels), so the
+        // D2H of a chunk is issued only after the kernels of the NEXT chunk are queued: the GPU never waits for
+        // the host thread.  (D2H(i) right behind kernels(i) left the GPU idle during every H2D: 470 instead
+        // of 387 ms per 65536 gates.)  With pinned memory the order makes no difference.
+        auto copy_out = [&](int i) {
+            const int g0 = bounds[i], n = bounds[i + 1] - g0;
+            const size_t off = (size_t) g0 * row, nb = (size_t) n * row * sizeof(int32_t);
+            cudaError_t e = cudaStreamWaitEvent(c->copy_out, ev[2 * i + 1], 0);
+            if (e == cudaSuccess) e = cudaMemcpyAsync(out + off, d_o + off, nb, cudaMemcpyDeviceToHost, c->copy_out);
+            if (e != cudaSuccess) rc = fail("D2H copy failed: %s", cudaGetErrorString(e));
+        };
+        int issued = 0;  // chunks whose kernels are queued
         for (int i = 0; i < nchunks && !rc; i++) {
             const int g0 = bounds[i], n = bounds[i + 1] - g0;
             const size_t off = (size_t) g0 * row, nb = (size_t) n * row * sizeof(int32_t);
@@ -877,10 +890,14 @@ static int host_gate_common(tfhe_b200_ctx *c, int gate, bool mux, int32_t *out, 
                      : tfhe_b200_gate(c, gate, d_o + off, d_a + off, d_b + off, n, st);
             if (rc) break;
             e = cudaEventRecord(ev[2 * i + 1], st);
-            if (e == cudaSuccess) e = cudaStreamWaitEvent(c->copy_out, ev[2 * i + 1], 0);
-            if (e == cudaSuccess) e = cudaMemcpyAsync(out + off, d_o + off, nb, cudaMemcpyDeviceToHost, c->copy_out);
-            if (e != cudaSuccess) rc = fail("D2H copy failed: %s", cudaGetErrorString(e));
+            if (e != cudaSuccess) {
+                rc = fail("event record failed: %s", cudaGetErrorString(e));
+                break;
+            }
+            issued = i + 1;
+            if (i > 0) copy_out(i - 1);
         }
+        if (!rc && issued > 0) copy_out(issued - 1);
         // everything the copy streams did must be over before the buffers go back to the pool
         cudaError_t e1 = cudaStreamSynchronize(c->copy_in), e2 = cudaStreamSynchronize(c->copy_out);
         if (!rc && (e1 != cudaSuccess || e2 != cudaSuccess))
