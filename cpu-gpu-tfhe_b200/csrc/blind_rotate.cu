@@ -593,17 +593,18 @@ __global__ void __launch_bounds__(kThreads, 1) blind_rotate_kernel(const BrLaunc
 // instructions per cycle over all, so the length of the per-lane instruction stream is what counts.  Here:
 //   - warp (o, q) (warps 0..3) decomposes accumulator polynomial o at digit level q only and runs pass 1 of
 //     that ONE row, split over lane pairs (br_core.cuh phase_f1h_*);
-//   - the key of an iteration (64 KiB) is double buffered whole in shared memory: one thread re-arms the
-//     buffer of iteration it for iteration it + 2 right behind the barrier that ends the Fourier section
-//     (one bulk-copy issue per iteration; no helper warps, no release counters, no polling);
+//   - the key of an iteration (64 KiB) is double buffered whole in shared memory: one thread of warp 4 (idle
+//     until the next barrier) re-arms the buffer of iteration it for iteration it + 2 right behind the barrier
+//     that ends the Fourier section (one bulk copy per iteration; no producer warps, counters or polling);
 //   - the Fourier section: pass 2 by warp cq (class octet cq, all four rows, in place), multiply and inverse
 //     pass 2 by the warps cq (position half 0) and cq + 4 (half 1) (br_core.cuh "Fourier section");
 //   - the inverse pass 1 + conversion + accumulator update of result polynomial o is shared by the warps
 //     (o, 0) and (o, 1) by halves of the slices (8 positions per lane, the last two stages through lane ^ 8
 //     and lane ^ 16); warps 4..7 wait at the next barrier during pass 1 and this part.
 // Two CTA barriers and three 64-thread barriers per iteration.  History (single gate, blind rotation):
-// two-warp kernel 2.30 ms; four warps by decomposed row with partial sums in shared memory and four helper
-// warps on the key rings 1.60 ms; sums over rows in registers 1.55 ms; this kernel 1.50 ms.
+// two-warp kernel 2.30 ms; four warps by decomposed row with partial sums in shared memory and four more
+// warps feeding per-row key rings 1.60 ms; sums over rows in registers 1.55 ms; eight warps with the key
+// double buffered 1.50 ms; pass 2 without redundant reads 1.44 ms (profiles/README.md).
 // Results are the same Torus32 words as the throughput kernel's: both return the exact integer product
 // (the fp64 sums are taken in a different order, far inside the rounding margin; tests/test_gpu_parity.py
 // compares the two kernels word for word).
@@ -839,7 +840,6 @@ cudaError_t launch_blind_rotate(const BrLaunch &L_in, int sm_count, cudaStream_t
     const int ngroups = (L.total + L.cts_per_group - 1) / L.cts_per_group;
     const int grid = ngroups < sm_count ? ngroups : sm_count;
     // at most one ciphertext per SM: the latency kernel (one ciphertext per CTA, eight warps).
-    // TFHE_B200_BR_QUAD=0 keeps such batches on the two-warp kernel (A/B measurements).
     // TFHE_B200_BR_LATENCY=0 keeps such batches on the two-warp kernel (A/B measurements)
     static const bool use_latency = [] {
         const char *v = getenv("TFHE_B200_BR_LATENCY");
