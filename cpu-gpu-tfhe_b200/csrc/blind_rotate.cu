@@ -596,15 +596,17 @@ __global__ void __launch_bounds__(kThreads, 1) blind_rotate_kernel(const BrLaunc
 //   - the key of an iteration (64 KiB) is double buffered whole in shared memory: one thread of warp 4 (idle
 //     until the next barrier) re-arms the buffer of iteration it for iteration it + 2 right behind the barrier
 //     that ends the Fourier section (one bulk copy per iteration; no producer warps, counters or polling);
-//   - the Fourier section: pass 2 by warp cq (class octet cq, all four rows, in place), multiply and inverse
-//     pass 2 by the warps cq (position half 0) and cq + 4 (half 1) (br_core.cuh "Fourier section");
+//   - the Fourier section: pass 2 by warp cq (class octet cq, all four rows, in place), multiply (by position
+//     pairs, both result polynomials per lane) and inverse pass 2 by the warps cq (position half 0) and
+//     cq + 4 (half 1) (br_core.cuh "Fourier section");
 //   - the inverse pass 1 + conversion + accumulator update of result polynomial o is shared by the warps
 //     (o, 0) and (o, 1) by halves of the slices (8 positions per lane, the last two stages through lane ^ 8
 //     and lane ^ 16); warps 4..7 wait at the next barrier during pass 1 and this part.
 // Two CTA barriers and three 64-thread barriers per iteration.  History (single gate, blind rotation):
 // two-warp kernel 2.30 ms; four warps by decomposed row with partial sums in shared memory and four more
 // warps feeding per-row key rings 1.60 ms; sums over rows in registers 1.55 ms; eight warps with the key
-// double buffered 1.50 ms; pass 2 without redundant reads 1.44 ms (profiles/README.md).
+// double buffered 1.50 ms; pass 2 without redundant reads 1.44 ms; multiply without redundant reads 1.42 ms
+// (profiles/README.md).
 // Results are the same Torus32 words as the throughput kernel's: both return the exact integer product
 // (the fp64 sums are taken in a different order, far inside the rounding margin; tests/test_gpu_parity.py
 // compares the two kernels word for word).
@@ -648,13 +650,14 @@ __global__ void __launch_bounds__(kThreads, 1) blind_rotate_octo_kernel(const Br
     // pass 1 / inverse pass 1 (warps 0..3): decomposed row r = 2o + q
     const int o = (warp >> 1) & 1, q = warp & 1, r = warp & 3;
     const bool edge = warp < 4;
-    // Fourier section: class octet cq, position half ph; lane (rr, c) / (g2, oo, c) / (kk, oo, c)
+    // Fourier section: class octet cq, position half ph; lane (rr, c) / (g4, c) / (kk, oo, c)
     const int cq = warp & 3, ph = warp >> 2;   // the octet's warps (cq, cq + 4) sit on the same sub-partition
     const int rr = lane >> 3, m1 = 8 * cq + (lane & 7);
-    const int g2 = lane >> 4, oo = (lane >> 3) & 1, gb = 2 * ph + g2;
-    cpx ic3, ic2;
-    phase_c_inv_consts(gb, S.e2 + m1 * kE2Row, ic3, ic2);
+    const int oo = (lane >> 3) & 1, kb4 = 2 * ph + (lane >> 4);   // inverse stages 1, 0: positions {kb4 + 4 m} of polynomial oo
     const cpx ig1 = S.e2[m1 * kE2Row + 1], ig0 = S.e2[m1 * kE2Row];
+    const int g4 = lane >> 3, p0 = 8 * ph + 2 * g4;   // multiply: positions p0, p0 + 1
+    cpx pc3, pk2;
+    phase_p_inv_consts(ph, g4, S.e2 + m1 * kE2Row, pc3, pk2);
 
     const GateIn I = resolve_inputs(L, g);
     // ---- accumulator initialisation
@@ -716,24 +719,37 @@ __global__ void __launch_bounds__(kThreads, 1) blind_rotate_octo_kernel(const Br
         named_sync(3 + cq, 64);
         PHASE_MARK(2);
         {
-            cpx zr[kKpl][4], acc[4];
-            phase_c_load_rows(gb, m1, W.exch, zr);
+            // multiply by position pairs (br_core.cuh): lane (g4, c): positions p0, p0 + 1, both result polynomials
+            cpx zr[kKpl][2], acc[kK + 1][2];
+            phase_p_load_rows(p0, m1, W.exch, zr);
 #pragma unroll
-            for (int i = 0; i < 4; i++) acc[i].x = 0.0, acc[i].y = 0.0;
+            for (int u = 0; u <= kK; u++) acc[u][0].x = 0.0, acc[u][0].y = 0.0, acc[u][1].x = 0.0, acc[u][1].y = 0.0;
             mbar_wait(full, parity);
-            const cpx *kb = S.key[it & 1] + oo * kBkHalfCplx + (4 * gb) * 32 + m1;
+            const cpx *kb = S.key[it & 1] + p0 * 32 + m1;
 #pragma unroll
             for (int row = 0; row < kKpl; row++)
 #pragma unroll
-                for (int i = 0; i < 4; i++) cmac(acc[i], zr[row][i], kb[row * kBkRowCplx + i * 32]);
+                for (int u = 0; u <= kK; u++)
+#pragma unroll
+                    for (int e = 0; e < 2; e++) cmac(acc[u][e], zr[row][e], kb[row * kBkRowCplx + u * kBkHalfCplx + e * 32]);
             PHASE_MARK(3);
-            phase_c_inv_a(ic3, ic2, acc);
-            phase_c_inv_a_store(gb, m1, W.inv[oo], acc);
+#pragma unroll
+            for (int u = 0; u <= kK; u++) {
+                bf_inv(acc[u][0], acc[u][1], pc3.x, pc3.y);   // inverse stage 3
+#pragma unroll
+                for (int e = 0; e < 2; e++) {                  // inverse stage 2 through lane ^ 8
+                    cpx recv;
+                    recv.x = __shfl_xor_sync(0xffffffffu, acc[u][e].x, 8);
+                    recv.y = __shfl_xor_sync(0xffffffffu, acc[u][e].y, 8);
+                    phase_p_inv_cross(g4 & 1, pk2, recv, acc[u][e]);
+                }
+                phase_p_inv_store(p0, m1, W.inv[u], acc[u]);
+            }
         }
         PHASE_MARK(4);
         named_sync(3 + cq, 64);  // stages 3, 2 of both position halves of this class octet are in place
         PHASE_MARK(5);
-        phase_o_inv_b_inplace(gb, m1, W.inv[oo], ig1, ig0);  // positions {k, k + 4, k + 8, k + 12}, k = 2 ph + (lane >> 4)
+        phase_o_inv_b_inplace(kb4, m1, W.inv[oo], ig1, ig0);
         PHASE_MARK(6);
         sync_all(2);  // the inverse pass-2 output is complete; nobody reads this iteration's key any more
         PHASE_MARK(7);

@@ -707,12 +707,13 @@ TFHE_HD void phase_i2_final(int lane, WarpSmem &ws, int o, const cpx (&x)[16], c
 // barriers, nothing else leaves the pair:
 //   pass 2:   warp cq, lane (rr, c): the 16-point transform of (row rr, class m1 = 8 cq + c) IN PLACE in the
 //             exchange buffer;
-//   multiply: warp cq + 4 ph (position half ph), lane (g2, oo, c) re-reads positions 8 ph + 4 g2 .. + 3 of all
-//             four rows of its class (a transposition through shared memory) and accumulates result
-//             polynomial oo over the four key rows: the sum over rows is a sum in registers;
-//   inverse:  stages 3, 2 inside that block of four positions, values to the inverse buffer; (pair barrier);
-//             stages 1, 0 on the four positions {k, k + 4, k + 8, k + 12}, k = 2 ph + kk, lane (kk, oo, c),
-//             in place.
+//   multiply: warp cq + 4 ph (position half ph), lane (g4, c) re-reads positions 8 ph + 2 g4, + 1 of all four
+//             rows of its class (a transposition through shared memory) and accumulates BOTH result
+//             polynomials over the four key rows: the sum over rows is a sum in registers ("multiply by
+//             position pairs" below);
+//   inverse:  stage 3 on the lane's pair, stage 2 through lane ^ 8, values to the inverse buffer; (pair
+//             barrier); stages 1, 0 on the four positions {k, k + 4, k + 8, k + 12}, k = 2 ph + kk, lane
+//             (kk, oo, c), in place.
 // Earlier versions: one warp per decomposed row all the way, the partial sums parked in shared memory and
 // three quarters of them read back (18 % of the iteration); then a sum over rows by warp shuffles (a 64-bit
 // shuffle pair moves 8 bytes per lane where a 128-bit shared-memory access moves 16).
@@ -727,44 +728,62 @@ TFHE_HD void phase_c_f2_inplace(int rr, int m1, cpx (*exch)[kExchPoly], const cp
     for (int pos = 0; pos < 16; pos++) row[pos] = z[pos];
 }
 
-// positions 4 g .. 4 g + 3 of class m1 of the four transformed rows
-TFHE_HD void phase_c_load_rows(int g, int m1, const cpx (*exch)[kExchPoly], cpx (&zr)[kKpl][4]) {
+// ---- multiply by POSITION PAIRS (latency kernel) ------------------------------------------------------
+// Lane (g4, c) of warp (cq, ph) takes the two positions p0 = 8 ph + 2 g4, p0 + 1 of class m1 for BOTH result
+// polynomials: every Fourier value is read once (the (g2, oo, c) layout read each one twice, once per result
+// polynomial: 256 of the 1,024 shared-memory wavefronts of the multiply phase, which saturates that pipe).
+// Inverse stage 3 pairs the lane's own two positions; stage 2 pairs position i of lane g4 = 2b with position i
+// of lane 2b + 1: one exchange through lane ^ 8 (u' = u + v on the even lane, v' = conj(c2) (u - v) on the
+// odd one: identical arithmetic in both lanes, out = kappa * (recv +- mine)).
+TFHE_HD cpx times_i(const cpx &c) {
+    cpx r;
+    r.x = -c.y;
+    r.y = c.x;
+    return r;
+}
+
+TFHE_HD void phase_p_load_rows(int p0, int m1, const cpx (*exch)[kExchPoly], cpx (&zr)[kKpl][2]) {
 #pragma unroll
     for (int row = 0; row < kKpl; row++) {
-        const cpx *src = exch[row] + m1 * kExchRow + 4 * g;
-#pragma unroll
-        for (int i = 0; i < 4; i++) zr[row][i] = src[i];
+        const cpx *src = exch[row] + m1 * kExchRow + p0;
+        zr[row][0] = src[0];
+        zr[row][1] = src[1];
     }
 }
 
-// lane constants of the inverse stages 3 and 2 for the block of four positions g (pass2_const)
-TFHE_HD void phase_c_inv_consts(int g, const cpx *e, cpx &c3, cpx &c2) {
+// lane constants: c3 = multiplier of inverse stage 3 for the pair p0 / 2; k2 = conj-multiplier of stage 2 for
+// the odd lane of a block of four positions, 1 for the even lane
+TFHE_HD void phase_p_inv_consts(int ph, int g4, const cpx *e, cpx &c3, cpx &k2) {
     const cpx g3 = e[3], g2 = e[2];
     cpx h4, h8, h38;
     h4.x = (g3.x - g3.y) * kSqrtHalf;
     h4.y = (g3.x + g3.y) * kSqrtHalf;
     h8 = cmul_const(g3, kCosPi8, kSinPi8);
     h38 = cmul_const(g3, kSinPi8, kCosPi8);
-    c3 = g == 0 ? g3 : (g == 1 ? h4 : (g == 2 ? h8 : h38));  // stage 3, blocks 2g (c3) and 2g + 1 (i * c3)
-    cpx b;
-    b.x = (g >> 1) ? (g2.x - g2.y) * kSqrtHalf : g2.x;       // stage 2, block g: base g >> 1, odd block times i
-    b.y = (g >> 1) ? (g2.x + g2.y) * kSqrtHalf : g2.y;
-    c2.x = (g & 1) ? -b.y : b.x;
-    c2.y = (g & 1) ? b.x : b.y;
+    const int base3 = 2 * ph + (g4 >> 1);                 // stage 3, block 4 ph + g4: base (4 ph + g4) >> 1
+    cpx b3 = base3 == 0 ? g3 : (base3 == 1 ? h4 : (base3 == 2 ? h8 : h38));
+    if (g4 & 1) b3 = times_i(b3);
+    c3 = b3;
+    cpx b2;                                                // stage 2, block 2 ph + (g4 >> 1): base ph
+    b2.x = ph ? (g2.x - g2.y) * kSqrtHalf : g2.x;
+    b2.y = ph ? (g2.x + g2.y) * kSqrtHalf : g2.y;
+    if ((g4 >> 1) & 1) b2 = times_i(b2);
+    k2.x = (g4 & 1) ? b2.x : 1.0;
+    k2.y = (g4 & 1) ? b2.y : 0.0;
 }
 
-// inverse stages 3 and 2 on positions 4 g .. 4 g + 3
-TFHE_HD void phase_c_inv_a(const cpx &c3, const cpx &c2, cpx (&z)[4]) {
-    bf_inv(z[0], z[1], c3.x, c3.y);
-    bf_inv(z[2], z[3], -c3.y, c3.x);
-    bf_inv(z[0], z[2], c2.x, c2.y);
-    bf_inv(z[1], z[3], c2.x, c2.y);
+// stage 2, second half: recv = the partner lane's value of the same element
+TFHE_HD void phase_p_inv_cross(int odd, const cpx &k2, const cpx &recv, cpx &z) {
+    const double sg = odd ? -1.0 : 1.0;
+    const double dx = fma(sg, z.x, recv.x), dy = fma(sg, z.y, recv.y);
+    z.x = fma(k2.x, dx, k2.y * dy);
+    z.y = fma(k2.x, dy, -(k2.y * dx));
 }
 
-TFHE_HD void phase_c_inv_a_store(int g, int m1, cpx *inv_o, const cpx (&z)[4]) {
-    cpx *d = inv_o + m1 * kExchRow + 4 * g;
-#pragma unroll
-    for (int i = 0; i < 4; i++) d[i] = z[i];
+TFHE_HD void phase_p_inv_store(int p0, int m1, cpx *inv_o, const cpx (&z)[2]) {
+    cpx *d = inv_o + m1 * kExchRow + p0;
+    d[0] = z[0];
+    d[1] = z[1];
 }
 
 // inverse stages 1 and 0 on positions {k, k + 4, k + 8, k + 12} of class m1, in place

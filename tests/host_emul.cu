@@ -244,22 +244,34 @@ int main() {
             {
                 for (int w = 0; w < 4; w++)   // pass 2 by warp w = class octet w, in place
                     for (int lane = 0; lane < 32; lane++) phase_c_f2_inplace(lane >> 3, 8 * w + (lane & 7), qs->exch, e2.data());
-                for (int v = 0; v < 8; v++)
+                for (int v = 0; v < 8; v++) {   // multiply by position pairs: lane (g4, c), both result polynomials
+                    static cpx accp[32][2][2], snd[32][2][2];
                     for (int lane = 0; lane < 32; lane++) {
-                        const int g2 = lane >> 4, oo = (lane >> 3) & 1, m1 = 8 * (v & 3) + (lane & 7), gb = 2 * (v >> 2) + g2;
-                        cpx zr[kKpl][4], accv[4];
-                        memset(accv, 0, sizeof(accv));
-                        phase_c_load_rows(gb, m1, qs->exch, zr);
+                        const int g4 = lane >> 3, ph = v >> 2, m1 = 8 * (v & 3) + (lane & 7), p0 = 8 * ph + 2 * g4;
+                        cpx zr[kKpl][2];
+                        memset(accp[lane], 0, sizeof(accp[lane]));
+                        phase_p_load_rows(p0, m1, qs->exch, zr);
                         for (int row = 0; row < kKpl; row++) {
                             const cpx *bkrow = bkdev.data() + ((size_t) i * kKpl + row) * kBkRowCplx;
-                            for (int p4 = 0; p4 < 4; p4++)
-                                cmac(accv[p4], zr[row][p4], bkrow[oo * kBkHalfCplx + (4 * gb + p4) * 32 + m1]);
+                            for (int oo = 0; oo < 2; oo++)
+                                for (int e = 0; e < 2; e++)
+                                    cmac(accp[lane][oo][e], zr[row][e], bkrow[oo * kBkHalfCplx + (p0 + e) * 32 + m1]);
                         }
-                        cpx c3, c2;
-                        phase_c_inv_consts(gb, e2.data() + m1 * kE2Row, c3, c2);
-                        phase_c_inv_a(c3, c2, accv);
-                        phase_c_inv_a_store(gb, m1, qs->inv[oo], accv);
+                        cpx c3, k2;
+                        phase_p_inv_consts(ph, g4, e2.data() + m1 * kE2Row, c3, k2);
+                        for (int oo = 0; oo < 2; oo++) bf_inv(accp[lane][oo][0], accp[lane][oo][1], c3.x, c3.y);
+                        memcpy(snd[lane], accp[lane], sizeof(snd[lane]));
                     }
+                    for (int lane = 0; lane < 32; lane++) {
+                        const int g4 = lane >> 3, ph = v >> 2, m1 = 8 * (v & 3) + (lane & 7), p0 = 8 * ph + 2 * g4;
+                        cpx c3, k2;
+                        phase_p_inv_consts(ph, g4, e2.data() + m1 * kE2Row, c3, k2);
+                        for (int oo = 0; oo < 2; oo++) {
+                            for (int e = 0; e < 2; e++) phase_p_inv_cross(g4 & 1, k2, snd[lane ^ 8][oo][e], accp[lane][oo][e]);
+                            phase_p_inv_store(p0, m1, qs->inv[oo], accp[lane][oo]);
+                        }
+                    }
+                }
                 for (int v = 0; v < 8; v++)   // (pair barrier)
                     for (int lane = 0; lane < 32; lane++) {
                         const int kk = lane >> 4, oo = (lane >> 3) & 1, m1 = 8 * (v & 3) + (lane & 7);
