@@ -1,2 +1,4 @@
-timeout 900 python -m pytest tests/test_gpu_parity.py tests/test_gpu_exact.py tests/test_gpu_circuits.py tests/test_gpu_compat.py -m gpu -x -q 2>&1 | tail -3
-timeout 300 python tools/latency_probe.py 2>&1 | tail -8
+timeout 1500 python bench.py > gpurun_out/final_bench_n1.json 2> gpurun_out/final_bench_n1.err; echo "bench rc=$?"
+python tools/prof_step.py 148 100 > gpurun_out/r2f_octo_plain.log 2>&1 &&
+ncu --set full --clock-control none --import-source on -k regex:blind_rotate_octo_kernel -s 1 -c 1 -f -o gpurun_out/r2f_octo_full python tools/prof_step.py 148 100 > gpurun_out/r2f_ncu4.log 2>&1
+echo done
