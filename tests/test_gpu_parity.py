@@ -390,6 +390,35 @@ def test_gpu_key_generation(pkg, oracle):
     eng.close()
 
 
+@pytest.mark.parametrize("count", [1, 37])
+def test_latency_kernel_key_buffers_with_skipped_iterations(engine, oracle, keys, count):
+    """Batches of at most one ciphertext per SM run on the latency kernel, whose two whole-key buffers are
+    re-armed by one thread every iteration — also in iterations every warp skips (bara = 0).  Skip patterns
+    that exercise that path: the first two iterations, the last two, alternating, runs of skips, random at
+    0.5 / 0.93; every ciphertext must equal the exact integer path word for word."""
+    rng = np.random.default_rng(900 + count)
+    n_iter = 26
+    acc = _rand_i32(rng, (count, 2, 1024))
+    bara = rng.integers(1, 2048, size=(count, n_iter)).astype(np.int32)
+    patterns = [
+        lambda b: b.__setitem__(slice(0, 2), 0),
+        lambda b: b.__setitem__(slice(n_iter - 2, n_iter), 0),
+        lambda b: b.__setitem__(slice(0, n_iter, 2), 0),
+        lambda b: b.__setitem__(slice(3, 11), 0),
+        lambda b: b.__setitem__(rng.random(n_iter) < 0.5, 0),
+        lambda b: b.__setitem__(rng.random(n_iter) < 0.93, 0),
+        lambda b: b.__setitem__(slice(0, n_iter), 0),
+    ]
+    for r in range(count):
+        if r % 8 != 7:
+            patterns[r % len(patterns)](bara[r])
+    got = engine.blind_rotate(engine.to_device(acc).clone(), engine.to_device(bara)).cpu().numpy()
+    exact_bar = 0 if engine.L.tfhe_b200_conversion_mode() == 0 else n_iter
+    for r in range(count) if count <= 8 else list(range(0, count, 5)) + [6, 7, count - 1]:
+        want = oracle.blind_rotate_exact(keys.bk, acc[r], bara[r])
+        assert np.abs(wrap32(got[r].astype(np.int64) - want.astype(np.int64))).max() <= exact_bar, r
+
+
 @pytest.mark.parametrize("skip", [0.0, 0.5, 0.93])
 def test_key_ring_stress_exact_results(engine, oracle, keys, skip):
     """The key ring of the blind-rotation kernel releases a stage right behind the last load of a
