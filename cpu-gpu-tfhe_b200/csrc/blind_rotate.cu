@@ -790,6 +790,168 @@ __global__ void __launch_bounds__(kThreads, 1) blind_rotate_octo_kernel(const Br
     if (L.acc_out != nullptr) phase_dump_acc_p(tid, kThreads, W.acc, L.acc_out + (size_t) g * (kK + 1) * kN);
 }
 
+// =================================================================================
+// LATENCY kernel for TWO ciphertexts per SM (batches of 149 .. 2 x #SMs gates): one ciphertext per CTA on FOUR
+// warps, two CTAs resident per SM (109 KB of shared memory and 128 x <= 255 registers each).
+// Same phases as the eight-warp kernel, except that (i) the whole Fourier section of a class octet is run by
+// ONE warp (br_core.cuh "by ONE warp per class octet": measured 0.5 % slower than the eight-warp split for a
+// lone ciphertext, and it needs no pair barriers), (ii) the key of an iteration has ONE buffer, re-armed by
+// thread 0 right behind the barrier that ends the Fourier section (the copy has the inverse pass 1, pass 1 and
+// pass 2 of the next iteration to land), (iii) the inverse pass-2 output and the extended accumulator copies
+// alias the exchange buffers (QuadSmem), which costs one more CTA barrier per iteration (between the
+// decomposition reads and the pass-1 stores).  Two such CTAs put two warps on every sub-partition: 296 gates
+// in ~2.0 ms instead of 2.62 ms on the two-warp kernel.
+struct __align__(128) QuadCtaSmem {
+    QuadSmem w;
+    cpx e2[32 * kE2Row];
+    cpx key[kBkIterCplx];
+    unsigned long long full;
+};
+static_assert(offsetof(QuadCtaSmem, key) % 128 == 0, "TMA destination alignment");
+static_assert(2 * (sizeof(QuadCtaSmem) + 1024) <= 227 * 1024, "two CTAs per SM");
+constexpr int kQuadThreads = 128;
+
+__device__ __forceinline__ void quad_fill(QuadCtaSmem &S, const BrLaunch &L, int it) {
+    const cpx *src = L.bk + (size_t) (L.bk_first + it) * kBkIterCplx;
+    mbar_arrive_expect_tx(&S.full, (uint32_t) (kBkIterCplx * sizeof(cpx)));
+    tma_load_1d(S.key, src, (uint32_t) (kBkIterCplx * sizeof(cpx)), &S.full);
+}
+
+__global__ void __launch_bounds__(kQuadThreads, 2) blind_rotate_quad_kernel(const BrLaunch L) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    QuadCtaSmem &S = *reinterpret_cast<QuadCtaSmem *>(smem_raw);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n_iter = L.n_iter;
+    const int g = blockIdx.x;  // one ciphertext per CTA
+    const bool rotate = (L.extern_only == 0);
+
+    build_e2(S.e2);
+    if (threadIdx.x == 0) {
+        mbar_init(&S.full, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        if (n_iter > 0) quad_fill(S, L, 0);
+    }
+    __syncthreads();
+
+    QuadSmem &W = S.w;
+    const int tid = threadIdx.x;
+    auto sync_all = [](int id) { named_sync(id, kQuadThreads); };
+    const int o = warp >> 1, q = warp & 1, r = warp;                   // pass 1 / inverse pass 1: row r = 2o + q
+    int32_t *ext_o = reinterpret_cast<int32_t *>(W.exch[2 + o]);      // extended copy of polynomial o
+    cpx *inv_o = W.exch[o];                                            // inverse pass-2 output of polynomial o
+    const int rr = lane >> 3, m1 = 8 * warp + (lane & 7);              // Fourier section: class octet = warp
+    cpx wc3, wc2;
+    phase_w_inv_consts(rr, S.e2 + m1 * kE2Row, wc3, wc2);
+    const cpx ig1 = S.e2[m1 * kE2Row + 1], ig0 = S.e2[m1 * kE2Row];
+
+    const GateIn I = resolve_inputs(L, g);
+    if (L.acc_in != nullptr) {
+        phase_load_acc_p(tid, kQuadThreads, W.acc, L.acc_in + (size_t) g * (kK + 1) * kN);
+    } else if (L.testvect != nullptr) {
+        const int barb = L.barb ? (__ldg(L.barb + g) & (2 * kN - 1)) : 0;
+        for (int j = tid; j < kN; j += kQuadThreads) {
+            const int s = (j + barb) & (2 * kN - 1);
+            const uint32_t v = (uint32_t) __ldg(L.testvect + (s & (kN - 1)));
+            W.acc[0][(j & 15) * kAccRow + (j >> 4)] = 0;
+            W.acc[kK][(j & 15) * kAccRow + (j >> 4)] = (int32_t) (s < kN ? v : 0u - v);
+        }
+    } else if (q == 0) {
+        int barb;
+        if (L.explicit_inputs != 0) barb = L.barb ? (__ldg(L.barb + g) & (2 * kN - 1)) : 0;
+        else barb = modswitch_2N(prologue_word(I, L.n, I.cst));
+        phase_init_p(lane, W.acc[o], o, barb, L.mu);
+    }
+    sync_all(1);
+    if (q == 0) phase_ext_build_p(lane, W.acc[o], ext_o);
+    sync_all(2);
+
+    int a_blk = 0;  // lane l holds bara of iteration (it & ~31) + l
+    for (int it = 0; it < n_iter; it++) {
+        if ((it & 31) == 0) a_blk = load_bara(L, I, g, it + lane, n_iter, rotate);
+        const int a = __shfl_sync(0xffffffffu, a_blk, it & 31);
+        const uint32_t parity = (uint32_t) it & 1u;
+        if (a == 0 && rotate) {  // tfhe_blindRotate_FFT :705: nothing to do; the key buffer moves on
+            if (threadIdx.x == 0) {
+                mbar_wait(&S.full, parity);
+                if (it + 1 < n_iter) quad_fill(S, L, it + 1);
+            }
+            continue;
+        }
+        {
+            // pass 1 of row (o, q) split over lane pairs (br_core.cuh phase_f1h_*)
+            const int hh = lane >> 4, j2 = lane & 15;
+            cpx x[16], w[16], recv[16];
+            phase_f1h_decomp_p(hh, j2, q, W.acc[o], ext_o, a, rotate, x);
+            sync_all(3);  // every warp has read the extended copies: their buffers take the pass-1 output of rows 2, 3
+            phase_f1h_cross_send(hh, x, w);
+#pragma unroll
+            for (int i = 0; i < 16; i++) {
+                recv[i].x = __shfl_xor_sync(0xffffffffu, w[i].x, 16);
+                recv[i].y = __shfl_xor_sync(0xffffffffu, w[i].y, 16);
+            }
+            phase_f1h_finish(hh, w, recv, x);
+            phase_f1h_store_p(hh, j2, W.exch[r], x);
+        }
+        sync_all(1);  // the pass-1 output of all four rows is in place
+        {
+            // the whole Fourier section of class octet `warp` (nothing leaves the warp)
+            phase_c_f2_inplace(rr, m1, W.exch, S.e2);
+            __syncwarp();
+            cpx acc2[kK + 1][4];
+#pragma unroll
+            for (int u = 0; u <= kK; u++)
+#pragma unroll
+                for (int i = 0; i < 4; i++) acc2[u][i].x = 0.0, acc2[u][i].y = 0.0;
+            {
+                cpx zr[kKpl][4];
+                phase_w_load_rows(rr, m1, W.exch, zr);
+                mbar_wait(&S.full, parity);
+                const cpx *kb = S.key + (4 * rr) * 32 + m1;
+#pragma unroll
+                for (int u = 0; u <= kK; u++)
+#pragma unroll
+                    for (int row = 0; row < kKpl; row++)
+#pragma unroll
+                        for (int i = 0; i < 4; i++) cmac(acc2[u][i], zr[row][i], kb[row * kBkRowCplx + u * kBkHalfCplx + i * 32]);
+            }
+            __syncwarp();  // every lane has read its rows: rows 0, 1 of this octet take the inverse pass-2 values
+#pragma unroll
+            for (int u = 0; u <= kK; u++) phase_w_inv_a_store(rr, m1, W.exch[u], wc3, wc2, acc2[u]);
+            __syncwarp();
+            phase_w_inv_b_inplace(rr & 1, m1, W.exch[rr >> 1], ig1, ig0);
+        }
+        sync_all(2);  // the inverse pass-2 output is complete; nobody reads this iteration's key any more
+        if (threadIdx.x == 0 && it + 1 < n_iter) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            quad_fill(S, L, it + 1);
+        }
+        {
+            // inverse pass 1 + conversion + update of result polynomial o, shared by the warps (o, 0) and (o, 1)
+            const int qq = lane >> 3;
+            cpx x[8], recv[8];
+            phase_q_i2_local(lane, q, inv_o, x);
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                recv[i].x = __shfl_xor_sync(0xffffffffu, x[i].x, 8);
+                recv[i].y = __shfl_xor_sync(0xffffffffu, x[i].y, 8);
+            }
+            phase_q_i2_cross((qq & 1) != 0, 1 + (qq >> 1), recv, x);
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                recv[i].x = __shfl_xor_sync(0xffffffffu, x[i].x, 16);
+                recv[i].y = __shfl_xor_sync(0xffffffffu, x[i].y, 16);
+            }
+            phase_q_i2_cross((qq >> 1) != 0, 0, recv, x);
+            if (!rotate) phase_q_acc_clear(lane, q, W.acc[o]);  // external product only: result replaces ACC
+            phase_q_final(lane, q, W.acc[o], ext_o, x);
+            named_sync(4 + o, 64);  // polynomial o and its extended copy are final for its two warps
+        }
+    }
+    sync_all(1);  // both polynomials are final for everybody
+    if (L.u_out != nullptr) phase_extract_p(tid, kQuadThreads, W.acc, L.u_out + (size_t) g * (kN + 1));
+    if (L.acc_out != nullptr) phase_dump_acc_p(tid, kQuadThreads, W.acc, L.acc_out + (size_t) g * (kK + 1) * kN);
+}
+
 // ------------------------------------------------------------ key conversion
 
 struct __align__(128) FwdSmem {
@@ -844,6 +1006,9 @@ cudaError_t blind_rotate_configure() {
     e = cudaFuncSetAttribute(blind_rotate_octo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              (int) sizeof(OctoCtaSmem));
     if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(blind_rotate_quad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int) sizeof(QuadCtaSmem));
+    if (e != cudaSuccess) return e;
     return cudaFuncSetAttribute(forward_polys_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 (int) sizeof(FwdSmem));
 }
@@ -863,6 +1028,11 @@ cudaError_t launch_blind_rotate(const BrLaunch &L_in, int sm_count, cudaStream_t
     }();
     if (use_latency && L.total <= sm_count) {
         blind_rotate_octo_kernel<<<L.total, kThreads, sizeof(OctoCtaSmem), stream>>>(L);
+        return cudaGetLastError();
+    }
+    // at most two ciphertexts per SM: the four-warp latency kernel, two CTAs per SM
+    if (use_latency && L.total <= 2 * sm_count) {
+        blind_rotate_quad_kernel<<<L.total, kQuadThreads, sizeof(QuadCtaSmem), stream>>>(L);
         return cudaGetLastError();
     }
     // small batches: the always-idle last slot of every CTA refills the key rings (ring_skip<true>)

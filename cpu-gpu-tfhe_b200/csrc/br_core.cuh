@@ -121,6 +121,16 @@ struct LatencySmem {
 };
 static_assert(16 * kExtRow <= kExtPolyWords, "extended copy must fit its buffer");
 
+// Working set of the FOUR-warp latency kernel (two CTAs per SM, blind_rotate_quad_kernel): the inverse pass-2
+// output of polynomial o lives in exchange buffer o, the extended copy of polynomial o in exchange buffer 2 + o
+// (8 KiB of its 8.5 KiB); the kernel's barriers separate the life times.
+struct QuadSmem {
+    cpx exch[kKpl][kExchPoly];
+    int32_t acc[kK + 1][kAccPoly];
+};
+static_assert(kExtPolyWords * 4 <= kExchPoly * 16, "extended copy must fit an exchange buffer");
+
+
 TFHE_HD int32_t *ext_poly(WarpSmem &ws, int o) { return ws.exw[2 * o]; }
 
 TFHE_HD constexpr int bitrev5(int v) {
@@ -726,6 +736,66 @@ TFHE_HD void phase_c_f2_inplace(int rr, int m1, cpx (*exch)[kExchPoly], const cp
     fwd16(z, e2 + m1 * kE2Row);
 #pragma unroll
     for (int pos = 0; pos < 16; pos++) row[pos] = z[pos];
+}
+
+// ---- the Fourier section by ONE warp per class octet (four-warp latency kernel, blind_rotate_quad_kernel) ----
+// Warp cq alone: pass 2 in place (phase_c_f2_inplace), then lane (g, c) re-reads positions 4 g .. 4 g + 3 of the
+// four rows of class m1 = 8 cq + c, accumulates BOTH result polynomials, runs inverse stages 3, 2 inside its block
+// of four positions and stores to the inverse buffer; after a __syncwarp lane (oo, k2, c) runs stages 1, 0 on
+// positions {2 k2, 2 k2 + 1} + {0, 4, 8, 12} of result polynomial oo in place.  No barrier inside the section.
+TFHE_HD void phase_w_load_rows(int g, int m1, const cpx (*exch)[kExchPoly], cpx (&zr)[kKpl][4]) {
+#pragma unroll
+    for (int row = 0; row < kKpl; row++) {
+        const cpx *src = exch[row] + m1 * kExchRow + 4 * g;
+#pragma unroll
+        for (int i = 0; i < 4; i++) zr[row][i] = src[i];
+    }
+}
+
+// lane constants of the inverse stages 3 and 2 for the block of four positions g (pass2_const)
+TFHE_HD void phase_w_inv_consts(int g, const cpx *e, cpx &c3, cpx &c2) {
+    const cpx g3 = e[3], g2 = e[2];
+    cpx h4, h8, h38;
+    h4.x = (g3.x - g3.y) * kSqrtHalf;
+    h4.y = (g3.x + g3.y) * kSqrtHalf;
+    h8 = cmul_const(g3, kCosPi8, kSinPi8);
+    h38 = cmul_const(g3, kSinPi8, kCosPi8);
+    c3 = g == 0 ? g3 : (g == 1 ? h4 : (g == 2 ? h8 : h38));  // stage 3, blocks 2g (c3) and 2g + 1 (i * c3)
+    cpx b;
+    b.x = (g >> 1) ? (g2.x - g2.y) * kSqrtHalf : g2.x;       // stage 2, block g: base g >> 1, odd block times i
+    b.y = (g >> 1) ? (g2.x + g2.y) * kSqrtHalf : g2.y;
+    c2.x = (g & 1) ? -b.y : b.x;
+    c2.y = (g & 1) ? b.x : b.y;
+}
+
+TFHE_HD void phase_w_inv_a_store(int g, int m1, cpx *inv_o, const cpx &c3, const cpx &c2, cpx (&z)[4]) {
+    bf_inv(z[0], z[1], c3.x, c3.y);
+    bf_inv(z[2], z[3], -c3.y, c3.x);
+    bf_inv(z[0], z[2], c2.x, c2.y);
+    bf_inv(z[1], z[3], c2.x, c2.y);
+    cpx *d = inv_o + m1 * kExchRow + 4 * g;
+#pragma unroll
+    for (int i = 0; i < 4; i++) d[i] = z[i];
+}
+
+TFHE_HD void phase_w_inv_b_inplace(int k2, int m1, cpx *inv_o, const cpx &g1, const cpx &g0) {
+    cpx *d = inv_o + m1 * kExchRow + 2 * k2;
+    cpx z[2][4];
+#pragma unroll
+    for (int e = 0; e < 2; e++)
+#pragma unroll
+        for (int m = 0; m < 4; m++) z[e][m] = d[e + 4 * m];
+#pragma unroll
+    for (int e = 0; e < 2; e++) {
+        bf_inv(z[e][0], z[e][1], g1.x, g1.y);    // stage 1, block 0
+        bf_inv(z[e][2], z[e][3], -g1.y, g1.x);   // stage 1, block 1: times i
+        bf_inv(z[e][0], z[e][2], g0.x, g0.y);    // stage 0
+        bf_inv(z[e][1], z[e][3], g0.x, g0.y);
+    }
+#pragma unroll
+    for (int e = 0; e < 2; e++)
+#pragma unroll
+        for (int m = 0; m < 4; m++) d[e + 4 * m] = z[e][m];
 }
 
 // ---- multiply by POSITION PAIRS (latency kernel) ------------------------------------------------------

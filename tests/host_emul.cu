@@ -215,7 +215,7 @@ int main() {
     // ---- B3. the same steps through the LATENCY kernel's split (eight warps per ciphertext) ---------
     // warp (o, q): decomposition + pass 1 of row (o, q); pass 2, multiply and inverse pass 2 on eight warps by
     // class octets and position halves; inverse pass 1 by halves of the slices on warps (o, 0), (o, 1).
-    {
+    for (int variant = 0; variant < 2; variant++) {   // 0: eight-warp kernel, 1: four-warp kernel (Fourier section by one warp)
         LatencySmem *qs = new LatencySmem();
         std::vector<int32_t> accq = acc0;
         int maxdiffq = 0;
@@ -241,6 +241,30 @@ int main() {
             // pass 2 by warp cq; Fourier multiply + inverse pass 2 on eight warps: warp v = (class octet v & 3,
             // position half v >> 2); transpositions through the exchange / inverse buffers
             static cpx x8[4][32][8];
+            if (variant == 1) {
+                for (int w = 0; w < 4; w++) {
+                    for (int lane = 0; lane < 32; lane++) phase_c_f2_inplace(lane >> 3, 8 * w + (lane & 7), qs->exch, e2.data());
+                    for (int lane = 0; lane < 32; lane++) {
+                        const int g = lane >> 3, m1 = 8 * w + (lane & 7);
+                        cpx zr[kKpl][4], accv[2][4];
+                        memset(accv, 0, sizeof(accv));
+                        phase_w_load_rows(g, m1, qs->exch, zr);
+                        for (int row = 0; row < kKpl; row++) {
+                            const cpx *bkrow = bkdev.data() + ((size_t) i * kKpl + row) * kBkRowCplx;
+                            for (int oo = 0; oo < 2; oo++)
+                                for (int p4 = 0; p4 < 4; p4++)
+                                    cmac(accv[oo][p4], zr[row][p4], bkrow[oo * kBkHalfCplx + (4 * g + p4) * 32 + m1]);
+                        }
+                        cpx c3, c2;
+                        phase_w_inv_consts(g, e2.data() + m1 * kE2Row, c3, c2);
+                        for (int oo = 0; oo < 2; oo++) phase_w_inv_a_store(g, m1, qs->inv[oo], c3, c2, accv[oo]);
+                    }
+                    for (int lane = 0; lane < 32; lane++) {
+                        const int rr = lane >> 3, m1 = 8 * w + (lane & 7);
+                        phase_w_inv_b_inplace(rr & 1, m1, qs->inv[rr >> 1], e2[m1 * kE2Row + 1], e2[m1 * kE2Row]);
+                    }
+                }
+            } else
             {
                 for (int w = 0; w < 4; w++)   // pass 2 by warp w = class octet w, in place
                     for (int lane = 0; lane < 32; lane++) phase_c_f2_inplace(lane >> 3, 8 * w + (lane & 7), qs->exch, e2.data());
@@ -302,7 +326,8 @@ int main() {
             }
             accq = got;
         }
-        printf("B3. latency-kernel split (eight warps per ciphertext) vs exact: max |diff| = %d LSB\n", maxdiffq);
+        printf("B3.%d latency-kernel split (%s warps per ciphertext) vs exact: max |diff| = %d LSB\n", variant,
+               variant ? "four" : "eight", maxdiffq);
 #if TFHE_B200_TRUNCATE_LIKE_REFERENCE
         CHECK(maxdiffq <= 1, "latency-kernel split differs from exact result by more than truncation");
 #else

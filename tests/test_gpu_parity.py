@@ -76,7 +76,7 @@ def test_mux_rotate_step_teacher_forced(engine, oracle, keys):
 
 def test_blind_rotate_is_independent_of_batch_layout(engine):
     """The same ciphertexts through the full-batch kernel (4 per SM, two passes over some SMs) and in
-    small batches (one per SM, the idle-slot refiller kernel) give identical words: the arithmetic
+    small batches (one or two per SM: the latency kernels; three per SM: the idle-slot refiller kernel) give identical words: the arithmetic
     of a ciphertext does not depend on its slot, on idle iterations (bara = 0, 40 % here) of its
     neighbours, or on which warp refills the key ring."""
     rng = np.random.default_rng(21)
@@ -86,10 +86,13 @@ def test_blind_rotate_is_independent_of_batch_layout(engine):
     bara[rng.random((count, n_iter)) < 0.4] = 0
     d_acc, d_bara = engine.to_device(acc), engine.to_device(bara)
     big = engine.blind_rotate(d_acc.clone(), d_bara).cpu().numpy()
-    parts = []
-    for lo in range(0, count, 100):
-        parts.append(engine.blind_rotate(d_acc[lo:lo + 100].clone(), d_bara[lo:lo + 100].contiguous()).cpu().numpy())
-    assert np.array_equal(big, np.concatenate(parts, 0))
+    # pieces of 100 (eight-warp latency kernel), 250 (four-warp latency kernel, two CTAs per SM), 400 (two-warp
+    # kernel with idle slots): every kernel returns the same words
+    for piece in (100, 250, 400):
+        parts = []
+        for lo in range(0, count, piece):
+            parts.append(engine.blind_rotate(d_acc[lo:lo + piece].clone(), d_bara[lo:lo + piece].contiguous()).cpu().numpy())
+        assert np.array_equal(big, np.concatenate(parts, 0)), piece
     assert not np.array_equal(big, acc)
 
 
@@ -390,10 +393,10 @@ def test_gpu_key_generation(pkg, oracle):
     eng.close()
 
 
-@pytest.mark.parametrize("count", [1, 37])
+@pytest.mark.parametrize("count", [1, 37, 190])
 def test_latency_kernel_key_buffers_with_skipped_iterations(engine, oracle, keys, count):
-    """Batches of at most one ciphertext per SM run on the latency kernel, whose two whole-key buffers are
-    re-armed by one thread every iteration — also in iterations every warp skips (bara = 0).  Skip patterns
+    """Batches of at most one (two) ciphertext(s) per SM run on the eight-warp (four-warp) latency kernel, whose
+    whole-key buffers are re-armed by one thread every iteration — also in iterations every warp skips (bara = 0).  Skip patterns
     that exercise that path: the first two iterations, the last two, alternating, runs of skips, random at
     0.5 / 0.93; every ciphertext must equal the exact integer path word for word."""
     rng = np.random.default_rng(900 + count)
@@ -414,7 +417,7 @@ def test_latency_kernel_key_buffers_with_skipped_iterations(engine, oracle, keys
             patterns[r % len(patterns)](bara[r])
     got = engine.blind_rotate(engine.to_device(acc).clone(), engine.to_device(bara)).cpu().numpy()
     exact_bar = 0 if engine.L.tfhe_b200_conversion_mode() == 0 else n_iter
-    for r in range(count) if count <= 8 else list(range(0, count, 5)) + [6, 7, count - 1]:
+    for r in range(count) if count <= 8 else list(range(0, count, 5 if count < 100 else 23)) + [6, 7, count - 1]:
         want = oracle.blind_rotate_exact(keys.bk, acc[r], bara[r])
         assert np.abs(wrap32(got[r].astype(np.int64) - want.astype(np.int64))).max() <= exact_bar, r
 
