@@ -23,6 +23,13 @@
  * Every function returns 0 on success, non-zero on failure;
  * tfhe_b200_last_error() describes the last failure of the calling thread.
  * There is no CPU fallback: without a CUDA device every compute call fails.
+ *
+ * Threads: the compute calls of a context (gates, MUX, bootstrap, key switch, circuit runs) may be issued
+ * from several host threads at once, each on its own stream (or all on the context's default stream, where
+ * they simply queue); per-call scratch is stream ordered and the error string is per thread.  Only the launch
+ * counter and the optional kernel timing are then approximate.  Loading keys, destroying the context and the
+ * host-buffer calls (tfhe_b200_gate_host / _mux_host, which drive the context's copy streams) must not
+ * overlap other calls on the same context; tfhe_compat.h serialises and coalesces the classic gates itself.
  */
 #ifndef TFHE_B200_H
 #define TFHE_B200_H
