@@ -881,7 +881,7 @@ __global__ void __launch_bounds__(kQuadThreads, 2) blind_rotate_quad_kernel(cons
             // pass 1 of row (o, q) split over lane pairs (br_core.cuh phase_f1h_*)
             const int hh = lane >> 4, j2 = lane & 15;
             cpx x[16], w[16], recv[16];
-            phase_f1h_decomp_p(hh, j2, q, W.acc[o], ext_o, a, rotate, x);
+            phase_f1h_decomp_p<true>(hh, j2, q, W.acc[o], ext_o, a, rotate, x);  // two CTAs per SM: the fp64 pipe binds
             sync_all(3);  // every warp has read the extended copies: their buffers take the pass-1 output of rows 2, 3
             phase_f1h_cross_send(hh, x, w);
 #pragma unroll

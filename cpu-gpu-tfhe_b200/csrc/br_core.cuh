@@ -158,10 +158,18 @@ TFHE_HD void bf_inv(cpx &a, cpx &b, double er, double ei) {
     b.y = fma(er, ti, -(ei * tr));
 }
 
-// Gadget digit in offset form (0..1023) -> double(digit - 512) without an I2F on the XU
-// pipe: the word 0x43300000:dig is the double 2^52 + dig, and the subtraction is exact.
+// Gadget digit in offset form (0..1023) -> double(digit - 512), two ways with the same value:
+//   kI2F = true : an integer subtraction and I2F.F64.S32.  The conversion runs on its own pipe and leaves the
+//                 fp64 pipe alone: the 64 conversions per warp and iteration are 4 % of the throughput kernel's
+//                 fp64 instructions, and that kernel IS bound by the fp64 pipe (measured, round 2: 386.4 ->
+//                 371.3 ms per 65536 gates, -3.9 %; two ciphertexts per SM: 2.32 -> 2.29 ms).
+//   kI2F = false: the word 0x43300000:dig is the double 2^52 + dig, and one exact DADD subtracts 2^52 + 512.
+//                 For a LONE warp on a sub-partition (eight-warp latency kernel) the fp64 pipe has room and the
+//                 quarter-rate conversion pipe is the longer path: 1.418 ms per gate against 1.451 with I2F.
+template <bool kI2F>
 TFHE_HD double digit_to_double(uint32_t dig) {
 #ifdef __CUDA_ARCH__
+    if (kI2F) return __int2double_rn((int) dig - 512);
     return __hiloint2double(0x43300000, (int) dig) - 4503599627371008.0;  // 2^52 + 512
 #else
     const uint64_t bits = (UINT64_C(0x43300000) << 32) | dig;
@@ -181,6 +189,9 @@ TFHE_HD double digit_to_double(uint32_t dig) {
 #ifndef TFHE_B200_TRUNCATE_LIKE_REFERENCE
 #define TFHE_B200_TRUNCATE_LIKE_REFERENCE 0
 #endif
+#ifndef TFHE_B200_OUT_F2I
+#define TFHE_B200_OUT_F2I 0
+#endif
 TFHE_HD uint32_t double_to_torus32(double x) {
 #if defined(TFHE_B200_CONV_PROBE) && !defined(__CUDA_ARCH__)
     TFHE_B200_CONV_PROBE(x);  // host emulation only: tests record the distance of x from the integers
@@ -188,6 +199,9 @@ TFHE_HD uint32_t double_to_torus32(double x) {
 #if TFHE_B200_TRUNCATE_LIKE_REFERENCE
     return (uint32_t) (int32_t) (long long) x;
 #else
+#if defined(__CUDA_ARCH__) && TFHE_B200_OUT_F2I
+    return (uint32_t) __double2ll_rn(x);   // F2I.S64.F64.RN on the conversion pipe: same result, -0.3 % measured
+#endif
     const double y = x + 6755399441055744.0;  // 2^52 + 2^51
 #ifdef __CUDA_ARCH__
     return (uint32_t) __double2loint(y);
@@ -308,6 +322,8 @@ template <int S, bool kInv>
 TFHE_HD void pass2_stage(cpx (&z)[16], const cpx *e) {
     const cpx g = e[S];
     cpx h4 = g, h8 = g, h38 = g;
+    // (derived, not tabulated: a table of all eight multipliers per class — 4 more 128-bit shared-memory loads
+    // per transform instead of 16 fp64 instructions — measured 3.5 % SLOWER: shared memory binds as well)
     if (S >= 2) {
         h4.x = (g.x - g.y) * kSqrtHalf;
         h4.y = (g.x + g.y) * kSqrtHalf;
@@ -445,7 +461,7 @@ TFHE_HD void phase_f1_decomp_p(int j2, int q, const int32_t *acc_o, const int32_
         for (int i = 0; i < 16; i++) {
             const int e = blk + i;
             const uint32_t t = vr[i] * sm + (vo[i] * cm + offm);
-            const double d = digit_to_double(t >> (32 - kBgbit));
+            const double d = digit_to_double<true>(t >> (32 - kBgbit));
             if (e < 32) x[e & 31].x = d;
             else x[e & 31].y = d;
         }
@@ -479,6 +495,7 @@ TFHE_HD void phase_f1_store(int lane, WarpSmem &ws, int o, const cpx (&x)[32]) {
 // bits from the throughput kernel's; the accumulator words do not (both are the exact product).
 
 // decomposition of the 32 coefficients lane (hh, j2) needs: e = 16 hh + i (real) and 32 + 16 hh + i (imag)
+template <bool kI2F = false>
 TFHE_HD void phase_f1h_decomp_p(int hh, int j2, int q, const int32_t *acc_o, const int32_t *ext_o, int a, bool rotate,
                                 cpx (&x)[16]) {
     const int a_lo = a & 15, a_hi = a >> 4;
@@ -505,7 +522,7 @@ TFHE_HD void phase_f1h_decomp_p(int hh, int j2, int q, const int32_t *acc_o, con
 #pragma unroll
         for (int i = 0; i < 16; i++) {
             const uint32_t t = vr[i] * sm + (vo[i] * cm + offm);
-            const double d = digit_to_double(t >> (32 - kBgbit));
+            const double d = digit_to_double<kI2F>(t >> (32 - kBgbit));
             if (part == 0) x[i].x = d;
             else x[i].y = d;
         }
