@@ -160,7 +160,7 @@ TFHE_HD void bf_inv(cpx &a, cpx &b, double er, double ei) {
 
 // Gadget digit in offset form (0..1023) -> double(digit - 512), two ways with the same value:
 //   kI2F = true : an integer subtraction and I2F.F64.S32.  The conversion runs on its own pipe and leaves the
-//                 fp64 pipe alone: the 64 conversions per warp and iteration are 4 % of the throughput kernel's
+//                 fp64 pipe alone: the 64 conversions per warp and iteration are 3.4 % of the throughput kernel's
 //                 fp64 instructions, and that kernel IS bound by the fp64 pipe (measured, round 2: 386.4 ->
 //                 371.3 ms per 65536 gates, -3.9 %; two ciphertexts per SM: 2.32 -> 2.29 ms).
 //   kI2F = false: the word 0x43300000:dig is the double 2^52 + dig, and one exact DADD subtracts 2^52 + 512.
