@@ -72,6 +72,14 @@ constexpr int kStages = 2 * (int) kRingStages;
 #ifndef TFHE_B200_RING_STRICT
 #define TFHE_B200_RING_STRICT 0
 #endif
+// TFHE_B200_E2_TMEM=1: the full-batch kernel keeps a lane's eight pass-2 multipliers (the four base values of its
+// frequency class and the four derived ones) in TENSOR MEMORY: 32 words per lane, written once with tcgen05.st,
+// read per stage with tcgen05.ld — instead of 4 LDS.128 and 16 fp64 instructions per transform (three transforms
+// per warp and iteration).  Tensor memory is lane private, which is exactly what these constants are; its load
+// path uses neither the shared-memory pipe nor the fp64 pipe, the two that bind this kernel.
+#ifndef TFHE_B200_E2_TMEM
+#define TFHE_B200_E2_TMEM 1
+#endif
 
 struct __align__(128) CtaSmem {
     WarpSmem w[kCtWarps];
@@ -79,6 +87,7 @@ struct __align__(128) CtaSmem {
     cpx ring[kStages][kChunkCplx];
     unsigned long long full[kStages];   // mbarriers: TMA completion of a ring stage
     unsigned int drained[kStages];      // warps that have finished with the stage's current chunk
+    uint32_t tmem_base;                 // tensor-memory allocation (TFHE_B200_E2_TMEM)
 };
 
 static_assert(sizeof(WarpSmem) % 16 == 0, "warp working set must keep 16 B alignment");
@@ -277,6 +286,142 @@ __device__ __forceinline__ void ring_skip(CtaSmem &S, const BrLaunch &L, int rol
     sp.advance((uint32_t) L.n_iter);
 }
 
+// ---- pass-2 multipliers in tensor memory (full-batch kernel) ---------------------------------------------
+// columns of a lane: 0 g0, 4 g1, 8 g2, 12 g2 e^{i pi/4}, 16 g3, 20 g3 e^{i pi/4}, 24 g3 e^{i pi/8}, 28 g3 e^{3 i pi/8}
+// (one complex double = 4 columns); the derived values are computed exactly as pass2_stage derives them.
+__device__ __forceinline__ void tm_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tm_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tm_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+__device__ __forceinline__ void tm_ld_cpx(uint32_t taddr, cpx &a) {
+    uint32_t v[4];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3])
+                 : "r"(taddr)
+                 : "memory");
+    a.x = __hiloint2double((int) v[1], (int) v[0]);
+    a.y = __hiloint2double((int) v[3], (int) v[2]);
+}
+
+// raw forms: the registers are only valid after tm_wait_ld()
+struct TmWords4 { uint32_t v[4]; };
+struct TmWords8 { uint32_t v[8]; };
+struct TmWords16 { uint32_t v[16]; };
+__device__ __forceinline__ void tm_ld4(uint32_t taddr, TmWords4 &w) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(w.v[0]), "=r"(w.v[1]), "=r"(w.v[2]), "=r"(w.v[3])
+                 : "r"(taddr)
+                 : "memory");
+}
+__device__ __forceinline__ void tm_ld8(uint32_t taddr, TmWords8 &w) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(w.v[0]), "=r"(w.v[1]), "=r"(w.v[2]), "=r"(w.v[3]), "=r"(w.v[4]), "=r"(w.v[5]), "=r"(w.v[6]), "=r"(w.v[7])
+                 : "r"(taddr)
+                 : "memory");
+}
+__device__ __forceinline__ void tm_ld16w(uint32_t taddr, TmWords16 &w) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(w.v[0]), "=r"(w.v[1]), "=r"(w.v[2]), "=r"(w.v[3]), "=r"(w.v[4]), "=r"(w.v[5]), "=r"(w.v[6]), "=r"(w.v[7]),
+          "=r"(w.v[8]), "=r"(w.v[9]), "=r"(w.v[10]), "=r"(w.v[11]), "=r"(w.v[12]), "=r"(w.v[13]), "=r"(w.v[14]), "=r"(w.v[15])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ cpx tm_cpx(const uint32_t *v) {
+    cpx a;
+    a.x = __hiloint2double((int) v[1], (int) v[0]);
+    a.y = __hiloint2double((int) v[3], (int) v[2]);
+    return a;
+}
+
+// every lane writes the eight multipliers of its frequency class (= lane) to its 32 columns
+__device__ __forceinline__ void tm_store_consts(uint32_t taddr, const cpx *e) {
+    const cpx g2 = e[2], g3 = e[3];
+    cpx c[8];
+    c[0] = e[0];
+    c[1] = e[1];
+    c[2] = g2;
+    c[3].x = (g2.x - g2.y) * kSqrtHalf;
+    c[3].y = (g2.x + g2.y) * kSqrtHalf;
+    c[4] = g3;
+    c[5].x = (g3.x - g3.y) * kSqrtHalf;
+    c[5].y = (g3.x + g3.y) * kSqrtHalf;
+    c[6] = cmul_const(g3, kCosPi8, kSinPi8);
+    c[7] = cmul_const(g3, kSinPi8, kCosPi8);
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+        uint32_t v[16];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            v[4 * k + 0] = (uint32_t) __double2loint(c[4 * h + k].x);
+            v[4 * k + 1] = (uint32_t) __double2hiint(c[4 * h + k].x);
+            v[4 * k + 2] = (uint32_t) __double2loint(c[4 * h + k].y);
+            v[4 * k + 3] = (uint32_t) __double2hiint(c[4 * h + k].y);
+        }
+        asm volatile(
+            "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" ::"r"(
+                taddr + 16u * (uint32_t) h),
+            "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]), "r"(v[10]),
+            "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
+            : "memory");
+    }
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+}
+
+// pass 2 forward / inverse with the multipliers streamed from tensor memory one stage ahead of their use
+// (w0: the first stage's multiplier, loaded by the caller ahead of the shared-memory reads of z)
+__device__ __forceinline__ void fwd16_tm(cpx (&z)[16], uint32_t ta, const TmWords4 &w0) {
+    TmWords4 w1;
+    TmWords8 w2;
+    TmWords16 w3;
+    tm_wait_ld();
+    tm_ld4(ta + 4, w1);
+    {
+        const cpx g = tm_cpx(w0.v);
+        Pass2Stage<0, false>::run(z, g, g, g, g);
+    }
+    tm_wait_ld();
+    tm_ld8(ta + 8, w2);
+    {
+        const cpx g = tm_cpx(w1.v);
+        Pass2Stage<1, false>::run(z, g, g, g, g);
+    }
+    tm_wait_ld();
+    tm_ld16w(ta + 16, w3);
+    {
+        const cpx g = tm_cpx(w2.v), h4 = tm_cpx(w2.v + 4);
+        Pass2Stage<2, false>::run(z, g, h4, g, g);
+    }
+    tm_wait_ld();
+    Pass2Stage<3, false>::run(z, tm_cpx(w3.v), tm_cpx(w3.v + 4), tm_cpx(w3.v + 8), tm_cpx(w3.v + 12));
+}
+
+// (w3: the first stage's four multipliers, loaded by the caller ahead of the hand-over additions)
+__device__ __forceinline__ void inv16_tm(cpx (&z)[16], uint32_t ta, const TmWords16 &w3) {
+    TmWords4 w0, w1;
+    TmWords8 w2;
+    tm_wait_ld();
+    tm_ld8(ta + 8, w2);
+    Pass2Stage<3, true>::run(z, tm_cpx(w3.v), tm_cpx(w3.v + 4), tm_cpx(w3.v + 8), tm_cpx(w3.v + 12));
+    tm_wait_ld();
+    tm_ld4(ta + 4, w1);
+    {
+        const cpx g = tm_cpx(w2.v), h4 = tm_cpx(w2.v + 4);
+        Pass2Stage<2, true>::run(z, g, h4, g, g);
+    }
+    tm_wait_ld();
+    tm_ld4(ta, w0);
+    {
+        const cpx g = tm_cpx(w1.v);
+        Pass2Stage<1, true>::run(z, g, g, g, g);
+    }
+    tm_wait_ld();
+    {
+        const cpx g = tm_cpx(w0.v);
+        Pass2Stage<0, true>::run(z, g, g, g, g);
+    }
+}
+
 // Operands of the gate prologue of bootstrap g (x = (0,cst) + sa*in0 + sb*in1 [+ sc*in2 [+ sd*in3]]).
 struct GateIn {
     const int32_t *in0 = nullptr, *in1 = nullptr, *in2 = nullptr, *in3 = nullptr;
@@ -443,7 +588,23 @@ __global__ void __launch_bounds__(kThreads, 1) blind_rotate_kernel(const BrLaunc
             for (uint32_t c = 0; c < kRingStages && c < kChunksPerIter * iters_total; c++)
                 ring_fill(S, L, r, c, r * kRingStages + c);
     }
+    constexpr bool kE2Tm = !HELPER && TFHE_B200_E2_TMEM;   // pass-2 multipliers in tensor memory (full batches)
+    if (kE2Tm) {
+        if (warp == 0) {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&S.tmem_base)), "n"(32)
+                         : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        }
+        tm_fence_before();
+    }
     __syncthreads();
+    uint32_t tm_e2 = 0;   // this lane's multipliers: its sub-partition's quarter of tensor memory, columns 0..31
+    if (kE2Tm) {
+        tm_fence_after();
+        tm_e2 = S.tmem_base + ((uint32_t) ((warp & 3) * 32) << 16);
+        tm_store_consts(tm_e2, S.e2 + lane * kE2Row);   // (both warps of a sub-partition write the same values)
+        __syncwarp();
+    }
     const bool rotate = (L.extern_only == 0);
 
     // -------------------- ciphertext warps ------------------------------------------
@@ -539,7 +700,16 @@ __global__ void __launch_bounds__(kThreads, 1) blind_rotate_kernel(const BrLaunc
                 cpx z[16];
                 const bool rdy_keep = ring_probe(S, sp, ring_base, 0);
                 const bool rdy_give = ring_probe(S, sp, ring_base, 1);
-                phase_f2_fft(lane, W, S.e2, row, z);
+                if (kE2Tm) {
+                    TmWords4 w0;
+                    tm_ld4(tm_e2, w0);
+                    const cpx *src = W.exch[row] + lane * kExchRow;
+#pragma unroll
+                    for (int j2 = 0; j2 < 16; j2++) z[j2] = src[j2];
+                    fwd16_tm(z, tm_e2, w0);
+                } else {
+                    phase_f2_fft(lane, W, S.e2, row, z);
+                }
                 PHASE_MARK(1);
                 mac_consume<HELPER>(S, L, role, lane, sp, ring_base, ring_chunks, rdy_keep, z, keep);
                 PHASE_MARK(2);
@@ -551,9 +721,18 @@ __global__ void __launch_bounds__(kThreads, 1) blind_rotate_kernel(const BrLaunc
             PHASE_MARK(4);
             pair_sync();
             PHASE_MARK(5);
+            TmWords16 w3;
+            if (kE2Tm) tm_ld16w(tm_e2 + 16, w3);
             phase_xchg_load(lane, W, role, keep);
             named_arrive(bar_partner, 64);  // done with the partner's B
-            phase_inv16_store(lane, W, S.e2, role, keep);
+            if (kE2Tm) {
+                inv16_tm(keep, tm_e2, w3);
+                cpx *d = W.exch[2 * role] + lane * kExchRow;
+#pragma unroll
+                for (int j2 = 0; j2 < 16; j2++) d[j2] = keep[j2];
+            } else {
+                phase_inv16_store(lane, W, S.e2, role, keep);
+            }
             __syncwarp();
             PHASE_MARK(6);
             {
@@ -580,6 +759,14 @@ __global__ void __launch_bounds__(kThreads, 1) blind_rotate_kernel(const BrLaunc
             if (L.acc_out != nullptr) phase_dump_acc(lane, W, L.acc_out + (size_t) g * (kK + 1) * kN);
         }
         pair_sync();
+    }
+    if (kE2Tm) {
+        tm_fence_before();
+        __syncthreads();
+        if (warp == 0) {
+            tm_fence_after();
+            asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(S.tmem_base), "n"(32) : "memory");
+        }
     }
 }
 
