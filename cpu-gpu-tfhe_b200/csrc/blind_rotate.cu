@@ -12,7 +12,7 @@
 //     barriers (two warps per SM sub-partition hide each other's latencies: ncu of
 //     the one-warp-per-ciphertext version showed 43 % fp64 pipe use);
 //   * the rotation X^a * ACC is read at immediate offsets from a negacyclically extended
-//     copy of the accumulator (br_core.cuh phase_f1q_decomp), sign / subtraction /
+//     copy of the accumulator (br_core.cuh phase_f1_decomp), sign / subtraction /
 //     decomposition offset / digit shift are two integer multiply-adds per coefficient;
 //   * 4 ciphertexts per CTA share each 16 KiB row of the bootstrapping key,
 //     streamed from L2/HBM with 1-D TMA bulk copies (cp.async.bulk + mbarrier
@@ -21,7 +21,12 @@
 //     there is no producer warp (small batches: the idle last slot of the CTA refills);
 //   * the gate's linear prologue and the mod-switch are computed on the fly
 //     from the input samples (no temporaries in global memory);
-//   * grid = min(#groups, #SMs) CTAs, each looping over groups of 4 ciphertexts.
+//   * grid = min(#groups, #SMs) CTAs, each looping over groups of 4 ciphertexts;
+//   * the two resources that bind it are the fp64 pipe and the shared-memory pipe: the gadget digits become
+//     doubles on the conversion pipe (I2F), and a lane's pass-2 multipliers live in tensor memory (lane-private
+//     constants: tcgen05.st once, tcgen05.ld per stage) instead of shared memory + derivations;
+//   * batches of at most one / two ciphertexts per SM run on two latency kernels (below) that spread ONE
+//     ciphertext over eight / four warps.
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdlib.h>
